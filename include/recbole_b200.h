@@ -1,0 +1,197 @@
+/*
+ * recbole_b200.h -- C ABI of the B200-native embedding hot path for ghazalehnt/RecBole.
+ *
+ * This is the drop-in boundary (last row).  The reference is pure
+ * Python/PyTorch and has no FFI of its own; each entry point below names the reference
+ * Python call it replaces (file:line relative to the reference repo) and is bound from Python
+ * with ctypes in recbole_b200/_lib.py (the stub a maintainer would add is shown in
+ * INTEGRATION.md).
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer unless its name starts with `h_`.  All buffers
+ *     (tables, optimizer state, id vectors, outputs, workspace) are owned by the caller
+ *     (PyTorch); the library allocates nothing persistent and frees nothing.
+ *   - Embedding tables are row-major fp32 [rows, dim]; ids are int64 with 0 = [PAD]
+ *     (reference: recbole/data/dataset/dataset.py:908-928,1699-1700).
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
+ *     Calls are asynchronous on that stream unless stated otherwise and re-entrant per
+ *     (device, stream); there is no global mutable state except the last-error string.
+ *   - Return value: 0 on success, otherwise a cudaError_t or one of the RB2_E* codes;
+ *     rb2_last_error() describes the failure.  There is no CPU fallback anywhere.
+ *   - Workspace: query the size with the matching *_workspace_bytes() and pass a device buffer
+ *     of at least that many bytes, 256-byte aligned.
+ */
+#ifndef RECBOLE_B200_H_
+#define RECBOLE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB2_ABI_VERSION 1
+
+#define RB2_EINVAL 10001   /* bad argument (dim not supported, null pointer, ...) */
+#define RB2_EWORKSPACE 10002 /* workspace too small */
+#define RB2_ERANGE 10003   /* an id is outside its table (reference: IndexError in F.embedding) */
+
+int rb2_abi_version(void);
+const char *rb2_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer description.  Replaces the torch.optim objects built by
+ * Trainer._build_optimizer (recbole/trainer/trainer.py:109-130) and stepped at trainer.py:173.
+ * Scalars are computed by the host in double exactly as torch/optim/adam.py does
+ * (bias_correction1 = 1 - beta1**t, step_size = lr / bias_correction1,
+ *  bias_correction2_sqrt = sqrt(1 - beta2**t)) and rounded to fp32 once.
+ * ---------------------------------------------------------------------------------------- */
+enum {
+  RB2_OPT_SGD = 0,        /* p -= lr * (g + wd*p)                  (torch.optim.SGD, momentum 0)     */
+  RB2_OPT_ADAM = 1,       /* row-sparse Adam: the dense formula on the rows touched by the batch    */
+  RB2_OPT_ADAM_LAZY = 2   /* row-sparse Adam that replays the zero-gradient steps a row missed, so
+                             the trajectory equals the reference's dense Adam (needs *_last arrays) */
+};
+
+typedef struct rb2_optim {
+  int32_t kind;
+  int32_t step;            /* t, 1-based, one counter per training run (adam.py: state['step'])      */
+  float lr;
+  float weight_decay;      /* L2 added to the gradient of touched rows (adam.py:416-429)             */
+  float beta1, beta2;
+  float one_minus_beta1;   /* (float)(1 - beta1) as torch passes to lerp_                            */
+  float one_minus_beta2;
+  float eps;
+  float step_size;         /* lr / (1 - beta1**t)                                                    */
+  float bc2_sqrt;          /* sqrt(1 - beta2**t)                                                     */
+  /* RB2_OPT_ADAM_LAZY only: DEVICE tables indexed by step j = 1..step (entry 0 unused) holding
+     lr/(1-beta1**j) and sqrt(1-beta2**j); NULL otherwise. */
+  const float *lazy_step_size;
+  const float *lazy_bc2_sqrt;
+} rb2_optim;
+
+/* ------------------------------------------------------------------------------------------
+ * (1) Fused BPR training step.
+ * Replaces, for one batch: BPR.calculate_loss (recbole/model/general_recommender/bpr.py:74-83),
+ * BPRLoss.forward (recbole/model/loss.py:43-49), loss.backward() (trainer.py:170) and
+ * optimizer.step() (trainer.py:173).  All gradients are evaluated at the parameters as they
+ * are on entry, duplicates of a row inside the batch are summed, then each touched row takes
+ * exactly one optimizer step.
+ *
+ * user_m/user_v/item_m/item_v may be NULL for RB2_OPT_SGD.  user_last/item_last (int32 per row,
+ * zero-initialised) are only read for RB2_OPT_ADAM_LAZY.
+ * loss_out[0]   = mean loss of this batch (fp32), as calculate_loss returns it.
+ * loss_accum[0] += loss_out[0] if loss_accum != NULL (fp64; the Trainer's running total_loss,
+ *                  trainer.py:168, kept on the device so the epoch needs one sync).
+ * ---------------------------------------------------------------------------------------- */
+size_t rb2_bpr_workspace_bytes(int64_t batch, int32_t dim);
+
+int rb2_bpr_train_step(float *user_p, float *user_m, float *user_v, int32_t *user_last,
+                       float *item_p, float *item_m, float *item_v, int32_t *item_last,
+                       int64_t n_users, int64_t n_items, int32_t dim,
+                       const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t batch,
+                       const rb2_optim *h_opt, float *loss_out, double *loss_accum,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* Forward only: loss_out[0] = BPR loss of the batch, parameters untouched (calculate_loss under
+ * torch.no_grad, bpr.py:74-83 + loss.py:48). */
+int rb2_bpr_loss(const float *user_p, const float *item_p, int64_t n_users, int64_t n_items, int32_t dim,
+                 const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t batch,
+                 float *loss_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Flush for RB2_OPT_ADAM_LAZY: bring every row to step `h_opt->step` (replaying the zero-gradient
+ * steps it missed) so the tables can be read by evaluation / checkpointing. */
+int rb2_adam_lazy_flush(float *p, float *m, float *v, int32_t *last, int64_t rows, int32_t dim,
+                        const rb2_optim *h_opt, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (1b) Gather-dot for explicit (user, item) pairs.  Replaces BPR.predict (bpr.py:85-89).
+ * ---------------------------------------------------------------------------------------- */
+int rb2_gather_dot(const float *user_p, const float *item_p, int64_t n_users, int64_t n_items, int32_t dim,
+                   const int64_t *user, const int64_t *item, int64_t n, float *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) Full-sort scorer with fused mask and top-K; the [users, n_items] score matrix is never
+ * written.  Replaces BPR.full_sort_predict (bpr.py:91-96) / SASRec.full_sort_predict
+ * (recbole/model/sequential_recommender/sasrec.py:152-158), the masking of
+ * Trainer._full_sort_batch_eval (trainer.py:342-345) and TopKEvaluator.collect's topk
+ * (recbole/evaluator/evaluators.py:68-72).
+ *
+ * Row r of the query is query_p[query_ids[r]] (query_ids == NULL: row r itself, e.g. sequence
+ * embeddings).  Candidates for row r: item ids item_base+1.. (id 0 = [PAD] is never a candidate)
+ * minus hist_indices[hist_indptr[r] .. hist_indptr[r+1]) (sorted ascending, global item ids;
+ * hist_indptr == NULL: no history).  Scores are the canonical fp32 chain
+ * s = fmaf(q[k], v[k], s), k ascending.  Order: score descending, ties by ascending item id.
+ * out_ids int64 [nq, k] (missing slots -1), out_scores fp32 [nq, k] (missing -inf).
+ * item_p points at the local shard [n_items_local, dim] whose first row has global id item_base.
+ *
+ * mode: RB2_SCORER_FP32   exact CUDA-core path.
+ *       RB2_SCORER_TC     tcgen05 bf16 tensor-core filter + exact fp32 re-score of the survivors,
+ *                         certified per row; rows whose certificate fails are redone in fp32.
+ * ---------------------------------------------------------------------------------------- */
+enum { RB2_SCORER_FP32 = 0, RB2_SCORER_TC = 1 };
+
+size_t rb2_fullsort_workspace_bytes(int64_t nq, int64_t n_items_local, int32_t dim, int32_t k, int32_t mode);
+
+int rb2_fullsort_topk(const float *query_p, const int64_t *query_ids, int64_t nq,
+                      const float *item_p, int64_t n_items_local, int64_t item_base, int32_t dim,
+                      const int64_t *hist_indptr, const int64_t *hist_indices, int32_t k, int32_t mode,
+                      int64_t *out_ids, float *out_scores,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* Merge `parts` per-shard top-K lists ([parts, nq, k], each sorted) into the global top-K
+ * (multi-GPU all-gather merge). */
+int rb2_topk_merge(const int64_t *ids, const float *scores, int32_t parts, int64_t nq, int32_t k,
+                   int64_t *out_ids, float *out_scores, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2b) Metrics on device.  Replaces TopKEvaluator.evaluate/_calculate_metrics
+ * (evaluators.py:78-105,122-141) and recbole/evaluator/metrics.py:27-164.
+ * pos CSR: the evaluated phase's positives per row (sorted).  discount[j] = 1/log2(j+2) and
+ * idcg[j] = sum_{i<=j} discount[i] (fp64, length k) are supplied by the host so that the
+ * per-user values are bit-identical to numpy's.
+ * sums[6*k] (fp64): metric-major sums over rows in the order
+ *   RB2_M_RECALL, RB2_M_MRR, RB2_M_NDCG, RB2_M_HIT, RB2_M_PRECISION, RB2_M_MAP; value at rank j+1.
+ * Optional outputs (NULL to skip): hit uint8 [nq, k]; ref_idx int64 [nq, k+1] = the reference's
+ * own `topk_idx | shape` matrix in its swapped+flipped coordinates (evaluators.py:68-75), so
+ * that an unmodified TopKEvaluator.evaluate can consume it.
+ * ---------------------------------------------------------------------------------------- */
+enum { RB2_M_RECALL = 0, RB2_M_MRR = 1, RB2_M_NDCG = 2, RB2_M_HIT = 3, RB2_M_PRECISION = 4, RB2_M_MAP = 5,
+       RB2_NUM_METRICS = 6 };
+
+size_t rb2_topk_metrics_workspace_bytes(int64_t nq, int32_t k);
+
+int rb2_topk_metrics(const int64_t *topk_ids, int64_t nq, int32_t k, int64_t n_items,
+                     const int64_t *pos_indptr, const int64_t *pos_indices,
+                     const double *discount, const double *idcg,
+                     double *sums, uint8_t *hit, int64_t *ref_idx,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) Negative sampler against a device-resident CSR of used ids.
+ * Replaces Sampler.sample_by_user_ids -> AbstractSampler.sample_by_key_ids
+ * (recbole/sampler/sampler.py:103-154,246-265).  Output layout as the reference:
+ * out[k*n_keys + i] is the k-th negative of key_ids[i].
+ *
+ * rb2_neg_sample_ref: the reference's own stream -- values are taken from `random_list`
+ *   (the once-shuffled candidate list, sampler.py:54-57) starting at *h_random_pr, re-drawing
+ *   rejected slots in order from the following entries (sampler.py:144-153); *h_random_pr is
+ *   advanced exactly as the reference advances it.  Synchronous (one host sync per round).
+ * rb2_neg_sample_hash: counter-based stream (seed, step, slot, attempt); one launch, async.
+ * ---------------------------------------------------------------------------------------- */
+size_t rb2_neg_sample_workspace_bytes(int64_t n_keys, int32_t num);
+
+int rb2_neg_sample_ref(const int64_t *key_ids, int64_t n_keys, int32_t num,
+                       const int64_t *random_list, int64_t random_list_length, int64_t *h_random_pr,
+                       const int64_t *used_indptr, const int64_t *used_indices, int64_t n_rows,
+                       int64_t *out, void *workspace, size_t workspace_bytes, void *stream);
+
+int rb2_neg_sample_hash(const int64_t *key_ids, int64_t n_keys, int32_t num, int64_t n_items,
+                        const int64_t *used_indptr, const int64_t *used_indices, int64_t n_rows,
+                        uint64_t seed, uint64_t step, int64_t *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECBOLE_B200_H_ */

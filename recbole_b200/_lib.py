@@ -1,0 +1,85 @@
+"""ctypes binding of librecbole_b200.so (the C ABI declared in include/recbole_b200.h).
+
+There is NO fallback: if the shared library has not been built (python -m recbole_b200.build, or
+__graft_entry__.build()), importing this module raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librecbole_b200.so")
+
+ABI_VERSION = 1
+
+# enums of include/recbole_b200.h
+OPT_SGD, OPT_ADAM, OPT_ADAM_LAZY = 0, 1, 2
+SCORER_FP32, SCORER_TC = 0, 1
+M_RECALL, M_MRR, M_NDCG, M_HIT, M_PRECISION, M_MAP = range(6)
+NUM_METRICS = 6
+METRIC_ORDER = ("recall", "mrr", "ndcg", "hit", "precision", "map")
+EINVAL, EWORKSPACE, ERANGE = 10001, 10002, 10003
+
+
+class RB2Optim(ctypes.Structure):
+    _fields_ = [
+        ("kind", ctypes.c_int32), ("step", ctypes.c_int32),
+        ("lr", ctypes.c_float), ("weight_decay", ctypes.c_float),
+        ("beta1", ctypes.c_float), ("beta2", ctypes.c_float),
+        ("one_minus_beta1", ctypes.c_float), ("one_minus_beta2", ctypes.c_float),
+        ("eps", ctypes.c_float), ("step_size", ctypes.c_float), ("bc2_sqrt", ctypes.c_float),
+        ("lazy_step_size", ctypes.c_void_p), ("lazy_bc2_sqrt", ctypes.c_void_p),
+    ]
+
+
+_p, _i64, _i32, _sz, _u64 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_size_t, ctypes.c_uint64
+
+# name -> (restype, argtypes); every symbol include/recbole_b200.h declares
+SIGNATURES = {
+    "rb2_abi_version": (ctypes.c_int, []),
+    "rb2_last_error": (ctypes.c_char_p, []),
+    "rb2_bpr_workspace_bytes": (_sz, [_i64, _i32]),
+    "rb2_bpr_train_step": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _i64,
+                                          ctypes.POINTER(RB2Optim), _p, _p, _p, _sz, _p]),
+    "rb2_bpr_loss": (ctypes.c_int, [_p, _p, _i64, _i64, _i32, _p, _p, _p, _i64, _p, _p, _sz, _p]),
+    "rb2_adam_lazy_flush": (ctypes.c_int, [_p, _p, _p, _p, _i64, _i32, ctypes.POINTER(RB2Optim), _p]),
+    "rb2_gather_dot": (ctypes.c_int, [_p, _p, _i64, _i64, _i32, _p, _p, _i64, _p, _p]),
+    "rb2_fullsort_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32, _i32]),
+    "rb2_fullsort_topk": (ctypes.c_int, [_p, _p, _i64, _p, _i64, _i64, _i32, _p, _p, _i32, _i32, _p, _p, _p, _sz,
+                                         _p]),
+    "rb2_topk_merge": (ctypes.c_int, [_p, _p, _i32, _i64, _i32, _p, _p, _p]),
+    "rb2_topk_metrics_workspace_bytes": (_sz, [_i64, _i32]),
+    "rb2_topk_metrics": (ctypes.c_int, [_p, _i64, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "rb2_neg_sample_workspace_bytes": (_sz, [_i64, _i32]),
+    "rb2_neg_sample_ref": (ctypes.c_int, [_p, _i64, _i32, _p, _i64, ctypes.POINTER(_i64), _p, _p, _i64, _p, _p,
+                                          _sz, _p]),
+    "rb2_neg_sample_hash": (ctypes.c_int, [_p, _i64, _i32, _i64, _p, _p, _i64, _u64, _u64, _p, _p]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "recbole_b200: %s is missing. Build it with `python -m recbole_b200.build` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.rb2_abi_version() != ABI_VERSION:
+        raise ImportError("recbole_b200: ABI version mismatch (library %d, binding %d)"
+                          % (lib.rb2_abi_version(), ABI_VERSION))
+    return lib
+
+
+lib = _load()
+
+
+class RB2Error(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib.rb2_last_error().decode("utf-8", "replace")
+        raise RB2Error("recbole_b200 C ABI call failed (code %d): %s" % (rc, msg))

@@ -1,0 +1,486 @@
+// fullsort.cu -- full-sort scorer (exact fp32 path), top-K merge and on-device metrics for sm_100a.
+//
+// Replaces BPR.full_sort_predict (bpr.py:91-96) + Trainer._full_sort_batch_eval masking
+// (trainer.py:342-345) + TopKEvaluator.collect's flip/topk (evaluators.py:68-72) +
+// TopKEvaluator.evaluate / metrics.py (evaluators.py:78-141, metrics.py:27-164).
+// The [users, n_items] score matrix never exists: every score is compared against the row's
+// running K-th best as soon as it is produced.
+//
+// k_fullsort_fp32: one thread owns one query row (its embedding lives in registers) and walks
+// the item table, which streams through shared memory in double-buffered tiles loaded by the
+// bulk-copy engine (cp.async.bulk + mbarrier).  All lanes of a warp read the same item element,
+// so the shared-memory reads are broadcasts.  Scores are the canonical chain
+// s = fmaf(q[k], v[k], s), k ascending (see oracle/csrc/oracle.c).  History / pad masking costs
+// nothing per element: it is only checked for the rare element that beats the running threshold.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kRows = 128;  // query rows (= threads) per block
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar` (TMA engine, UBLKCP in SASS)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ bool csr_contains(const int64_t *__restrict__ a, int64_t n, int64_t x) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (a[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo < n && a[lo] == x;
+}
+
+// rare path: candidate beat the running threshold.  Lists live in shared memory, element j of
+// the thread's list at [j * kRows + tid] (conflict-free).
+__device__ __noinline__ void topk_insert(float *sc, int *id, int K, float s, int64_t item,
+                                         const int64_t *__restrict__ hist, int64_t hlen, float &tau) {
+  if (item == 0) return;                          // [PAD], trainer.py:343
+  if (hlen > 0 && csr_contains(hist, hlen, item)) return;  // trainer.py:344-345
+  int j = K - 1;
+  while (j > 0 && sc[(j - 1) * kRows] < s) {      // equal scores stay in front: lower id first
+    sc[j * kRows] = sc[(j - 1) * kRows];
+    id[j * kRows] = id[(j - 1) * kRows];
+    --j;
+  }
+  sc[j * kRows] = s;
+  id[j * kRows] = (int)item;
+  tau = sc[(K - 1) * kRows];
+}
+
+template <int D>
+struct FsCfg {
+  static constexpr int TI = (4096 / D) < 8 ? 8 : (4096 / D);  // items per tile (16 KB)
+  static constexpr int TILE_FLOATS = TI * D;
+};
+
+template <int D>
+__global__ void __launch_bounds__(kRows) k_fullsort_fp32(const float *__restrict__ query_p,
+                                                          const int64_t *__restrict__ query_ids, int64_t nq,
+                                                          const float *__restrict__ item_p, int64_t n_local,
+                                                          int64_t item_base, const int64_t *__restrict__ hist_indptr,
+                                                          const int64_t *__restrict__ hist_indices, int K,
+                                                          int64_t items_per_split, int64_t *__restrict__ out_ids,
+                                                          float *__restrict__ out_scores) {
+  constexpr int TI = FsCfg<D>::TI;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float *tile0 = reinterpret_cast<float *>(smem_raw);
+  float *tile1 = tile0 + FsCfg<D>::TILE_FLOATS;
+  float *lsc = tile1 + FsCfg<D>::TILE_FLOATS;               // [K][kRows]
+  int *lid = reinterpret_cast<int *>(lsc + (size_t)K * kRows);  // [K][kRows]
+  __shared__ __align__(8) uint64_t bars[2];
+
+  const int tid = threadIdx.x;
+  const int64_t r = (int64_t)blockIdx.x * kRows + tid;
+  const bool active = r < nq;
+  const int64_t i_begin = (int64_t)blockIdx.y * items_per_split;
+  const int64_t i_end = min(i_begin + items_per_split, n_local);
+  const int64_t n_tiles = (i_end - i_begin + TI - 1) / TI;
+
+  // query row -> registers
+  float q[D];
+  {
+    int64_t row = active ? (query_ids ? query_ids[r] : r) : 0;
+    const float4 *src = reinterpret_cast<const float4 *>(query_p + row * D);
+#pragma unroll
+    for (int k = 0; k < D / 4; ++k) {
+      float4 v = active ? __ldg(src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      q[4 * k] = v.x; q[4 * k + 1] = v.y; q[4 * k + 2] = v.z; q[4 * k + 3] = v.w;
+    }
+  }
+  const int64_t *hist = nullptr;
+  int64_t hlen = 0;
+  if (active && hist_indptr) {
+    int64_t h0 = hist_indptr[r];
+    hlen = hist_indptr[r + 1] - h0;
+    hist = hist_indices + h0;
+  }
+  for (int j = 0; j < K; ++j) {
+    lsc[j * kRows + tid] = -INFINITY;
+    lid[j * kRows + tid] = -1;
+  }
+  float tau = -INFINITY;
+  float *my_sc = lsc + tid;
+  int *my_id = lid + tid;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int64_t t) {
+    int64_t i0 = i_begin + t * TI;
+    uint32_t bytes = (uint32_t)(min((int64_t)TI, i_end - i0) * D * sizeof(float));
+    uint64_t *bar = &bars[t & 1];
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s((t & 1) ? tile1 : tile0, item_p + i0 * D, bytes, bar);
+  };
+  if (tid == 0 && n_tiles > 0) issue(0);
+
+  for (int64_t t = 0; t < n_tiles; ++t) {
+    if (tid == 0 && t + 1 < n_tiles) issue(t + 1);
+    mbar_wait(&bars[t & 1], (uint32_t)((t >> 1) & 1));
+    const float4 *vt = reinterpret_cast<const float4 *>((t & 1) ? tile1 : tile0);
+    const int64_t i0 = i_begin + t * TI;
+    const int cnt = (int)min((int64_t)TI, i_end - i0);
+    if (active) {
+      int i = 0;
+      for (; i + 4 <= cnt; i += 4) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        const float4 *v0 = vt + (size_t)(i + 0) * (D / 4);
+        const float4 *v1 = vt + (size_t)(i + 1) * (D / 4);
+        const float4 *v2 = vt + (size_t)(i + 2) * (D / 4);
+        const float4 *v3 = vt + (size_t)(i + 3) * (D / 4);
+#pragma unroll
+        for (int k = 0; k < D / 4; ++k) {
+          float4 a = v0[k], b = v1[k], c = v2[k], d = v3[k];
+          s0 = fmaf(q[4 * k], a.x, s0); s1 = fmaf(q[4 * k], b.x, s1);
+          s2 = fmaf(q[4 * k], c.x, s2); s3 = fmaf(q[4 * k], d.x, s3);
+          s0 = fmaf(q[4 * k + 1], a.y, s0); s1 = fmaf(q[4 * k + 1], b.y, s1);
+          s2 = fmaf(q[4 * k + 1], c.y, s2); s3 = fmaf(q[4 * k + 1], d.y, s3);
+          s0 = fmaf(q[4 * k + 2], a.z, s0); s1 = fmaf(q[4 * k + 2], b.z, s1);
+          s2 = fmaf(q[4 * k + 2], c.z, s2); s3 = fmaf(q[4 * k + 2], d.z, s3);
+          s0 = fmaf(q[4 * k + 3], a.w, s0); s1 = fmaf(q[4 * k + 3], b.w, s1);
+          s2 = fmaf(q[4 * k + 3], c.w, s2); s3 = fmaf(q[4 * k + 3], d.w, s3);
+        }
+        const int64_t g = item_base + i0 + i;
+        if (s0 > tau) topk_insert(my_sc, my_id, K, s0, g + 0, hist, hlen, tau);
+        if (s1 > tau) topk_insert(my_sc, my_id, K, s1, g + 1, hist, hlen, tau);
+        if (s2 > tau) topk_insert(my_sc, my_id, K, s2, g + 2, hist, hlen, tau);
+        if (s3 > tau) topk_insert(my_sc, my_id, K, s3, g + 3, hist, hlen, tau);
+      }
+      for (; i < cnt; ++i) {
+        float s = 0.f;
+        const float4 *v0 = vt + (size_t)i * (D / 4);
+#pragma unroll
+        for (int k = 0; k < D / 4; ++k) {
+          float4 a = v0[k];
+          s = fmaf(q[4 * k], a.x, s);
+          s = fmaf(q[4 * k + 1], a.y, s);
+          s = fmaf(q[4 * k + 2], a.z, s);
+          s = fmaf(q[4 * k + 3], a.w, s);
+        }
+        if (s > tau) topk_insert(my_sc, my_id, K, s, item_base + i0 + i, hist, hlen, tau);
+      }
+    }
+    __syncthreads();  // everyone is done with this buffer before it is refilled
+  }
+
+  if (active) {
+    int64_t o = ((int64_t)blockIdx.y * nq + r) * K;
+    for (int j = 0; j < K; ++j) {
+      out_ids[o + j] = (int64_t)my_id[j * kRows];
+      out_scores[o + j] = my_sc[j * kRows];
+    }
+  }
+}
+
+// merge `parts` sorted lists per row; order (score desc, id asc); id -1 = empty slot
+__global__ void k_topk_merge(const int64_t *__restrict__ ids, const float *__restrict__ scores, int parts, int64_t nq,
+                             int K, int64_t *__restrict__ out_ids, float *__restrict__ out_scores) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nq) return;
+  unsigned char head[64];
+  for (int p = 0; p < parts; ++p) head[p] = 0;
+  for (int j = 0; j < K; ++j) {
+    int best = -1;
+    float bs = -INFINITY;
+    int64_t bi = -1;
+    for (int p = 0; p < parts; ++p) {
+      if (head[p] >= K) continue;
+      int64_t o = ((int64_t)p * nq + r) * K + head[p];
+      int64_t id = ids[o];
+      if (id < 0) continue;
+      float s = scores[o];
+      if (best < 0 || s > bs || (s == bs && id < bi)) { best = p; bs = s; bi = id; }
+    }
+    if (best >= 0) head[best]++;
+    out_ids[r * K + j] = bi;
+    out_scores[r * K + j] = best >= 0 ? bs : -INFINITY;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// metrics
+__device__ __forceinline__ int64_t count_le(const int64_t *__restrict__ a, int64_t n, int64_t x) {
+  int64_t lo = 0, hi = n;  // number of elements <= x
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (a[mid] <= x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// column the reference's swap puts item t in (general_dataloader.py:325-327, trainer.py:347-350)
+__device__ int64_t ref_column(const int64_t *__restrict__ pos, int64_t p, int64_t t) {
+  if (p == 0) return t;
+  const int64_t c = count_le(pos, p, p - 1);  // positives already inside [0, p)
+  const int64_t m = p - c;                    // length of each swap list
+  const bool is_pos = csr_contains(pos, p, t);
+  if (is_pos && t >= p) {
+    int64_t i = count_le(pos, p, t) - c;      // t = b_i (1-based)
+    int64_t want = m + 1 - i;                 // partner a_want: want-th non-positive column in [0, p)
+    int64_t lo = 0, hi = p - 1;
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if (mid + 1 - count_le(pos, p, mid) >= want) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+  }
+  if (!is_pos && t < p) {
+    int64_t i = t + 1 - count_le(pos, p, t);  // t = a_i
+    return pos[p - i];                        // partner b_{m+1-i} = pos[c + (m+1-i) - 1]
+  }
+  return t;
+}
+
+constexpr int kMetricThreads = 128;
+
+__global__ void __launch_bounds__(kMetricThreads) k_topk_metrics(
+    const int64_t *__restrict__ topk, int64_t nq, int K, int64_t n_items, const int64_t *__restrict__ pos_indptr,
+    const int64_t *__restrict__ pos_indices, const double *__restrict__ discount, const double *__restrict__ idcg,
+    double *__restrict__ block_part, uint8_t *__restrict__ hit_out, int64_t *__restrict__ ref_idx) {
+  extern __shared__ double wsum[];  // [warps][6][K]
+  const int warps = kMetricThreads / 32;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = r < nq;
+  const int64_t *pos = nullptr;
+  int64_t plen = 0;
+  if (active) {
+    int64_t p0 = pos_indptr[r];
+    plen = pos_indptr[r + 1] - p0;
+    pos = pos_indices + p0;
+  }
+  int cum = 0, first = -1;
+  double dcg = 0.0, sum_pre = 0.0;
+  for (int j = 0; j < K; ++j) {
+    double vals[RB2_NUM_METRICS] = {0, 0, 0, 0, 0, 0};
+    if (active) {
+      int64_t id = topk[r * K + j];
+      bool h = id >= 0 && plen > 0 && csr_contains(pos, plen, id);
+      if (hit_out) hit_out[r * K + j] = h ? 1 : 0;
+      if (ref_idx) ref_idx[r * (K + 1) + j] = n_items - 1 - ref_column(pos, plen, id >= 0 ? id : 0);
+      if (h) {
+        ++cum;
+        if (first < 0) first = j;
+        dcg += discount[j];
+        sum_pre += (double)cum / (double)(j + 1);
+      }
+      if (plen > 0) {
+        int64_t lim = plen < (int64_t)(j + 1) ? plen : (int64_t)(j + 1);
+        vals[RB2_M_RECALL] = (double)cum / (double)plen;      // metrics.py:110
+        vals[RB2_M_MRR] = first >= 0 ? 1.0 / (double)(first + 1) : 0.0;  // metrics.py:57-64
+        vals[RB2_M_NDCG] = dcg / idcg[lim - 1];               // metrics.py:131-146
+        vals[RB2_M_HIT] = cum > 0 ? 1.0 : 0.0;                // metrics.py:41-42
+        vals[RB2_M_PRECISION] = (double)cum / (double)(j + 1);  // metrics.py:164
+        vals[RB2_M_MAP] = sum_pre / (double)lim;              // metrics.py:84-92
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < RB2_NUM_METRICS; ++m) {
+      double v = vals[m];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) wsum[(warp * RB2_NUM_METRICS + m) * K + j] = v;
+    }
+  }
+  if (active && ref_idx) ref_idx[r * (K + 1) + K] = n_items;  // shape column, evaluators.py:69,75
+  __syncthreads();
+  for (int e = threadIdx.x; e < RB2_NUM_METRICS * K; e += blockDim.x) {
+    double s = 0.0;
+    for (int w2 = 0; w2 < warps; ++w2) s += wsum[w2 * RB2_NUM_METRICS * K + e];
+    block_part[(int64_t)blockIdx.x * RB2_NUM_METRICS * K + e] = s;
+  }
+}
+
+__global__ void k_metrics_reduce(const double *__restrict__ block_part, int64_t n_blocks, int n, double *sums) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double s = 0.0;
+  for (int64_t b = 0; b < n_blocks; ++b) s += block_part[b * n + e];
+  sums[e] = s;
+}
+
+struct FsPlan {
+  int n_split;
+  int64_t items_per_split;
+  size_t smem;
+};
+
+template <int D>
+FsPlan plan_fp32(int64_t nq, int64_t n_local, int K) {
+  constexpr int TI = FsCfg<D>::TI;
+  int64_t bx = (nq + kRows - 1) / kRows;
+  int64_t want = ((int64_t)rb2_num_sms() * 2 + bx - 1) / bx;
+  int64_t max_split = (n_local + TI - 1) / TI;
+  int64_t ns = want < 1 ? 1 : want;
+  if (ns > 64) ns = 64;
+  if (ns > max_split) ns = max_split;
+  if (ns < 1) ns = 1;
+  int64_t per = (n_local + ns - 1) / ns;
+  per = (per + TI - 1) / TI * TI;
+  ns = (n_local + per - 1) / per;
+  if (ns < 1) ns = 1;
+  FsPlan p;
+  p.n_split = (int)ns;
+  p.items_per_split = per;
+  p.smem = 2 * FsCfg<D>::TILE_FLOATS * sizeof(float) + (size_t)K * kRows * (sizeof(float) + sizeof(int));
+  return p;
+}
+
+FsPlan plan_any(int dim, int64_t nq, int64_t n_local, int K) {
+  switch (dim) {
+    case 16: return plan_fp32<16>(nq, n_local, K);
+    case 32: return plan_fp32<32>(nq, n_local, K);
+    case 64: return plan_fp32<64>(nq, n_local, K);
+    case 128: return plan_fp32<128>(nq, n_local, K);
+    default: { FsPlan p; p.n_split = 0; p.items_per_split = 0; p.smem = 0; return p; }
+  }
+}
+
+}  // namespace
+
+// implemented in fullsort_tc.cu
+size_t rb2_fullsort_tc_workspace_bytes(int64_t nq, int64_t n_items_local, int32_t dim, int32_t k);
+int rb2_fullsort_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p,
+                    int64_t n_items_local, int64_t item_base, int32_t dim, const int64_t *hist_indptr,
+                    const int64_t *hist_indices, int32_t k, int64_t *out_ids, float *out_scores, void *workspace,
+                    size_t workspace_bytes, cudaStream_t st);
+
+extern "C" size_t rb2_fullsort_workspace_bytes(int64_t nq, int64_t n_items_local, int32_t dim, int32_t k,
+                                               int32_t mode) {
+  if (mode == RB2_SCORER_TC) return rb2_fullsort_tc_workspace_bytes(nq, n_items_local, dim, k);
+  FsPlan p = plan_any(dim, nq, n_items_local, k);
+  Carver c(nullptr);
+  c.take<int64_t>((size_t)p.n_split * nq * k);
+  c.take<float>((size_t)p.n_split * nq * k);
+  return c.off + 256;
+}
+
+int rb2_fullsort_fp32(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p,
+                      int64_t n_items_local, int64_t item_base, int32_t dim, const int64_t *hist_indptr,
+                      const int64_t *hist_indices, int32_t k, int64_t *out_ids, float *out_scores, void *workspace,
+                      size_t workspace_bytes, cudaStream_t st) {
+  FsPlan p = plan_any(dim, nq, n_items_local, k);
+  RB2_REQUIRE(p.n_split > 0, RB2_EINVAL, "rb2_fullsort_topk: embedding dim %d not supported by the fp32 scorer (16, 32, 64, 128)",
+              (int)dim);
+  RB2_REQUIRE(p.smem <= 200 * 1024, RB2_EINVAL, "rb2_fullsort_topk: k=%d too large", (int)k);
+  Carver c(workspace);
+  int64_t *part_ids = c.take<int64_t>((size_t)p.n_split * nq * k);
+  float *part_sc = c.take<float>((size_t)p.n_split * nq * k);
+  RB2_REQUIRE(c.off <= workspace_bytes, RB2_EWORKSPACE, "rb2_fullsort_topk: workspace %zu < %zu", workspace_bytes,
+              c.off);
+  const bool direct = p.n_split == 1;
+  dim3 grid((unsigned)((nq + kRows - 1) / kRows), (unsigned)p.n_split);
+#define RB2_FS(D_)                                                                                              \
+  {                                                                                                             \
+    RB2_CUDA(cudaFuncSetAttribute(k_fullsort_fp32<D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem)); \
+    k_fullsort_fp32<D_><<<grid, kRows, p.smem, st>>>(query_p, query_ids, nq, item_p, n_items_local, item_base,  \
+                                                     hist_indptr, hist_indices, k, p.items_per_split,           \
+                                                     direct ? out_ids : part_ids, direct ? out_scores : part_sc); \
+  }
+  switch (dim) {
+    case 16: RB2_FS(16) break;
+    case 32: RB2_FS(32) break;
+    case 64: RB2_FS(64) break;
+    case 128: RB2_FS(128) break;
+  }
+#undef RB2_FS
+  RB2_CUDA(cudaGetLastError());
+  if (!direct) {
+    k_topk_merge<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(part_ids, part_sc, p.n_split, nq, k, out_ids,
+                                                               out_scores);
+    RB2_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+extern "C" int rb2_fullsort_topk(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p,
+                                 int64_t n_items_local, int64_t item_base, int32_t dim, const int64_t *hist_indptr,
+                                 const int64_t *hist_indices, int32_t k, int32_t mode, int64_t *out_ids,
+                                 float *out_scores, void *workspace, size_t workspace_bytes, void *stream) {
+  RB2_REQUIRE(query_p && item_p && out_ids && out_scores && workspace, RB2_EINVAL, "rb2_fullsort_topk: null argument");
+  RB2_REQUIRE(k >= 1 && k <= 128, RB2_EINVAL, "rb2_fullsort_topk: k=%d outside 1..128", (int)k);
+  RB2_REQUIRE(n_items_local >= 1 && item_base >= 0, RB2_EINVAL, "rb2_fullsort_topk: bad item shard");
+  RB2_REQUIRE(item_base + n_items_local < ((int64_t)1 << 31), RB2_EINVAL, "rb2_fullsort_topk: item ids must fit int32");
+  RB2_REQUIRE((hist_indptr == nullptr) == (hist_indices == nullptr) || hist_indptr != nullptr, RB2_EINVAL,
+              "rb2_fullsort_topk: hist_indices without hist_indptr");
+  if (nq <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == RB2_SCORER_TC)
+    return rb2_fullsort_tc(query_p, query_ids, nq, item_p, n_items_local, item_base, dim, hist_indptr, hist_indices,
+                           k, out_ids, out_scores, workspace, workspace_bytes, st);
+  RB2_REQUIRE(mode == RB2_SCORER_FP32, RB2_EINVAL, "rb2_fullsort_topk: unknown mode %d", (int)mode);
+  return rb2_fullsort_fp32(query_p, query_ids, nq, item_p, n_items_local, item_base, dim, hist_indptr, hist_indices,
+                           k, out_ids, out_scores, workspace, workspace_bytes, st);
+}
+
+extern "C" int rb2_topk_merge(const int64_t *ids, const float *scores, int32_t parts, int64_t nq, int32_t k,
+                              int64_t *out_ids, float *out_scores, void *stream) {
+  RB2_REQUIRE(ids && scores && out_ids && out_scores, RB2_EINVAL, "rb2_topk_merge: null argument");
+  RB2_REQUIRE(parts >= 1 && parts <= 64, RB2_EINVAL, "rb2_topk_merge: parts=%d outside 1..64", (int)parts);
+  if (nq <= 0) return 0;
+  k_topk_merge<<<(unsigned)((nq + 127) / 128), 128, 0, (cudaStream_t)stream>>>(ids, scores, parts, nq, k, out_ids,
+                                                                              out_scores);
+  RB2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" size_t rb2_topk_metrics_workspace_bytes(int64_t nq, int32_t k) {
+  int64_t blocks = (nq + kMetricThreads - 1) / kMetricThreads;
+  return rb2_align((size_t)blocks * RB2_NUM_METRICS * k * sizeof(double)) + 256;
+}
+
+extern "C" int rb2_topk_metrics(const int64_t *topk_ids, int64_t nq, int32_t k, int64_t n_items,
+                                const int64_t *pos_indptr, const int64_t *pos_indices, const double *discount,
+                                const double *idcg, double *sums, uint8_t *hit, int64_t *ref_idx, void *workspace,
+                                size_t workspace_bytes, void *stream) {
+  RB2_REQUIRE(topk_ids && pos_indptr && pos_indices && discount && idcg && sums && workspace, RB2_EINVAL,
+              "rb2_topk_metrics: null argument");
+  RB2_REQUIRE(k >= 1 && k <= 128, RB2_EINVAL, "rb2_topk_metrics: k=%d outside 1..128", (int)k);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t blocks = (nq + kMetricThreads - 1) / kMetricThreads;
+  RB2_REQUIRE(workspace_bytes >= rb2_topk_metrics_workspace_bytes(nq, k) - 256, RB2_EWORKSPACE,
+              "rb2_topk_metrics: workspace too small");
+  if (nq <= 0) {
+    RB2_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * RB2_NUM_METRICS * k, st));
+    return 0;
+  }
+  double *part = reinterpret_cast<double *>(workspace);
+  size_t smem = (size_t)(kMetricThreads / 32) * RB2_NUM_METRICS * k * sizeof(double);
+  RB2_CUDA(cudaFuncSetAttribute(k_topk_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_topk_metrics<<<(unsigned)blocks, kMetricThreads, smem, st>>>(topk_ids, nq, k, n_items, pos_indptr, pos_indices,
+                                                                discount, idcg, part, hit, ref_idx);
+  int n = RB2_NUM_METRICS * k;
+  k_metrics_reduce<<<(n + 127) / 128, 128, 0, st>>>(part, blocks, n, sums);
+  RB2_CUDA(cudaGetLastError());
+  return 0;
+}

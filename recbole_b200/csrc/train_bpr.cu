@@ -1,0 +1,495 @@
+// train_bpr.cu -- fused BPR-MF training step for sm_100a (HBM-bound gather / row-sparse update).
+//
+// Replaces, per batch, the reference's  BPR.calculate_loss (bpr.py:74-83) + BPRLoss (loss.py:43-49)
+// + autograd's dense embedding backward (trainer.py:170) + dense torch.optim step (trainer.py:173).
+//
+// Data flow:
+//   k_make_keys   ids -> (row key, occurrence) pairs for the user side (B) and the item side (2B)
+//   radix sort    both pair lists by row id (cub::DeviceRadixSort, only the bits the table needs)
+//   k_user_side   one lane-group walks a tile of T sorted user occurrences.  For every sample it
+//                 gathers the positive and negative item rows, computes x = u.(vi - vj), the loss
+//                 term and g = dL/dx, accumulates du += g*(vi - vj) for the run of equal user ids,
+//                 stores gu[s] = g*u (the only per-sample intermediate, 4*d bytes) and, when the run
+//                 is complete inside the tile, applies the optimizer step to the user row in place.
+//   k_fixup       runs that straddle tile boundaries are reduced tile-by-tile in a fixed order and
+//                 stepped once (deterministic: no float atomics anywhere).
+//   k_item_side   same walk over the 2B sorted item occurrences: dv += (+/-) gu[s]; step the item row.
+//   k_fixup       ditto for items.
+//   k_loss        fixed-order reduction of the per-tile loss partials.
+// Every touched row is read (p, m, v) and written (p, m, v) exactly once per step.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr float kGamma = 1e-10f;  // BPRLoss gamma, loss.py:43
+constexpr int64_t kLossParts = 131072;  // capacity of the per-group loss partial buffer (forward-only path)
+
+struct BprWs {
+  WsHeader *hdr;
+  uint32_t *ukey, *uval, *ukey_s, *uval_s;  // [B]
+  uint32_t *ikey, *ival, *ikey_s, *ival_s;  // [2B]
+  int2 *pn;                                 // [B] (pos, neg) as int32
+  float *gu;                                // [B, D]
+  float *u_head, *u_tail, *i_head, *i_tail; // [tiles, D]
+  uint8_t *u_fh, *u_ft, *i_fh, *i_ft;       // [tiles] flags
+  double *loss_part;                        // [user tiles]
+  void *cub_tmp;
+  size_t cub_bytes;
+};
+
+// tile length: long enough that few runs straddle tiles, short enough to fill the machine
+inline int pick_tile(int64_t n_occ, int lanes) {
+  int64_t groups_wanted = (int64_t)rb2_num_sms() * 2048 / lanes;  // one full wave of lane groups
+  int64_t t = n_occ / (groups_wanted > 0 ? groups_wanted : 1);
+  if (t < 8) t = 8;
+  if (t > 64) t = 64;
+  return (int)t;
+}
+
+inline int64_t max_tiles(int64_t n_occ) { return (n_occ + 7) / 8; }
+
+size_t carve(BprWs &w, void *base, int64_t B, int dim) {
+  Carver c(base);
+  w.hdr = c.take<WsHeader>(1);
+  w.ukey = c.take<uint32_t>(B);
+  w.uval = c.take<uint32_t>(B);
+  w.ukey_s = c.take<uint32_t>(B);
+  w.uval_s = c.take<uint32_t>(B);
+  w.ikey = c.take<uint32_t>(2 * B);
+  w.ival = c.take<uint32_t>(2 * B);
+  w.ikey_s = c.take<uint32_t>(2 * B);
+  w.ival_s = c.take<uint32_t>(2 * B);
+  w.pn = c.take<int2>(B);
+  w.gu = c.take<float>(B * dim);
+  int64_t tu = max_tiles(B), ti = max_tiles(2 * B);
+  w.u_head = c.take<float>(tu * dim);
+  w.u_tail = c.take<float>(tu * dim);
+  w.i_head = c.take<float>(ti * dim);
+  w.i_tail = c.take<float>(ti * dim);
+  w.u_fh = c.take<uint8_t>(tu);
+  w.u_ft = c.take<uint8_t>(tu);
+  w.i_fh = c.take<uint8_t>(ti);
+  w.i_ft = c.take<uint8_t>(ti);
+  w.loss_part = c.take<double>(tu > kLossParts ? tu : kLossParts);
+  size_t b1 = 0, b2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b1, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                  (uint32_t *)nullptr, (int)B, 0, 32);
+  cub::DeviceRadixSort::SortPairs(nullptr, b2, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                  (uint32_t *)nullptr, (int)(2 * B), 0, 32);
+  w.cub_bytes = b1 > b2 ? b1 : b2;
+  w.cub_tmp = c.take<char>(w.cub_bytes);
+  return c.off;
+}
+
+inline int bits_for(int64_t n) {
+  int b = 1;
+  while (b < 32 && ((int64_t)1 << b) < n) ++b;
+  return b;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void k_make_keys(const int64_t *__restrict__ user, const int64_t *__restrict__ pos,
+                            const int64_t *__restrict__ neg, int64_t B, int64_t n_users, int64_t n_items,
+                            BprWs w) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B) return;
+  int64_t u = user[s], p = pos[s], n = neg[s];
+  bool bad = (u < 0) | (u >= n_users) | (p < 0) | (p >= n_items) | (n < 0) | (n >= n_items);
+  if (bad) {
+    w.hdr->range_error = 1;
+    u = min(max(u, (int64_t)0), n_users - 1);
+    p = min(max(p, (int64_t)0), n_items - 1);
+    n = min(max(n, (int64_t)0), n_items - 1);
+  }
+  w.ukey[s] = (uint32_t)u;
+  w.uval[s] = (uint32_t)s;
+  w.ikey[2 * s] = (uint32_t)p;
+  w.ival[2 * s] = (uint32_t)(2 * s);
+  w.ikey[2 * s + 1] = (uint32_t)n;
+  w.ival[2 * s + 1] = (uint32_t)(2 * s + 1);
+  w.pn[s] = make_int2((int)p, (int)n);
+}
+
+struct Tables {
+  float *up, *um, *uv;
+  int32_t *ul;
+  float *ip, *im, *iv;
+  int32_t *il;
+};
+
+__device__ __forceinline__ void bpr_sample(float x, float inv_b, float &loss_term, float &g) {
+  // loss.py:48   -log(gamma + sigmoid(x)) ;  d/dx = -sig*(1-sig)/(gamma+sig), times 1/B for the mean
+  float sig = 1.f / (1.f + expf(-x));
+  float den = kGamma + sig;
+  loss_term = -logf(den);
+  g = -inv_b * sig * (1.f - sig) / den;
+}
+
+// ---------------------------------------------------------------------------------------------
+// user side
+template <int D, bool LAZY>
+__global__ void __launch_bounds__(kThreads) k_user_side(Tables t, BprWs w, int64_t B, int T, int64_t n_tiles,
+                                                         float inv_b, OptScalars o) {
+  constexpr int LANES = RowCfg<D>::LANES;
+  constexpr int UNR = 4;
+  const int lane = threadIdx.x % LANES;
+  const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x % 32) / LANES * LANES));
+  const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  if (tile >= n_tiles) return;
+  const int64_t lo = tile * T, hi = min(lo + (int64_t)T, B);
+  const uint32_t *__restrict__ keys = w.ukey_s;
+  const uint32_t *__restrict__ vals = w.uval_s;
+  const uint32_t kInvalid = 0xffffffffu;
+  const uint32_t prev_key = lo > 0 ? keys[lo - 1] : kInvalid;
+
+  uint32_t cur = kInvalid;
+  bool started_before = false;
+  Row<D> u = row_zero<D>(), acc = row_zero<D>();
+  float loss_local = 0.f;
+  uint8_t fh = 0, ft = 0;
+
+  auto finish_run = [&](bool continues) {
+    if (cur == kInvalid) return;
+    if (!started_before && !continues) {
+      if (LAZY) {
+        row_update_full<D, true>(t.up, t.um, t.uv, t.ul, cur, lane, acc, o);
+      } else {
+        row_update<D>(t.up, t.um, t.uv, cur, lane, u, acc, o);
+      }
+    } else if (started_before) {
+      row_st<D>(w.u_head, tile, lane, acc);
+      fh = continues ? 2 : 1;
+    } else {
+      row_st<D>(w.u_tail, tile, lane, acc);
+      ft = 1;
+    }
+  };
+
+  for (int64_t base = lo; base < hi; base += UNR) {
+    uint32_t k[UNR], s[UNR];
+    Row<D> a[UNR], b[UNR], ur[UNR];
+#pragma unroll
+    for (int j = 0; j < UNR; ++j) {
+      int64_t p = base + j;
+      bool ok = p < hi;
+      k[j] = ok ? keys[p] : kInvalid;
+      s[j] = ok ? vals[p] : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < UNR; ++j) {
+      if (k[j] != kInvalid) {
+        int2 pn = w.pn[s[j]];
+        a[j] = row_ld_effective<D, LAZY>(t.ip, t.im, t.iv, t.il, pn.x, lane, o);
+        b[j] = row_ld_effective<D, LAZY>(t.ip, t.im, t.iv, t.il, pn.y, lane, o);
+        ur[j] = row_ld_effective<D, LAZY>(t.up, t.um, t.uv, t.ul, k[j], lane, o);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < UNR; ++j) {
+      if (k[j] == kInvalid) break;
+      if (k[j] != cur) {
+        finish_run(false);
+        cur = k[j];
+        u = ur[j];
+        acc = row_zero<D>();
+        started_before = (base + j == lo) && (cur == prev_key);
+      }
+      // x = <u, vi> - <u, vj>   (bpr.py:81: two dots, then the difference)
+      float ps = group_sum<LANES>(row_dot_lane<D>(u, a[j]), gmask);
+      float ns = group_sum<LANES>(row_dot_lane<D>(u, b[j]), gmask);
+      float lt, g;
+      bpr_sample(ps - ns, inv_b, lt, g);
+      loss_local += lt;
+      row_fma<D>(acc, g, a[j]);    // du += g*vi - g*vj
+      row_fma<D>(acc, -g, b[j]);
+      row_st<D>(w.gu, s[j], lane, row_scale<D>(g, u));  // dvi = g*u ; dvj = -g*u
+    }
+  }
+  finish_run(hi < B && keys[hi] == cur);
+  if (lane == 0) {
+    w.u_fh[tile] = fh;
+    w.u_ft[tile] = ft;
+    w.loss_part[tile] = (double)loss_local;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// item side: value = 2*s + is_neg ; contribution = (+/-) gu[s]
+template <int D, bool LAZY>
+__global__ void __launch_bounds__(kThreads) k_item_side(Tables t, BprWs w, int64_t n_occ, int T, int64_t n_tiles,
+                                                         OptScalars o) {
+  constexpr int LANES = RowCfg<D>::LANES;
+  constexpr int UNR = 4;
+  const int lane = threadIdx.x % LANES;
+  const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  if (tile >= n_tiles) return;
+  const int64_t lo = tile * T, hi = min(lo + (int64_t)T, n_occ);
+  const uint32_t *__restrict__ keys = w.ikey_s;
+  const uint32_t *__restrict__ vals = w.ival_s;
+  const uint32_t kInvalid = 0xffffffffu;
+  const uint32_t prev_key = lo > 0 ? keys[lo - 1] : kInvalid;
+
+  uint32_t cur = kInvalid;
+  bool started_before = false;
+  Row<D> acc = row_zero<D>();
+  uint8_t fh = 0, ft = 0;
+
+  auto finish_run = [&](bool continues) {
+    if (cur == kInvalid) return;
+    if (!started_before && !continues) {
+      row_update_full<D, LAZY>(t.ip, t.im, t.iv, t.il, cur, lane, acc, o);
+    } else if (started_before) {
+      row_st<D>(w.i_head, tile, lane, acc);
+      fh = continues ? 2 : 1;
+    } else {
+      row_st<D>(w.i_tail, tile, lane, acc);
+      ft = 1;
+    }
+  };
+
+  for (int64_t base = lo; base < hi; base += UNR) {
+    uint32_t k[UNR], s[UNR];
+    Row<D> c[UNR];
+#pragma unroll
+    for (int j = 0; j < UNR; ++j) {
+      int64_t p = base + j;
+      bool ok = p < hi;
+      k[j] = ok ? keys[p] : kInvalid;
+      s[j] = ok ? vals[p] : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < UNR; ++j)
+      if (k[j] != kInvalid) c[j] = row_ld<D>(w.gu, s[j] >> 1, lane);
+#pragma unroll
+    for (int j = 0; j < UNR; ++j) {
+      if (k[j] == kInvalid) break;
+      if (k[j] != cur) {
+        finish_run(false);
+        cur = k[j];
+        acc = row_zero<D>();
+        started_before = (base + j == lo) && (cur == prev_key);
+      }
+      row_fma<D>(acc, (s[j] & 1u) ? -1.f : 1.f, c[j]);
+    }
+  }
+  finish_run(hi < n_occ && keys[hi] == cur);
+  if (lane == 0) {
+    w.i_fh[tile] = fh;
+    w.i_ft[tile] = ft;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// runs that straddle tiles: tile `t` holds the head of such a run in tail[t]; the following tiles
+// hold its continuation in head[t+1..] (flag 2 = continues further).  Fixed summation order.
+template <int D, bool LAZY>
+__global__ void __launch_bounds__(kThreads) k_fixup(float *P, float *M, float *V, int32_t *L,
+                                                     const uint32_t *__restrict__ keys_sorted,
+                                                     const float *__restrict__ head, const float *__restrict__ tail,
+                                                     const uint8_t *__restrict__ fh, const uint8_t *__restrict__ ft,
+                                                     int64_t n_occ, int T, int64_t n_tiles, OptScalars o) {
+  constexpr int LANES = RowCfg<D>::LANES;
+  const int lane = threadIdx.x % LANES;
+  const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  if (tile >= n_tiles || !ft[tile]) return;
+  int64_t last_pos = min((tile + 1) * (int64_t)T, n_occ) - 1;
+  uint32_t key = keys_sorted[last_pos];
+  Row<D> acc = row_ld<D>(tail, tile, lane);
+  for (int64_t j = tile + 1; j < n_tiles; ++j) {
+    uint8_t f = fh[j];
+    if (!f) break;  // cannot happen for a well-formed sort; defensive
+    row_add<D>(acc, row_ld<D>(head, j, lane));
+    if (f != 2) break;
+  }
+  row_update_full<D, LAZY>(P, M, V, L, key, lane, acc, o);
+}
+
+__global__ void k_loss(const double *__restrict__ part, int64_t n, double inv_b, float *loss_out,
+                       double *loss_accum) {
+  // single block, fixed order: thread i sums part[i], part[i+blockDim], ... then a tree
+  __shared__ double sm[256];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float l = (float)(sm[0] * inv_b);
+    loss_out[0] = l;
+    if (loss_accum) loss_accum[0] += (double)l;
+  }
+}
+
+// forward-only loss (calculate_loss without the step)
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_bpr_loss(const float *__restrict__ up, const float *__restrict__ ip,
+                                                        const int64_t *__restrict__ user,
+                                                        const int64_t *__restrict__ pos,
+                                                        const int64_t *__restrict__ neg, int64_t B, int64_t n_users,
+                                                        int64_t n_items, double *part, WsHeader *hdr) {
+  constexpr int LANES = RowCfg<D>::LANES;
+  const int lane = threadIdx.x % LANES;
+  const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x % 32) / LANES * LANES));
+  int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  int64_t ngroups = (int64_t)gridDim.x * blockDim.x / LANES;
+  float local = 0.f;
+  for (int64_t s = gid; s < B; s += ngroups) {
+    int64_t u = user[s], p = pos[s], n = neg[s];
+    if ((u < 0) | (u >= n_users) | (p < 0) | (p >= n_items) | (n < 0) | (n >= n_items)) {
+      hdr->range_error = 1;
+      u = min(max(u, (int64_t)0), n_users - 1);
+      p = min(max(p, (int64_t)0), n_items - 1);
+      n = min(max(n, (int64_t)0), n_items - 1);
+    }
+    Row<D> ur = row_ldg<D>(up, u, lane), a = row_ldg<D>(ip, p, lane), b = row_ldg<D>(ip, n, lane);
+    float ps = group_sum<LANES>(row_dot_lane<D>(ur, a), gmask);
+    float ns = group_sum<LANES>(row_dot_lane<D>(ur, b), gmask);
+    float lt, g;
+    bpr_sample(ps - ns, 1.f, lt, g);
+    local += lt;
+  }
+  if (lane == 0 && gid < ngroups) part[gid] = (double)local;
+}
+
+template <int D, bool LAZY>
+int launch_step(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, const OptScalars &o, float *loss_out,
+                double *loss_accum, cudaStream_t st) {
+  constexpr int LANES = RowCfg<D>::LANES;
+  const int Tu = pick_tile(B, LANES), Ti = pick_tile(2 * B, LANES);
+  const int64_t ntu = (B + Tu - 1) / Tu, nti = (2 * B + Ti - 1) / Ti;
+  auto blocks = [](int64_t groups) { return (unsigned)((groups * LANES + kThreads - 1) / kThreads); };
+
+  size_t tmp = w.cub_bytes;
+  RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ukey, w.ukey_s, w.uval, w.uval_s, (int)B, 0,
+                                           bits_for(n_users), st));
+  tmp = w.cub_bytes;
+  RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ikey, w.ikey_s, w.ival, w.ival_s, (int)(2 * B), 0,
+                                           bits_for(n_items), st));
+  k_user_side<D, LAZY><<<blocks(ntu), kThreads, 0, st>>>(t, w, B, Tu, ntu, 1.f / (float)B, o);
+  k_fixup<D, LAZY><<<blocks(ntu), kThreads, 0, st>>>(t.up, t.um, t.uv, t.ul, w.ukey_s, w.u_head, w.u_tail, w.u_fh,
+                                                     w.u_ft, B, Tu, ntu, o);
+  k_item_side<D, LAZY><<<blocks(nti), kThreads, 0, st>>>(t, w, 2 * B, Ti, nti, o);
+  k_fixup<D, LAZY><<<blocks(nti), kThreads, 0, st>>>(t.ip, t.im, t.iv, t.il, w.ikey_s, w.i_head, w.i_tail, w.i_fh,
+                                                     w.i_ft, 2 * B, Ti, nti, o);
+  k_loss<<<1, 256, 0, st>>>(w.loss_part, ntu, 1.0 / (double)B, loss_out, loss_accum);
+  RB2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_lazy_flush(float *P, float *M, float *V, int32_t *L, int64_t rows,
+                                                          OptScalars o) {
+  constexpr int LANES = RowCfg<D>::LANES;
+  const int lane = threadIdx.x % LANES;
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  if (row >= rows) return;
+  int last = L[row];
+  if (last >= o.step || (last == 0 && o.wd == 0.f)) {
+    if (lane == 0 && last < o.step) L[row] = o.step;
+    return;
+  }
+  Row<D> p = row_ld<D>(P, row, lane), m = row_ld<D>(M, row, lane), v = row_ld<D>(V, row, lane);
+  row_replay<D>(p, m, v, last, o.step, o);
+  row_st<D>(P, row, lane, p);
+  row_st<D>(M, row, lane, m);
+  row_st<D>(V, row, lane, v);
+  if (lane == 0) L[row] = o.step;
+}
+
+}  // namespace
+
+#define RB2_DISPATCH_DIM(dim, ...)                                                           \
+  switch (dim) {                                                                              \
+    case 16: { constexpr int D_ = 16; __VA_ARGS__; } break;                                          \
+    case 32: { constexpr int D_ = 32; __VA_ARGS__; } break;                                          \
+    case 64: { constexpr int D_ = 64; __VA_ARGS__; } break;                                          \
+    case 128: { constexpr int D_ = 128; __VA_ARGS__; } break;                                        \
+    case 256: { constexpr int D_ = 256; __VA_ARGS__; } break;                                        \
+    default:                                                                                  \
+      rb2_set_error("embedding dim %d not supported (16, 32, 64, 128, 256)", (int)(dim));     \
+      return RB2_EINVAL;                                                                      \
+  }
+
+extern "C" size_t rb2_bpr_workspace_bytes(int64_t batch, int32_t dim) {
+  BprWs w;
+  return carve(w, nullptr, batch, dim);
+}
+
+extern "C" int rb2_bpr_train_step(float *user_p, float *user_m, float *user_v, int32_t *user_last, float *item_p,
+                                  float *item_m, float *item_v, int32_t *item_last, int64_t n_users,
+                                  int64_t n_items, int32_t dim, const int64_t *user, const int64_t *pos,
+                                  const int64_t *neg, int64_t batch, const rb2_optim *h_opt, float *loss_out,
+                                  double *loss_accum, void *workspace, size_t workspace_bytes, void *stream) {
+  RB2_REQUIRE(user_p && item_p && user && pos && neg && h_opt && loss_out && workspace, RB2_EINVAL,
+              "rb2_bpr_train_step: null argument");
+  RB2_REQUIRE(batch > 0 && batch < ((int64_t)1 << 30), RB2_EINVAL, "rb2_bpr_train_step: batch %lld out of range",
+              (long long)batch);
+  RB2_REQUIRE(n_users > 0 && n_items > 0 && n_users < ((int64_t)1 << 32) - 1 && n_items < ((int64_t)1 << 32) - 1,
+              RB2_EINVAL, "rb2_bpr_train_step: table sizes must fit 32 bits");
+  OptScalars o = rb2_opt_scalars(h_opt);
+  RB2_REQUIRE(o.kind == RB2_OPT_SGD || o.kind == RB2_OPT_ADAM || o.kind == RB2_OPT_ADAM_LAZY, RB2_EINVAL,
+              "rb2_bpr_train_step: unknown optimizer kind %d", o.kind);
+  if (o.kind != RB2_OPT_SGD)
+    RB2_REQUIRE(user_m && user_v && item_m && item_v, RB2_EINVAL, "rb2_bpr_train_step: Adam needs m and v");
+  if (o.kind == RB2_OPT_ADAM_LAZY)
+    RB2_REQUIRE(user_last && item_last && o.lazy_step_size && o.lazy_bc2_sqrt, RB2_EINVAL,
+                "rb2_bpr_train_step: RB2_OPT_ADAM_LAZY needs *_last and the lazy tables");
+  BprWs w;
+  size_t need = carve(w, workspace, batch, dim);
+  RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_bpr_train_step: workspace %zu < %zu", workspace_bytes,
+              need);
+  cudaStream_t st = (cudaStream_t)stream;
+  Tables t{user_p, user_m, user_v, user_last, item_p, item_m, item_v, item_last};
+  k_make_keys<<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(user, pos, neg, batch, n_users, n_items, w);
+  const bool lazy = o.kind == RB2_OPT_ADAM_LAZY;
+  RB2_DISPATCH_DIM(dim, {
+    int rc = lazy ? launch_step<D_, true>(t, w, batch, n_users, n_items, o, loss_out, loss_accum, st)
+                  : launch_step<D_, false>(t, w, batch, n_users, n_items, o, loss_out, loss_accum, st);
+    if (rc) return rc;
+  });
+  return 0;
+}
+
+extern "C" int rb2_bpr_loss(const float *user_p, const float *item_p, int64_t n_users, int64_t n_items, int32_t dim,
+                            const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t batch,
+                            float *loss_out, void *workspace, size_t workspace_bytes, void *stream) {
+  RB2_REQUIRE(user_p && item_p && user && pos && neg && loss_out && workspace, RB2_EINVAL,
+              "rb2_bpr_loss: null argument");
+  RB2_REQUIRE(batch > 0, RB2_EINVAL, "rb2_bpr_loss: empty batch");
+  BprWs w;
+  size_t need = carve(w, workspace, batch, dim);
+  RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_bpr_loss: workspace %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  RB2_DISPATCH_DIM(dim, {
+    constexpr int LANES = RowCfg<D_>::LANES;
+    int64_t want = (batch * LANES + kThreads - 1) / kThreads;
+    unsigned blocks = (unsigned)std::min<int64_t>(want, kLossParts * LANES / kThreads);
+    int64_t ngroups = (int64_t)blocks * kThreads / LANES;  // <= kLossParts
+    k_bpr_loss<D_><<<blocks, kThreads, 0, st>>>(user_p, item_p, user, pos, neg, batch, n_users, n_items,
+                                                w.loss_part, w.hdr);
+    k_loss<<<1, 256, 0, st>>>(w.loss_part, ngroups, 1.0 / (double)batch, loss_out, nullptr);
+  });
+  RB2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int rb2_adam_lazy_flush(float *p, float *m, float *v, int32_t *last, int64_t rows, int32_t dim,
+                                   const rb2_optim *h_opt, void *stream) {
+  RB2_REQUIRE(p && m && v && last && h_opt, RB2_EINVAL, "rb2_adam_lazy_flush: null argument");
+  OptScalars o = rb2_opt_scalars(h_opt);
+  RB2_REQUIRE(o.lazy_step_size && o.lazy_bc2_sqrt, RB2_EINVAL, "rb2_adam_lazy_flush: lazy tables missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  RB2_DISPATCH_DIM(dim, {
+    constexpr int LANES = RowCfg<D_>::LANES;
+    unsigned blocks = (unsigned)((rows * LANES + kThreads - 1) / kThreads);
+    k_lazy_flush<D_><<<blocks, kThreads, 0, st>>>(p, m, v, last, rows, o);
+  });
+  RB2_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,134 @@
+"""Device-resident index structures for the hot path (host logic; torch ops are plumbing).
+
+``EvalIndex`` holds what ``GeneralFullDataLoader`` precomputes per user with Python loops
+(recbole/data/dataloader/general_dataloader.py:294-328) -- evaluated users, their history
+(= used ids of the phase minus its positives, sampler.py:206-227) and their positives -- as two
+sorted CSRs in HBM, built once.
+"""
+import numpy as np
+import torch
+
+
+def build_csr(n_rows, rows, cols, n_cols, device):
+    """Sorted, de-duplicated CSR of (row, col) pairs: (indptr int64[n_rows+1], indices int64)."""
+    rows = torch.as_tensor(rows, dtype=torch.int64, device=device)
+    cols = torch.as_tensor(cols, dtype=torch.int64, device=device)
+    if rows.numel() == 0:
+        return torch.zeros(n_rows + 1, dtype=torch.int64, device=device), torch.zeros(0, dtype=torch.int64,
+                                                                                      device=device)
+    key = torch.unique(rows * int(n_cols) + cols)  # sorted
+    r = torch.div(key, int(n_cols), rounding_mode="floor")
+    c = key - r * int(n_cols)
+    counts = torch.bincount(r, minlength=n_rows)
+    indptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=device)
+    indptr[1:] = torch.cumsum(counts, 0)
+    return indptr, c.contiguous()
+
+
+def csr_difference(a, b, n_cols):
+    """Rows of CSR a minus rows of CSR b (same row count)."""
+    device = a[0].device
+    n_rows = a[0].numel() - 1
+    ra = torch.repeat_interleave(torch.arange(n_rows, device=device), a[0][1:] - a[0][:-1])
+    rb = torch.repeat_interleave(torch.arange(n_rows, device=device), b[0][1:] - b[0][:-1])
+    ka, kb = ra * int(n_cols) + a[1], rb * int(n_cols) + b[1]
+    keep = ~torch.isin(ka, kb)
+    return build_csr(n_rows, ra[keep], a[1][keep], n_cols, device)
+
+
+class EvalIndex:
+    def __init__(self, uid_list, hist, pos, n_items):
+        self.uid_list = uid_list        # int64[U] evaluated users (ascending), device
+        self.hist_indptr, self.hist_indices = hist
+        self.pos_indptr, self.pos_indices = pos
+        self.n_items = int(n_items)
+
+    @property
+    def n_eval_users(self):
+        return int(self.uid_list.numel())
+
+    def pos_len(self):
+        return self.pos_indptr[1:] - self.pos_indptr[:-1]
+
+    @classmethod
+    def from_phase_pairs(cls, n_users, n_items, phase_pairs, phase, device):
+        """phase_pairs: [(users, items)] for train, valid, test; evaluate phase `phase`.
+        used = union of phases 0..phase (sampler.py:213-218); positives = this phase's pairs;
+        history = used - positives (general_dataloader.py:319-321)."""
+        pu = torch.as_tensor(phase_pairs[phase][0], dtype=torch.int64, device=device)
+        pi = torch.as_tensor(phase_pairs[phase][1], dtype=torch.int64, device=device)
+        uid_list = torch.unique(pu)
+        remap = torch.full((n_users,), -1, dtype=torch.int64, device=device)
+        remap[uid_list] = torch.arange(uid_list.numel(), device=device)
+        pos = build_csr(uid_list.numel(), remap[pu], pi, n_items, device)
+        hu = torch.cat([torch.as_tensor(phase_pairs[p][0], dtype=torch.int64, device=device)
+                        for p in range(phase + 1)])
+        hi = torch.cat([torch.as_tensor(phase_pairs[p][1], dtype=torch.int64, device=device)
+                        for p in range(phase + 1)])
+        keep = remap[hu] >= 0
+        used = build_csr(uid_list.numel(), remap[hu[keep]], hi[keep], n_items, device)
+        hist = csr_difference(used, pos, n_items)
+        return cls(uid_list, hist, pos, n_items)
+
+    @classmethod
+    def from_reference_dataloader(cls, eval_data, device):
+        """From an unmodified reference GeneralFullDataLoader: its public per-user arrays
+        uid_list / uid2history_item (general_dataloader.py:294-313) and the phase's interactions."""
+        ds = eval_data.dataset
+        n_items = ds.item_num
+        uid_list = torch.as_tensor(np.asarray(eval_data.uid_list), dtype=torch.int64, device=device)
+        n_users = ds.user_num
+        remap = torch.full((n_users,), -1, dtype=torch.int64, device=device)
+        remap[uid_list] = torch.arange(uid_list.numel(), device=device)
+        pu = ds.inter_feat[ds.uid_field].to(device)
+        pi = ds.inter_feat[ds.iid_field].to(device)
+        pos = build_csr(uid_list.numel(), remap[pu], pi, n_items, device)
+        rows, cols = [], []
+        for r, u in enumerate(uid_list.tolist()):
+            h = eval_data.uid2history_item[u]
+            if h is not None and len(h):
+                rows.append(torch.full((len(h),), r, dtype=torch.int64))
+                cols.append(torch.as_tensor(h, dtype=torch.int64))
+        if rows:
+            hist = build_csr(uid_list.numel(), torch.cat(rows), torch.cat(cols), n_items, device)
+        else:
+            hist = build_csr(uid_list.numel(), [], [], n_items, device)
+        return cls(uid_list, hist, pos, n_items)
+
+
+# ---- synthetic workloads of BASELINE.json -------------------------------------------
+
+def synth_interactions(n_users, n_items, n_inter, seed, device, zipf_alpha=1.0):
+    """(user, item) pairs on the device: log-normal user activity, Zipf item popularity, no
+    duplicate pairs.  ids start at 1 (0 = [PAD])."""
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    act = torch.exp(torch.randn(n_users - 1, generator=g, device=device) * 1.0)
+    user = 1 + torch.multinomial(act / act.sum(), n_inter, replacement=True, generator=g) \
+        if n_users - 1 <= (1 << 24) else 1 + torch.randint(0, n_users - 1, (n_inter,), generator=g, device=device)
+    # Zipf via inverse CDF on ranks: rank ~ exp(U * log(N)) gives p(rank) ~ 1/rank for alpha = 1
+    u = torch.rand(n_inter, generator=g, device=device, dtype=torch.float64)
+    if abs(zipf_alpha - 1.0) < 1e-9:
+        rank = torch.exp(u * np.log(n_items - 1))
+    else:
+        a = 1.0 - zipf_alpha
+        rank = ((u * ((n_items - 1) ** a - 1.0)) + 1.0) ** (1.0 / a)
+    item = torch.clamp(rank.to(torch.int64), 1, n_items - 1)
+    perm = torch.randperm(n_items - 1, generator=g, device=device) + 1  # popularity not tied to id order
+    item = perm[item - 1]
+    key = torch.unique(user * n_items + item)
+    key = key[torch.randperm(key.numel(), generator=g, device=device)]
+    user = torch.div(key, n_items, rounding_mode="floor")
+    return user.contiguous(), (key - user * n_items).contiguous()
+
+
+def split_by_ratio(user, item, ratios=(0.8, 0.1, 0.1), seed=0):
+    """Random 0.8/0.1/0.1 split of the pairs (reference: RO_RS, dataset.py:1281-1315 splits per
+    user; a global random split has the same expected shape and is enough for synthetic data)."""
+    n = user.numel()
+    g = torch.Generator(device=user.device)
+    g.manual_seed(int(seed))
+    r = torch.rand(n, generator=g, device=user.device)
+    a, b = ratios[0], ratios[0] + ratios[1]
+    m0, m1, m2 = r < a, (r >= a) & (r < b), r >= b
+    return [(user[m], item[m]) for m in (m0, m1, m2)]

@@ -1,0 +1,225 @@
+"""Thin tensor-level wrappers over the C ABI: validate, pass data_ptr(), raise on error.
+
+PyTorch is plumbing here (device memory, streams); every operation below is one call into
+librecbole_b200.so.  Nothing in this module computes on the CPU or through ATen.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import RB2Optim, check, lib
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, dtype=None, allow_none=False):
+    if t is None:
+        if allow_none:
+            return None
+        raise ValueError("required tensor is None")
+    if not t.is_cuda:
+        raise ValueError("recbole_b200: tensor must live on a CUDA device (there is no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("expected %s, got %s" % (dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class Workspace:
+    """Device scratch owned by the caller side (the library never allocates).  The first bytes
+    hold sticky error flags (an id outside its table) which are checked whenever the host
+    synchronises anyway."""
+
+    def __init__(self, nbytes, device):
+        self.buf = torch.zeros(int(nbytes) + 256, dtype=torch.uint8, device=device)
+        self.nbytes = int(nbytes)
+
+    def ptr(self):
+        return ctypes.c_void_p(self.buf.data_ptr())
+
+    def check_flags(self):
+        flag = int(self.buf[:4].view(torch.int32).item())
+        if flag:
+            self.buf[:4].zero_()
+            raise IndexError("recbole_b200: an id was outside its embedding table "
+                             "(the reference raises IndexError in F.embedding)")
+
+
+class Optim:
+    """Optimizer hyper-parameters + step counter (replaces the torch.optim object of
+    recbole/trainer/trainer.py:109-130).  Scalars are derived in Python doubles exactly as
+    torch/optim/adam.py:531-536 derives them."""
+
+    def __init__(self, kind="adam", lr=1e-3, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8):
+        kinds = {"sgd": _lib.OPT_SGD, "adam": _lib.OPT_ADAM, "adam_lazy": _lib.OPT_ADAM_LAZY}
+        if kind not in kinds:
+            raise ValueError("optimizer kind must be one of %s" % sorted(kinds))
+        self.kind_name = kind
+        self.kind = kinds[kind]
+        self.lr, self.weight_decay, self.betas, self.eps = float(lr), float(weight_decay), tuple(betas), float(eps)
+        self.step = 0
+        self._lazy = None  # (step_size_tab, bc2_sqrt_tab) device tensors
+
+    def _lazy_tables(self, device, upto):
+        cap = 0 if self._lazy is None else self._lazy[0].numel()
+        if upto + 1 > cap:
+            n = max(1024, 2 * (upto + 1))
+            j = np.arange(n, dtype=np.float64)
+            b1, b2 = self.betas
+            with np.errstate(divide="ignore"):
+                ss = self.lr / (1.0 - np.power(b1, j))
+                bs = np.sqrt(1.0 - np.power(b2, j))
+            ss[0], bs[0] = 0.0, 1.0
+            self._lazy = (torch.from_numpy(ss.astype(np.float32)).to(device),
+                          torch.from_numpy(bs.astype(np.float32)).to(device))
+        return self._lazy
+
+    def c_struct(self, device=None, step=None):
+        t = self.step if step is None else step
+        b1, b2 = self.betas
+        o = RB2Optim()
+        o.kind, o.step = self.kind, int(t)
+        o.lr, o.weight_decay = self.lr, self.weight_decay
+        o.beta1, o.beta2 = b1, b2
+        o.one_minus_beta1, o.one_minus_beta2 = 1 - b1, 1 - b2
+        o.eps = self.eps
+        if self.kind != _lib.OPT_SGD and t >= 1:
+            o.step_size = self.lr / (1 - b1 ** t)
+            o.bc2_sqrt = math.sqrt(1 - b2 ** t)
+        else:
+            o.step_size, o.bc2_sqrt = self.lr, 1.0
+        if self.kind == _lib.OPT_ADAM_LAZY:
+            ss, bs = self._lazy_tables(device, int(t))
+            o.lazy_step_size, o.lazy_bc2_sqrt = ss.data_ptr(), bs.data_ptr()
+        return o
+
+
+def bpr_workspace(batch, dim, device):
+    return Workspace(lib.rb2_bpr_workspace_bytes(int(batch), int(dim)), device)
+
+
+def bpr_train_step(U, V, state, user, pos, neg, optim, loss_out, loss_accum, ws):
+    """One fused step (include/recbole_b200.h: rb2_bpr_train_step).  `state` holds mU, vU, mV, vV
+    (and lastU, lastV for adam_lazy).  optim.step is incremented here (t starts at 1)."""
+    optim.step += 1
+    o = optim.c_struct(U.device)
+    f32, i64 = torch.float32, torch.int64
+    check(lib.rb2_bpr_train_step(
+        _ptr(U, f32), _ptr(state.get("mU"), f32, True), _ptr(state.get("vU"), f32, True),
+        _ptr(state.get("lastU"), torch.int32, True),
+        _ptr(V, f32), _ptr(state.get("mV"), f32, True), _ptr(state.get("vV"), f32, True),
+        _ptr(state.get("lastV"), torch.int32, True),
+        U.shape[0], V.shape[0], U.shape[1], _ptr(user, i64), _ptr(pos, i64), _ptr(neg, i64), user.numel(),
+        ctypes.byref(o), _ptr(loss_out, f32), _ptr(loss_accum, torch.float64, True), ws.ptr(), ws.nbytes, _stream()))
+
+
+def bpr_loss(U, V, user, pos, neg, loss_out, ws):
+    f32, i64 = torch.float32, torch.int64
+    check(lib.rb2_bpr_loss(_ptr(U, f32), _ptr(V, f32), U.shape[0], V.shape[0], U.shape[1], _ptr(user, i64),
+                           _ptr(pos, i64), _ptr(neg, i64), user.numel(), _ptr(loss_out, f32), ws.ptr(), ws.nbytes,
+                           _stream()))
+
+
+def adam_lazy_flush(P, M, V, last, optim):
+    o = optim.c_struct(P.device)
+    check(lib.rb2_adam_lazy_flush(_ptr(P, torch.float32), _ptr(M, torch.float32), _ptr(V, torch.float32),
+                                  _ptr(last, torch.int32), P.shape[0], P.shape[1], ctypes.byref(o), _stream()))
+
+
+def gather_dot(U, V, user, item):
+    out = torch.empty(user.numel(), dtype=torch.float32, device=U.device)
+    check(lib.rb2_gather_dot(_ptr(U, torch.float32), _ptr(V, torch.float32), U.shape[0], V.shape[0], U.shape[1],
+                             _ptr(user, torch.int64), _ptr(item, torch.int64), user.numel(), _ptr(out), _stream()))
+    return out
+
+
+def fullsort_topk(Q, query_ids, V, k, hist_indptr=None, hist_indices=None, item_base=0, mode="fp32", ws=None,
+                  out=None):
+    """Top-k item ids / scores per query row (rb2_fullsort_topk).  Returns (ids int64[nq,k],
+    scores fp32[nq,k])."""
+    nq = int(query_ids.numel()) if query_ids is not None else int(Q.shape[0])
+    dev = V.device
+    m = {"fp32": _lib.SCORER_FP32, "tc": _lib.SCORER_TC}[mode]
+    need = lib.rb2_fullsort_workspace_bytes(nq, V.shape[0], V.shape[1], int(k), m)
+    if ws is None or ws.nbytes < need:
+        ws = Workspace(need, dev)
+    if out is None:
+        ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    else:
+        ids, sc = out
+    check(lib.rb2_fullsort_topk(
+        _ptr(Q, torch.float32), _ptr(query_ids, torch.int64, True), nq, _ptr(V, torch.float32), V.shape[0],
+        int(item_base), V.shape[1], _ptr(hist_indptr, torch.int64, True), _ptr(hist_indices, torch.int64, True),
+        int(k), m, _ptr(ids), _ptr(sc), ws.ptr(), ws.nbytes, _stream()))
+    return ids, sc
+
+
+def topk_merge(ids, scores):
+    """[parts, nq, k] sorted lists -> global [nq, k]."""
+    parts, nq, k = ids.shape
+    out_ids = torch.empty((nq, k), dtype=torch.int64, device=ids.device)
+    out_sc = torch.empty((nq, k), dtype=torch.float32, device=ids.device)
+    check(lib.rb2_topk_merge(_ptr(ids, torch.int64), _ptr(scores, torch.float32), parts, nq, k, _ptr(out_ids),
+                             _ptr(out_sc), _stream()))
+    return out_ids, out_sc
+
+
+_DISCOUNT_CACHE = {}
+
+
+def _discount_tables(k, device):
+    key = (k, str(device))
+    if key not in _DISCOUNT_CACHE:
+        # metrics.py:131-141, float64 exactly as numpy computes them
+        iranks = np.arange(1, k + 1, dtype=np.float64)
+        disc = 1.0 / np.log2(iranks + 1)
+        _DISCOUNT_CACHE[key] = (torch.from_numpy(disc).to(device), torch.from_numpy(np.cumsum(disc)).to(device))
+    return _DISCOUNT_CACHE[key]
+
+
+def topk_metrics(topk_ids, pos_indptr, pos_indices, n_items, want_hit=False, want_ref_idx=False):
+    """Sums over rows of the six metrics at every rank (rb2_topk_metrics).
+    Returns dict(sums=float64[6,k] (device), hit=uint8[nq,k]|None, ref_idx=int64[nq,k+1]|None)."""
+    nq, k = topk_ids.shape
+    dev = topk_ids.device
+    disc, idcg = _discount_tables(k, dev)
+    sums = torch.empty((_lib.NUM_METRICS, k), dtype=torch.float64, device=dev)
+    hit = torch.empty((nq, k), dtype=torch.uint8, device=dev) if want_hit else None
+    ref = torch.empty((nq, k + 1), dtype=torch.int64, device=dev) if want_ref_idx else None
+    ws = Workspace(lib.rb2_topk_metrics_workspace_bytes(nq, k), dev)
+    check(lib.rb2_topk_metrics(_ptr(topk_ids, torch.int64), nq, k, int(n_items), _ptr(pos_indptr, torch.int64),
+                               _ptr(pos_indices, torch.int64), _ptr(disc), _ptr(idcg), _ptr(sums),
+                               _ptr(hit, None, True), _ptr(ref, None, True), ws.ptr(), ws.nbytes, _stream()))
+    return dict(sums=sums, hit=hit, ref_idx=ref)
+
+
+def neg_sample_ref(key_ids, num, random_list, random_pr, used_indptr, used_indices):
+    """Reference-stream sampler (rb2_neg_sample_ref).  Returns (ids int64[num*n], new random_pr)."""
+    n = key_ids.numel()
+    dev = key_ids.device
+    out = torch.empty(n * num, dtype=torch.int64, device=dev)
+    ws = Workspace(lib.rb2_neg_sample_workspace_bytes(n, num), dev)
+    pr = ctypes.c_int64(int(random_pr))
+    check(lib.rb2_neg_sample_ref(_ptr(key_ids, torch.int64), n, num, _ptr(random_list, torch.int64),
+                                 random_list.numel(), ctypes.byref(pr), _ptr(used_indptr, torch.int64),
+                                 _ptr(used_indices, torch.int64), used_indptr.numel() - 1, _ptr(out), ws.ptr(),
+                                 ws.nbytes, _stream()))
+    ws.check_flags()
+    return out, pr.value
+
+
+def neg_sample_hash(key_ids, num, n_items, used_indptr, used_indices, seed, step, out=None):
+    n = key_ids.numel()
+    if out is None:
+        out = torch.empty(n * num, dtype=torch.int64, device=key_ids.device)
+    check(lib.rb2_neg_sample_hash(_ptr(key_ids, torch.int64), n, num, int(n_items), _ptr(used_indptr, torch.int64),
+                                  _ptr(used_indices, torch.int64), used_indptr.numel() - 1, int(seed), int(step),
+                                  _ptr(out), _stream()))
+    return out

@@ -1,0 +1,193 @@
+"""GPU parity: full-sort scorer + top-K + metrics + sampler (through the C ABI) vs the oracle and
+the reference golden vectors.  Bar: top-K ids and metrics bit-exact (ties -> lower item id)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import fullsort as ofs
+from oracle import metrics as ometrics
+from oracle import sampler as osampler
+
+pytestmark = pytest.mark.gpu
+
+
+def _csrs(g):
+    uid = g["uid_list"]
+    n_users = int(max(g["used_user"].max(), uid.max())) + 1
+    remap = -np.ones(n_users, dtype=np.int64)
+    remap[uid] = np.arange(len(uid))
+    pos = ofs.build_csr(len(uid), remap[g["pos_user"]], g["pos_item"])
+    keep = remap[g["used_user"]] >= 0
+    used = ofs.build_csr(len(uid), remap[g["used_user"][keep]], g["used_item"][keep])
+    hp, hi = [0], []
+    for r in range(len(uid)):
+        h = np.setdiff1d(used[1][used[0][r]:used[0][r + 1]], pos[1][pos[0][r]:pos[0][r + 1]])
+        hi.append(h)
+        hp.append(hp[-1] + len(h))
+    return (np.array(hp), np.concatenate(hi).astype(np.int64)), pos
+
+
+@pytest.mark.parametrize("name", ["fullsort_small.npz", "fullsort_ml100k.npz"])
+def test_fullsort_vs_reference_golden(golden, name):
+    from recbole_b200 import ops
+    from gpu_util import t
+    g = golden(name)
+    hist, pos = _csrs(g)
+    K, N = int(g["topk"].max()), int(g["n_items"])
+    U, V = t(g["U"]), t(g["V"])
+    ids, sc = ops.fullsort_topk(U, t(g["uid_list"]), V, K, t(hist[0]), t(hist[1]))
+    o_ids, o_sc = ofs.full_sort_topk(g["U"], g["V"], g["uid_list"], hist[0], hist[1], K)
+    np.testing.assert_array_equal(ids.cpu().numpy(), o_ids)          # bit-exact ids vs the oracle
+    np.testing.assert_array_equal(sc.cpu().numpy(), o_sc)            # bit-exact canonical scores
+    m = ops.topk_metrics(ids, t(pos[0]), t(pos[1]), N, want_hit=True, want_ref_idx=True)
+    np.testing.assert_array_equal(m["hit"].cpu().numpy().astype(bool), ofs.hits(o_ids, pos[0], pos[1]))
+    # the reference's own matrix (TopKEvaluator.collect) in its swapped+flipped coordinates
+    np.testing.assert_array_equal(m["ref_idx"].cpu().numpy(), g["topk_matrix"])
+    # metric dict == the reference's Trainer.evaluate output
+    names = [str(x) for x in g["metrics"]]
+    sums = m["sums"].cpu().numpy() / len(g["uid_list"])
+    res = {}
+    for nme in names:
+        for k in g["topk"].tolist():
+            res["%s@%d" % (nme, k)] = round(float(sums[ometrics.METRIC_ORDER.index(nme)][k - 1]), 4)
+    assert res == dict(zip(g["result_keys"].tolist(), g["result_vals"].tolist()))
+    # per-metric sums bit-close to numpy's float64 (same per-user values, different sum order)
+    ref_full = ometrics.calculate_metrics(ofs.hits(o_ids, pos[0], pos[1]), np.diff(pos[0]), list(ometrics.METRIC_ORDER))
+    np.testing.assert_allclose(sums, ref_full, rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("dim", [16, 32, 64, 128])
+@pytest.mark.parametrize("nq,N,K", [(300, 5000, 10), (1, 37, 5), (1000, 257, 20), (130, 9, 10)])
+def test_fullsort_ties_and_edges(dim, nq, N, K):
+    """Embeddings on a dyadic grid => every dot product is exact => many exact ties; the order
+    must be (score desc, item id asc).  N < K + masked exercises the empty-slot path."""
+    from recbole_b200 import ops
+    from gpu_util import t
+    rng = np.random.default_rng(dim + nq)
+    Q = (rng.integers(-4, 5, (nq, dim)) / 8.0).astype(np.float32)
+    V = (rng.integers(-4, 5, (N, dim)) / 8.0).astype(np.float32)
+    hp = [0]
+    hi = []
+    for r in range(nq):
+        h = np.sort(rng.choice(np.arange(1, N), size=min(rng.integers(0, 6), N - 1), replace=False))
+        hi.append(h)
+        hp.append(hp[-1] + len(h))
+    hp, hi = np.array(hp, dtype=np.int64), np.concatenate(hi).astype(np.int64)
+    ids, sc = ops.fullsort_topk(t(Q), None, t(V), K, t(hp), t(hi))
+    o_ids, o_sc = ofs.full_sort_topk(Q, V, np.arange(nq), hp, hi, K)
+    np.testing.assert_array_equal(ids.cpu().numpy(), o_ids)
+    np.testing.assert_array_equal(sc.cpu().numpy(), o_sc)
+    # no history at all (sequential full-sort batches, sequential_dataloader.py:269-280)
+    ids2, _ = ops.fullsort_topk(t(Q), None, t(V), K)
+    o2, _ = ofs.full_sort_topk(Q, V, np.arange(nq), np.zeros(nq + 1, np.int64), np.zeros(0, np.int64), K)
+    np.testing.assert_array_equal(ids2.cpu().numpy(), o2)
+
+
+def test_fullsort_shards_and_merge():
+    """Row-sharded item table: per-shard top-K + merge == single-table top-K."""
+    from recbole_b200 import ops
+    from gpu_util import t
+    rng = np.random.default_rng(5)
+    nq, N, dim, K, G = 500, 4001, 64, 10, 4
+    Q = rng.standard_normal((nq, dim)).astype(np.float32)
+    V = (rng.integers(-8, 9, (N, dim)) / 16.0).astype(np.float32)
+    hp = np.arange(0, 3 * nq + 1, 3, dtype=np.int64)
+    hi = np.sort(rng.integers(1, N, (nq, 3)), axis=1).reshape(-1).astype(np.int64)
+    full_ids, full_sc = ops.fullsort_topk(t(Q), None, t(V), K, t(hp), t(hi))
+    bounds = np.linspace(0, N, G + 1).astype(int)
+    parts_i, parts_s = [], []
+    for gidx in range(G):
+        a, b = bounds[gidx], bounds[gidx + 1]
+        i, s = ops.fullsort_topk(t(Q), None, t(V[a:b]), K, t(hp), t(hi), item_base=int(a))
+        parts_i.append(i)
+        parts_s.append(s)
+    m_ids, m_sc = ops.topk_merge(torch.stack(parts_i), torch.stack(parts_s))
+    assert torch.equal(m_ids, full_ids) and torch.equal(m_sc, full_sc)
+    o_ids, _ = ofs.full_sort_topk(Q, V, np.arange(nq), hp, hi, K)
+    np.testing.assert_array_equal(full_ids.cpu().numpy(), o_ids)
+
+
+def test_metrics_known_answer_on_device():
+    """reference tests/metrics/test_topk_metrics.py:15-79 pushed through the device reducer."""
+    from recbole_b200 import ops
+    from gpu_util import t
+    pos_len = [1, 3, 4, 2]
+    hit = np.array([[0, 0, 0], [1, 1, 1], [1, 0, 1], [0, 0, 1]])
+    # build top-k ids / positives that realise this hit pattern: positives are ids 100.., misses 1..
+    indptr, indices, topk = [0], [], []
+    for r in range(4):
+        p = list(range(100 + 10 * r, 100 + 10 * r + pos_len[r]))
+        indices += p
+        indptr.append(len(indices))
+        row, nxt = [], 0
+        for j in range(3):
+            if hit[r, j]:
+                row.append(p[nxt]); nxt += 1
+            else:
+                row.append(1 + j)
+        topk.append(row)
+    m = ops.topk_metrics(t(np.array(topk, dtype=np.int64)), t(np.array(indptr, dtype=np.int64)),
+                         t(np.array(indices, dtype=np.int64)), 1000, want_hit=True)
+    np.testing.assert_array_equal(m["hit"].cpu().numpy(), hit)
+    ref = ometrics.calculate_metrics(hit.astype(bool), np.array(pos_len), list(ometrics.METRIC_ORDER))
+    np.testing.assert_allclose(m["sums"].cpu().numpy() / 4.0, ref, rtol=1e-15, atol=0)
+
+
+def test_sampler_ref_stream_vs_reference_golden(golden):
+    from recbole_b200 import ops
+    from gpu_util import t
+    g = golden("sampler.npz")
+    used = ofs.build_csr(int(g["n_users"]), g["used_user"], g["used_item"])
+    rl, ip, ix = t(g["random_list"]), t(used[0]), t(used[1])
+    L = len(g["random_list"])
+    for c in range(4):
+        out, pr = ops.neg_sample_ref(t(g["users%d" % c]), int(g["num%d" % c]), rl, int(g["pr_before%d" % c]), ip, ix)
+        np.testing.assert_array_equal(out.cpu().numpy(), g["out%d" % c])
+        assert pr % L == int(g["pr_after%d" % c]) % L
+
+
+def test_sampler_hash_stream_vs_oracle(golden):
+    from recbole_b200 import ops
+    from gpu_util import t
+    g = golden("sampler.npz")
+    n_items = int(g["n_items"])
+    used = ofs.build_csr(int(g["n_users"]), g["used_user"], g["used_item"])
+    users = g["users1"]
+    out = ops.neg_sample_hash(t(users), 3, n_items, t(used[0]), t(used[1]), 2021, 7).cpu().numpy()
+    np.testing.assert_array_equal(out, osampler.hash_sample(users, 3, n_items, used[0], used[1], 2021, 7))
+    # dense user: deterministic scan path
+    n_items = 12
+    ui = np.array([i for i in range(1, n_items) if i not in (4, 9)], dtype=np.int64)
+    ip = np.array([0, 0, len(ui)], dtype=np.int64)
+    keys = np.ones(50, dtype=np.int64)
+    out = ops.neg_sample_hash(t(keys), 1, n_items, t(ip), t(ui), 1, 1).cpu().numpy()
+    np.testing.assert_array_equal(out, osampler.hash_sample(keys, 1, n_items, ip, ui, 1, 1))
+
+
+def test_full_size_cfg2_eval_properties():
+    """BASELINE cfg2 shape (138 494 users x 26 745 items, d=64, K=10): size-independent
+    properties on all users + bit-exact ids on a random subset vs the oracle."""
+    from recbole_b200 import ops
+    from gpu_util import t
+    n_users, n_items, dim, K = 138494, 26745, 64, 10
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(7)
+    U = torch.randn(n_users, dim, device="cuda", generator=gen) * 0.1
+    V = torch.randn(n_items, dim, device="cuda", generator=gen) * 0.1
+    users = torch.arange(1, n_users, device="cuda")
+    nq = users.numel()
+    hist_cols = torch.sort(torch.randint(1, n_items, (nq, 20), device="cuda", generator=gen), dim=1).values
+    hp = torch.arange(0, 20 * nq + 1, 20, device="cuda", dtype=torch.int64)
+    hi = hist_cols.reshape(-1).contiguous()
+    ids, sc = ops.fullsort_topk(U, users, V, K, hp, hi)
+    assert (ids >= 1).all() and (ids < n_items).all()
+    assert (sc[:, :-1] >= sc[:, 1:]).all()                                    # sorted
+    assert not (ids.unsqueeze(2) == hist_cols.unsqueeze(1)).any()            # history masked
+    assert (torch.sort(ids, dim=1).values[:, 1:] != torch.sort(ids, dim=1).values[:, :-1]).all()  # distinct
+    # idempotence: scoring only the winners returns the same order
+    sub = torch.randperm(nq, device="cuda", generator=gen)[:64]
+    o_ids, o_sc = ofs.full_sort_topk(U.cpu().numpy(), V.cpu().numpy(), users[sub].cpu().numpy(),
+                                     np.arange(0, 20 * 64 + 1, 20), hist_cols[sub].cpu().numpy().reshape(-1), K)
+    np.testing.assert_array_equal(ids[sub].cpu().numpy(), o_ids)
+    np.testing.assert_array_equal(sc[sub].cpu().numpy(), o_sc)
