@@ -1,0 +1,123 @@
+"""Synthetic workloads of BASELINE.json, generated on the CPU with numpy from fixed
+seeds so that the CUDA arm, the CPU-baseline leg and `bench.py --impl reference` all consume
+IDENTICAL inputs and identical pre-sampled negative ids.  Bench / test support, not product.
+"""
+import numpy as np
+
+WORKLOADS = {
+    # name: n_users, n_items (both incl. the [PAD] row 0), dim, interactions, default train batch
+    "cfg2": dict(n_users=138_494, n_items=26_745, dim=64, n_inter=20_000_263, batch=1 << 20,
+                 desc="BPR-MF synthetic ml-20m shape (138k users x 27k items, 20M inters, d=64)"),
+    "cfg2-small": dict(n_users=20_000, n_items=5_000, dim=64, n_inter=1_000_000, batch=1 << 16,
+                       desc="1/20 scale of cfg2 (CI / CPU smoke)"),
+    "cfg3": dict(n_users=10_000_001, n_items=2_000_001, dim=128, n_inter=1_000_000_000, batch=1 << 20,
+                 desc="BPR-MF synthetic 10M users x 2M items x d=128"),
+}
+
+
+def xavier_tables(n_users, n_items, dim, seed=2020):
+    """xavier-normal fp32 tables, std = sqrt(2 / (rows + d))  (recbole/model/init.py:27)."""
+    rng = np.random.default_rng(seed)
+    U = (rng.standard_normal((n_users, dim), dtype=np.float32) * np.float32(np.sqrt(2.0 / (n_users + dim))))
+    V = (rng.standard_normal((n_items, dim), dtype=np.float32) * np.float32(np.sqrt(2.0 / (n_items + dim))))
+    return U, V
+
+
+def _sorted_unique(keys):
+    keys = np.sort(keys)
+    keep = np.ones(len(keys), dtype=bool)
+    keep[1:] = keys[1:] != keys[:-1]
+    return keys[keep]
+
+
+def interactions(n_users, n_items, n_inter, seed=2020):
+    """Unique (user, item) pairs: log-normal user activity, Zipf(1) item popularity (popularity
+    rank decoupled from the id by a permutation).  Returns int64 arrays in random order."""
+    rng = np.random.default_rng(seed)
+    act = np.exp(rng.standard_normal(n_users - 1))
+    prob = act / act.sum()
+    perm = rng.permutation(n_items - 1) + 1
+    keys = np.zeros(0, dtype=np.int64)
+    while len(keys) < n_inter:  # duplicates of hot (user, item) pairs are dropped; top up until exact
+        n = int((n_inter - len(keys)) * 1.5) + 1024
+        counts = np.floor(prob * n).astype(np.int64) + (rng.random(n_users - 1) < (prob * n) % 1.0)
+        user = np.repeat(np.arange(1, n_users, dtype=np.int64), counts)
+        rank = np.exp(rng.random(len(user), dtype=np.float32) * np.float32(np.log(n_items - 1))).astype(np.int64)
+        item = perm[rank.clip(1, n_items - 1) - 1]
+        keys = _sorted_unique(np.concatenate([keys, user * n_items + item]))
+    keys = keys[rng.permutation(len(keys))[:n_inter]]
+    return keys // n_items, keys % n_items
+
+
+def split(user, item, seed=2020, ratios=(0.8, 0.1, 0.1)):
+    rng = np.random.default_rng(seed + 1)
+    r = rng.random(len(user))
+    a, b = ratios[0], ratios[0] + ratios[1]
+    masks = (r < a, (r >= a) & (r < b), r >= b)
+    return [(user[m], item[m]) for m in masks]
+
+
+def sample_negatives(users, n_items, used_keys_sorted, seed=2021):
+    """One uniform negative per entry of `users`, never one of the user's used (train) items and
+    never the pad id (the contract of sampler.py:103-154).  Vectorised rejection."""
+    rng = np.random.default_rng(seed)
+    neg = rng.integers(1, n_items, len(users))
+    pending = np.arange(len(users))
+    while len(pending):
+        k = users[pending].astype(np.int64) * n_items + neg[pending]
+        pos = np.searchsorted(used_keys_sorted, k)
+        pos[pos >= len(used_keys_sorted)] = len(used_keys_sorted) - 1
+        bad = used_keys_sorted[pos] == k
+        pending = pending[bad]
+        neg[pending] = rng.integers(1, n_items, len(pending))
+    return neg
+
+
+def csr_from_pairs(n_rows, rows, cols, n_cols):
+    key = _sorted_unique(rows.astype(np.int64) * n_cols + cols)
+    r, c = key // n_cols, key % n_cols
+    indptr = np.zeros(n_rows + 1, dtype=np.int64)
+    indptr[1:] = np.cumsum(np.bincount(r, minlength=n_rows))
+    return indptr, c
+
+
+class BprWorkload:
+    """Everything both arms need for one named workload."""
+
+    def __init__(self, name, batch=None, n_batches=8, eval_users=None, max_inter=None, seed=2020):
+        w = WORKLOADS[name]
+        self.name, self.desc = name, w["desc"]
+        self.n_users, self.n_items, self.dim = w["n_users"], w["n_items"], w["dim"]
+        self.batch = int(batch or w["batch"])
+        n_inter = w["n_inter"] if max_inter is None else min(w["n_inter"], max_inter)
+        self.n_inter = n_inter
+        user, item = interactions(self.n_users, self.n_items, n_inter, seed)
+        self.phases = split(user, item, seed)
+        tu, ti = self.phases[0]
+        self.train_keys = np.sort(tu * self.n_items + ti)
+        need = self.batch * n_batches
+        reps = (need + len(tu) - 1) // len(tu)
+        idx = np.concatenate([np.random.default_rng(seed + 7 + r).permutation(len(tu)) for r in range(reps)])[:need]
+        bu, bp = tu[idx], ti[idx]
+        bn = sample_negatives(bu, self.n_items, self.train_keys, seed + 1)
+        self.batches = [(bu[i * self.batch:(i + 1) * self.batch], bp[i * self.batch:(i + 1) * self.batch],
+                         bn[i * self.batch:(i + 1) * self.batch]) for i in range(n_batches)]
+        # evaluation of the test phase: history = train + valid, positives = test
+        eu, ei = self.phases[2]
+        uid = _sorted_unique(eu)
+        if eval_users is not None and eval_users < len(uid):
+            uid = np.sort(np.random.default_rng(seed + 3).choice(uid, eval_users, replace=False))
+        remap = -np.ones(self.n_users, dtype=np.int64)
+        remap[uid] = np.arange(len(uid))
+        m = remap[eu] >= 0
+        self.uid_list = uid
+        self.pos = csr_from_pairs(len(uid), remap[eu[m]], ei[m], self.n_items)
+        hu = np.concatenate([self.phases[0][0], self.phases[1][0]])
+        hi = np.concatenate([self.phases[0][1], self.phases[1][1]])
+        m = remap[hu] >= 0
+        self.hist = csr_from_pairs(len(uid), remap[hu[m]], hi[m], self.n_items)
+        self.U0, self.V0 = xavier_tables(self.n_users, self.n_items, self.dim, seed)
+
+    def describe(self):
+        return dict(workload=self.name, desc=self.desc, n_users=self.n_users, n_items=self.n_items, dim=self.dim,
+                    interactions=self.n_inter, train_batch=self.batch, eval_users=int(len(self.uid_list)), topk=10)

@@ -41,6 +41,24 @@ int rb2_abi_version(void);
 const char *rb2_last_error(void);
 
 /* ------------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py).  With profiling on, every stage of the calls below is bracketed
+ * by a pair of cudaEvents on the caller's stream; rb2_profile_read synchronises the device and
+ * returns, per stage, the summed device time (ms), the number of times the stage ran and the
+ * number of kernel launches it issued since the last read, then resets the counters.  The
+ * reference has no counterpart (it wraps Trainer.fit in torch.autograd.profiler,
+ * recbole/quick_start/quick_start.py:57-61).
+ * ---------------------------------------------------------------------------------------- */
+enum {
+  RB2_ST_KEYS = 0, RB2_ST_SORT_USER = 1, RB2_ST_SORT_ITEM = 2, RB2_ST_USER_SIDE = 3, RB2_ST_USER_FIXUP = 4,
+  RB2_ST_ITEM_SIDE = 5, RB2_ST_ITEM_FIXUP = 6, RB2_ST_LOSS = 7, RB2_ST_FULLSORT = 8, RB2_ST_TOPK_MERGE = 9,
+  RB2_ST_METRICS = 10, RB2_ST_SAMPLER = 11, RB2_ST_GATHER_DOT = 12, RB2_ST_TC_CONVERT = 13, RB2_ST_TC_SCORE = 14,
+  RB2_ST_TC_REFINE = 15, RB2_ST_FM_FWD = 16, RB2_ST_FM_UPDATE = 17, RB2_ST_MISC = 18, RB2_NUM_STAGES = 19
+};
+int rb2_profile_enable(int on);
+int rb2_profile_read(float *h_ms /* [RB2_NUM_STAGES] */, int64_t *h_calls /* [RB2_NUM_STAGES] */,
+                     int64_t *h_launches /* [RB2_NUM_STAGES] */);
+
+/* ------------------------------------------------------------------------------------------
  * Optimizer description.  Replaces the torch.optim objects built by
  * Trainer._build_optimizer (recbole/trainer/trainer.py:109-130) and stepped at trainer.py:173.
  * Scalars are computed by the host in double exactly as torch/optim/adam.py does

@@ -1,6 +1,6 @@
 """ctypes binding of librecbole_b200.so (the C ABI declared in include/recbole_b200.h).
 
-There is NO fallback: if the shared library has not been built (python -m recbole_b200.build, or
+There is NO fallback: if the shared library has not been built (python recbole_b200/build.py, or
 __graft_entry__.build()), importing this module raises.
 """
 import ctypes
@@ -18,6 +18,9 @@ M_RECALL, M_MRR, M_NDCG, M_HIT, M_PRECISION, M_MAP = range(6)
 NUM_METRICS = 6
 METRIC_ORDER = ("recall", "mrr", "ndcg", "hit", "precision", "map")
 EINVAL, EWORKSPACE, ERANGE = 10001, 10002, 10003
+STAGES = ("keys", "sort_user", "sort_item", "user_side", "user_fixup", "item_side", "item_fixup", "loss", "fullsort",
+          "topk_merge", "metrics", "sampler", "gather_dot", "tc_convert", "tc_score", "tc_refine", "fm_fwd",
+          "fm_update", "misc")
 
 
 class RB2Optim(ctypes.Structure):
@@ -37,6 +40,8 @@ _p, _i64, _i32, _sz, _u64 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, cty
 SIGNATURES = {
     "rb2_abi_version": (ctypes.c_int, []),
     "rb2_last_error": (ctypes.c_char_p, []),
+    "rb2_profile_enable": (ctypes.c_int, [ctypes.c_int]),
+    "rb2_profile_read": (ctypes.c_int, [_p, _p, _p]),
     "rb2_bpr_workspace_bytes": (_sz, [_i64, _i32]),
     "rb2_bpr_train_step": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _i64,
                                           ctypes.POINTER(RB2Optim), _p, _p, _p, _sz, _p]),
@@ -59,7 +64,7 @@ SIGNATURES = {
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            "recbole_b200: %s is missing. Build it with `python -m recbole_b200.build` "
+            "recbole_b200: %s is missing. Build it with `python recbole_b200/build.py` "
             "(nvcc, sm_100a). There is no CPU or PyTorch fallback." % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():

@@ -1,6 +1,6 @@
 """Builds recbole_b200/librecbole_b200.so in-tree with nvcc for sm_100a.
 
-    python -m recbole_b200.build [--force] [--verbose]
+    python recbole_b200/build.py [--force] [--verbose]
 
 One translation unit per .cu under csrc/, compiled in parallel, linked into a single shared
 library with a C ABI (include/recbole_b200.h).  nvcc cross-compiles without a GPU.

@@ -14,6 +14,70 @@ void rb2_set_error(const char *fmt, ...) {
 }
 
 extern "C" const char *rb2_last_error(void) { return g_err; }
+
+// ---- profiling hooks ---------------------------------------------------------------------------
+#include <mutex>
+#include <vector>
+namespace {
+struct StageProf {
+  std::vector<cudaEvent_t> beg, end;  // pool, grown on demand
+  size_t used = 0;
+  int64_t calls = 0, launches = 0;
+};
+bool g_prof_on = false;
+StageProf g_prof[RB2_NUM_STAGES];
+std::mutex g_prof_mu;
+}  // namespace
+
+void rb2_prof_begin(int stage, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  StageProf &p = g_prof[stage];
+  if (p.used == p.beg.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    p.beg.push_back(a);
+    p.end.push_back(b);
+  }
+  cudaEventRecord(p.beg[p.used], st);
+}
+
+void rb2_prof_end(int stage, cudaStream_t st, int launches) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  StageProf &p = g_prof[stage];
+  cudaEventRecord(p.end[p.used], st);
+  p.used++;
+  p.calls++;
+  p.launches += launches;
+}
+
+extern "C" int rb2_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  return 0;
+}
+
+extern "C" int rb2_profile_read(float *h_ms, int64_t *h_calls, int64_t *h_launches) {
+  RB2_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int s = 0; s < RB2_NUM_STAGES; ++s) {
+    StageProf &p = g_prof[s];
+    float tot = 0.f;
+    for (size_t i = 0; i < p.used; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, p.beg[i], p.end[i]) == cudaSuccess) tot += ms;
+    }
+    if (h_ms) h_ms[s] = tot;
+    if (h_calls) h_calls[s] = p.calls;
+    if (h_launches) h_launches[s] = p.launches;
+    p.used = 0;
+    p.calls = 0;
+    p.launches = 0;
+  }
+  return 0;
+}
 extern "C" int rb2_abi_version(void) { return RB2_ABI_VERSION; }
 
 namespace {
@@ -43,6 +107,7 @@ extern "C" int rb2_gather_dot(const float *user_p, const float *item_p, int64_t 
   RB2_REQUIRE(user_p && item_p && user && item && out, RB2_EINVAL, "rb2_gather_dot: null argument");
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(RB2_ST_GATHER_DOT, st);
 #define RB2_GD(D_)                                                                                     \
   {                                                                                                    \
     constexpr int LANES = RowCfg<D_>::LANES;                                                           \

@@ -26,6 +26,20 @@ void rb2_set_error(const char *fmt, ...);
     }                                \
   } while (0)
 
+// optional per-stage device timing + launch counting (api.cu); off by default, costs two event
+// records per stage when on.  Stage ids are part of the ABI (include/recbole_b200.h).
+void rb2_prof_begin(int stage, cudaStream_t st);
+void rb2_prof_end(int stage, cudaStream_t st, int launches);
+
+struct ProfScope {
+  int stage, launches;
+  cudaStream_t st;
+  ProfScope(int stage_, cudaStream_t st_, int launches_ = 1) : stage(stage_), launches(launches_), st(st_) {
+    rb2_prof_begin(stage, st);
+  }
+  ~ProfScope() { rb2_prof_end(stage, st, launches); }
+};
+
 static inline size_t rb2_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 // Carves a workspace buffer into aligned pieces; `p == nullptr` just measures.

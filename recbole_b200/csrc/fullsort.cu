@@ -407,15 +407,19 @@ int rb2_fullsort_fp32(const float *query_p, const int64_t *query_ids, int64_t nq
                                                      hist_indptr, hist_indices, k, p.items_per_split,           \
                                                      direct ? out_ids : part_ids, direct ? out_scores : part_sc); \
   }
-  switch (dim) {
-    case 16: RB2_FS(16) break;
-    case 32: RB2_FS(32) break;
-    case 64: RB2_FS(64) break;
-    case 128: RB2_FS(128) break;
+  {
+    ProfScope prof(RB2_ST_FULLSORT, st);
+    switch (dim) {
+      case 16: RB2_FS(16) break;
+      case 32: RB2_FS(32) break;
+      case 64: RB2_FS(64) break;
+      case 128: RB2_FS(128) break;
+    }
   }
 #undef RB2_FS
   RB2_CUDA(cudaGetLastError());
   if (!direct) {
+    ProfScope prof(RB2_ST_TOPK_MERGE, st);
     k_topk_merge<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(part_ids, part_sc, p.n_split, nq, k, out_ids,
                                                                out_scores);
     RB2_CUDA(cudaGetLastError());
@@ -475,6 +479,7 @@ extern "C" int rb2_topk_metrics(const int64_t *topk_ids, int64_t nq, int32_t k, 
     return 0;
   }
   double *part = reinterpret_cast<double *>(workspace);
+  ProfScope prof(RB2_ST_METRICS, st, 2);
   size_t smem = (size_t)(kMetricThreads / 32) * RB2_NUM_METRICS * k * sizeof(double);
   RB2_CUDA(cudaFuncSetAttribute(k_topk_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_topk_metrics<<<(unsigned)blocks, kMetricThreads, smem, st>>>(topk_ids, nq, k, n_items, pos_indptr, pos_indices,

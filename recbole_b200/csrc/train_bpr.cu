@@ -366,18 +366,40 @@ int launch_step(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, 
   auto blocks = [](int64_t groups) { return (unsigned)((groups * LANES + kThreads - 1) / kThreads); };
 
   size_t tmp = w.cub_bytes;
-  RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ukey, w.ukey_s, w.uval, w.uval_s, (int)B, 0,
-                                           bits_for(n_users), st));
+  {
+    // cub one-sweep radix sort: histogram + scan + one kernel per 8-bit digit pass
+    ProfScope prof(RB2_ST_SORT_USER, st, 2 + (bits_for(n_users) + 7) / 8);
+    RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ukey, w.ukey_s, w.uval, w.uval_s, (int)B, 0,
+                                             bits_for(n_users), st));
+  }
   tmp = w.cub_bytes;
-  RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ikey, w.ikey_s, w.ival, w.ival_s, (int)(2 * B), 0,
-                                           bits_for(n_items), st));
-  k_user_side<D, LAZY><<<blocks(ntu), kThreads, 0, st>>>(t, w, B, Tu, ntu, 1.f / (float)B, o);
-  k_fixup<D, LAZY><<<blocks(ntu), kThreads, 0, st>>>(t.up, t.um, t.uv, t.ul, w.ukey_s, w.u_head, w.u_tail, w.u_fh,
-                                                     w.u_ft, B, Tu, ntu, o);
-  k_item_side<D, LAZY><<<blocks(nti), kThreads, 0, st>>>(t, w, 2 * B, Ti, nti, o);
-  k_fixup<D, LAZY><<<blocks(nti), kThreads, 0, st>>>(t.ip, t.im, t.iv, t.il, w.ikey_s, w.i_head, w.i_tail, w.i_fh,
-                                                     w.i_ft, 2 * B, Ti, nti, o);
-  k_loss<<<1, 256, 0, st>>>(w.loss_part, ntu, 1.0 / (double)B, loss_out, loss_accum);
+  {
+    ProfScope prof(RB2_ST_SORT_ITEM, st, 2 + (bits_for(n_items) + 7) / 8);
+    RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ikey, w.ikey_s, w.ival, w.ival_s, (int)(2 * B), 0,
+                                             bits_for(n_items), st));
+  }
+  {
+    ProfScope prof(RB2_ST_USER_SIDE, st);
+    k_user_side<D, LAZY><<<blocks(ntu), kThreads, 0, st>>>(t, w, B, Tu, ntu, 1.f / (float)B, o);
+  }
+  {
+    ProfScope prof(RB2_ST_USER_FIXUP, st);
+    k_fixup<D, LAZY><<<blocks(ntu), kThreads, 0, st>>>(t.up, t.um, t.uv, t.ul, w.ukey_s, w.u_head, w.u_tail, w.u_fh,
+                                                       w.u_ft, B, Tu, ntu, o);
+  }
+  {
+    ProfScope prof(RB2_ST_ITEM_SIDE, st);
+    k_item_side<D, LAZY><<<blocks(nti), kThreads, 0, st>>>(t, w, 2 * B, Ti, nti, o);
+  }
+  {
+    ProfScope prof(RB2_ST_ITEM_FIXUP, st);
+    k_fixup<D, LAZY><<<blocks(nti), kThreads, 0, st>>>(t.ip, t.im, t.iv, t.il, w.ikey_s, w.i_head, w.i_tail, w.i_fh,
+                                                       w.i_ft, 2 * B, Ti, nti, o);
+  }
+  {
+    ProfScope prof(RB2_ST_LOSS, st);
+    k_loss<<<1, 256, 0, st>>>(w.loss_part, ntu, 1.0 / (double)B, loss_out, loss_accum);
+  }
   RB2_CUDA(cudaGetLastError());
   return 0;
 }
@@ -446,7 +468,10 @@ extern "C" int rb2_bpr_train_step(float *user_p, float *user_m, float *user_v, i
               need);
   cudaStream_t st = (cudaStream_t)stream;
   Tables t{user_p, user_m, user_v, user_last, item_p, item_m, item_v, item_last};
-  k_make_keys<<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(user, pos, neg, batch, n_users, n_items, w);
+  {
+    ProfScope prof(RB2_ST_KEYS, st);
+    k_make_keys<<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(user, pos, neg, batch, n_users, n_items, w);
+  }
   const bool lazy = o.kind == RB2_OPT_ADAM_LAZY;
   RB2_DISPATCH_DIM(dim, {
     int rc = lazy ? launch_step<D_, true>(t, w, batch, n_users, n_items, o, loss_out, loss_accum, st)

@@ -223,3 +223,18 @@ def neg_sample_hash(key_ids, num, n_items, used_indptr, used_indices, seed, step
                                   _ptr(used_indices, torch.int64), used_indptr.numel() - 1, int(seed), int(step),
                                   _ptr(out), _stream()))
     return out
+
+
+def profile_enable(on=True):
+    check(lib.rb2_profile_enable(1 if on else 0))
+
+
+def profile_read():
+    """{stage: (ms, calls, launches)} since the last read (synchronises the device)."""
+    n = len(_lib.STAGES)
+    ms = (ctypes.c_float * n)()
+    calls = (ctypes.c_int64 * n)()
+    launches = (ctypes.c_int64 * n)()
+    check(lib.rb2_profile_read(ms, calls, launches))
+    return {name: (float(ms[i]), int(calls[i]), int(launches[i])) for i, name in enumerate(_lib.STAGES)
+            if calls[i]}

@@ -98,7 +98,7 @@ def test_random_batches_vs_oracle(dim, B, n_users, n_items, kind):
     st_o = obpr.new_state(U0, V0)
     U, V = t(U0), t(V0)
     st = adam_state(U, V, lazy=(kind == "adam_lazy")) if kind != "sgd" else {}
-    lr = 0.05 if kind == "sgd" else 1e-2
+    lr = 0.05 if kind == "sgd" else 2e-3  # error of the normalised Adam step scales with lr
     opt = ops.Optim(kind, lr=lr)
     loss = torch.zeros(1, device=U.device)
     ws = ops.bpr_workspace(B, dim, U.device)
