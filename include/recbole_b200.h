@@ -158,6 +158,10 @@ int rb2_fullsort_topk(const float *query_p, const int64_t *query_ids, int64_t nq
                       int64_t *out_ids, float *out_scores,
                       void *workspace, size_t workspace_bytes, void *stream);
 
+/* Diagnostic: how many rows of the last RB2_SCORER_TC call failed the certificate and were redone by
+ * the fp32 kernel (or nq if the shape is not covered by the MMA tiling: dim not in {64,128}, k > 16). */
+int32_t rb2_fullsort_tc_last_fallback_rows(void);
+
 /* Merge `parts` per-shard top-K lists ([parts, nq, k], each sorted) into the global top-K
  * (multi-GPU all-gather merge). */
 int rb2_topk_merge(const int64_t *ids, const float *scores, int32_t parts, int64_t nq, int32_t k,

@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(kRows) k_fullsort_fp32(const float *__restrict
                                                           int64_t item_base, const int64_t *__restrict__ hist_indptr,
                                                           const int64_t *__restrict__ hist_indices, int K,
                                                           int64_t items_per_split, int64_t *__restrict__ out_ids,
-                                                          float *__restrict__ out_scores) {
+                                                          float *__restrict__ out_scores,
+                                                          const int32_t *__restrict__ row_map, int scatter_out) {
   constexpr int TI = FsCfg<D>::TI;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *tile0 = reinterpret_cast<float *>(smem_raw);
@@ -96,8 +97,10 @@ __global__ void __launch_bounds__(kRows) k_fullsort_fp32(const float *__restrict
   __shared__ __align__(8) uint64_t bars[2];
 
   const int tid = threadIdx.x;
-  const int64_t r = (int64_t)blockIdx.x * kRows + tid;
-  const bool active = r < nq;
+  const int64_t rc = (int64_t)blockIdx.x * kRows + tid;   // compact row (position in row_map)
+  const bool active = rc < nq;
+  // row_map (optional): the rows of the caller's problem this launch redoes (tensor-core fallback)
+  const int64_t r = (active && row_map) ? (int64_t)row_map[rc] : rc;
   const int64_t i_begin = (int64_t)blockIdx.y * items_per_split;
   const int64_t i_end = min(i_begin + items_per_split, n_local);
   const int64_t n_tiles = (i_end - i_begin + TI - 1) / TI;
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(kRows) k_fullsort_fp32(const float *__restrict
   }
 
   if (active) {
-    int64_t o = ((int64_t)blockIdx.y * nq + r) * K;
+    int64_t o = ((int64_t)blockIdx.y * nq + (scatter_out ? r : rc)) * K;
     for (int j = 0; j < K; ++j) {
       out_ids[o + j] = (int64_t)my_id[j * kRows];
       out_scores[o + j] = my_sc[j * kRows];
@@ -204,9 +207,11 @@ __global__ void __launch_bounds__(kRows) k_fullsort_fp32(const float *__restrict
 
 // merge `parts` sorted lists per row; order (score desc, id asc); id -1 = empty slot
 __global__ void k_topk_merge(const int64_t *__restrict__ ids, const float *__restrict__ scores, int parts, int64_t nq,
-                             int K, int64_t *__restrict__ out_ids, float *__restrict__ out_scores) {
+                             int K, int64_t *__restrict__ out_ids, float *__restrict__ out_scores,
+                             const int32_t *__restrict__ row_map) {
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nq) return;
+  const int64_t ro = row_map ? (int64_t)row_map[r] : r;
   unsigned char head[64];
   for (int p = 0; p < parts; ++p) head[p] = 0;
   for (int j = 0; j < K; ++j) {
@@ -222,8 +227,8 @@ __global__ void k_topk_merge(const int64_t *__restrict__ ids, const float *__res
       if (best < 0 || s > bs || (s == bs && id < bi)) { best = p; bs = s; bi = id; }
     }
     if (best >= 0) head[best]++;
-    out_ids[r * K + j] = bi;
-    out_scores[r * K + j] = best >= 0 ? bs : -INFINITY;
+    out_ids[ro * K + j] = bi;
+    out_scores[ro * K + j] = best >= 0 ? bs : -INFINITY;
   }
 }
 
@@ -368,6 +373,7 @@ FsPlan plan_any(int dim, int64_t nq, int64_t n_local, int K) {
 
 }  // namespace
 
+size_t rb2_fullsort_fp32_workspace(int64_t nq, int64_t n_items_local, int32_t dim, int32_t k);
 // implemented in fullsort_tc.cu
 size_t rb2_fullsort_tc_workspace_bytes(int64_t nq, int64_t n_items_local, int32_t dim, int32_t k);
 int rb2_fullsort_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p,
@@ -378,17 +384,25 @@ int rb2_fullsort_tc(const float *query_p, const int64_t *query_ids, int64_t nq, 
 extern "C" size_t rb2_fullsort_workspace_bytes(int64_t nq, int64_t n_items_local, int32_t dim, int32_t k,
                                                int32_t mode) {
   if (mode == RB2_SCORER_TC) return rb2_fullsort_tc_workspace_bytes(nq, n_items_local, dim, k);
+  return rb2_fullsort_fp32_workspace(nq, n_items_local, dim, k);
+}
+
+size_t rb2_fullsort_fp32_workspace(int64_t nq, int64_t n_items_local, int32_t dim, int32_t k) {
   FsPlan p = plan_any(dim, nq, n_items_local, k);
+  // a later call on fewer rows (tensor-core fallback) may split the items further: size for 64 parts
+  int64_t parts = p.n_split > 0 ? 64 : 0;
+  int64_t rows = nq < 4096 ? nq : (nq * p.n_split + 63) / 64;  // enough for nq rows at n_split, or few rows at 64
+  if (rows < 1) rows = 1;
   Carver c(nullptr);
-  c.take<int64_t>((size_t)p.n_split * nq * k);
-  c.take<float>((size_t)p.n_split * nq * k);
+  c.take<int64_t>((size_t)parts * rows * k);
+  c.take<float>((size_t)parts * rows * k);
   return c.off + 256;
 }
 
 int rb2_fullsort_fp32(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p,
                       int64_t n_items_local, int64_t item_base, int32_t dim, const int64_t *hist_indptr,
                       const int64_t *hist_indices, int32_t k, int64_t *out_ids, float *out_scores, void *workspace,
-                      size_t workspace_bytes, cudaStream_t st) {
+                      size_t workspace_bytes, cudaStream_t st, const int32_t *row_map) {
   FsPlan p = plan_any(dim, nq, n_items_local, k);
   RB2_REQUIRE(p.n_split > 0, RB2_EINVAL, "rb2_fullsort_topk: embedding dim %d not supported by the fp32 scorer (16, 32, 64, 128)",
               (int)dim);
@@ -405,7 +419,8 @@ int rb2_fullsort_fp32(const float *query_p, const int64_t *query_ids, int64_t nq
     RB2_CUDA(cudaFuncSetAttribute(k_fullsort_fp32<D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem)); \
     k_fullsort_fp32<D_><<<grid, kRows, p.smem, st>>>(query_p, query_ids, nq, item_p, n_items_local, item_base,  \
                                                      hist_indptr, hist_indices, k, p.items_per_split,           \
-                                                     direct ? out_ids : part_ids, direct ? out_scores : part_sc); \
+                                                     direct ? out_ids : part_ids, direct ? out_scores : part_sc, \
+                                                     row_map, direct ? 1 : 0);                                  \
   }
   {
     ProfScope prof(RB2_ST_FULLSORT, st);
@@ -421,7 +436,7 @@ int rb2_fullsort_fp32(const float *query_p, const int64_t *query_ids, int64_t nq
   if (!direct) {
     ProfScope prof(RB2_ST_TOPK_MERGE, st);
     k_topk_merge<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(part_ids, part_sc, p.n_split, nq, k, out_ids,
-                                                               out_scores);
+                                                               out_scores, row_map);
     RB2_CUDA(cudaGetLastError());
   }
   return 0;
@@ -444,7 +459,7 @@ extern "C" int rb2_fullsort_topk(const float *query_p, const int64_t *query_ids,
                            k, out_ids, out_scores, workspace, workspace_bytes, st);
   RB2_REQUIRE(mode == RB2_SCORER_FP32, RB2_EINVAL, "rb2_fullsort_topk: unknown mode %d", (int)mode);
   return rb2_fullsort_fp32(query_p, query_ids, nq, item_p, n_items_local, item_base, dim, hist_indptr, hist_indices,
-                           k, out_ids, out_scores, workspace, workspace_bytes, st);
+                           k, out_ids, out_scores, workspace, workspace_bytes, st, nullptr);
 }
 
 extern "C" int rb2_topk_merge(const int64_t *ids, const float *scores, int32_t parts, int64_t nq, int32_t k,
@@ -453,7 +468,7 @@ extern "C" int rb2_topk_merge(const int64_t *ids, const float *scores, int32_t p
   RB2_REQUIRE(parts >= 1 && parts <= 64, RB2_EINVAL, "rb2_topk_merge: parts=%d outside 1..64", (int)parts);
   if (nq <= 0) return 0;
   k_topk_merge<<<(unsigned)((nq + 127) / 128), 128, 0, (cudaStream_t)stream>>>(ids, scores, parts, nq, k, out_ids,
-                                                                              out_scores);
+                                                                              out_scores, nullptr);
   RB2_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,10 +1,635 @@
-// fullsort_tc.cu -- tcgen05/TMA tensor-core full-sort scorer (placeholder until the kernel lands).
+// fullsort_tc.cu -- tensor-core full-sort scorer for sm_100a: tcgen05.mma + TMEM + TMA, with a
+// certified exact top-K.
+//
+// Same contract as the fp32 path (fullsort.cu): replaces BPR.full_sort_predict (bpr.py:91-96) /
+// SASRec.full_sort_predict (sasrec.py:152-158) + the mask of Trainer._full_sort_batch_eval
+// (trainer.py:342-345) + TopKEvaluator.collect's topk (evaluators.py:68-72); the score matrix is
+// never written.
+//
+//   k_convert_rows   fp32 rows -> bf16 rows (queries are gathered by id), plus per-row ||u|| and
+//                    ||u - bf16(u)|| and, for the item side, max ||bf16(v)|| / max ||v - bf16(v)||.
+//   k_fullsort_tc    persistent, warp-specialised: warp 0 = TMA producer (128B-swizzled tiles),
+//                    warp 1 = single-thread tcgen05.mma issuer (bf16 x bf16 -> fp32 in TMEM, two
+//                    256-column accumulator stages), warps 2-5 = epilogue: tcgen05.ld 32 columns at
+//                    a time, group max against the row's running threshold, rare insert into a
+//                    K' = 32 candidate list in shared memory (pad / history checked only there).
+//   k_refine         candidates are re-scored with the canonical fp32 chain s = fmaf(q[k], v[k], s)
+//                    and ordered (score desc, id asc).  Certificate per row:
+//                        exact_K  >  max_part(approx K'-th score) + E,
+//                        E = ||du||*max||bv|| + ||u||*max||dv|| + slack      (Cauchy-Schwarz on
+//                        u.v - bu.bv = du.bv + u.dv)
+//                    proves no non-candidate can be in the exact top-K.  Rows that fail are
+//                    compacted and redone by the fp32 kernel, so the result is always exact.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
-size_t rb2_fullsort_tc_workspace_bytes(int64_t, int64_t, int32_t, int32_t) { return 256; }
+// fp32 path (fullsort.cu), used for the rows whose certificate fails and for dims the MMA tiling
+// does not cover
+int rb2_fullsort_fp32(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p,
+                      int64_t n_items_local, int64_t item_base, int32_t dim, const int64_t *hist_indptr,
+                      const int64_t *hist_indices, int32_t k, int64_t *out_ids, float *out_scores, void *workspace,
+                      size_t workspace_bytes, cudaStream_t st, const int32_t *row_map);
+size_t rb2_fullsort_fp32_workspace(int64_t nq, int64_t n_items_local, int32_t dim, int32_t k);
 
-int rb2_fullsort_tc(const float *, const int64_t *, int64_t, const float *, int64_t, int64_t, int32_t,
-                    const int64_t *, const int64_t *, int32_t, int64_t *, float *, void *, size_t, cudaStream_t) {
-  rb2_set_error("rb2_fullsort_topk: RB2_SCORER_TC is not built into this library yet");
-  return RB2_EINVAL;
+// number of rows the last RB2_SCORER_TC call had to redo in fp32 (diagnostic for bench / tests)
+static int32_t g_last_tc_fallback_rows = 0;
+extern "C" int32_t rb2_fullsort_tc_last_fallback_rows(void) { return g_last_tc_fallback_rows; }
+
+namespace {
+
+constexpr int BM = 128;       // query rows per CTA tile (= TMEM lanes)
+constexpr int BN = 256;       // items per accumulator stage (= MMA N)
+constexpr int BK = 64;        // bf16 elements per 128-byte swizzle row
+constexpr int KP = 32;        // candidates kept per row (K' > K)
+constexpr int UNIT_BYTES = BN * BK * 2;   // one B ring slot: 256 items x 64 k
+constexpr int A_KB_BYTES = BM * BK * 2;
+constexpr int kThreadsTc = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TC_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TC_DONE;\n"
+      "bra TC_WAIT;\n"
+      "TC_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128-byte swizzle, 8-row groups 1024 bytes apart (mma_sm100_desc.hpp SmemDescriptor)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);   // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: c=f32, a=b=bf16, both K-major, N=256, M=128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+#define TC_LD32(taddr, v)                                                                                       \
+  asm volatile(                                                                                                 \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, " \
+      "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"            \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),       \
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), \
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),           \
+        "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),           \
+        "=r"(v[30]), "=r"(v[31])                                                                               \
+      : "r"(taddr))
+
+__device__ __forceinline__ bool csr_has(const int64_t *__restrict__ a, int64_t n, int64_t x) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (a[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo < n && a[lo] == x;
+}
+
+// rare path; candidate lists: element j of row `t` at [j * BM + t]
+__device__ __noinline__ void cand_insert(float *sc, int *id, float s, int64_t item, int64_t item_limit,
+                                         const int64_t *__restrict__ hist, int64_t hlen, float &tau) {
+  if (item == 0 || item >= item_limit) return;             // [PAD] / zero-filled rows past the table
+  if (hlen > 0 && csr_has(hist, hlen, item)) return;
+  int j = KP - 1;
+  while (j > 0 && sc[(j - 1) * BM] < s) {
+    sc[j * BM] = sc[(j - 1) * BM];
+    id[j * BM] = id[(j - 1) * BM];
+    --j;
+  }
+  sc[j * BM] = s;
+  id[j * BM] = (int)item;
+  tau = sc[(KP - 1) * BM];
+}
+
+struct TcParams {
+  int64_t nq, n_local, item_base;
+  int n_ut, n_split, tiles_per_split;   // work decomposition
+  const int64_t *hist_indptr, *hist_indices;
+  int *cand_ids;      // [n_split][nq][KP]
+  float *cand_sc;     // [n_split][nq][KP]  approximate (bf16) scores
+};
+
+template <int KB, int NSTAGE>
+struct TcSmem {
+  static constexpr size_t A_BYTES = (size_t)KB * A_KB_BYTES;
+  static constexpr size_t B_BYTES = (size_t)NSTAGE * UNIT_BYTES;
+  static constexpr size_t LIST_BYTES = (size_t)KP * BM * 8;
+  static constexpr size_t TOTAL = 1024 /*align slack*/ + A_BYTES + B_BYTES + LIST_BYTES + 256 /*barriers*/;
+};
+
+template <int KB, int NSTAGE>
+__global__ void __launch_bounds__(kThreadsTc, 1)
+k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char *sA = smem;                                  // [KB][128 rows][128 B]
+  unsigned char *sB = sA + TcSmem<KB, NSTAGE>::A_BYTES;      // [NSTAGE][256 rows][128 B]
+  float *lsc = reinterpret_cast<float *>(sB + TcSmem<KB, NSTAGE>::B_BYTES);
+  int *lid = reinterpret_cast<int *>(lsc + KP * BM);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(lid + KP * BM);
+  uint64_t *full = bars;                 // [NSTAGE]
+  uint64_t *empty = bars + NSTAGE;       // [NSTAGE]
+  uint64_t *a_full = bars + 2 * NSTAGE;  // [1]
+  uint64_t *a_empty = a_full + 1;        // [1]
+  uint64_t *t_full = a_empty + 1;        // [2]
+  uint64_t *t_empty = t_full + 2;        // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int n_work = p.n_ut * p.n_split;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    mbar_init(&t_full[0], 1); mbar_init(&t_full[1], 1);
+    mbar_init(&t_empty[0], 128); mbar_init(&t_empty[1], 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {  // TMEM: all 512 columns (two 256-column accumulator stages)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int ut = w % p.n_ut, sp = w / p.n_ut;
+        mbar_wait(a_empty, a_phase ^ 1);
+        mbar_expect_tx(a_full, KB * A_KB_BYTES);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * A_KB_BYTES, &tmA, kb * BK, ut * BM, a_full);
+        a_phase ^= 1;
+        const int t0 = sp * p.tiles_per_split;
+        const int t1 = min(t0 + p.tiles_per_split, (int)((p.n_local + BN - 1) / BN));
+        for (int it = t0; it < t1; ++it) {
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], UNIT_BYTES);
+            tma_load_2d(sB + (size_t)stage * UNIT_BYTES, &tmB, kb * BK, it * BN, &full[stage]);
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int sp = w / p.n_ut;
+        mbar_wait(a_full, a_phase);
+        a_phase ^= 1;
+        const int t0 = sp * p.tiles_per_split;
+        const int t1 = min(t0 + p.tiles_per_split, (int)((p.n_local + BN - 1) / BN));
+        for (int it = t0; it < t1; ++it) {
+          mbar_wait(&t_empty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint64_t adesc = make_smem_desc(smem_u32(sA + kb * A_KB_BYTES));
+            const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)stage * UNIT_BYTES));
+#pragma unroll
+            for (int k4 = 0; k4 < BK / 16; ++k4) {
+              // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in 16-byte units
+              tc_mma_bf16(tmem_d, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), kIdesc,
+                          (kb | k4) ? 1u : 0u);
+            }
+            tc_commit(&empty[stage]);   // frees the ring slot once these MMAs have read it
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(&t_full[acc]);      // accumulator stage complete
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        tc_commit(a_empty);             // every MMA that reads this A tile has completed
+      }
+    }
+  } else {
+    // ===================== epilogue: 4 warps, thread <-> TMEM lane <-> query row =====================
+    const int quarter = warp & 3;                 // TMEM lanes this warp may touch: [32*quarter, +32)
+    const int t = quarter * 32 + lane;            // row inside the tile
+    float *my_sc = lsc + t;
+    int *my_id = lid + t;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int ut = w % p.n_ut, sp = w / p.n_ut;
+      const int64_t r = (int64_t)ut * BM + t;
+      const bool active = r < p.nq;
+      const int64_t *hist = nullptr;
+      int64_t hlen = 0;
+      if (active && p.hist_indptr) {
+        int64_t h0 = p.hist_indptr[r];
+        hlen = p.hist_indptr[r + 1] - h0;
+        hist = p.hist_indices + h0;
+      }
+#pragma unroll 4
+      for (int j = 0; j < KP; ++j) { my_sc[j * BM] = -INFINITY; my_id[j * BM] = -1; }
+      float tau = active ? -INFINITY : INFINITY;   // inactive rows never insert
+      const int64_t item_limit = p.item_base + p.n_local;
+      const int t0 = sp * p.tiles_per_split;
+      const int t1 = min(t0 + p.tiles_per_split, (int)((p.n_local + BN - 1) / BN));
+      for (int it = t0; it < t1; ++it) {
+        mbar_wait(&t_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+        const int64_t g0 = p.item_base + (int64_t)it * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+          uint32_t v[32], u[32];
+          TC_LD32(taddr + c0, v);
+          TC_LD32(taddr + c0 + 32, u);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(u[0]);
+#pragma unroll
+          for (int j = 1; j < 32; ++j) {
+            m0 = fmaxf(m0, __uint_as_float(v[j]));
+            m1 = fmaxf(m1, __uint_as_float(u[j]));
+          }
+          if (m0 > tau) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float s = __uint_as_float(v[j]);
+              if (s > tau) cand_insert(my_sc, my_id, s, g0 + c0 + j, item_limit, hist, hlen, tau);
+            }
+          }
+          if (m1 > tau) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float s = __uint_as_float(u[j]);
+              if (s > tau) cand_insert(my_sc, my_id, s, g0 + c0 + 32 + j, item_limit, hist, hlen, tau);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&t_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (active) {
+        int64_t o = ((int64_t)sp * p.nq + r) * KP;
+        for (int j = 0; j < KP; ++j) {
+          p.cand_ids[o + j] = my_id[j * BM];
+          p.cand_sc[o + j] = my_sc[j * BM];
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 -> bf16 rows (+ norms).  One lane group per row.
+template <int D>
+__global__ void __launch_bounds__(256) k_convert_rows(const float *__restrict__ src, const int64_t *__restrict__ ids,
+                                                       int64_t rows, int64_t src_rows, __nv_bfloat16 *__restrict__ dst,
+                                                       float *__restrict__ row_norm, float *__restrict__ row_dnorm,
+                                                       float *__restrict__ max_bnorm, float *__restrict__ max_dnorm) {
+  constexpr int LANES = RowCfg<D>::LANES;
+  constexpr int VPL = RowCfg<D>::VPL;
+  const int lane = threadIdx.x % LANES;
+  const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x % 32) / LANES * LANES));
+  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  if (r >= rows) return;
+  int64_t sr = ids ? min(max(ids[r], (int64_t)0), src_rows - 1) : r;
+  Row<D> x = row_ldg<D>(src, sr, lane);
+  float n2 = 0.f, d2 = 0.f, b2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    float f[4] = {x.v[i].x, x.v[i].y, x.v[i].z, x.v[i].w};
+    __nv_bfloat16 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      h[e] = __float2bfloat16_rn(f[e]);
+      float back = __bfloat162float(h[e]);
+      n2 = fmaf(f[e], f[e], n2);
+      b2 = fmaf(back, back, b2);
+      d2 = fmaf(f[e] - back, f[e] - back, d2);
+    }
+    uint2 packed;
+    packed.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+    packed.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+    reinterpret_cast<uint2 *>(dst + r * D)[i * LANES + lane] = packed;
+  }
+  n2 = group_sum<LANES>(n2, gmask);
+  d2 = group_sum<LANES>(d2, gmask);
+  b2 = group_sum<LANES>(b2, gmask);
+  if (lane == 0) {
+    // round the norms UP so the certificate stays rigorous
+    float nn = sqrtf(n2) * 1.0001f, dd = sqrtf(d2) * 1.0001f, bb = sqrtf(b2) * 1.0001f;
+    if (row_norm) row_norm[r] = nn;
+    if (row_dnorm) row_dnorm[r] = dd;
+    if (max_bnorm) atomicMax(reinterpret_cast<int *>(max_bnorm), __float_as_int(bb));   // non-negative floats
+    if (max_dnorm) atomicMax(reinterpret_cast<int *>(max_dnorm), __float_as_int(dd));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact re-score + order + certificate.  One warp per query row.
+template <int D>
+__global__ void __launch_bounds__(128) k_refine(const float *__restrict__ query_p, const int64_t *__restrict__ query_ids,
+                                                 int64_t nq, const float *__restrict__ item_p, int64_t item_base,
+                                                 const int *__restrict__ cand_ids, const float *__restrict__ cand_sc,
+                                                 int parts, int K, const float *__restrict__ qnorm,
+                                                 const float *__restrict__ qdnorm, const float *__restrict__ maxes,
+                                                 int64_t *__restrict__ out_ids, float *__restrict__ out_scores,
+                                                 int32_t *__restrict__ fail_rows, int32_t *__restrict__ fail_count) {
+  const int lane = threadIdx.x % 32;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  if (r >= nq) return;
+  const int64_t qrow = query_ids ? query_ids[r] : r;
+  const float *q = query_p + qrow * D;
+  // every lane re-scores candidates lane, lane+32, ... with the canonical chain
+  float best_s[2 * 8];  // up to 16 parts*KP/32 = parts candidates per lane; parts <= 16
+  int best_i[2 * 8];
+  float tau_max = -INFINITY;
+  bool all_short = true;  // every part saw fewer than KP candidates => nothing was cut off
+  const int per_lane = parts;  // parts * KP / 32 with KP == 32
+  for (int c = 0; c < per_lane; ++c) {
+    int64_t o = ((int64_t)c * nq + r) * KP + lane;
+    int id = cand_ids[o];
+    float s = -INFINITY;
+    if (id >= 0) {
+      const float4 *v4 = reinterpret_cast<const float4 *>(item_p + ((int64_t)id - item_base) * D);
+      const float4 *q4 = reinterpret_cast<const float4 *>(q);
+      s = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < D / 4; ++k) {
+        float4 a = __ldg(q4 + k), b = __ldg(v4 + k);
+        s = fmaf(a.x, b.x, s);
+        s = fmaf(a.y, b.y, s);
+        s = fmaf(a.z, b.z, s);
+        s = fmaf(a.w, b.w, s);
+      }
+      if (s == -INFINITY || !(s == s)) id = -1;  // the exact path never selects -inf / NaN
+    }
+    best_s[c] = (id >= 0) ? s : -INFINITY;
+    best_i[c] = id;
+    // part's K'-th approximate score (last list entry): held by lane 31
+    float last = __shfl_sync(0xffffffffu, cand_sc[o], 31);
+    int last_id = __shfl_sync(0xffffffffu, cand_ids[o], 31);
+    if (last_id >= 0) { all_short = false; tau_max = fmaxf(tau_max, last); }
+  }
+  // K rounds of warp arg-max with the (score desc, id asc) order
+  float kth = -INFINITY;
+  int found = 0;
+  for (int j = 0; j < K; ++j) {
+    float bs = -INFINITY;
+    int bi = 0x7fffffff, bc = -1;
+    for (int c = 0; c < per_lane; ++c) {
+      if (best_i[c] >= 0 && (best_s[c] > bs || (best_s[c] == bs && best_i[c] < bi))) { bs = best_s[c]; bi = best_i[c]; bc = c; }
+    }
+    float ws = bs;
+    int wi = bc >= 0 ? bi : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float os = __shfl_xor_sync(0xffffffffu, ws, o);
+      int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+      if (os > ws || (os == ws && oi < wi)) { ws = os; wi = oi; }
+    }
+    const bool have = wi != 0x7fffffff;
+    if (have && bc >= 0 && bi == wi) best_i[bc] = -1;  // remove the winner (ids are unique per row)
+    if (lane == 0) {
+      out_ids[r * K + j] = have ? (int64_t)wi : -1;
+      out_scores[r * K + j] = have ? ws : -INFINITY;
+    }
+    if (have) { kth = ws; ++found; }
+  }
+  if (lane == 0 && !all_short) {
+    // |approx - exact| <= ||du||*max||bv|| + ||u||*max||dv||  (+ fp32 accumulation slack)
+    float E = qdnorm[r] * maxes[0] + qnorm[r] * maxes[1] + 1.6e-5f * qnorm[r] * maxes[0];
+    bool ok = (found == K) && (kth > tau_max + E);
+    if (!ok) {
+      int slot = atomicAdd(fail_count, 1);
+      fail_rows[slot] = (int32_t)r;
+    }
+  }
+}
+
+struct TcWs {
+  __nv_bfloat16 *qb, *vb;
+  float *qnorm, *qdnorm, *maxes;  // maxes[0] = max ||bf16(v)||, maxes[1] = max ||v - bf16(v)||
+  int *cand_ids;
+  float *cand_sc;
+  int32_t *fail_rows, *fail_count;
+  int64_t *fb_ids;
+  float *fb_sc;
+  void *fp32_ws;
+  size_t fp32_bytes;
+};
+
+struct TcPlan {
+  int n_ut, n_split, tiles_per_split, grid;
+};
+
+TcPlan make_plan(int64_t nq, int64_t n_local) {
+  TcPlan pl;
+  pl.n_ut = (int)((nq + BM - 1) / BM);
+  int n_tiles = (int)((n_local + BN - 1) / BN);
+  int sms = rb2_num_sms();
+  int want = (2 * sms + pl.n_ut - 1) / pl.n_ut;   // aim for >= 2 work items per SM
+  if (want < 1) want = 1;
+  if (want > 16) want = 16;
+  if (want > n_tiles) want = n_tiles;
+  pl.tiles_per_split = (n_tiles + want - 1) / want;
+  pl.n_split = (n_tiles + pl.tiles_per_split - 1) / pl.tiles_per_split;
+  int work = pl.n_ut * pl.n_split;
+  pl.grid = work < sms ? work : sms;
+  return pl;
+}
+
+size_t carve_tc(TcWs &w, void *base, int64_t nq, int64_t n_local, int dim, int k) {
+  Carver c(base);
+  TcPlan pl = make_plan(nq, n_local);
+  int64_t nq_pad = (nq + BM - 1) / BM * BM;
+  w.qb = c.take<__nv_bfloat16>(nq_pad * dim);
+  w.vb = c.take<__nv_bfloat16>(n_local * dim);
+  w.qnorm = c.take<float>(nq);
+  w.qdnorm = c.take<float>(nq);
+  w.maxes = c.take<float>(4);
+  w.cand_ids = c.take<int>((size_t)pl.n_split * nq * KP);
+  w.cand_sc = c.take<float>((size_t)pl.n_split * nq * KP);
+  w.fail_rows = c.take<int32_t>(nq);
+  w.fail_count = c.take<int32_t>(4);
+  w.fb_ids = c.take<int64_t>(nq * k);
+  w.fb_sc = c.take<float>(nq * k);
+  w.fp32_bytes = rb2_fullsort_fp32_workspace(nq, n_local, dim, k);
+  w.fp32_ws = c.take<char>(w.fp32_bytes);
+  return c.off;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap *m, void *base, int64_t rows, int dim, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  RB2_REQUIRE(fn != nullptr, RB2_EINVAL, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)dim * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RB2_REQUIRE(rc == CUDA_SUCCESS, RB2_EINVAL, "cuTensorMapEncodeTiled failed with %d", (int)rc);
+  return 0;
+}
+
+template <int D>
+int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p, int64_t n_local,
+           int64_t item_base, const int64_t *hist_indptr, const int64_t *hist_indices, int k, int64_t *out_ids,
+           float *out_scores, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+  constexpr int KB = D / BK;
+  constexpr int NSTAGE = (KB == 1) ? 4 : 4;
+  TcWs w;
+  size_t need = carve_tc(w, workspace, nq, n_local, D, k);
+  RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_fullsort_topk(tc): workspace %zu < %zu", workspace_bytes, need);
+  TcPlan pl = make_plan(nq, n_local);
+  constexpr int LANES = RowCfg<D>::LANES;
+  const int64_t nq_pad = (nq + BM - 1) / BM * BM;
+  {
+    ProfScope prof(RB2_ST_TC_CONVERT, st, 4);
+    RB2_CUDA(cudaMemsetAsync(w.maxes, 0, 4 * sizeof(float), st));
+    RB2_CUDA(cudaMemsetAsync(w.fail_count, 0, 4 * sizeof(int32_t), st));
+    if (nq_pad > nq) RB2_CUDA(cudaMemsetAsync(w.qb + nq * D, 0, (size_t)(nq_pad - nq) * D * 2, st));
+    k_convert_rows<D><<<(unsigned)((nq * LANES + 255) / 256), 256, 0, st>>>(query_p, query_ids, nq, INT64_MAX, w.qb,
+                                                                            w.qnorm, w.qdnorm, nullptr, nullptr);
+    k_convert_rows<D><<<(unsigned)((n_local * LANES + 255) / 256), 256, 0, st>>>(item_p, nullptr, n_local, n_local,
+                                                                                 w.vb, nullptr, nullptr, w.maxes,
+                                                                                 w.maxes + 1);
+  }
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, w.qb, nq_pad, D, BM);
+  if (rc) return rc;
+  rc = make_map(&tmB, w.vb, n_local, D, BN);
+  if (rc) return rc;
+  TcParams p;
+  p.nq = nq; p.n_local = n_local; p.item_base = item_base;
+  p.n_ut = pl.n_ut; p.n_split = pl.n_split; p.tiles_per_split = pl.tiles_per_split;
+  p.hist_indptr = hist_indptr; p.hist_indices = hist_indices;
+  p.cand_ids = w.cand_ids; p.cand_sc = w.cand_sc;
+  const size_t smem = TcSmem<KB, NSTAGE>::TOTAL;
+  {
+    ProfScope prof(RB2_ST_TC_SCORE, st);
+    RB2_CUDA(cudaFuncSetAttribute(k_fullsort_tc<KB, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fullsort_tc<KB, NSTAGE><<<pl.grid, kThreadsTc, smem, st>>>(tmA, tmB, p);
+    RB2_CUDA(cudaGetLastError());
+  }
+  {
+    ProfScope prof(RB2_ST_TC_REFINE, st);
+    k_refine<D><<<(unsigned)((nq * 32 + 127) / 128), 128, 0, st>>>(query_p, query_ids, nq, item_p, item_base,
+                                                                  w.cand_ids, w.cand_sc, pl.n_split, k, w.qnorm,
+                                                                  w.qdnorm, w.maxes, out_ids, out_scores, w.fail_rows,
+                                                                  w.fail_count);
+    RB2_CUDA(cudaGetLastError());
+  }
+  // rows whose certificate failed: redo exactly (one small D2H per call)
+  int32_t n_fail = 0;
+  RB2_CUDA(cudaMemcpyAsync(&n_fail, w.fail_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  RB2_CUDA(cudaStreamSynchronize(st));
+  g_last_tc_fallback_rows = n_fail;
+  if (n_fail > 0) {
+    rc = rb2_fullsort_fp32(query_p, query_ids, n_fail, item_p, n_local, item_base, D, hist_indptr, hist_indices, k,
+                           out_ids, out_scores, w.fp32_ws, w.fp32_bytes, st, w.fail_rows);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace
+
+size_t rb2_fullsort_tc_workspace_bytes(int64_t nq, int64_t n_items_local, int32_t dim, int32_t k) {
+  if (dim != 64 && dim != 128) return rb2_fullsort_fp32_workspace(nq, n_items_local, dim, k) + 256;
+  TcWs w;
+  return carve_tc(w, nullptr, nq, n_items_local, dim, k) + 256;
+}
+
+int rb2_fullsort_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p,
+                    int64_t n_items_local, int64_t item_base, int32_t dim, const int64_t *hist_indptr,
+                    const int64_t *hist_indices, int32_t k, int64_t *out_ids, float *out_scores, void *workspace,
+                    size_t workspace_bytes, cudaStream_t st) {
+  if ((dim != 64 && dim != 128) || k > 16) {
+    // the MMA tiling covers d = 64 / 128 and K <= 16 (K' = 32 candidates); other shapes take the
+    // exact CUDA-core kernel
+    g_last_tc_fallback_rows = (int32_t)(nq > INT32_MAX ? INT32_MAX : nq);
+    return rb2_fullsort_fp32(query_p, query_ids, nq, item_p, n_items_local, item_base, dim, hist_indptr,
+                             hist_indices, k, out_ids, out_scores, workspace, workspace_bytes, st, nullptr);
+  }
+  if (dim == 64)
+    return run_tc<64>(query_p, query_ids, nq, item_p, n_items_local, item_base, hist_indptr, hist_indices, k,
+                      out_ids, out_scores, workspace, workspace_bytes, st);
+  return run_tc<128>(query_p, query_ids, nq, item_p, n_items_local, item_base, hist_indptr, hist_indices, k, out_ids,
+                     out_scores, workspace, workspace_bytes, st);
 }

@@ -191,3 +191,86 @@ def test_full_size_cfg2_eval_properties():
                                      np.arange(0, 20 * 64 + 1, 20), hist_cols[sub].cpu().numpy().reshape(-1), K)
     np.testing.assert_array_equal(ids[sub].cpu().numpy(), o_ids)
     np.testing.assert_array_equal(sc[sub].cpu().numpy(), o_sc)
+
+
+# ---- tensor-core scorer (tcgen05 + TMA), certified exact ------------------------------------------
+
+def _tc_case(dim, nq, N, K, seed, dyadic=False, hist_per_row=4, scale=1.0):
+    rng = np.random.default_rng(seed)
+    if dyadic:
+        Q = (rng.integers(-4, 5, (nq, dim)) / 8.0).astype(np.float32)
+        V = (rng.integers(-4, 5, (N, dim)) / 8.0).astype(np.float32)
+    else:
+        Q = (rng.standard_normal((nq, dim)) * scale).astype(np.float32)
+        V = (rng.standard_normal((N, dim)) * scale).astype(np.float32)
+    hp, hi = [0], []
+    for r in range(nq):
+        h = np.sort(rng.choice(np.arange(1, N), size=min(hist_per_row, N - 1), replace=False))
+        hi.append(h)
+        hp.append(hp[-1] + len(h))
+    return Q, V, np.array(hp, dtype=np.int64), np.concatenate(hi).astype(np.int64)
+
+
+@pytest.mark.parametrize("dim", [64, 128])
+@pytest.mark.parametrize("nq,N,K", [(300, 5000, 10), (128, 256, 10), (1, 1000, 5), (1000, 70001, 10), (77, 300, 16)])
+def test_fullsort_tc_random_exact(dim, nq, N, K):
+    """bf16 tensor-core filter + fp32 re-score + certificate == the oracle, bit for bit."""
+    from recbole_b200 import ops
+    from recbole_b200._lib import lib
+    from gpu_util import t
+    Q, V, hp, hi = _tc_case(dim, nq, N, K, seed=dim + nq + N)
+    ids, sc = ops.fullsort_topk(t(Q), None, t(V), K, t(hp), t(hi), mode="tc")
+    o_ids, o_sc = ofs.full_sort_topk(Q, V, np.arange(nq), hp, hi, K)
+    np.testing.assert_array_equal(ids.cpu().numpy(), o_ids)
+    np.testing.assert_array_equal(sc.cpu().numpy(), o_sc)
+    # on gaussian data the certificate must hold for (almost) every row: the tensor path did the work
+    assert lib.rb2_fullsort_tc_last_fallback_rows() <= max(1, nq // 50)
+
+
+@pytest.mark.parametrize("dim", [64, 128])
+def test_fullsort_tc_ties_fall_back_and_stay_exact(dim):
+    """Dyadic grid => massive exact ties around the K'-th candidate => certificates fail => those
+    rows are redone in fp32; the answer is still the oracle's."""
+    from recbole_b200 import ops
+    from gpu_util import t
+    Q, V, hp, hi = _tc_case(dim, 200, 3000, 10, seed=3, dyadic=True)
+    ids, sc = ops.fullsort_topk(t(Q), None, t(V), 10, t(hp), t(hi), mode="tc")
+    o_ids, o_sc = ofs.full_sort_topk(Q, V, np.arange(200), hp, hi, 10)
+    np.testing.assert_array_equal(ids.cpu().numpy(), o_ids)
+    np.testing.assert_array_equal(sc.cpu().numpy(), o_sc)
+
+
+def test_fullsort_tc_query_ids_shards_and_golden(golden):
+    from recbole_b200 import ops
+    from gpu_util import t
+    g = golden("fullsort_ml100k.npz")
+    hist, pos = _csrs(g)
+    ids, sc = ops.fullsort_topk(t(g["U"]), t(g["uid_list"]), t(g["V"]), 10, t(hist[0]), t(hist[1]), mode="tc")
+    o_ids, o_sc = ofs.full_sort_topk(g["U"], g["V"], g["uid_list"], hist[0], hist[1], 10)
+    np.testing.assert_array_equal(ids.cpu().numpy(), o_ids)
+    np.testing.assert_array_equal(sc.cpu().numpy(), o_sc)
+    # item shards with a base offset, merged
+    N = g["V"].shape[0]
+    parts_i, parts_s = [], []
+    for a, b in ((0, 700), (700, N)):
+        i, s = ops.fullsort_topk(t(g["U"]), t(g["uid_list"]), t(g["V"][a:b]), 10, t(hist[0]), t(hist[1]),
+                                 item_base=a, mode="tc")
+        parts_i.append(i)
+        parts_s.append(s)
+    m_ids, m_sc = ops.topk_merge(torch.stack(parts_i), torch.stack(parts_s))
+    np.testing.assert_array_equal(m_ids.cpu().numpy(), o_ids)
+
+
+def test_fullsort_tc_unsupported_shapes_use_fp32_kernel():
+    """d = 32 or K > 16 are outside the MMA tiling: the call is served by the exact CUDA-core
+    kernel (still on the GPU, still exact)."""
+    from recbole_b200 import ops
+    from gpu_util import t
+    Q, V, hp, hi = _tc_case(32, 50, 500, 10, seed=9)
+    ids, _ = ops.fullsort_topk(t(Q), None, t(V), 10, t(hp), t(hi), mode="tc")
+    o_ids, _ = ofs.full_sort_topk(Q, V, np.arange(50), hp, hi, 10)
+    np.testing.assert_array_equal(ids.cpu().numpy(), o_ids)
+    Q, V, hp, hi = _tc_case(64, 50, 500, 20, seed=9)
+    ids, _ = ops.fullsort_topk(t(Q), None, t(V), 20, t(hp), t(hi), mode="tc")
+    o_ids, _ = ofs.full_sort_topk(Q, V, np.arange(50), hp, hi, 20)
+    np.testing.assert_array_equal(ids.cpu().numpy(), o_ids)
