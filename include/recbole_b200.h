@@ -161,6 +161,10 @@ int rb2_fullsort_topk(const float *query_p, const int64_t *query_ids, int64_t nq
 /* Diagnostic: how many rows of the last RB2_SCORER_TC call failed the certificate and were redone by
  * the fp32 kernel (or nq if the shape is not covered by the MMA tiling: dim not in {64,128}, k > 16). */
 int32_t rb2_fullsort_tc_last_fallback_rows(void);
+/* Tuning knob of RB2_SCORER_TC: candidates kept per (row, list): 16, 32, or 0 = automatic (32, or 16
+ * when k <= 8).  More candidates = looser certificate, more epilogue work.  The result is exact either
+ * way. */
+int rb2_fullsort_tc_set_kprime(int32_t kprime);
 
 /* Merge `parts` per-shard top-K lists ([parts, nq, k], each sorted) into the global top-K
  * (multi-GPU all-gather merge). */

@@ -10,9 +10,12 @@
 //                    ||u - bf16(u)|| and, for the item side, max ||bf16(v)|| / max ||v - bf16(v)||.
 //   k_fullsort_tc    persistent, warp-specialised: warp 0 = TMA producer (128B-swizzled tiles),
 //                    warp 1 = single-thread tcgen05.mma issuer (bf16 x bf16 -> fp32 in TMEM, two
-//                    256-column accumulator stages), warps 2-5 = epilogue: tcgen05.ld 32 columns at
-//                    a time, group max against the row's running threshold, rare insert into a
-//                    K' = 32 candidate list in shared memory (pad / history checked only there).
+//                    256-column accumulator stages), warps 2-9 = two epilogue warp sets, one per
+//                    accumulator stage (thread <-> TMEM lane <-> query row): tcgen05.ld 32 columns
+//                    at a time, FMNMX3 max tree against the row's running threshold, rare insert
+//                    into a K' (16 or 32) candidate list held in REGISTERS (branch-free bubble);
+//                    pad / history are checked only there, history through a per-row Bloom filter
+//                    in shared memory so that the CSR binary search is almost never taken.
 //   k_refine         candidates are re-scored with the canonical fp32 chain s = fmaf(q[k], v[k], s)
 //                    and ordered (score desc, id asc).  Certificate per row:
 //                        exact_K  >  max_part(approx K'-th score) + E,
@@ -35,6 +38,12 @@ size_t rb2_fullsort_fp32_workspace(int64_t nq, int64_t n_items_local, int32_t di
 
 // number of rows the last RB2_SCORER_TC call had to redo in fp32 (diagnostic for bench / tests)
 static int32_t g_last_tc_fallback_rows = 0;
+static int32_t g_tc_kprime = 0;  // 0 = automatic, 16 or 32 = forced (rb2_fullsort_tc_set_kprime)
+extern "C" int rb2_fullsort_tc_set_kprime(int32_t kp) {
+  if (kp != 0 && kp != 16 && kp != 32) return RB2_EINVAL;
+  g_tc_kprime = kp;
+  return 0;
+}
 extern "C" int32_t rb2_fullsort_tc_last_fallback_rows(void) { return g_last_tc_fallback_rows; }
 
 namespace {
@@ -42,10 +51,10 @@ namespace {
 constexpr int BM = 128;       // query rows per CTA tile (= TMEM lanes)
 constexpr int BN = 256;       // items per accumulator stage (= MMA N)
 constexpr int BK = 64;        // bf16 elements per 128-byte swizzle row
-constexpr int KP = 32;        // candidates kept per row (K' > K)
 constexpr int UNIT_BYTES = BN * BK * 2;   // one B ring slot: 256 items x 64 k
 constexpr int A_KB_BYTES = BM * BK * 2;
-constexpr int kThreadsTc = 192;
+constexpr int kThreadsTc = 320;          // producer warp + MMA warp + 2 x 4 epilogue warps
+constexpr int BLOOM_WORDS = 64;          // 2048 bits per row, 2 hashes
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -129,48 +138,62 @@ __device__ __forceinline__ bool csr_has(const int64_t *__restrict__ a, int64_t n
   return lo < n && a[lo] == x;
 }
 
-// rare path; candidate lists: element j of row `t` at [j * BM + t]
-__device__ __noinline__ void cand_insert(float *sc, int *id, float s, int64_t item, int64_t item_limit,
-                                         const int64_t *__restrict__ hist, int64_t hlen, float &tau) {
-  if (item == 0 || item >= item_limit) return;             // [PAD] / zero-filled rows past the table
-  if (hlen > 0 && csr_has(hist, hlen, item)) return;
-  int j = KP - 1;
-  while (j > 0 && sc[(j - 1) * BM] < s) {
-    sc[j * BM] = sc[(j - 1) * BM];
-    id[j * BM] = id[(j - 1) * BM];
-    --j;
-  }
-  sc[j * BM] = s;
-  id[j * BM] = (int)item;
-  tau = sc[(KP - 1) * BM];
-}
-
 struct TcParams {
   int64_t nq, n_local, item_base;
   int n_ut, n_split, tiles_per_split;   // work decomposition
   const int64_t *hist_indptr, *hist_indices;
-  int *cand_ids;      // [n_split][nq][KP]
-  float *cand_sc;     // [n_split][nq][KP]  approximate (bf16) scores
+  int *cand_ids;      // [n_split * 2][nq][KP]   (x2: one list per epilogue warp set)
+  float *cand_sc;     // approximate (bf16) scores, each list sorted descending
 };
 
 template <int KB, int NSTAGE>
 struct TcSmem {
   static constexpr size_t A_BYTES = (size_t)KB * A_KB_BYTES;
   static constexpr size_t B_BYTES = (size_t)NSTAGE * UNIT_BYTES;
-  static constexpr size_t LIST_BYTES = (size_t)KP * BM * 8;
-  static constexpr size_t TOTAL = 1024 /*align slack*/ + A_BYTES + B_BYTES + LIST_BYTES + 256 /*barriers*/;
+  static constexpr size_t BLOOM_BYTES = (size_t)BLOOM_WORDS * BM * 4;
+  static constexpr size_t TOTAL = 1024 /*align slack*/ + A_BYTES + B_BYTES + BLOOM_BYTES + 256 /*barriers*/;
 };
 
-template <int KB, int NSTAGE>
+__device__ __forceinline__ uint32_t bloom_h1(uint32_t x) { return (x * 0x9E3779B1u) >> 21; }
+__device__ __forceinline__ uint32_t bloom_h2(uint32_t x) { return (x * 0x85EBCA77u) >> 21; }
+
+// sorted (descending) candidate list in registers; precondition s > ls[KP-1].  Branch-free bubble:
+// the new entry replaces the tail and climbs while it is strictly greater than its neighbour.
+template <int KP>
+__device__ __forceinline__ void list_insert(float (&ls)[KP], int (&li)[KP], float s, int id) {
+  ls[KP - 1] = s;
+  li[KP - 1] = id;
+#pragma unroll
+  for (int i = KP - 2; i >= 0; --i) {
+    const bool sw = ls[i + 1] > ls[i];
+    const float a = ls[i], b = ls[i + 1];
+    const int ia = li[i], ib = li[i + 1];
+    ls[i] = sw ? b : a;
+    ls[i + 1] = sw ? a : b;
+    li[i] = sw ? ib : ia;
+    li[i + 1] = sw ? ia : ib;
+  }
+}
+
+__device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
+  float m[11];
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+    m[i] = fmaxf(fmaxf(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1])), __uint_as_float(v[3 * i + 2]));
+  m[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+  float a = fmaxf(fmaxf(m[0], m[1]), m[2]), b = fmaxf(fmaxf(m[3], m[4]), m[5]), c = fmaxf(fmaxf(m[6], m[7]), m[8]);
+  return fmaxf(fmaxf(fmaxf(a, b), c), fmaxf(m[9], m[10]));
+}
+
+template <int KB, int NSTAGE, int KP>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char *sA = smem;                                  // [KB][128 rows][128 B]
   unsigned char *sB = sA + TcSmem<KB, NSTAGE>::A_BYTES;      // [NSTAGE][256 rows][128 B]
-  float *lsc = reinterpret_cast<float *>(sB + TcSmem<KB, NSTAGE>::B_BYTES);
-  int *lid = reinterpret_cast<int *>(lsc + KP * BM);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(lid + KP * BM);
+  uint32_t *bloom = reinterpret_cast<uint32_t *>(sB + TcSmem<KB, NSTAGE>::B_BYTES);  // [BLOOM_WORDS][BM]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(bloom + BLOOM_WORDS * BM);
   uint64_t *full = bars;                 // [NSTAGE]
   uint64_t *empty = bars + NSTAGE;       // [NSTAGE]
   uint64_t *a_full = bars + 2 * NSTAGE;  // [1]
@@ -181,6 +204,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int n_work = p.n_ut * p.n_split;
+  const int n_tiles_all = (int)((p.n_local + BN - 1) / BN);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -213,7 +237,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * A_KB_BYTES, &tmA, kb * BK, ut * BM, a_full);
         a_phase ^= 1;
         const int t0 = sp * p.tiles_per_split;
-        const int t1 = min(t0 + p.tiles_per_split, (int)((p.n_local + BN - 1) / BN));
+        const int t1 = min(t0 + p.tiles_per_split, n_tiles_all);
         for (int it = t0; it < t1; ++it) {
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
@@ -227,16 +251,17 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+      int stage = 0;
+      uint32_t phase = 0, a_phase = 0, tcount = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         const int sp = w / p.n_ut;
         mbar_wait(a_full, a_phase);
         a_phase ^= 1;
         const int t0 = sp * p.tiles_per_split;
-        const int t1 = min(t0 + p.tiles_per_split, (int)((p.n_local + BN - 1) / BN));
-        for (int it = t0; it < t1; ++it) {
-          mbar_wait(&t_empty[acc], acc_phase ^ 1);
+        const int t1 = min(t0 + p.tiles_per_split, n_tiles_all);
+        for (int it = t0; it < t1; ++it, ++tcount) {
+          const int acc = tcount & 1;
+          mbar_wait(&t_empty[acc], ((tcount >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
           for (int kb = 0; kb < KB; ++kb) {
@@ -254,19 +279,17 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
           tc_commit(&t_full[acc]);      // accumulator stage complete
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         tc_commit(a_empty);             // every MMA that reads this A tile has completed
       }
     }
   } else {
-    // ===================== epilogue: 4 warps, thread <-> TMEM lane <-> query row =====================
+    // ===================== epilogue: 2 warp sets x 4 warps; thread <-> TMEM lane <-> query row ========
+    const int ws = (warp - 2) >> 2;               // warp set = accumulator stage it drains
     const int quarter = warp & 3;                 // TMEM lanes this warp may touch: [32*quarter, +32)
     const int t = quarter * 32 + lane;            // row inside the tile
-    float *my_sc = lsc + t;
-    int *my_id = lid + t;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t *my_bloom = bloom + t;               // word i at my_bloom[i * BM]
+    uint32_t tcount = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const int ut = w % p.n_ut, sp = w / p.n_ut;
       const int64_t r = (int64_t)ut * BM + t;
@@ -278,14 +301,43 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         hlen = p.hist_indptr[r + 1] - h0;
         hist = p.hist_indices + h0;
       }
-#pragma unroll 4
-      for (int j = 0; j < KP; ++j) { my_sc[j * BM] = -INFINITY; my_id[j * BM] = -1; }
+      // everyone is done with the previous work item's filter
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ws == 0) {
+        for (int i = 0; i < BLOOM_WORDS; ++i) my_bloom[i * BM] = 0u;
+        for (int64_t h = 0; h < hlen; ++h) {
+          uint32_t x = (uint32_t)hist[h];
+          uint32_t a = bloom_h1(x), b = bloom_h2(x);
+          my_bloom[(a >> 5) * BM] |= 1u << (a & 31);
+          my_bloom[(b >> 5) * BM] |= 1u << (b & 31);
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+
+      float ls[KP];
+      int li[KP];
+#pragma unroll
+      for (int j = 0; j < KP; ++j) { ls[j] = -INFINITY; li[j] = -1; }
       float tau = active ? -INFINITY : INFINITY;   // inactive rows never insert
       const int64_t item_limit = p.item_base + p.n_local;
       const int t0 = sp * p.tiles_per_split;
-      const int t1 = min(t0 + p.tiles_per_split, (int)((p.n_local + BN - 1) / BN));
-      for (int it = t0; it < t1; ++it) {
-        mbar_wait(&t_full[acc], acc_phase);
+      const int t1 = min(t0 + p.tiles_per_split, n_tiles_all);
+
+      auto consider = [&](float s, int64_t item) {
+        if (item == 0 || item >= item_limit) return;            // [PAD] / zero-filled rows past the table
+        if (hlen > 0) {
+          uint32_t x = (uint32_t)item, a = bloom_h1(x), b = bloom_h2(x);
+          bool maybe = ((my_bloom[(a >> 5) * BM] >> (a & 31)) & (my_bloom[(b >> 5) * BM] >> (b & 31)) & 1u) != 0u;
+          if (maybe && csr_has(hist, hlen, item)) return;       // trainer.py:344-345
+        }
+        list_insert<KP>(ls, li, s, (int)item);
+        tau = ls[KP - 1];
+      };
+
+      for (int it = t0; it < t1; ++it, ++tcount) {
+        const int acc = tcount & 1;
+        if (acc != ws) continue;
+        mbar_wait(&t_full[acc], (tcount >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
         const int64_t g0 = p.item_base + (int64_t)it * BN;
@@ -295,36 +347,30 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           TC_LD32(taddr + c0, v);
           TC_LD32(taddr + c0 + 32, u);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(u[0]);
-#pragma unroll
-          for (int j = 1; j < 32; ++j) {
-            m0 = fmaxf(m0, __uint_as_float(v[j]));
-            m1 = fmaxf(m1, __uint_as_float(u[j]));
-          }
-          if (m0 > tau) {
+          if (max32(v) > tau) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               float s = __uint_as_float(v[j]);
-              if (s > tau) cand_insert(my_sc, my_id, s, g0 + c0 + j, item_limit, hist, hlen, tau);
+              if (s > tau) consider(s, g0 + c0 + j);
             }
           }
-          if (m1 > tau) {
+          if (max32(u) > tau) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               float s = __uint_as_float(u[j]);
-              if (s > tau) cand_insert(my_sc, my_id, s, g0 + c0 + 32 + j, item_limit, hist, hlen, tau);
+              if (s > tau) consider(s, g0 + c0 + 32 + j);
             }
           }
         }
         tc_fence_before();
         mbar_arrive(&t_empty[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (active) {
-        int64_t o = ((int64_t)sp * p.nq + r) * KP;
+        int64_t o = (((int64_t)sp * 2 + ws) * p.nq + r) * KP;
+#pragma unroll
         for (int j = 0; j < KP; ++j) {
-          p.cand_ids[o + j] = my_id[j * BM];
-          p.cand_sc[o + j] = my_sc[j * BM];
+          p.cand_ids[o + j] = li[j];
+          p.cand_sc[o + j] = ls[j];
         }
       }
     }
@@ -385,8 +431,9 @@ __global__ void __launch_bounds__(256) k_convert_rows(const float *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// exact re-score + order + certificate.  One warp per query row.
-template <int D>
+// exact re-score + order + certificate.  One warp per query row; `parts` sorted lists of KP
+// candidates each (parts * KP <= 1024).
+template <int D, int KP>
 __global__ void __launch_bounds__(128) k_refine(const float *__restrict__ query_p, const int64_t *__restrict__ query_ids,
                                                  int64_t nq, const float *__restrict__ item_p, int64_t item_base,
                                                  const int *__restrict__ cand_ids, const float *__restrict__ cand_sc,
@@ -394,68 +441,79 @@ __global__ void __launch_bounds__(128) k_refine(const float *__restrict__ query_
                                                  const float *__restrict__ qdnorm, const float *__restrict__ maxes,
                                                  int64_t *__restrict__ out_ids, float *__restrict__ out_scores,
                                                  int32_t *__restrict__ fail_rows, int32_t *__restrict__ fail_count) {
+  constexpr int MAXC = 32;  // candidates per lane
   const int lane = threadIdx.x % 32;
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
   if (r >= nq) return;
   const int64_t qrow = query_ids ? query_ids[r] : r;
-  const float *q = query_p + qrow * D;
-  // every lane re-scores candidates lane, lane+32, ... with the canonical chain
-  float best_s[2 * 8];  // up to 16 parts*KP/32 = parts candidates per lane; parts <= 16
-  int best_i[2 * 8];
-  float tau_max = -INFINITY;
-  bool all_short = true;  // every part saw fewer than KP candidates => nothing was cut off
-  const int per_lane = parts;  // parts * KP / 32 with KP == 32
-  for (int c = 0; c < per_lane; ++c) {
-    int64_t o = ((int64_t)c * nq + r) * KP + lane;
-    int id = cand_ids[o];
-    float s = -INFINITY;
-    if (id >= 0) {
-      const float4 *v4 = reinterpret_cast<const float4 *>(item_p + ((int64_t)id - item_base) * D);
-      const float4 *q4 = reinterpret_cast<const float4 *>(q);
-      s = 0.f;
+  const float4 *q4 = reinterpret_cast<const float4 *>(query_p + qrow * D);
+  const int total = parts * KP;
+  float cs[MAXC];
+  int ci[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) { cs[c] = -INFINITY; ci[c] = -1; }
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    int idx = c * 32 + lane;
+    if (idx < total) {
+      int part = idx / KP, slot = idx % KP;
+      int id = cand_ids[((int64_t)part * nq + r) * KP + slot];
+      if (id >= 0) {
+        const float4 *v4 = reinterpret_cast<const float4 *>(item_p + ((int64_t)id - item_base) * D);
+        float s = 0.f;
 #pragma unroll 8
-      for (int k = 0; k < D / 4; ++k) {
-        float4 a = __ldg(q4 + k), b = __ldg(v4 + k);
-        s = fmaf(a.x, b.x, s);
-        s = fmaf(a.y, b.y, s);
-        s = fmaf(a.z, b.z, s);
-        s = fmaf(a.w, b.w, s);
+        for (int k = 0; k < D / 4; ++k) {
+          float4 a = __ldg(q4 + k), b = __ldg(v4 + k);
+          s = fmaf(a.x, b.x, s);
+          s = fmaf(a.y, b.y, s);
+          s = fmaf(a.z, b.z, s);
+          s = fmaf(a.w, b.w, s);
+        }
+        if (s != -INFINITY && s == s) { cs[c] = s; ci[c] = id; }  // the exact path never selects -inf / NaN
       }
-      if (s == -INFINITY || !(s == s)) id = -1;  // the exact path never selects -inf / NaN
     }
-    best_s[c] = (id >= 0) ? s : -INFINITY;
-    best_i[c] = id;
-    // part's K'-th approximate score (last list entry): held by lane 31
-    float last = __shfl_sync(0xffffffffu, cand_sc[o], 31);
-    int last_id = __shfl_sync(0xffffffffu, cand_ids[o], 31);
-    if (last_id >= 0) { all_short = false; tau_max = fmaxf(tau_max, last); }
   }
+  // cut-off thresholds: a FULL list (tail valid) may have dropped items with approx <= its tail score
+  float tau_max = -INFINITY;
+  bool any_full = false;
+  for (int part = lane; part < parts; part += 32) {
+    int64_t o = ((int64_t)part * nq + r) * KP + (KP - 1);
+    if (cand_ids[o] >= 0) { any_full = true; tau_max = fmaxf(tau_max, cand_sc[o]); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tau_max = fmaxf(tau_max, __shfl_xor_sync(0xffffffffu, tau_max, o));
+  any_full = __any_sync(0xffffffffu, any_full);
   // K rounds of warp arg-max with the (score desc, id asc) order
   float kth = -INFINITY;
   int found = 0;
   for (int j = 0; j < K; ++j) {
     float bs = -INFINITY;
-    int bi = 0x7fffffff, bc = -1;
-    for (int c = 0; c < per_lane; ++c) {
-      if (best_i[c] >= 0 && (best_s[c] > bs || (best_s[c] == bs && best_i[c] < bi))) { bs = best_s[c]; bi = best_i[c]; bc = c; }
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      bool better = ci[c] >= 0 && (cs[c] > bs || (cs[c] == bs && ci[c] < bi));
+      bs = better ? cs[c] : bs;
+      bi = better ? ci[c] : bi;
     }
-    float ws = bs;
-    int wi = bc >= 0 ? bi : 0x7fffffff;
+    float wsc = bs;
+    int wi = bi;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      float os = __shfl_xor_sync(0xffffffffu, ws, o);
+      float os = __shfl_xor_sync(0xffffffffu, wsc, o);
       int oi = __shfl_xor_sync(0xffffffffu, wi, o);
-      if (os > ws || (os == ws && oi < wi)) { ws = os; wi = oi; }
+      if (oi != 0x7fffffff && (wi == 0x7fffffff || os > wsc || (os == wsc && oi < wi))) { wsc = os; wi = oi; }
     }
     const bool have = wi != 0x7fffffff;
-    if (have && bc >= 0 && bi == wi) best_i[bc] = -1;  // remove the winner (ids are unique per row)
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (ci[c] == wi) ci[c] = -1;  // remove the winner everywhere (an id may sit in two lists of one row? no: lists partition the items)
     if (lane == 0) {
       out_ids[r * K + j] = have ? (int64_t)wi : -1;
-      out_scores[r * K + j] = have ? ws : -INFINITY;
+      out_scores[r * K + j] = have ? wsc : -INFINITY;
     }
-    if (have) { kth = ws; ++found; }
+    if (have) { kth = wsc; ++found; }
   }
-  if (lane == 0 && !all_short) {
+  if (lane == 0 && any_full) {
     // |approx - exact| <= ||du||*max||bv|| + ||u||*max||dv||  (+ fp32 accumulation slack)
     float E = qdnorm[r] * maxes[0] + qnorm[r] * maxes[1] + 1.6e-5f * qnorm[r] * maxes[0];
     bool ok = (found == K) && (kth > tau_max + E);
@@ -490,13 +548,16 @@ TcPlan make_plan(int64_t nq, int64_t n_local) {
   int want = (2 * sms + pl.n_ut - 1) / pl.n_ut;   // aim for >= 2 work items per SM
   if (want < 1) want = 1;
   if (want > 16) want = 16;
-  if (want > n_tiles) want = n_tiles;
+  if (want > (n_tiles + 1) / 2) want = (n_tiles + 1) / 2;   // at least two tiles per work item (two warp sets)
+  if (want < 1) want = 1;
   pl.tiles_per_split = (n_tiles + want - 1) / want;
   pl.n_split = (n_tiles + pl.tiles_per_split - 1) / pl.tiles_per_split;
   int work = pl.n_ut * pl.n_split;
   pl.grid = work < sms ? work : sms;
   return pl;
 }
+
+constexpr int KP_MAX = 32;
 
 size_t carve_tc(TcWs &w, void *base, int64_t nq, int64_t n_local, int dim, int k) {
   Carver c(base);
@@ -507,8 +568,8 @@ size_t carve_tc(TcWs &w, void *base, int64_t nq, int64_t n_local, int dim, int k
   w.qnorm = c.take<float>(nq);
   w.qdnorm = c.take<float>(nq);
   w.maxes = c.take<float>(4);
-  w.cand_ids = c.take<int>((size_t)pl.n_split * nq * KP);
-  w.cand_sc = c.take<float>((size_t)pl.n_split * nq * KP);
+  w.cand_ids = c.take<int>((size_t)pl.n_split * 2 * nq * KP_MAX);
+  w.cand_sc = c.take<float>((size_t)pl.n_split * 2 * nq * KP_MAX);
   w.fail_rows = c.take<int32_t>(nq);
   w.fail_count = c.take<int32_t>(4);
   w.fb_ids = c.take<int64_t>(nq * k);
@@ -547,12 +608,12 @@ int make_map(CUtensorMap *m, void *base, int64_t rows, int dim, int box_rows) {
   return 0;
 }
 
-template <int D>
+template <int D, int KP>
 int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p, int64_t n_local,
            int64_t item_base, const int64_t *hist_indptr, const int64_t *hist_indices, int k, int64_t *out_ids,
            float *out_scores, void *workspace, size_t workspace_bytes, cudaStream_t st) {
   constexpr int KB = D / BK;
-  constexpr int NSTAGE = (KB == 1) ? 4 : 4;
+  constexpr int NSTAGE = 4;
   TcWs w;
   size_t need = carve_tc(w, workspace, nq, n_local, D, k);
   RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_fullsort_topk(tc): workspace %zu < %zu", workspace_bytes, need);
@@ -583,14 +644,15 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
   const size_t smem = TcSmem<KB, NSTAGE>::TOTAL;
   {
     ProfScope prof(RB2_ST_TC_SCORE, st);
-    RB2_CUDA(cudaFuncSetAttribute(k_fullsort_tc<KB, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_fullsort_tc<KB, NSTAGE><<<pl.grid, kThreadsTc, smem, st>>>(tmA, tmB, p);
+    RB2_CUDA(cudaFuncSetAttribute(k_fullsort_tc<KB, NSTAGE, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    k_fullsort_tc<KB, NSTAGE, KP><<<pl.grid, kThreadsTc, smem, st>>>(tmA, tmB, p);
     RB2_CUDA(cudaGetLastError());
   }
   {
     ProfScope prof(RB2_ST_TC_REFINE, st);
-    k_refine<D><<<(unsigned)((nq * 32 + 127) / 128), 128, 0, st>>>(query_p, query_ids, nq, item_p, item_base,
-                                                                  w.cand_ids, w.cand_sc, pl.n_split, k, w.qnorm,
+    k_refine<D, KP><<<(unsigned)((nq * 32 + 127) / 128), 128, 0, st>>>(query_p, query_ids, nq, item_p, item_base,
+                                                                  w.cand_ids, w.cand_sc, pl.n_split * 2, k, w.qnorm,
                                                                   w.qdnorm, w.maxes, out_ids, out_scores, w.fail_rows,
                                                                   w.fail_count);
     RB2_CUDA(cudaGetLastError());
@@ -627,9 +689,17 @@ int rb2_fullsort_tc(const float *query_p, const int64_t *query_ids, int64_t nq, 
     return rb2_fullsort_fp32(query_p, query_ids, nq, item_p, n_items_local, item_base, dim, hist_indptr,
                              hist_indices, k, out_ids, out_scores, workspace, workspace_bytes, st, nullptr);
   }
-  if (dim == 64)
-    return run_tc<64>(query_p, query_ids, nq, item_p, n_items_local, item_base, hist_indptr, hist_indices, k,
-                      out_ids, out_scores, workspace, workspace_bytes, st);
-  return run_tc<128>(query_p, query_ids, nq, item_p, n_items_local, item_base, hist_indptr, hist_indices, k, out_ids,
-                     out_scores, workspace, workspace_bytes, st);
+  // K' = 16 candidates per list when the item range is a shard of a larger table (item_base > 0 or the
+  // caller merges shards: the global K-th score sits far above a shard's 16th), 32 otherwise
+  const bool small_list = (g_tc_kprime == 16) || (g_tc_kprime == 0 && k <= 8);
+#define RB2_TC(D_, KP_)                                                                                        \
+  return run_tc<D_, KP_>(query_p, query_ids, nq, item_p, n_items_local, item_base, hist_indptr, hist_indices, k, \
+                         out_ids, out_scores, workspace, workspace_bytes, st)
+  if (dim == 64) {
+    if (small_list) RB2_TC(64, 16);
+    RB2_TC(64, 32);
+  }
+  if (small_list) RB2_TC(128, 16);
+  RB2_TC(128, 32);
+#undef RB2_TC
 }

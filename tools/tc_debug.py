@@ -10,7 +10,7 @@ def case(dim, nq, N, K, hist=4, seed=0):
     rng = np.random.default_rng(seed)
     Q = rng.standard_normal((nq, dim)).astype(np.float32)
     V = rng.standard_normal((N, dim)).astype(np.float32)
-    hp = np.arange(0, hist * nq + 1, hist, dtype=np.int64)
+    hp = np.arange(nq + 1, dtype=np.int64) * hist
     hi = np.sort(rng.integers(1, N, (nq, hist)), axis=1).reshape(-1).astype(np.int64)
     dev = torch.device("cuda:0")
     t = lambda a: torch.from_numpy(a).to(dev)
@@ -32,3 +32,7 @@ if __name__ == "__main__":
     case(128, 300, 5000, 10)
     case(128, 1000, 70001, 10)
     case(64, 4096, 200000, 10, hist=0)
+    lib.rb2_fullsort_tc_set_kprime(16)
+    case(128, 1000, 70001, 10)
+    case(64, 300, 5000, 10, hist=50)
+    lib.rb2_fullsort_tc_set_kprime(0)
