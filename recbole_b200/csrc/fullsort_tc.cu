@@ -151,7 +151,8 @@ struct TcSmem {
   static constexpr size_t A_BYTES = (size_t)KB * A_KB_BYTES;
   static constexpr size_t B_BYTES = (size_t)NSTAGE * UNIT_BYTES;
   static constexpr size_t BLOOM_BYTES = (size_t)BLOOM_WORDS * BM * 4;
-  static constexpr size_t TOTAL = 1024 /*align slack*/ + A_BYTES + B_BYTES + BLOOM_BYTES + 256 /*barriers*/;
+  static constexpr size_t STAGE_BYTES = 32 * 256 * 4;
+  static constexpr size_t TOTAL = 1024 /*align slack*/ + A_BYTES + B_BYTES + BLOOM_BYTES + STAGE_BYTES + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ uint32_t bloom_h1(uint32_t x) { return (x * 0x9E3779B1u) >> 21; }
@@ -193,7 +194,8 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   unsigned char *sA = smem;                                  // [KB][128 rows][128 B]
   unsigned char *sB = sA + TcSmem<KB, NSTAGE>::A_BYTES;      // [NSTAGE][256 rows][128 B]
   uint32_t *bloom = reinterpret_cast<uint32_t *>(sB + TcSmem<KB, NSTAGE>::B_BYTES);  // [BLOOM_WORDS][BM]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(bloom + BLOOM_WORDS * BM);
+  float *stage_buf = reinterpret_cast<float *>(bloom + BLOOM_WORDS * BM);            // [32][256]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(stage_buf + 32 * 256);
   uint64_t *full = bars;                 // [NSTAGE]
   uint64_t *empty = bars + NSTAGE;       // [NSTAGE]
   uint64_t *a_full = bars + 2 * NSTAGE;  // [1]
@@ -289,6 +291,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int quarter = warp & 3;                 // TMEM lanes this warp may touch: [32*quarter, +32)
     const int t = quarter * 32 + lane;            // row inside the tile
     uint32_t *my_bloom = bloom + t;               // word i at my_bloom[i * BM]
+    float *my_stage = stage_buf + (ws * BM + t);  // score j of the current chunk at my_stage[j * 256]
     uint32_t tcount = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const int ut = w % p.n_ut, sp = w / p.n_ut;
@@ -342,23 +345,24 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
         const int64_t g0 = p.item_base + (int64_t)it * BN;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 64) {
-          uint32_t v[32], u[32];
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
           TC_LD32(taddr + c0, v);
-          TC_LD32(taddr + c0 + 32, u);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (max32(v) > tau) {
+            // rare path, kept compact (one copy of the insert): stage the 32 scores in shared memory
+            // so that the passing ones can be fetched by a run-time index
+            uint32_t mask = 0u;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float s = __uint_as_float(v[j]);
-              if (s > tau) consider(s, g0 + c0 + j);
+              my_stage[j * 256] = __uint_as_float(v[j]);
+              mask |= (__uint_as_float(v[j]) > tau ? 1u : 0u) << j;
             }
-          }
-          if (max32(u) > tau) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float s = __uint_as_float(u[j]);
-              if (s > tau) consider(s, g0 + c0 + 32 + j);
+            while (mask) {
+              const int j = __ffs(mask) - 1;
+              mask &= mask - 1;
+              const float s = my_stage[j * 256];
+              if (s > tau) consider(s, g0 + c0 + j);
             }
           }
         }
