@@ -356,7 +356,7 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--n-batches", type=int, default=8, dest="n_batches")
-    ap.add_argument("--scorer", default="fp32", choices=["fp32", "tc"])
+    ap.add_argument("--scorer", default="tc", choices=["fp32", "tc"])
     ap.add_argument("--eval-reps", type=int, default=3, dest="eval_reps")
     ap.add_argument("--cpu-steps", type=int, default=4, dest="cpu_steps")
     ap.add_argument("--ref-eval-users", type=int, default=4096, dest="ref_eval_users")

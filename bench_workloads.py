@@ -118,6 +118,22 @@ class BprWorkload:
         self.hist = csr_from_pairs(len(uid), remap[hu[m]], hi[m], self.n_items)
         self.U0, self.V0 = xavier_tables(self.n_users, self.n_items, self.dim, seed)
 
+    def rank_batches(self, rank, world, n_batches, seed=2020):
+        """Per-rank batches for the user-partitioned multi-GPU run: `batch` triples per rank and step,
+        drawn from the interactions of the users this rank owns (weak scaling)."""
+        lo, hi = (rank * self.n_users) // world, ((rank + 1) * self.n_users) // world
+        tu, ti = self.phases[0]
+        m = (tu >= lo) & (tu < hi)
+        tu, ti = tu[m], ti[m]
+        need = self.batch * n_batches
+        reps = (need + len(tu) - 1) // len(tu)
+        idx = np.concatenate([np.random.default_rng(seed + 100 + 17 * rank + r).permutation(len(tu))
+                              for r in range(reps)])[:need]
+        bu, bp = tu[idx], ti[idx]
+        bn = sample_negatives(bu, self.n_items, self.train_keys, seed + 31 + rank)
+        B = self.batch
+        return [(bu[i * B:(i + 1) * B], bp[i * B:(i + 1) * B], bn[i * B:(i + 1) * B]) for i in range(n_batches)]
+
     def describe(self):
         return dict(workload=self.name, desc=self.desc, n_users=self.n_users, n_items=self.n_items, dim=self.dim,
                     interactions=self.n_inter, train_batch=self.batch, eval_users=int(len(self.uid_list)), topk=10)

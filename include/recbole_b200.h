@@ -112,6 +112,31 @@ int rb2_bpr_train_step(float *user_p, float *user_m, float *user_v, int32_t *use
                        const rb2_optim *h_opt, float *loss_out, double *loss_accum,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (1c) The same step when the item table is row-sharded over several GPUs (the
+ * reference has no multi-device code).  The caller fetched the item rows its local batch touches
+ * from their owners into the compact table `item_rows` [n_item_rows, dim] and rewrote pos / neg as
+ * indices into it.  The user side runs exactly as above (users are partitioned with their
+ * interactions, so it is local); the item side only SUMS the gradient per compact row into
+ * item_grad_out [n_item_rows, dim] (every compact row must occur in the batch), to be sent back to
+ * the owners, who apply it with rb2_sparse_rows_update.  The loss and its gradient are scaled by
+ * 1/global_batch (mean over the union of all ranks' batches); all-reduce loss_out with SUM.
+ * ---------------------------------------------------------------------------------------- */
+int rb2_bpr_train_step_sharded(float *user_p, float *user_m, float *user_v, int32_t *user_last,
+                               const float *item_rows, int64_t n_users, int64_t n_item_rows, int32_t dim,
+                               const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t batch,
+                               int64_t global_batch, const rb2_optim *h_opt, float *loss_out, double *loss_accum,
+                               float *item_grad_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Row-sparse optimizer step from explicit gradient rows: grads[j, :] belongs to row ids[j]; duplicate
+ * ids are summed (fixed order), then every touched row takes one step.  Owner side of the sharded
+ * training step; also the generic replacement for "dense grad + dense optimizer.step()"
+ * (trainer.py:170-173) for any embedding table. */
+size_t rb2_sparse_rows_update_workspace_bytes(int64_t count, int32_t dim);
+int rb2_sparse_rows_update(float *p, float *m, float *v, int32_t *last, int64_t n_rows, int32_t dim,
+                           const int64_t *ids, const float *grads, int64_t count, const rb2_optim *h_opt,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
 /* Forward only: loss_out[0] = BPR loss of the batch, parameters untouched (calculate_loss under
  * torch.no_grad, bpr.py:74-83 + loss.py:48). */
 int rb2_bpr_loss(const float *user_p, const float *item_p, int64_t n_users, int64_t n_items, int32_t dim,

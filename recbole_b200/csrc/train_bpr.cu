@@ -118,6 +118,7 @@ struct Tables {
   int32_t *ul;
   float *ip, *im, *iv;
   int32_t *il;
+  float *ig;  // optional [n_items, d]: the item side writes the summed gradient here instead of stepping
 };
 
 __device__ __forceinline__ void bpr_sample(float x, float inv_b, float &loss_term, float &g) {
@@ -240,7 +241,8 @@ __global__ void __launch_bounds__(kThreads) k_item_side(Tables t, BprWs w, int64
   auto finish_run = [&](bool continues) {
     if (cur == kInvalid) return;
     if (!started_before && !continues) {
-      row_update_full<D, LAZY>(t.ip, t.im, t.iv, t.il, cur, lane, acc, o);
+      if (t.ig) row_st<D>(t.ig, cur, lane, acc);
+      else row_update_full<D, LAZY>(t.ip, t.im, t.iv, t.il, cur, lane, acc, o);
     } else if (started_before) {
       row_st<D>(w.i_head, tile, lane, acc);
       fh = continues ? 2 : 1;
@@ -290,7 +292,8 @@ __global__ void __launch_bounds__(kThreads) k_fixup(float *P, float *M, float *V
                                                      const uint32_t *__restrict__ keys_sorted,
                                                      const float *__restrict__ head, const float *__restrict__ tail,
                                                      const uint8_t *__restrict__ fh, const uint8_t *__restrict__ ft,
-                                                     int64_t n_occ, int T, int64_t n_tiles, OptScalars o) {
+                                                     int64_t n_occ, int T, int64_t n_tiles, OptScalars o,
+                                                     float *__restrict__ grad_out) {
   constexpr int LANES = RowCfg<D>::LANES;
   const int lane = threadIdx.x % LANES;
   const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
@@ -304,7 +307,8 @@ __global__ void __launch_bounds__(kThreads) k_fixup(float *P, float *M, float *V
     row_add<D>(acc, row_ld<D>(head, j, lane));
     if (f != 2) break;
   }
-  row_update_full<D, LAZY>(P, M, V, L, key, lane, acc, o);
+  if (grad_out) row_st<D>(grad_out, key, lane, acc);
+  else row_update_full<D, LAZY>(P, M, V, L, key, lane, acc, o);
 }
 
 __global__ void k_loss(const double *__restrict__ part, int64_t n, double inv_b, float *loss_out,
@@ -359,7 +363,7 @@ __global__ void __launch_bounds__(kThreads) k_bpr_loss(const float *__restrict__
 
 template <int D, bool LAZY>
 int launch_step(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, const OptScalars &o, float *loss_out,
-                double *loss_accum, cudaStream_t st) {
+                double *loss_accum, cudaStream_t st, int64_t global_batch) {
   constexpr int LANES = RowCfg<D>::LANES;
   const int Tu = pick_tile(B, LANES), Ti = pick_tile(2 * B, LANES);
   const int64_t ntu = (B + Tu - 1) / Tu, nti = (2 * B + Ti - 1) / Ti;
@@ -380,12 +384,12 @@ int launch_step(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, 
   }
   {
     ProfScope prof(RB2_ST_USER_SIDE, st);
-    k_user_side<D, LAZY><<<blocks(ntu), kThreads, 0, st>>>(t, w, B, Tu, ntu, 1.f / (float)B, o);
+    k_user_side<D, LAZY><<<blocks(ntu), kThreads, 0, st>>>(t, w, B, Tu, ntu, 1.f / (float)global_batch, o);
   }
   {
     ProfScope prof(RB2_ST_USER_FIXUP, st);
     k_fixup<D, LAZY><<<blocks(ntu), kThreads, 0, st>>>(t.up, t.um, t.uv, t.ul, w.ukey_s, w.u_head, w.u_tail, w.u_fh,
-                                                       w.u_ft, B, Tu, ntu, o);
+                                                       w.u_ft, B, Tu, ntu, o, nullptr);
   }
   {
     ProfScope prof(RB2_ST_ITEM_SIDE, st);
@@ -394,11 +398,11 @@ int launch_step(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, 
   {
     ProfScope prof(RB2_ST_ITEM_FIXUP, st);
     k_fixup<D, LAZY><<<blocks(nti), kThreads, 0, st>>>(t.ip, t.im, t.iv, t.il, w.ikey_s, w.i_head, w.i_tail, w.i_fh,
-                                                       w.i_ft, 2 * B, Ti, nti, o);
+                                                       w.i_ft, 2 * B, Ti, nti, o, t.ig);
   }
   {
     ProfScope prof(RB2_ST_LOSS, st);
-    k_loss<<<1, 256, 0, st>>>(w.loss_part, ntu, 1.0 / (double)B, loss_out, loss_accum);
+    k_loss<<<1, 256, 0, st>>>(w.loss_part, ntu, 1.0 / (double)global_batch, loss_out, loss_accum);
   }
   RB2_CUDA(cudaGetLastError());
   return 0;
@@ -443,11 +447,11 @@ extern "C" size_t rb2_bpr_workspace_bytes(int64_t batch, int32_t dim) {
   return carve(w, nullptr, batch, dim);
 }
 
-extern "C" int rb2_bpr_train_step(float *user_p, float *user_m, float *user_v, int32_t *user_last, float *item_p,
-                                  float *item_m, float *item_v, int32_t *item_last, int64_t n_users,
-                                  int64_t n_items, int32_t dim, const int64_t *user, const int64_t *pos,
-                                  const int64_t *neg, int64_t batch, const rb2_optim *h_opt, float *loss_out,
-                                  double *loss_accum, void *workspace, size_t workspace_bytes, void *stream) {
+static int bpr_step_impl(float *user_p, float *user_m, float *user_v, int32_t *user_last, float *item_p,
+                         float *item_m, float *item_v, int32_t *item_last, int64_t n_users, int64_t n_items,
+                         int32_t dim, const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t batch,
+                         const rb2_optim *h_opt, float *loss_out, double *loss_accum, void *workspace,
+                         size_t workspace_bytes, void *stream, float *item_grad_out, int64_t global_batch) {
   RB2_REQUIRE(user_p && item_p && user && pos && neg && h_opt && loss_out && workspace, RB2_EINVAL,
               "rb2_bpr_train_step: null argument");
   RB2_REQUIRE(batch > 0 && batch < ((int64_t)1 << 30), RB2_EINVAL, "rb2_bpr_train_step: batch %lld out of range",
@@ -458,26 +462,159 @@ extern "C" int rb2_bpr_train_step(float *user_p, float *user_m, float *user_v, i
   RB2_REQUIRE(o.kind == RB2_OPT_SGD || o.kind == RB2_OPT_ADAM || o.kind == RB2_OPT_ADAM_LAZY, RB2_EINVAL,
               "rb2_bpr_train_step: unknown optimizer kind %d", o.kind);
   if (o.kind != RB2_OPT_SGD)
-    RB2_REQUIRE(user_m && user_v && item_m && item_v, RB2_EINVAL, "rb2_bpr_train_step: Adam needs m and v");
+    RB2_REQUIRE(user_m && user_v && (item_grad_out || (item_m && item_v)), RB2_EINVAL,
+                "rb2_bpr_train_step: Adam needs m and v");
   if (o.kind == RB2_OPT_ADAM_LAZY)
-    RB2_REQUIRE(user_last && item_last && o.lazy_step_size && o.lazy_bc2_sqrt, RB2_EINVAL,
+    RB2_REQUIRE(user_last && (item_grad_out || item_last) && o.lazy_step_size && o.lazy_bc2_sqrt, RB2_EINVAL,
                 "rb2_bpr_train_step: RB2_OPT_ADAM_LAZY needs *_last and the lazy tables");
+  if (global_batch <= 0) global_batch = batch;
   BprWs w;
   size_t need = carve(w, workspace, batch, dim);
   RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_bpr_train_step: workspace %zu < %zu", workspace_bytes,
               need);
   cudaStream_t st = (cudaStream_t)stream;
-  Tables t{user_p, user_m, user_v, user_last, item_p, item_m, item_v, item_last};
+  Tables t{user_p, user_m, user_v, user_last, item_p, item_m, item_v, item_last, item_grad_out};
   {
     ProfScope prof(RB2_ST_KEYS, st);
     k_make_keys<<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(user, pos, neg, batch, n_users, n_items, w);
   }
-  const bool lazy = o.kind == RB2_OPT_ADAM_LAZY;
+  // with item_grad_out the item rows are read as they are (a compact table fetched from their owners,
+  // already brought up to date there), so the lazy catch-up only concerns the user side
+  const bool lazy = o.kind == RB2_OPT_ADAM_LAZY && !item_grad_out;
+  RB2_REQUIRE(!(o.kind == RB2_OPT_ADAM_LAZY && item_grad_out), RB2_EINVAL,
+              "rb2_bpr_train_step_sharded: adam_lazy is not available on the sharded path");
   RB2_DISPATCH_DIM(dim, {
-    int rc = lazy ? launch_step<D_, true>(t, w, batch, n_users, n_items, o, loss_out, loss_accum, st)
-                  : launch_step<D_, false>(t, w, batch, n_users, n_items, o, loss_out, loss_accum, st);
+    int rc = lazy ? launch_step<D_, true>(t, w, batch, n_users, n_items, o, loss_out, loss_accum, st, global_batch)
+                  : launch_step<D_, false>(t, w, batch, n_users, n_items, o, loss_out, loss_accum, st, global_batch);
     if (rc) return rc;
   });
+  return 0;
+}
+
+extern "C" int rb2_bpr_train_step(float *user_p, float *user_m, float *user_v, int32_t *user_last, float *item_p,
+                                  float *item_m, float *item_v, int32_t *item_last, int64_t n_users,
+                                  int64_t n_items, int32_t dim, const int64_t *user, const int64_t *pos,
+                                  const int64_t *neg, int64_t batch, const rb2_optim *h_opt, float *loss_out,
+                                  double *loss_accum, void *workspace, size_t workspace_bytes, void *stream) {
+  return bpr_step_impl(user_p, user_m, user_v, user_last, item_p, item_m, item_v, item_last, n_users, n_items, dim,
+                       user, pos, neg, batch, h_opt, loss_out, loss_accum, workspace, workspace_bytes, stream,
+                       nullptr, 0);
+}
+
+extern "C" int rb2_bpr_train_step_sharded(float *user_p, float *user_m, float *user_v, int32_t *user_last,
+                                          const float *item_rows, int64_t n_users, int64_t n_item_rows, int32_t dim,
+                                          const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t batch,
+                                          int64_t global_batch, const rb2_optim *h_opt, float *loss_out,
+                                          double *loss_accum, float *item_grad_out, void *workspace,
+                                          size_t workspace_bytes, void *stream) {
+  RB2_REQUIRE(item_grad_out != nullptr, RB2_EINVAL, "rb2_bpr_train_step_sharded: item_grad_out is null");
+  return bpr_step_impl(user_p, user_m, user_v, user_last, const_cast<float *>(item_rows), nullptr, nullptr, nullptr,
+                       n_users, n_item_rows, dim, user, pos, neg, batch, h_opt, loss_out, loss_accum, workspace,
+                       workspace_bytes, stream, item_grad_out, global_batch);
+}
+
+// ---------------------------------------------------------------------------------------------
+// rb2_sparse_rows_update: (ids[M], grads[M, d]) with duplicate ids -> sum per row, one optimizer step
+// per touched row.  The owner side of the sharded step (gradients arriving from every rank).
+namespace {
+struct RowsWs {
+  WsHeader *hdr;
+  uint32_t *key, *val, *key_s, *val_s;
+  float *head, *tail;
+  uint8_t *fh, *ft;
+  void *cub_tmp;
+  size_t cub_bytes;
+};
+size_t carve_rows(RowsWs &w, void *base, int64_t M, int dim) {
+  Carver c(base);
+  w.hdr = c.take<WsHeader>(1);
+  w.key = c.take<uint32_t>(M);
+  w.val = c.take<uint32_t>(M);
+  w.key_s = c.take<uint32_t>(M);
+  w.val_s = c.take<uint32_t>(M);
+  int64_t tiles = max_tiles(M);
+  w.head = c.take<float>(tiles * dim);
+  w.tail = c.take<float>(tiles * dim);
+  w.fh = c.take<uint8_t>(tiles);
+  w.ft = c.take<uint8_t>(tiles);
+  size_t b = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                  (uint32_t *)nullptr, (int)M, 0, 32);
+  w.cub_bytes = b;
+  w.cub_tmp = c.take<char>(b);
+  return c.off;
+}
+__global__ void k_rows_keys(const int64_t *__restrict__ ids, int64_t M, int64_t n_rows, RowsWs w) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  int64_t r = ids[j];
+  if (r < 0 || r >= n_rows) {
+    w.hdr->range_error = 1;
+    r = min(max(r, (int64_t)0), n_rows - 1);
+  }
+  w.key[j] = (uint32_t)r;
+  w.val[j] = (uint32_t)(2 * j);  // item-side encoding: value = 2*source_row + is_neg
+}
+}  // namespace
+
+extern "C" size_t rb2_sparse_rows_update_workspace_bytes(int64_t m, int32_t dim) {
+  RowsWs w;
+  return carve_rows(w, nullptr, m, dim);
+}
+
+extern "C" int rb2_sparse_rows_update(float *p, float *m, float *v, int32_t *last, int64_t n_rows, int32_t dim,
+                                      const int64_t *ids, const float *grads, int64_t count, const rb2_optim *h_opt,
+                                      void *workspace, size_t workspace_bytes, void *stream) {
+  RB2_REQUIRE(p && ids && grads && h_opt && workspace, RB2_EINVAL, "rb2_sparse_rows_update: null argument");
+  if (count <= 0) return 0;
+  RB2_REQUIRE(count < ((int64_t)1 << 30) && n_rows < ((int64_t)1 << 32) - 1, RB2_EINVAL,
+              "rb2_sparse_rows_update: sizes out of range");
+  OptScalars o = rb2_opt_scalars(h_opt);
+  if (o.kind != RB2_OPT_SGD) RB2_REQUIRE(m && v, RB2_EINVAL, "rb2_sparse_rows_update: Adam needs m and v");
+  if (o.kind == RB2_OPT_ADAM_LAZY)
+    RB2_REQUIRE(last && o.lazy_step_size && o.lazy_bc2_sqrt, RB2_EINVAL, "rb2_sparse_rows_update: lazy state missing");
+  RowsWs rw;
+  size_t need = carve_rows(rw, workspace, count, dim);
+  RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_sparse_rows_update: workspace %zu < %zu", workspace_bytes,
+              need);
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    ProfScope prof(RB2_ST_KEYS, st);
+    k_rows_keys<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(ids, count, n_rows, rw);
+  }
+  size_t tmp = rw.cub_bytes;
+  {
+    ProfScope prof(RB2_ST_SORT_ITEM, st, 2 + (bits_for(n_rows) + 7) / 8);
+    RB2_CUDA(cub::DeviceRadixSort::SortPairs(rw.cub_tmp, tmp, rw.key, rw.key_s, rw.val, rw.val_s, (int)count, 0,
+                                             bits_for(n_rows), st));
+  }
+  BprWs w{};
+  w.hdr = rw.hdr;
+  w.ikey_s = rw.key_s;
+  w.ival_s = rw.val_s;
+  w.gu = const_cast<float *>(grads);
+  w.i_head = rw.head;
+  w.i_tail = rw.tail;
+  w.i_fh = rw.fh;
+  w.i_ft = rw.ft;
+  Tables t{nullptr, nullptr, nullptr, nullptr, p, m, v, last, nullptr};
+  const bool lazy = o.kind == RB2_OPT_ADAM_LAZY;
+  RB2_DISPATCH_DIM(dim, {
+    constexpr int LANES = RowCfg<D_>::LANES;
+    const int Ti = pick_tile(count, LANES);
+    const int64_t nti = (count + Ti - 1) / Ti;
+    unsigned blocks = (unsigned)((nti * LANES + kThreads - 1) / kThreads);
+    if (lazy) {
+      { ProfScope prof(RB2_ST_ITEM_SIDE, st); k_item_side<D_, true><<<blocks, kThreads, 0, st>>>(t, w, count, Ti, nti, o); }
+      { ProfScope prof(RB2_ST_ITEM_FIXUP, st);
+        k_fixup<D_, true><<<blocks, kThreads, 0, st>>>(p, m, v, last, rw.key_s, rw.head, rw.tail, rw.fh, rw.ft, count, Ti, nti, o, nullptr); }
+    } else {
+      { ProfScope prof(RB2_ST_ITEM_SIDE, st); k_item_side<D_, false><<<blocks, kThreads, 0, st>>>(t, w, count, Ti, nti, o); }
+      { ProfScope prof(RB2_ST_ITEM_FIXUP, st);
+        k_fixup<D_, false><<<blocks, kThreads, 0, st>>>(p, m, v, last, rw.key_s, rw.head, rw.tail, rw.fh, rw.ft, count, Ti, nti, o, nullptr); }
+    }
+  });
+  RB2_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -1,0 +1,263 @@
+"""Multi-GPU path (the reference has no multi-device code at all).
+
+One process per GPU.  Users are range-partitioned together with their interactions, their rows of
+the user table and their optimizer state, so the user side of a step is local.  The ITEM table
+(+ m, v) is row-sharded in contiguous blocks.  Per training step each rank
+
+  1. de-duplicates the item ids of its local batch (sorted unique => already grouped by owner),
+  2. all-to-all #1: unique ids out, item rows back  -> compact table C [n_uniq, d],
+  3. runs the fused user side + per-compact-row gradient sums on C (rb2_bpr_train_step_sharded),
+  4. all-to-all #2: gradient rows back to the owners,
+  5. owners sum what every rank sent and take one optimizer step per touched row
+     (rb2_sparse_rows_update),
+  6. all-reduces one scalar (the loss, a mean over the GLOBAL batch).
+
+The result equals the single-GPU step on the union of the ranks' batches up to fp32 summation
+order.  Evaluation: the user table is all-gathered once, every rank scores every evaluated user
+against its item shard (mask from its column-slice of the history CSR), the per-shard top-K lists
+go to the users' owners (all-to-all), are merged (rb2_topk_merge) and reduced to metric sums
+(rb2_topk_metrics); one all-reduce of 6*K doubles finishes the job.
+
+Collectives go through torch.distributed (NCCL over NVLink on the GPU box).  `Comm(staged=True)`
+stages them through host memory over gloo so that several ranks can share ONE GPU in tests.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n, world):
+    """Contiguous blocks: rank g owns [b[g], b[g+1])."""
+    return np.array([(g * n) // world for g in range(world + 1)], dtype=np.int64)
+
+
+class Comm:
+    def __init__(self, group=None, staged=False):
+        self.group = group
+        self.staged = staged
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def _stage(self, t):
+        return t.cpu() if (self.staged and t.is_cuda) else t
+
+    def exchange_counts(self, send_counts):
+        """send_counts: python list [world] -> what every rank sends me."""
+        if self.world == 1:
+            return list(send_counts)
+        on_gpu = (not self.staged) and dist.get_backend(self.group) == "nccl"
+        dev = torch.cuda.current_device() if on_gpu else "cpu"
+        s = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+        r = torch.empty_like(s)
+        dist.all_to_all_single(r, s, group=self.group)
+        return r.tolist()
+
+    def all_to_all(self, inp, send_counts, recv_counts):
+        """Rows of `inp` (first dim) split by send_counts -> concatenation of what each rank sent me."""
+        out_shape = (int(sum(recv_counts)),) + tuple(inp.shape[1:])
+        if self.world == 1:
+            return inp.clone()
+        if self.staged:
+            src = inp.cpu().contiguous()
+            out = torch.empty(out_shape, dtype=inp.dtype)
+            dist.all_to_all_single(out, src, list(recv_counts), list(send_counts), group=self.group)
+            return out.to(inp.device)
+        out = torch.empty(out_shape, dtype=inp.dtype, device=inp.device)
+        dist.all_to_all_single(out, inp.contiguous(), list(recv_counts), list(send_counts), group=self.group)
+        return out
+
+    def all_reduce_sum(self, t):
+        if self.world == 1:
+            return t
+        if self.staged and t.is_cuda:
+            c = t.cpu()
+            dist.all_reduce(c, group=self.group)
+            t.copy_(c)
+            return t
+        dist.all_reduce(t, group=self.group)
+        return t
+
+    def all_gather_rows(self, local, counts):
+        """Concatenate every rank's rows (uneven counts allowed)."""
+        if self.world == 1:
+            return local
+        mx = int(max(counts))
+        pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[: local.shape[0]] = local
+        if self.staged:
+            src = pad.cpu()
+            out = torch.empty((self.world * mx,) + tuple(local.shape[1:]), dtype=local.dtype)
+            dist.all_gather_into_tensor(out, src, group=self.group)
+            out = out.to(local.device)
+        else:
+            out = torch.empty((self.world * mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+            dist.all_gather_into_tensor(out, pad, group=self.group)
+        if all(int(c) == mx for c in counts):
+            return out
+        return torch.cat([out[g * mx: g * mx + int(c)] for g, c in enumerate(counts)], dim=0)
+
+    def barrier(self):
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+
+# ---- exchange plumbing (pure index work; unit-tested on CPU with gloo) ------------------------------
+
+def plan_item_exchange(items, item_bounds):
+    """items int64[n] (global ids).  Returns (uniq sorted, inverse, send_counts list): uniq is
+    grouped by owner because shards are contiguous id ranges."""
+    uniq, inv = torch.unique(items, sorted=True, return_inverse=True)
+    cut = torch.searchsorted(uniq, torch.as_tensor(item_bounds, device=uniq.device))
+    send_counts = (cut[1:] - cut[:-1]).tolist()
+    return uniq, inv, send_counts
+
+
+def fetch_rows(comm, uniq, send_counts, gather_fn, row_base):
+    """all-to-all #1.  gather_fn(local_row_idx) -> rows [n, d] of the local shard.
+    Returns (C [n_uniq, d], requested local idx, recv_counts)."""
+    recv_counts = comm.exchange_counts(send_counts)
+    req = comm.all_to_all(uniq, send_counts, recv_counts)          # ids other ranks want from me
+    local_idx = req - int(row_base)
+    rows = gather_fn(local_idx)
+    C = comm.all_to_all(rows, recv_counts, send_counts)            # rows come back in uniq order
+    return C, local_idx, recv_counts
+
+
+def return_grads(comm, G, send_counts, recv_counts):
+    """all-to-all #2: gradient rows (uniq order) to their owners; arrives aligned with the
+    `local_idx` returned by fetch_rows."""
+    return comm.all_to_all(G, send_counts, recv_counts)
+
+
+class ShardedBPR:
+    """BPR-MF with range-partitioned users and a row-sharded item table."""
+
+    def __init__(self, n_users, n_items, dim, comm, device, U_full=None, V_full=None, seed=2020):
+        from . import ops
+        self.ops = ops
+        self.comm, self.device, self.dim = comm, device, dim
+        self.n_users, self.n_items = n_users, n_items
+        self.user_bounds = shard_bounds(n_users, comm.world)
+        self.item_bounds = shard_bounds(n_items, comm.world)
+        self.u_lo, self.u_hi = int(self.user_bounds[comm.rank]), int(self.user_bounds[comm.rank + 1])
+        self.i_lo, self.i_hi = int(self.item_bounds[comm.rank]), int(self.item_bounds[comm.rank + 1])
+        if U_full is not None:
+            self.U = torch.as_tensor(U_full[self.u_lo:self.u_hi]).to(device).contiguous().clone()
+            self.V = torch.as_tensor(V_full[self.i_lo:self.i_hi]).to(device).contiguous().clone()
+        else:
+            g = torch.Generator(device=device)
+            g.manual_seed(seed + comm.rank)
+            self.U = torch.randn(self.u_hi - self.u_lo, dim, device=device, generator=g) * (2.0 / (n_users + dim)) ** 0.5
+            self.V = torch.randn(self.i_hi - self.i_lo, dim, device=device, generator=g) * (2.0 / (n_items + dim)) ** 0.5
+        self.optim = None
+        self.state = {}
+        self.loss_out = torch.zeros(1, dtype=torch.float32, device=device)
+        self.loss_accum = torch.zeros(1, dtype=torch.float64, device=device)
+        self._ws = {}
+        self._rows_ws = None
+
+    def build_optimizer(self, kind="adam", lr=1e-3, weight_decay=0.0):
+        if kind not in ("adam", "sgd"):
+            raise ValueError("the sharded path implements learner in {adam, sgd}")
+        self.optim = self.ops.Optim(kind, lr, weight_decay)
+        if kind != "sgd":
+            z = torch.zeros_like
+            self.state = dict(mU=z(self.U), vU=z(self.U), mV=z(self.V), vV=z(self.V))
+
+    def _workspace(self, batch):
+        key = int(batch)
+        if key not in self._ws:
+            self._ws = {key: self.ops.bpr_workspace(batch, self.dim, self.device)}
+        return self._ws[key]
+
+    def train_step(self, user, pos, neg, global_batch=None):
+        """user/pos/neg: int64 device vectors with GLOBAL ids; every user must belong to this rank.
+        Returns the device scalar holding this rank's share of the global mean loss (after the
+        all-reduce: the global mean loss)."""
+        ops, comm = self.ops, self.comm
+        B = int(user.numel())
+        if global_batch is None:
+            global_batch = B * comm.world
+        self.optim.step += 1
+        t = self.optim.step
+        uniq, inv, send_counts = plan_item_exchange(torch.cat([pos, neg]), self.item_bounds)
+        C, local_idx, recv_counts = fetch_rows(comm, uniq, send_counts, lambda idx: self.V.index_select(0, idx),
+                                               self.i_lo)
+        G = torch.empty_like(C)
+        user_local = (user - self.u_lo).contiguous()
+        ops.bpr_train_step_sharded(self.U, self.state, C, user_local, inv[:B].contiguous(), inv[B:].contiguous(),
+                                   global_batch, self.optim, self.loss_out, None, G, self._workspace(B), step=t)
+        grads = return_grads(comm, G, send_counts, recv_counts)
+        self._rows_ws = ops.sparse_rows_update(self.V, self.state.get("mV"), self.state.get("vV"), None,
+                                               local_idx.contiguous(), grads, self.optim, self._rows_ws, step=t)
+        comm.all_reduce_sum(self.loss_out)
+        self.loss_accum += self.loss_out.double()
+        return self.loss_out
+
+    # ---- evaluation ------------------------------------------------------------------------------------
+    def gather_user_table(self):
+        counts = (self.user_bounds[1:] - self.user_bounds[:-1]).tolist()
+        return self.comm.all_gather_rows(self.U, counts)
+
+    @torch.no_grad()
+    def evaluate(self, index, evaluator, mode="tc", user_tile=1 << 20):
+        """index: ShardedEvalIndex.  Returns the metric dict over ALL evaluated users (identical on
+        every rank)."""
+        ops, comm = self.ops, self.comm
+        K = evaluator.max_k
+        U_all = self.gather_user_table()
+        n = int(index.uid_all.numel())
+        ids = torch.empty((n, K), dtype=torch.int64, device=self.device)
+        sc = torch.empty((n, K), dtype=torch.float32, device=self.device)
+        for lo in range(0, n, user_tile):
+            hi = min(lo + user_tile, n)
+            ptr = index.hist_indptr[lo:hi + 1].contiguous()
+            i, s = ops.fullsort_topk(U_all, index.uid_all[lo:hi].contiguous(), self.V, K, ptr, index.hist_indices,
+                                     item_base=self.i_lo, mode=mode)
+            ids[lo:hi], sc[lo:hi] = i, s
+        # per-shard lists -> the users' owners
+        send_counts = index.owner_counts
+        recv_counts = [index.n_own] * comm.world
+        r_ids = comm.all_to_all(ids, send_counts, recv_counts).view(comm.world, index.n_own, K)
+        r_sc = comm.all_to_all(sc, send_counts, recv_counts).view(comm.world, index.n_own, K)
+        if index.n_own > 0:
+            m_ids, _ = ops.topk_merge(r_ids.contiguous(), r_sc.contiguous())
+            sums = ops.topk_metrics(m_ids, index.pos_indptr, index.pos_indices, self.n_items)["sums"]
+        else:
+            m_ids = torch.empty((0, K), dtype=torch.int64, device=self.device)
+            sums = torch.zeros((6, K), dtype=torch.float64, device=self.device)
+        comm.all_reduce_sum(sums)
+        self.last_topk = m_ids
+        return evaluator.result(sums, n)
+
+
+class ShardedEvalIndex:
+    """Per-rank evaluation index: every evaluated user's history restricted to this rank's item
+    shard, and the positives of the users this rank owns."""
+
+    def __init__(self, uid_all, hist, pos_own, owner_counts, n_own):
+        self.uid_all = uid_all
+        self.hist_indptr, self.hist_indices = hist
+        self.pos_indptr, self.pos_indices = pos_own
+        self.owner_counts, self.n_own = owner_counts, n_own
+
+    @classmethod
+    def from_global(cls, uid_list, hist, pos, user_bounds, item_bounds, rank, device):
+        """uid_list (sorted), hist / pos numpy CSRs over uid_list rows (what every rank can derive
+        from the shared dataset description)."""
+        uid_list = np.asarray(uid_list)
+        i_lo, i_hi = int(item_bounds[rank]), int(item_bounds[rank + 1])
+        hp, hi = np.asarray(hist[0]), np.asarray(hist[1])
+        keep = (hi >= i_lo) & (hi < i_hi)
+        rows = np.repeat(np.arange(len(uid_list)), np.diff(hp))[keep]
+        nhp = np.zeros(len(uid_list) + 1, dtype=np.int64)
+        nhp[1:] = np.cumsum(np.bincount(rows, minlength=len(uid_list)))
+        cuts = np.searchsorted(uid_list, user_bounds)
+        owner_counts = np.diff(cuts).tolist()
+        a, b = int(cuts[rank]), int(cuts[rank + 1])
+        pp, pi = np.asarray(pos[0]), np.asarray(pos[1])
+        own_ptr = (pp[a:b + 1] - pp[a]).astype(np.int64)
+        own_idx = pi[pp[a]:pp[b]]
+        t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(device)  # noqa: E731
+        return cls(t(uid_list.astype(np.int64)), (t(nhp), t(hi[keep].astype(np.int64))),
+                   (t(own_ptr), t(own_idx.astype(np.int64))), owner_counts, b - a)

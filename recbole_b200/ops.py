@@ -119,6 +119,36 @@ def bpr_train_step(U, V, state, user, pos, neg, optim, loss_out, loss_accum, ws)
         ctypes.byref(o), _ptr(loss_out, f32), _ptr(loss_accum, torch.float64, True), ws.ptr(), ws.nbytes, _stream()))
 
 
+def bpr_train_step_sharded(U, state, item_rows, user, pos_c, neg_c, global_batch, optim, loss_out, loss_accum,
+                           item_grad_out, ws, step=None):
+    """User side + per-compact-row item gradient sums (rb2_bpr_train_step_sharded).  optim.step is NOT
+    incremented here (the owner-side update of the same logical step shares it)."""
+    o = optim.c_struct(U.device, step)
+    f32, i64 = torch.float32, torch.int64
+    check(lib.rb2_bpr_train_step_sharded(
+        _ptr(U, f32), _ptr(state.get("mU"), f32, True), _ptr(state.get("vU"), f32, True),
+        _ptr(state.get("lastU"), torch.int32, True), _ptr(item_rows, f32), U.shape[0], item_rows.shape[0],
+        U.shape[1], _ptr(user, i64), _ptr(pos_c, i64), _ptr(neg_c, i64), user.numel(), int(global_batch),
+        ctypes.byref(o), _ptr(loss_out, f32), _ptr(loss_accum, torch.float64, True), _ptr(item_grad_out, f32),
+        ws.ptr(), ws.nbytes, _stream()))
+
+
+def sparse_rows_update(P, M, V, last, ids, grads, optim, ws=None, step=None):
+    """Sum duplicate rows of `grads` by `ids`, then one optimizer step per touched row."""
+    o = optim.c_struct(P.device, step)
+    n = int(ids.numel())
+    if n == 0:
+        return ws
+    need = lib.rb2_sparse_rows_update_workspace_bytes(n, P.shape[1])
+    if ws is None or ws.nbytes < need:
+        ws = Workspace(need, P.device)
+    f32 = torch.float32
+    check(lib.rb2_sparse_rows_update(_ptr(P, f32), _ptr(M, f32, True), _ptr(V, f32, True),
+                                     _ptr(last, torch.int32, True), P.shape[0], P.shape[1], _ptr(ids, torch.int64),
+                                     _ptr(grads, f32), n, ctypes.byref(o), ws.ptr(), ws.nbytes, _stream()))
+    return ws
+
+
 def bpr_loss(U, V, user, pos, neg, loss_out, ws):
     f32, i64 = torch.float32, torch.int64
     check(lib.rb2_bpr_loss(_ptr(U, f32), _ptr(V, f32), U.shape[0], V.shape[0], U.shape[1], _ptr(user, i64),

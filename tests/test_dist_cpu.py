@@ -1,0 +1,81 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: id de-duplication and bucketing by
+owner, all-to-all #1 (rows out) and #2 (gradients back), uneven all-gather, the eval index split.
+The compute kernels are stood in for by torch index ops here -- this file checks the PLUMBING; the
+kernels themselves are checked on the GPU (tests/test_gpu_dist.py)."""
+import numpy as np
+import torch
+
+from dist_util import run_ranks
+
+
+def _exchange_rank(rank, world, seed):
+    from recbole_b200.dist import Comm, fetch_rows, plan_item_exchange, return_grads, shard_bounds
+    comm = Comm()
+    n_items, d = 1001, 8
+    bounds = shard_bounds(n_items, world)
+    rng = np.random.default_rng(seed)
+    V_full = torch.from_numpy(rng.standard_normal((n_items, d)).astype(np.float32))
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    V_local = V_full[lo:hi].clone()
+    items = torch.from_numpy(np.random.default_rng(seed + 10 + rank).integers(1, n_items, 5000))
+    uniq, inv, send_counts = plan_item_exchange(items, bounds)
+    assert torch.equal(uniq[inv], items) and sum(send_counts) == uniq.numel()
+    C, local_idx, recv_counts = fetch_rows(comm, uniq, send_counts, lambda idx: V_local.index_select(0, idx), lo)
+    assert torch.equal(C, V_full[uniq])                       # every rank got exactly the rows it asked for
+    assert (local_idx >= 0).all() and (local_idx < hi - lo).all()
+    # gradients: row value = item id * (rank + 1); the owner must receive the sum over ranks
+    G = uniq.to(torch.float32).unsqueeze(1).repeat(1, d) * (rank + 1)
+    grads = return_grads(comm, G, send_counts, recv_counts)
+    acc = torch.zeros_like(V_local)
+    acc.index_add_(0, local_idx, grads)                       # stand-in for rb2_sparse_rows_update
+    # expected: sum over ranks that requested the item
+    exp = torch.zeros_like(V_local)
+    for r in range(world):
+        it = torch.from_numpy(np.random.default_rng(seed + 10 + r).integers(1, n_items, 5000)).unique()
+        it = it[(it >= lo) & (it < hi)]
+        exp[it - lo] += it.to(torch.float32).unsqueeze(1) * (r + 1)
+    assert torch.equal(acc, exp)
+    # uneven all-gather
+    rows = torch.full((3 + rank, 2), float(rank))
+    out = comm.all_gather_rows(rows, [3 + r for r in range(world)])
+    assert out.shape[0] == sum(3 + r for r in range(world)) and out[-1, 0] == world - 1
+    t = torch.tensor([1.0 + rank])
+    comm.all_reduce_sum(t)
+    assert t.item() == sum(1.0 + r for r in range(world))
+    return True
+
+
+def test_exchange_plumbing_world2():
+    assert run_ranks(_exchange_rank, 2, 123) == [True, True]
+
+
+def test_exchange_plumbing_world3():
+    assert run_ranks(_exchange_rank, 3, 7) == [True, True, True]
+
+
+def test_sharded_eval_index_split():
+    from oracle import fullsort as ofs
+    from recbole_b200.dist import ShardedEvalIndex, shard_bounds
+    rng = np.random.default_rng(0)
+    n_users, n_items, world = 50, 40, 3
+    pairs = [(rng.integers(1, n_users, 300), rng.integers(1, n_items, 300)) for _ in range(3)]
+    uid, hist, pos = ofs.eval_index(n_users, pairs, 2)
+    ub, ib = shard_bounds(n_users, world), shard_bounds(n_items, world)
+    seen_hist, seen_pos, total_own = [], [], 0
+    for r in range(world):
+        idx = ShardedEvalIndex.from_global(uid, hist, pos, ub, ib, r, "cpu")
+        assert sum(idx.owner_counts) == len(uid)
+        total_own += idx.n_own
+        hp, hi = idx.hist_indptr.numpy(), idx.hist_indices.numpy()
+        assert ((hi >= ib[r]) & (hi < ib[r + 1])).all()
+        rows = np.repeat(np.arange(len(uid)), np.diff(hp))
+        seen_hist += list(zip(rows.tolist(), hi.tolist()))
+        a = sum(idx.owner_counts[:r])
+        pp, pi = idx.pos_indptr.numpy(), idx.pos_indices.numpy()
+        rows = np.repeat(np.arange(idx.n_own), np.diff(pp)) + a
+        seen_pos += list(zip(rows.tolist(), pi.tolist()))
+        assert ((uid[a:a + idx.n_own] >= ub[r]) & (uid[a:a + idx.n_own] < ub[r + 1])).all()
+    assert total_own == len(uid)
+    all_hist = list(zip(np.repeat(np.arange(len(uid)), np.diff(hist[0])).tolist(), hist[1].tolist()))
+    all_pos = list(zip(np.repeat(np.arange(len(uid)), np.diff(pos[0])).tolist(), pos[1].tolist()))
+    assert sorted(seen_hist) == sorted(all_hist) and sorted(seen_pos) == sorted(all_pos)

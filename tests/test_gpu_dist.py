@@ -1,0 +1,79 @@
+"""GPU parity of the sharded (multi-GPU) path: 2 ranks sharing ONE GPU (collectives staged through
+gloo), compared with the oracle's single-device step on the union of the ranks' batches."""
+import numpy as np
+import pytest
+import torch
+
+from dist_util import run_ranks
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(seed=0, n_users=400, n_items=301, d=64, B=3000, steps=2):
+    rng = np.random.default_rng(seed)
+    U0 = (rng.standard_normal((n_users, d)) * 0.3).astype(np.float32)
+    V0 = (rng.standard_normal((n_items, d)) * 0.3).astype(np.float32)
+    batches = []
+    for _ in range(steps):
+        batches.append((rng.integers(1, n_users, B), np.minimum(np.exp(rng.random(B) * np.log(n_items - 1)).astype(np.int64),
+                                                                n_items - 1).clip(1), rng.integers(1, n_items, B)))
+    # evaluation data
+    pairs = [(rng.integers(1, n_users, 4000), rng.integers(1, n_items, 4000)) for _ in range(3)]
+    return U0, V0, batches, pairs
+
+
+def _rank_fn(rank, world, kind, mode):
+    from oracle import fullsort as ofs
+    from recbole_b200.dist import Comm, ShardedBPR, ShardedEvalIndex
+    from recbole_b200.evaluator import FusedTopKEvaluator
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda:0")
+    U0, V0, batches, pairs = _case()
+    n_users, n_items, d = U0.shape[0], V0.shape[0], U0.shape[1]
+    comm = Comm(staged=True)
+    m = ShardedBPR(n_users, n_items, d, comm, dev, U_full=U0, V_full=V0)
+    m.build_optimizer(kind, lr=0.05 if kind == "sgd" else 2e-3)
+    losses = []
+    for (u, p, n) in batches:
+        mine = (u >= m.u_lo) & (u < m.u_hi)            # users are partitioned: a rank trains its own users' samples
+        t = lambda a: torch.from_numpy(a[mine]).to(dev)  # noqa: E731
+        lo = m.train_step(t(u), t(p), t(n), global_batch=len(u))
+        losses.append(float(lo.item()))
+
+    class Cfg(dict):
+        def __getitem__(self, k):
+            return self.get(k)
+
+    ev = FusedTopKEvaluator(Cfg(metrics=["Recall", "MRR", "NDCG", "Hit", "Precision", "MAP"], topk=[1, 5, 10],
+                                metric_decimal_place=4))
+    uid, hist, pos = ofs.eval_index(n_users, pairs, 2)
+    idx = ShardedEvalIndex.from_global(uid, hist, pos, m.user_bounds, m.item_bounds, rank, dev)
+    res = m.evaluate(idx, ev, mode=mode)
+    return dict(losses=losses, U=m.U.cpu().numpy(), V=m.V.cpu().numpy(), res=res, topk=m.last_topk.cpu().numpy(),
+                u_lo=m.u_lo, i_lo=m.i_lo)
+
+
+@pytest.mark.parametrize("kind", ["adam", "sgd"])
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
+def test_two_ranks_equal_single_device_oracle(kind, mode):
+    from oracle import bpr as obpr
+    from oracle import fullsort as ofs
+    out = run_ranks(_rank_fn, 2, kind, mode, timeout=300)
+    U0, V0, batches, pairs = _case()
+    st = obpr.new_state(U0, V0)
+    lr = 0.05 if kind == "sgd" else 2e-3
+    for s, (u, p, n) in enumerate(batches):
+        lo = obpr.bpr_train_step(st, u, p, n, s + 1, optimizer=kind, lr=lr, dense=False)
+        for r in range(2):
+            assert abs(out[r]["losses"][s] - lo) <= 1e-5 * abs(lo)
+    U = np.concatenate([out[0]["U"], out[1]["U"]])
+    V = np.concatenate([out[0]["V"], out[1]["V"]])
+    assert np.abs(U - st["U"]).max() <= 1e-5 * np.abs(st["U"]).max()
+    assert np.abs(V - st["V"]).max() <= 1e-5 * np.abs(st["V"]).max()
+    # evaluation on the tables the ranks actually hold (so that ids can be compared bit for bit)
+    uid, hist, pos = ofs.eval_index(U0.shape[0], pairs, 2)
+    o_ids, _ = ofs.full_sort_topk(U, V, uid, hist[0], hist[1], 10)
+    got = np.concatenate([out[0]["topk"], out[1]["topk"]])
+    np.testing.assert_array_equal(got, o_ids)
+    ref = ofs.evaluate(o_ids, pos[0], pos[1], ["recall", "mrr", "ndcg", "hit", "precision", "map"], [1, 5, 10])
+    assert out[0]["res"] == ref and out[1]["res"] == ref
