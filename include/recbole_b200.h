@@ -126,7 +126,13 @@ int rb2_bpr_train_step_sharded(float *user_p, float *user_m, float *user_v, int3
                                const float *item_rows, int64_t n_users, int64_t n_item_rows, int32_t dim,
                                const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t batch,
                                int64_t global_batch, const rb2_optim *h_opt, float *loss_out, double *loss_accum,
-                               float *item_grad_out, void *workspace, size_t workspace_bytes, void *stream);
+                               float *item_grad_out, int32_t *item_touched /* nullable: [n_item_rows], set to 1 for
+                               every row written */, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Owner side of the replicated-small-table exchange (all-gather rows, reduce-scatter gradients):
+ * rows with touched[row] > 0 take one optimizer step with grads[row, :]. */
+int rb2_dense_rows_update(float *p, float *m, float *v, int64_t n_rows, int32_t dim, const float *grads,
+                          const int32_t *touched, const rb2_optim *h_opt, void *stream);
 
 /* Row-sparse optimizer step from explicit gradient rows: grads[j, :] belongs to row ids[j]; duplicate
  * ids are summed (fixed order), then every touched row takes one step.  Owner side of the sharded

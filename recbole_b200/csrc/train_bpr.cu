@@ -119,6 +119,7 @@ struct Tables {
   float *ip, *im, *iv;
   int32_t *il;
   float *ig;  // optional [n_items, d]: the item side writes the summed gradient here instead of stepping
+  int32_t *itouched;  // optional [n_items]: set to 1 for every row the item side wrote to ig
 };
 
 __device__ __forceinline__ void bpr_sample(float x, float inv_b, float &loss_term, float &g) {
@@ -241,8 +242,12 @@ __global__ void __launch_bounds__(kThreads) k_item_side(Tables t, BprWs w, int64
   auto finish_run = [&](bool continues) {
     if (cur == kInvalid) return;
     if (!started_before && !continues) {
-      if (t.ig) row_st<D>(t.ig, cur, lane, acc);
-      else row_update_full<D, LAZY>(t.ip, t.im, t.iv, t.il, cur, lane, acc, o);
+      if (t.ig) {
+        row_st<D>(t.ig, cur, lane, acc);
+        if (t.itouched && lane == 0) t.itouched[cur] = 1;
+      } else {
+        row_update_full<D, LAZY>(t.ip, t.im, t.iv, t.il, cur, lane, acc, o);
+      }
     } else if (started_before) {
       row_st<D>(w.i_head, tile, lane, acc);
       fh = continues ? 2 : 1;
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(kThreads) k_fixup(float *P, float *M, float *V
                                                      const float *__restrict__ head, const float *__restrict__ tail,
                                                      const uint8_t *__restrict__ fh, const uint8_t *__restrict__ ft,
                                                      int64_t n_occ, int T, int64_t n_tiles, OptScalars o,
-                                                     float *__restrict__ grad_out) {
+                                                     float *__restrict__ grad_out, int32_t *__restrict__ touched) {
   constexpr int LANES = RowCfg<D>::LANES;
   const int lane = threadIdx.x % LANES;
   const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
@@ -307,8 +312,12 @@ __global__ void __launch_bounds__(kThreads) k_fixup(float *P, float *M, float *V
     row_add<D>(acc, row_ld<D>(head, j, lane));
     if (f != 2) break;
   }
-  if (grad_out) row_st<D>(grad_out, key, lane, acc);
-  else row_update_full<D, LAZY>(P, M, V, L, key, lane, acc, o);
+  if (grad_out) {
+    row_st<D>(grad_out, key, lane, acc);
+    if (touched && lane == 0) touched[key] = 1;
+  } else {
+    row_update_full<D, LAZY>(P, M, V, L, key, lane, acc, o);
+  }
 }
 
 __global__ void k_loss(const double *__restrict__ part, int64_t n, double inv_b, float *loss_out,
@@ -389,7 +398,7 @@ int launch_step(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, 
   {
     ProfScope prof(RB2_ST_USER_FIXUP, st);
     k_fixup<D, LAZY><<<blocks(ntu), kThreads, 0, st>>>(t.up, t.um, t.uv, t.ul, w.ukey_s, w.u_head, w.u_tail, w.u_fh,
-                                                       w.u_ft, B, Tu, ntu, o, nullptr);
+                                                       w.u_ft, B, Tu, ntu, o, nullptr, nullptr);
   }
   {
     ProfScope prof(RB2_ST_ITEM_SIDE, st);
@@ -398,7 +407,7 @@ int launch_step(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, 
   {
     ProfScope prof(RB2_ST_ITEM_FIXUP, st);
     k_fixup<D, LAZY><<<blocks(nti), kThreads, 0, st>>>(t.ip, t.im, t.iv, t.il, w.ikey_s, w.i_head, w.i_tail, w.i_fh,
-                                                       w.i_ft, 2 * B, Ti, nti, o, t.ig);
+                                                       w.i_ft, 2 * B, Ti, nti, o, t.ig, t.itouched);
   }
   {
     ProfScope prof(RB2_ST_LOSS, st);
@@ -451,7 +460,8 @@ static int bpr_step_impl(float *user_p, float *user_m, float *user_v, int32_t *u
                          float *item_m, float *item_v, int32_t *item_last, int64_t n_users, int64_t n_items,
                          int32_t dim, const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t batch,
                          const rb2_optim *h_opt, float *loss_out, double *loss_accum, void *workspace,
-                         size_t workspace_bytes, void *stream, float *item_grad_out, int64_t global_batch) {
+                         size_t workspace_bytes, void *stream, float *item_grad_out, int64_t global_batch,
+                         int32_t *item_touched) {
   RB2_REQUIRE(user_p && item_p && user && pos && neg && h_opt && loss_out && workspace, RB2_EINVAL,
               "rb2_bpr_train_step: null argument");
   RB2_REQUIRE(batch > 0 && batch < ((int64_t)1 << 30), RB2_EINVAL, "rb2_bpr_train_step: batch %lld out of range",
@@ -473,7 +483,7 @@ static int bpr_step_impl(float *user_p, float *user_m, float *user_v, int32_t *u
   RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_bpr_train_step: workspace %zu < %zu", workspace_bytes,
               need);
   cudaStream_t st = (cudaStream_t)stream;
-  Tables t{user_p, user_m, user_v, user_last, item_p, item_m, item_v, item_last, item_grad_out};
+  Tables t{user_p, user_m, user_v, user_last, item_p, item_m, item_v, item_last, item_grad_out, item_touched};
   {
     ProfScope prof(RB2_ST_KEYS, st);
     k_make_keys<<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(user, pos, neg, batch, n_users, n_items, w);
@@ -498,19 +508,19 @@ extern "C" int rb2_bpr_train_step(float *user_p, float *user_m, float *user_v, i
                                   double *loss_accum, void *workspace, size_t workspace_bytes, void *stream) {
   return bpr_step_impl(user_p, user_m, user_v, user_last, item_p, item_m, item_v, item_last, n_users, n_items, dim,
                        user, pos, neg, batch, h_opt, loss_out, loss_accum, workspace, workspace_bytes, stream,
-                       nullptr, 0);
+                       nullptr, 0, nullptr);
 }
 
 extern "C" int rb2_bpr_train_step_sharded(float *user_p, float *user_m, float *user_v, int32_t *user_last,
                                           const float *item_rows, int64_t n_users, int64_t n_item_rows, int32_t dim,
                                           const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t batch,
                                           int64_t global_batch, const rb2_optim *h_opt, float *loss_out,
-                                          double *loss_accum, float *item_grad_out, void *workspace,
-                                          size_t workspace_bytes, void *stream) {
+                                          double *loss_accum, float *item_grad_out, int32_t *item_touched,
+                                          void *workspace, size_t workspace_bytes, void *stream) {
   RB2_REQUIRE(item_grad_out != nullptr, RB2_EINVAL, "rb2_bpr_train_step_sharded: item_grad_out is null");
   return bpr_step_impl(user_p, user_m, user_v, user_last, const_cast<float *>(item_rows), nullptr, nullptr, nullptr,
                        n_users, n_item_rows, dim, user, pos, neg, batch, h_opt, loss_out, loss_accum, workspace,
-                       workspace_bytes, stream, item_grad_out, global_batch);
+                       workspace_bytes, stream, item_grad_out, global_batch, item_touched);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -557,6 +567,43 @@ __global__ void k_rows_keys(const int64_t *__restrict__ ids, int64_t M, int64_t 
 }
 }  // namespace
 
+namespace {
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_dense_rows_update(float *P, float *M, float *V, int64_t rows,
+                                                                 const float *__restrict__ grads,
+                                                                 const int32_t *__restrict__ touched, OptScalars o) {
+  constexpr int LANES = RowCfg<D>::LANES;
+  const int lane = threadIdx.x % LANES;
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  if (row >= rows || touched[row] <= 0) return;
+  Row<D> p = row_ld<D>(P, row, lane);
+  Row<D> g = row_ldg<D>(grads, row, lane);
+  row_update<D>(P, M, V, row, lane, p, g, o);
+}
+}  // namespace
+
+// Owner side of the "replicated small table" exchange: grads [n_rows, d] is the reduce-scattered sum
+// of every rank's per-row gradient, touched[row] > 0 marks the rows that occurred in some rank's batch;
+// exactly those rows take one optimizer step (row-sparse semantics, as everywhere else).
+extern "C" int rb2_dense_rows_update(float *p, float *m, float *v, int64_t n_rows, int32_t dim, const float *grads,
+                                     const int32_t *touched, const rb2_optim *h_opt, void *stream) {
+  RB2_REQUIRE(p && grads && touched && h_opt, RB2_EINVAL, "rb2_dense_rows_update: null argument");
+  OptScalars o = rb2_opt_scalars(h_opt);
+  RB2_REQUIRE(o.kind == RB2_OPT_SGD || o.kind == RB2_OPT_ADAM, RB2_EINVAL,
+              "rb2_dense_rows_update: optimizer kind %d not supported here", o.kind);
+  if (o.kind != RB2_OPT_SGD) RB2_REQUIRE(m && v, RB2_EINVAL, "rb2_dense_rows_update: Adam needs m and v");
+  if (n_rows <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(RB2_ST_ITEM_SIDE, st);
+  RB2_DISPATCH_DIM(dim, {
+    constexpr int LANES = RowCfg<D_>::LANES;
+    unsigned blocks = (unsigned)((n_rows * LANES + kThreads - 1) / kThreads);
+    k_dense_rows_update<D_><<<blocks, kThreads, 0, st>>>(p, m, v, n_rows, grads, touched, o);
+  });
+  RB2_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" size_t rb2_sparse_rows_update_workspace_bytes(int64_t m, int32_t dim) {
   RowsWs w;
   return carve_rows(w, nullptr, m, dim);
@@ -597,7 +644,7 @@ extern "C" int rb2_sparse_rows_update(float *p, float *m, float *v, int32_t *las
   w.i_tail = rw.tail;
   w.i_fh = rw.fh;
   w.i_ft = rw.ft;
-  Tables t{nullptr, nullptr, nullptr, nullptr, p, m, v, last, nullptr};
+  Tables t{nullptr, nullptr, nullptr, nullptr, p, m, v, last, nullptr, nullptr};
   const bool lazy = o.kind == RB2_OPT_ADAM_LAZY;
   RB2_DISPATCH_DIM(dim, {
     constexpr int LANES = RowCfg<D_>::LANES;
@@ -607,11 +654,11 @@ extern "C" int rb2_sparse_rows_update(float *p, float *m, float *v, int32_t *las
     if (lazy) {
       { ProfScope prof(RB2_ST_ITEM_SIDE, st); k_item_side<D_, true><<<blocks, kThreads, 0, st>>>(t, w, count, Ti, nti, o); }
       { ProfScope prof(RB2_ST_ITEM_FIXUP, st);
-        k_fixup<D_, true><<<blocks, kThreads, 0, st>>>(p, m, v, last, rw.key_s, rw.head, rw.tail, rw.fh, rw.ft, count, Ti, nti, o, nullptr); }
+        k_fixup<D_, true><<<blocks, kThreads, 0, st>>>(p, m, v, last, rw.key_s, rw.head, rw.tail, rw.fh, rw.ft, count, Ti, nti, o, nullptr, nullptr); }
     } else {
       { ProfScope prof(RB2_ST_ITEM_SIDE, st); k_item_side<D_, false><<<blocks, kThreads, 0, st>>>(t, w, count, Ti, nti, o); }
       { ProfScope prof(RB2_ST_ITEM_FIXUP, st);
-        k_fixup<D_, false><<<blocks, kThreads, 0, st>>>(p, m, v, last, rw.key_s, rw.head, rw.tail, rw.fh, rw.ft, count, Ti, nti, o, nullptr); }
+        k_fixup<D_, false><<<blocks, kThreads, 0, st>>>(p, m, v, last, rw.key_s, rw.head, rw.tail, rw.fh, rw.ft, count, Ti, nti, o, nullptr, nullptr); }
     }
   });
   RB2_CUDA(cudaGetLastError());

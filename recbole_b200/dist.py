@@ -27,8 +27,10 @@ import torch.distributed as dist
 
 
 def shard_bounds(n, world):
-    """Contiguous blocks: rank g owns [b[g], b[g+1])."""
-    return np.array([(g * n) // world for g in range(world + 1)], dtype=np.int64)
+    """Contiguous equal blocks of ceil(n / world) rows (the last ones may be short or empty): rank g
+    owns [b[g], b[g+1]).  Equal blocks let all-gather / reduce-scatter run without padding copies."""
+    s = (n + world - 1) // world
+    return np.array([min(g * s, n) for g in range(world + 1)], dtype=np.int64)
 
 
 class Comm:
@@ -64,6 +66,34 @@ class Comm:
             return out.to(inp.device)
         out = torch.empty(out_shape, dtype=inp.dtype, device=inp.device)
         dist.all_to_all_single(out, inp.contiguous(), list(recv_counts), list(send_counts), group=self.group)
+        return out
+
+    def all_gather_equal(self, local):
+        """all-gather of equally sized blocks -> [world * rows, ...]."""
+        if self.world == 1:
+            return local
+        shape = (self.world * local.shape[0],) + tuple(local.shape[1:])
+        if self.staged:
+            out = torch.empty(shape, dtype=local.dtype)
+            dist.all_gather_into_tensor(out, local.cpu().contiguous(), group=self.group)
+            return out.to(local.device)
+        out = torch.empty(shape, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+        return out
+
+    def reduce_scatter_sum(self, full):
+        """[world * rows, ...] summed over ranks -> my block [rows, ...]."""
+        if self.world == 1:
+            return full
+        rows = full.shape[0] // self.world
+        shape = (rows,) + tuple(full.shape[1:])
+        if self.staged:
+            # gloo has no reduce_scatter: all-reduce on the host, keep my block
+            c = full.cpu().contiguous()
+            dist.all_reduce(c, group=self.group)
+            return c[self.rank * rows:(self.rank + 1) * rows].to(full.device)
+        out = torch.empty(shape, dtype=full.dtype, device=full.device)
+        dist.reduce_scatter_tensor(out, full.contiguous(), group=self.group)
         return out
 
     def all_reduce_sum(self, t):
@@ -132,7 +162,7 @@ def return_grads(comm, G, send_counts, recv_counts):
 class ShardedBPR:
     """BPR-MF with range-partitioned users and a row-sharded item table."""
 
-    def __init__(self, n_users, n_items, dim, comm, device, U_full=None, V_full=None, seed=2020):
+    def __init__(self, n_users, n_items, dim, comm, device, U_full=None, V_full=None, seed=2020, exchange="auto"):
         from . import ops
         self.ops = ops
         self.comm, self.device, self.dim = comm, device, dim
@@ -141,14 +171,25 @@ class ShardedBPR:
         self.item_bounds = shard_bounds(n_items, comm.world)
         self.u_lo, self.u_hi = int(self.user_bounds[comm.rank]), int(self.user_bounds[comm.rank + 1])
         self.i_lo, self.i_hi = int(self.item_bounds[comm.rank]), int(self.item_bounds[comm.rank + 1])
+        # every rank allocates the full block size (tail ranks pad), so collectives need no re-packing
+        self.u_block = int(self.user_bounds[1] - self.user_bounds[0])
+        self.i_block = int(self.item_bounds[1] - self.item_bounds[0])
+        self.U = torch.zeros(self.u_block, dim, device=device)
+        self.V = torch.zeros(self.i_block, dim, device=device)
         if U_full is not None:
-            self.U = torch.as_tensor(U_full[self.u_lo:self.u_hi]).to(device).contiguous().clone()
-            self.V = torch.as_tensor(V_full[self.i_lo:self.i_hi]).to(device).contiguous().clone()
+            self.U[: self.u_hi - self.u_lo] = torch.as_tensor(U_full[self.u_lo:self.u_hi]).to(device)
+            self.V[: self.i_hi - self.i_lo] = torch.as_tensor(V_full[self.i_lo:self.i_hi]).to(device)
         else:
             g = torch.Generator(device=device)
             g.manual_seed(seed + comm.rank)
-            self.U = torch.randn(self.u_hi - self.u_lo, dim, device=device, generator=g) * (2.0 / (n_users + dim)) ** 0.5
-            self.V = torch.randn(self.i_hi - self.i_lo, dim, device=device, generator=g) * (2.0 / (n_items + dim)) ** 0.5
+            self.U[: self.u_hi - self.u_lo] = torch.randn(self.u_hi - self.u_lo, dim, device=device, generator=g) * (2.0 / (n_users + dim)) ** 0.5
+            self.V[: self.i_hi - self.i_lo] = torch.randn(self.i_hi - self.i_lo, dim, device=device, generator=g) * (2.0 / (n_items + dim)) ** 0.5
+        # "dense": all-gather the item rows, reduce-scatter their gradients (no data-dependent sizes,
+        #          no host sync; right when the table is small next to the batch).
+        # "sparse": all-to-all of the de-duplicated rows the batch touches (large tables).
+        if exchange == "auto":
+            exchange = "dense" if n_items * dim * 4 <= (64 << 20) else "sparse"
+        self.exchange = exchange
         self.optim = None
         self.state = {}
         self.loss_out = torch.zeros(1, dtype=torch.float32, device=device)
@@ -180,6 +221,8 @@ class ShardedBPR:
             global_batch = B * comm.world
         self.optim.step += 1
         t = self.optim.step
+        if self.exchange == "dense":
+            return self._train_step_dense(user, pos, neg, global_batch, t)
         uniq, inv, send_counts = plan_item_exchange(torch.cat([pos, neg]), self.item_bounds)
         C, local_idx, recv_counts = fetch_rows(comm, uniq, send_counts, lambda idx: self.V.index_select(0, idx),
                                                self.i_lo)
@@ -194,10 +237,29 @@ class ShardedBPR:
         self.loss_accum += self.loss_out.double()
         return self.loss_out
 
+    def _train_step_dense(self, user, pos, neg, global_batch, t):
+        ops, comm = self.ops, self.comm
+        B = int(user.numel())
+        V_all = comm.all_gather_equal(self.V)                       # [world * i_block, d]; global id == row
+        if not hasattr(self, "_G_all") or self._G_all.shape != V_all.shape:
+            self._G_all = torch.empty_like(V_all)
+            self._touched_all = torch.empty(V_all.shape[0], dtype=torch.int32, device=self.device)
+        self._G_all.zero_()
+        self._touched_all.zero_()
+        user_local = (user - self.u_lo).contiguous()
+        ops.bpr_train_step_sharded(self.U, self.state, V_all, user_local, pos, neg, global_batch, self.optim,
+                                   self.loss_out, None, self._G_all, self._workspace(B), step=t,
+                                   item_touched=self._touched_all)
+        G = comm.reduce_scatter_sum(self._G_all)
+        touched = comm.reduce_scatter_sum(self._touched_all)
+        ops.dense_rows_update(self.V, self.state.get("mV"), self.state.get("vV"), G, touched, self.optim, step=t)
+        comm.all_reduce_sum(self.loss_out)
+        self.loss_accum += self.loss_out.double()
+        return self.loss_out
+
     # ---- evaluation ------------------------------------------------------------------------------------
     def gather_user_table(self):
-        counts = (self.user_bounds[1:] - self.user_bounds[:-1]).tolist()
-        return self.comm.all_gather_rows(self.U, counts)
+        return self.comm.all_gather_equal(self.U)
 
     @torch.no_grad()
     def evaluate(self, index, evaluator, mode="tc", user_tile=1 << 20):
@@ -209,10 +271,15 @@ class ShardedBPR:
         n = int(index.uid_all.numel())
         ids = torch.empty((n, K), dtype=torch.int64, device=self.device)
         sc = torch.empty((n, K), dtype=torch.float32, device=self.device)
-        for lo in range(0, n, user_tile):
+        n_local = self.i_hi - self.i_lo
+        if n_local <= 0:                      # more ranks than item blocks: nothing to contribute
+            ids.fill_(-1)
+            sc.fill_(float("-inf"))
+        V_local = self.V[:n_local]
+        for lo in range(0, n if n_local > 0 else 0, user_tile):
             hi = min(lo + user_tile, n)
             ptr = index.hist_indptr[lo:hi + 1].contiguous()
-            i, s = ops.fullsort_topk(U_all, index.uid_all[lo:hi].contiguous(), self.V, K, ptr, index.hist_indices,
+            i, s = ops.fullsort_topk(U_all, index.uid_all[lo:hi].contiguous(), V_local, K, ptr, index.hist_indices,
                                      item_base=self.i_lo, mode=mode)
             ids[lo:hi], sc[lo:hi] = i, s
         # per-shard lists -> the users' owners

@@ -120,7 +120,7 @@ def bpr_train_step(U, V, state, user, pos, neg, optim, loss_out, loss_accum, ws)
 
 
 def bpr_train_step_sharded(U, state, item_rows, user, pos_c, neg_c, global_batch, optim, loss_out, loss_accum,
-                           item_grad_out, ws, step=None):
+                           item_grad_out, ws, step=None, item_touched=None):
     """User side + per-compact-row item gradient sums (rb2_bpr_train_step_sharded).  optim.step is NOT
     incremented here (the owner-side update of the same logical step shares it)."""
     o = optim.c_struct(U.device, step)
@@ -130,7 +130,14 @@ def bpr_train_step_sharded(U, state, item_rows, user, pos_c, neg_c, global_batch
         _ptr(state.get("lastU"), torch.int32, True), _ptr(item_rows, f32), U.shape[0], item_rows.shape[0],
         U.shape[1], _ptr(user, i64), _ptr(pos_c, i64), _ptr(neg_c, i64), user.numel(), int(global_batch),
         ctypes.byref(o), _ptr(loss_out, f32), _ptr(loss_accum, torch.float64, True), _ptr(item_grad_out, f32),
-        ws.ptr(), ws.nbytes, _stream()))
+        _ptr(item_touched, torch.int32, True), ws.ptr(), ws.nbytes, _stream()))
+
+
+def dense_rows_update(P, M, V, grads, touched, optim, step=None):
+    o = optim.c_struct(P.device, step)
+    f32 = torch.float32
+    check(lib.rb2_dense_rows_update(_ptr(P, f32), _ptr(M, f32, True), _ptr(V, f32, True), P.shape[0], P.shape[1],
+                                    _ptr(grads, f32), _ptr(touched, torch.int32), ctypes.byref(o), _stream()))
 
 
 def sparse_rows_update(P, M, V, last, ids, grads, optim, ws=None, step=None):

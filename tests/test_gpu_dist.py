@@ -22,7 +22,7 @@ def _case(seed=0, n_users=400, n_items=301, d=64, B=3000, steps=2):
     return U0, V0, batches, pairs
 
 
-def _rank_fn(rank, world, kind, mode):
+def _rank_fn(rank, world, kind, mode, exchange):
     from oracle import fullsort as ofs
     from recbole_b200.dist import Comm, ShardedBPR, ShardedEvalIndex
     from recbole_b200.evaluator import FusedTopKEvaluator
@@ -31,7 +31,7 @@ def _rank_fn(rank, world, kind, mode):
     U0, V0, batches, pairs = _case()
     n_users, n_items, d = U0.shape[0], V0.shape[0], U0.shape[1]
     comm = Comm(staged=True)
-    m = ShardedBPR(n_users, n_items, d, comm, dev, U_full=U0, V_full=V0)
+    m = ShardedBPR(n_users, n_items, d, comm, dev, U_full=U0, V_full=V0, exchange=exchange)
     m.build_optimizer(kind, lr=0.05 if kind == "sgd" else 2e-3)
     losses = []
     for (u, p, n) in batches:
@@ -49,16 +49,16 @@ def _rank_fn(rank, world, kind, mode):
     uid, hist, pos = ofs.eval_index(n_users, pairs, 2)
     idx = ShardedEvalIndex.from_global(uid, hist, pos, m.user_bounds, m.item_bounds, rank, dev)
     res = m.evaluate(idx, ev, mode=mode)
-    return dict(losses=losses, U=m.U.cpu().numpy(), V=m.V.cpu().numpy(), res=res, topk=m.last_topk.cpu().numpy(),
-                u_lo=m.u_lo, i_lo=m.i_lo)
+    return dict(losses=losses, U=m.U[: m.u_hi - m.u_lo].cpu().numpy(), V=m.V[: m.i_hi - m.i_lo].cpu().numpy(), res=res,
+                topk=m.last_topk.cpu().numpy(), u_lo=m.u_lo, i_lo=m.i_lo)
 
 
-@pytest.mark.parametrize("kind", ["adam", "sgd"])
-@pytest.mark.parametrize("mode", ["fp32", "tc"])
-def test_two_ranks_equal_single_device_oracle(kind, mode):
+@pytest.mark.parametrize("kind,mode,exchange", [("adam", "tc", "sparse"), ("sgd", "fp32", "sparse"),
+                                                ("adam", "fp32", "dense"), ("sgd", "tc", "dense")])
+def test_two_ranks_equal_single_device_oracle(kind, mode, exchange):
     from oracle import bpr as obpr
     from oracle import fullsort as ofs
-    out = run_ranks(_rank_fn, 2, kind, mode, timeout=300)
+    out = run_ranks(_rank_fn, 2, kind, mode, exchange, timeout=300)
     U0, V0, batches, pairs = _case()
     st = obpr.new_state(U0, V0)
     lr = 0.05 if kind == "sgd" else 2e-3
