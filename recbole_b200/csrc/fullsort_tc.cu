@@ -87,6 +87,30 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// half of a B slot, written into BOTH CTAs of the pair (same smem offset, same mbarrier offset)
+__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+      "%4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
@@ -205,11 +229,16 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int n_work = p.n_ut * p.n_split;
+  // CTA pair (cluster of 2): both CTAs walk the same item tiles for two different query tiles; each
+  // loads half of every B slot and multicasts it to both, halving the L2 -> SM traffic per FLOP
+  const int crank = (int)cluster_ctarank();
+  const int n_utp = (p.n_ut + 1) / 2;                 // query-tile pairs
+  const int n_work = n_utp * p.n_split;               // work items per CLUSTER
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   const int n_tiles_all = (int)((p.n_local + BN - 1) / BN);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }  // empty: both CTAs' MMAs
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
     mbar_init(&t_full[0], 1); mbar_init(&t_full[1], 1);
@@ -224,6 +253,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -232,8 +262,8 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int ut = w % p.n_ut, sp = w / p.n_ut;
+      for (int w = cluster_id; w < n_work; w += n_clusters) {
+        const int ut = 2 * (w % n_utp) + crank, sp = w / n_utp;
         mbar_wait(a_empty, a_phase ^ 1);
         mbar_expect_tx(a_full, KB * A_KB_BYTES);
         for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * A_KB_BYTES, &tmA, kb * BK, ut * BM, a_full);
@@ -242,9 +272,10 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const int t1 = min(t0 + p.tiles_per_split, n_tiles_all);
         for (int it = t0; it < t1; ++it) {
           for (int kb = 0; kb < KB; ++kb) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], UNIT_BYTES);
-            tma_load_2d(sB + (size_t)stage * UNIT_BYTES, &tmB, kb * BK, it * BN, &full[stage]);
+            mbar_wait(&empty[stage], phase ^ 1);       // both CTAs are done reading this slot
+            mbar_expect_tx(&full[stage], UNIT_BYTES);  // my half + the peer's half
+            tma_load_2d_mc(sB + (size_t)stage * UNIT_BYTES + (size_t)crank * (UNIT_BYTES / 2), &tmB, kb * BK,
+                           it * BN + crank * (BN / 2), &full[stage], (uint16_t)0x3);
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
         }
@@ -255,8 +286,8 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, a_phase = 0, tcount = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int sp = w / p.n_ut;
+      for (int w = cluster_id; w < n_work; w += n_clusters) {
+        const int sp = w / n_utp;
         mbar_wait(a_full, a_phase);
         a_phase ^= 1;
         const int t0 = sp * p.tiles_per_split;
@@ -277,7 +308,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               tc_mma_bf16(tmem_d, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), kIdesc,
                           (kb | k4) ? 1u : 0u);
             }
-            tc_commit(&empty[stage]);   // frees the ring slot once these MMAs have read it
+            tc_commit_mc(&empty[stage], (uint16_t)0x3);   // tell both producers this CTA is done with the slot
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
           tc_commit(&t_full[acc]);      // accumulator stage complete
@@ -293,8 +324,8 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     uint32_t *my_bloom = bloom + t;               // word i at my_bloom[i * BM]
     float *my_stage = stage_buf + (ws * BM + t);  // score j of the current chunk at my_stage[j * 256]
     uint32_t tcount = 0;
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const int ut = w % p.n_ut, sp = w / p.n_ut;
+    for (int w = cluster_id; w < n_work; w += n_clusters) {
+      const int ut = 2 * (w % n_utp) + crank, sp = w / n_utp;
       const int64_t r = (int64_t)ut * BM + t;
       const bool active = r < p.nq;
       const int64_t *hist = nullptr;
@@ -382,6 +413,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();   // nobody leaves while the peer may still write into this CTA's smem / barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -549,15 +581,16 @@ TcPlan make_plan(int64_t nq, int64_t n_local) {
   pl.n_ut = (int)((nq + BM - 1) / BM);
   int n_tiles = (int)((n_local + BN - 1) / BN);
   int sms = rb2_num_sms();
-  int want = (2 * sms + pl.n_ut - 1) / pl.n_ut;   // aim for >= 2 work items per SM
+  int want = (2 * (sms / 2) + (pl.n_ut + 1) / 2 - 1) / ((pl.n_ut + 1) / 2);   // >= 2 work items per CTA pair
   if (want < 1) want = 1;
   if (want > 16) want = 16;
   if (want > (n_tiles + 1) / 2) want = (n_tiles + 1) / 2;   // at least two tiles per work item (two warp sets)
   if (want < 1) want = 1;
   pl.tiles_per_split = (n_tiles + want - 1) / want;
   pl.n_split = (n_tiles + pl.tiles_per_split - 1) / pl.tiles_per_split;
-  int work = pl.n_ut * pl.n_split;
-  pl.grid = work < sms ? work : sms;
+  int work = ((pl.n_ut + 1) / 2) * pl.n_split;       // work items per CTA pair
+  int clusters = sms / 2;
+  pl.grid = 2 * (work < clusters ? work : clusters);
   return pl;
 }
 
@@ -566,7 +599,7 @@ constexpr int KP_MAX = 32;
 size_t carve_tc(TcWs &w, void *base, int64_t nq, int64_t n_local, int dim, int k) {
   Carver c(base);
   TcPlan pl = make_plan(nq, n_local);
-  int64_t nq_pad = (nq + BM - 1) / BM * BM;
+  int64_t nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM);
   w.qb = c.take<__nv_bfloat16>(nq_pad * dim);
   w.vb = c.take<__nv_bfloat16>(n_local * dim);
   w.qnorm = c.take<float>(nq);
@@ -623,7 +656,7 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
   RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_fullsort_topk(tc): workspace %zu < %zu", workspace_bytes, need);
   TcPlan pl = make_plan(nq, n_local);
   constexpr int LANES = RowCfg<D>::LANES;
-  const int64_t nq_pad = (nq + BM - 1) / BM * BM;
+  const int64_t nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM);
   {
     ProfScope prof(RB2_ST_TC_CONVERT, st, 4);
     RB2_CUDA(cudaMemsetAsync(w.maxes, 0, 4 * sizeof(float), st));
@@ -638,7 +671,7 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, w.qb, nq_pad, D, BM);
   if (rc) return rc;
-  rc = make_map(&tmB, w.vb, n_local, D, BN);
+  rc = make_map(&tmB, w.vb, n_local, D, BN / 2);   // each CTA of the pair loads half a slot
   if (rc) return rc;
   TcParams p;
   p.nq = nq; p.n_local = n_local; p.item_base = item_base;
@@ -650,7 +683,19 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
     ProfScope prof(RB2_ST_TC_SCORE, st);
     RB2_CUDA(cudaFuncSetAttribute(k_fullsort_tc<KB, NSTAGE, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
-    k_fullsort_tc<KB, NSTAGE, KP><<<pl.grid, kThreadsTc, smem, st>>>(tmA, tmB, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)pl.grid);
+    cfg.blockDim = dim3(kThreadsTc);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RB2_CUDA(cudaLaunchKernelEx(&cfg, k_fullsort_tc<KB, NSTAGE, KP>, tmA, tmB, p));
     RB2_CUDA(cudaGetLastError());
   }
   {
