@@ -155,6 +155,28 @@ int rb2_adam_lazy_flush(float *p, float *m, float *v, int32_t *last, int64_t row
                         const rb2_optim *h_opt, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * (1d) Fused FM (factorization machine, TOKEN fields) training step: multi-field embedding bag.
+ * Replaces, per batch: ContextRecommender.embed_input_fields + FMEmbedding (abstract_recommender.py:
+ * 220-224,361-412; layers.py:141-144), BaseFactorizationMachine (layers.py:164-171),
+ * FMFirstOrderLinear (layers.py:1021-1061), FM.forward/calculate_loss with nn.BCELoss
+ * (recbole/model/context_aware_recommender/fm.py:47-56), loss.backward() and optimizer.step().
+ *   E [n_rows, dim]  = token_embedding_table.embedding.weight       (all token fields share it)
+ *   W [n_rows]       = first_order_linear.token_embedding_table.embedding.weight  (output_dim 1)
+ *   bias3 [3]        = first_order_linear.bias and its Adam moments (b, m, v)
+ *   ids [batch, n_fields] raw per-field ids; row = ids[s, f] + offsets[f]   (layers.py:142)
+ * dim in {16, 32, 64, 128}; optimizer RB2_OPT_SGD or RB2_OPT_ADAM (row-sparse; the bias is dense).
+ * rb2_fm_predict: y[s] = sigmoid(first_order + fm)  (FM.predict, fm.py:58-59).
+ * ---------------------------------------------------------------------------------------- */
+size_t rb2_fm_workspace_bytes(int64_t batch, int32_t n_fields, int32_t dim);
+int rb2_fm_train_step(float *E, float *mE, float *vE, float *W, float *mW, float *vW, float *bias3,
+                      int64_t n_rows, int32_t dim, const int64_t *ids, const int64_t *offsets, int32_t n_fields,
+                      const float *label, int64_t batch, const rb2_optim *h_opt, float *loss_out,
+                      double *loss_accum, void *workspace, size_t workspace_bytes, void *stream);
+int rb2_fm_predict(const float *E, const float *W, const float *bias3, int64_t n_rows, int32_t dim,
+                   const int64_t *ids, const int64_t *offsets, int32_t n_fields, int64_t batch, float *y_out,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * (1b) Gather-dot for explicit (user, item) pairs.  Replaces BPR.predict (bpr.py:85-89).
  * ---------------------------------------------------------------------------------------- */
 int rb2_gather_dot(const float *user_p, const float *item_p, int64_t n_users, int64_t n_items, int32_t dim,

@@ -61,6 +61,16 @@ struct WsHeader {
   int32_t pad[63];
 };
 
+// tile length for the sorted-occurrence walks: long enough that few runs straddle tiles, short
+// enough to fill the machine
+static inline int rb2_num_sms();
+static inline int64_t rb2_max_tiles(int64_t n_occ) { return (n_occ + 7) / 8; }
+static inline int rb2_bits_for(int64_t n) {
+  int b = 1;
+  while (b < 32 && ((int64_t)1 << b) < n) ++b;
+  return b;
+}
+
 static inline int rb2_num_sms() {
   static int n = 0;
   if (!n) {
@@ -70,6 +80,14 @@ static inline int rb2_num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+static inline int rb2_pick_tile(int64_t n_occ, int lanes) {
+  int64_t groups_wanted = (int64_t)rb2_num_sms() * 2048 / lanes;  // one full wave of lane groups
+  int64_t t = n_occ / (groups_wanted > 0 ? groups_wanted : 1);
+  if (t < 8) t = 8;
+  if (t > 64) t = 64;
+  return (int)t;
 }
 
 // ---- row vectors: one embedding row spread over a "group" of LANES lanes ---------------------

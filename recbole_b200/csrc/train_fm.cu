@@ -1,0 +1,397 @@
+// train_fm.cu -- fused FM (factorization machine, token fields) training step for sm_100a:
+// multi-field embedding bag forward, BCE loss, backward as a de-duplicated row-sparse update.
+//
+// Replaces, per batch: ContextRecommender.embed_input_fields + FMEmbedding (id + per-field offset
+// into ONE table, recbole/model/abstract_recommender.py:220-224,361-412, recbole/model/layers.py:141-144),
+// BaseFactorizationMachine 0.5*sum_k[(sum_f v)^2 - sum_f v^2] (layers.py:164-171), FMFirstOrderLinear
+// (d = 1 table + bias, layers.py:1021-1061), FM.forward/calculate_loss: sigmoid + nn.BCELoss
+// (recbole/model/context_aware_recommender/fm.py:47-56), loss.backward() and the dense Adam step
+// (trainer.py:170-173).
+//
+//   k_fm_forward  one warp per sample; its lane groups (d/4 lanes each) take the fields round-robin:
+//                 gather v_f (second-order row) and w_f (first-order scalar), S = sum_f v_f,
+//                 z = sum_f w_f + b + 0.5*sum_k(S_k^2 - sum_f v_fk^2), y = sigmoid(z), BCE term,
+//                 gz = dLoss/dz.  Stores gs[s] = gz*S (d floats) and gz[s]: the only intermediates.
+//   radix sort    B*F (row, occurrence) pairs by row id.
+//   k_fm_rows     walks tiles of sorted occurrences; for the run of one row r:
+//                     dE_r = sum_s gs[s] - (sum_s gz[s]) * v_r        (d z/d v_f = S - v_f)
+//                     dW_r = sum_s gz[s]
+//                 complete runs are stepped in place (p, m, v of the row and of its first-order scalar),
+//                 straddling runs go through the fixed-order fix-up (no float atomics).
+//   k_fm_bias     db = sum_s gz[s], dense Adam on the scalar bias; loss reduction.
+// Algorithmic bytes per sample: F*(24*d + 24) + 8*F + 4.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct FmWs {
+  WsHeader *hdr;
+  uint32_t *key, *val, *key_s, *val_s;   // [B*F]
+  float *gs;                             // [B, D]
+  float *gz;                             // [B]
+  float *head, *tail;                    // [tiles, D]
+  float *head_z, *tail_z;                // [tiles]
+  uint8_t *fh, *ft;
+  double *loss_part, *gz_part;           // [warps blocks]
+  void *cub_tmp;
+  size_t cub_bytes;
+  int64_t n_parts;
+};
+
+size_t carve(FmWs &w, void *base, int64_t B, int F, int dim) {
+  Carver c(base);
+  const int64_t M = B * F;
+  w.hdr = c.take<WsHeader>(1);
+  w.key = c.take<uint32_t>(M);
+  w.val = c.take<uint32_t>(M);
+  w.key_s = c.take<uint32_t>(M);
+  w.val_s = c.take<uint32_t>(M);
+  w.gs = c.take<float>(B * dim);
+  w.gz = c.take<float>(B);
+  int64_t tiles = rb2_max_tiles(M);
+  w.head = c.take<float>(tiles * dim);
+  w.tail = c.take<float>(tiles * dim);
+  w.head_z = c.take<float>(tiles);
+  w.tail_z = c.take<float>(tiles);
+  w.fh = c.take<uint8_t>(tiles);
+  w.ft = c.take<uint8_t>(tiles);
+  w.n_parts = (B + 7) / 8 + 64;
+  w.loss_part = c.take<double>(w.n_parts);
+  w.gz_part = c.take<double>(w.n_parts);
+  size_t b = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                  (uint32_t *)nullptr, (int)M, 0, 32);
+  w.cub_bytes = b;
+  w.cub_tmp = c.take<char>(b);
+  return c.off;
+}
+
+struct FmTables {
+  float *E, *mE, *vE;   // [rows, D]
+  float *W, *mW, *vW;   // [rows]
+  float *bias;          // [3]: b, m, v
+};
+
+// ---------------------------------------------------------------------------------------------
+// forward (+ intermediates for the backward when TRAIN)
+template <int D, bool TRAIN>
+__global__ void __launch_bounds__(kThreads) k_fm_forward(FmTables t, const int64_t *__restrict__ ids,
+                                                          const int64_t *__restrict__ offsets,
+                                                          const float *__restrict__ label, int64_t B, int F,
+                                                          int64_t n_rows, float inv_b, FmWs w,
+                                                          float *__restrict__ y_out) {
+  constexpr int LANES = RowCfg<D>::LANES;
+  constexpr int GROUPS = RowCfg<D>::GROUPS;
+  static_assert(RowCfg<D>::VPL == 1, "FM path supports d <= 128");
+  const int lane = threadIdx.x % 32, gl = lane % LANES, g = lane / LANES;
+  const int warp_in_block = threadIdx.x / 32;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  const int64_t n_warps = (int64_t)gridDim.x * blockDim.x / 32;
+  const float bias = t.bias[0];
+  float loss_local = 0.f, gz_local = 0.f;
+  for (int64_t s = warp_global; s < B; s += n_warps) {
+    float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sq = 0.f, first = 0.f;
+    for (int f = g; f < F; f += GROUPS) {
+      int64_t row = ids[s * F + f] + offsets[f];
+      if (row < 0 || row >= n_rows) {
+        w.hdr->range_error = 1;
+        row = min(max(row, (int64_t)0), n_rows - 1);
+      }
+      float4 v = __ldg(reinterpret_cast<const float4 *>(t.E + row * D) + gl);
+      S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
+      sq = fmaf(v.x, v.x, sq); sq = fmaf(v.y, v.y, sq); sq = fmaf(v.z, v.z, sq); sq = fmaf(v.w, v.w, sq);
+      if (gl == 0) first += __ldg(t.W + row);
+      if (TRAIN && gl == 0) {
+        int64_t o = s * F + f;
+        w.key[o] = (uint32_t)row;
+        w.val[o] = (uint32_t)o;
+      }
+    }
+    // across the lane groups of the warp: S (per lane-in-group), sq and first (everything)
+#pragma unroll
+    for (int o = LANES; o < 32; o <<= 1) {
+      S.x += __shfl_xor_sync(0xffffffffu, S.x, o);
+      S.y += __shfl_xor_sync(0xffffffffu, S.y, o);
+      S.z += __shfl_xor_sync(0xffffffffu, S.z, o);
+      S.w += __shfl_xor_sync(0xffffffffu, S.w, o);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      first += __shfl_xor_sync(0xffffffffu, first, o);
+    }
+    // sum_k S_k^2 over the d elements: every group holds the full S after the reduction above
+    float ss = S.x * S.x + S.y * S.y + S.z * S.z + S.w * S.w;
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float z = first + bias + 0.5f * (ss - sq);      // fm.py:49, layers.py:164-171,1061
+    const float y = 1.f / (1.f + expf(-z));
+    if (y_out && lane == 0) y_out[s] = y;
+    if (TRAIN) {
+      const float lab = label[s];
+      // nn.BCELoss: log terms clamped at -100; backward divides by max(y(1-y), 1e-12)
+      const float ly = fmaxf(logf(y), -100.f), l1y = fmaxf(logf(1.f - y), -100.f);
+      const float yy = y * (1.f - y);
+      const float gz = inv_b * (y - lab) * (yy / fmaxf(yy, 1e-12f));
+      if (lane == 0) {
+        loss_local += -(lab * ly + (1.f - lab) * l1y);
+        gz_local += gz;
+        w.gz[s] = gz;
+      }
+      if (g == 0) reinterpret_cast<float4 *>(w.gs + s * D)[gl] = make_float4(gz * S.x, gz * S.y, gz * S.z, gz * S.w);
+    }
+  }
+  if (TRAIN && lane == 0 && warp_global < w.n_parts) {
+    w.loss_part[warp_global] = (double)loss_local;
+    w.gz_part[warp_global] = (double)gz_local;
+  }
+  (void)warp_in_block;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ void fm_row_step(const FmTables &t, int64_t row, int lane, const Row<D> &gsum, float zsum,
+                                            const OptScalars &o) {
+  // dE = sum gs - zsum * v ;  dW = zsum
+  Row<D> p = row_ld<D>(t.E, row, lane);
+  Row<D> g = gsum;
+  row_fma<D>(g, -zsum, p);
+  row_update<D>(t.E, t.mE, t.vE, row, lane, p, g, o);
+  if (lane == 0) {
+    float pw = t.W[row];
+    if (o.kind == RB2_OPT_SGD) {
+      sgd_elem(pw, zsum, o);
+    } else {
+      float m = t.mW[row], v = t.vW[row];
+      adam_elem(pw, m, v, zsum, o);
+      t.mW[row] = m;
+      t.vW[row] = v;
+    }
+    t.W[row] = pw;
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_fm_rows(FmTables t, FmWs w, int64_t n_occ, int F, int T,
+                                                       int64_t n_tiles, OptScalars o) {
+  constexpr int LANES = RowCfg<D>::LANES;
+  constexpr int UNR = 4;
+  const int lane = threadIdx.x % LANES;
+  const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  if (tile >= n_tiles) return;
+  const int64_t lo = tile * T, hi = min(lo + (int64_t)T, n_occ);
+  const uint32_t *__restrict__ keys = w.key_s;
+  const uint32_t *__restrict__ vals = w.val_s;
+  const uint32_t kInvalid = 0xffffffffu;
+  const uint32_t prev_key = lo > 0 ? keys[lo - 1] : kInvalid;
+  uint32_t cur = kInvalid;
+  bool started_before = false;
+  Row<D> acc = row_zero<D>();
+  float zacc = 0.f;
+  uint8_t fh = 0, ft = 0;
+
+  auto finish_run = [&](bool continues) {
+    if (cur == kInvalid) return;
+    if (!started_before && !continues) {
+      fm_row_step<D>(t, cur, lane, acc, zacc, o);
+    } else if (started_before) {
+      row_st<D>(w.head, tile, lane, acc);
+      if (lane == 0) w.head_z[tile] = zacc;
+      fh = continues ? 2 : 1;
+    } else {
+      row_st<D>(w.tail, tile, lane, acc);
+      if (lane == 0) w.tail_z[tile] = zacc;
+      ft = 1;
+    }
+  };
+
+  for (int64_t base = lo; base < hi; base += UNR) {
+    uint32_t k[UNR], s[UNR];
+    Row<D> c[UNR];
+    float z[UNR];
+#pragma unroll
+    for (int j = 0; j < UNR; ++j) {
+      int64_t p = base + j;
+      bool ok = p < hi;
+      k[j] = ok ? keys[p] : kInvalid;
+      s[j] = ok ? vals[p] / (uint32_t)F : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < UNR; ++j)
+      if (k[j] != kInvalid) {
+        c[j] = row_ld<D>(w.gs, s[j], lane);
+        z[j] = w.gz[s[j]];
+      }
+#pragma unroll
+    for (int j = 0; j < UNR; ++j) {
+      if (k[j] == kInvalid) break;
+      if (k[j] != cur) {
+        finish_run(false);
+        cur = k[j];
+        acc = row_zero<D>();
+        zacc = 0.f;
+        started_before = (base + j == lo) && (cur == prev_key);
+      }
+      row_add<D>(acc, c[j]);
+      zacc += z[j];
+    }
+  }
+  finish_run(hi < n_occ && keys[hi] == cur);
+  if (lane == 0) {
+    w.fh[tile] = fh;
+    w.ft[tile] = ft;
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_fm_fixup(FmTables t, FmWs w, int64_t n_occ, int T, int64_t n_tiles,
+                                                        OptScalars o) {
+  constexpr int LANES = RowCfg<D>::LANES;
+  const int lane = threadIdx.x % LANES;
+  const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  if (tile >= n_tiles || !w.ft[tile]) return;
+  int64_t last_pos = min((tile + 1) * (int64_t)T, n_occ) - 1;
+  uint32_t key = w.key_s[last_pos];
+  Row<D> acc = row_ld<D>(w.tail, tile, lane);
+  float zacc = w.tail_z[tile];
+  for (int64_t j = tile + 1; j < n_tiles; ++j) {
+    uint8_t f = w.fh[j];
+    if (!f) break;
+    row_add<D>(acc, row_ld<D>(w.head, j, lane));
+    zacc += w.head_z[j];
+    if (f != 2) break;
+  }
+  fm_row_step<D>(t, key, lane, acc, zacc, o);
+}
+
+// bias step + loss reduction (single block, fixed order)
+__global__ void k_fm_bias_loss(FmTables t, FmWs w, int64_t n_parts, double inv_b, OptScalars o, float *loss_out,
+                               double *loss_accum) {
+  __shared__ double sl[256], sg[256];
+  double l = 0.0, g = 0.0;
+  for (int64_t i = threadIdx.x; i < n_parts; i += blockDim.x) { l += w.loss_part[i]; g += w.gz_part[i]; }
+  sl[threadIdx.x] = l;
+  sg[threadIdx.x] = g;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) { sl[threadIdx.x] += sl[threadIdx.x + s]; sg[threadIdx.x] += sg[threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float loss = (float)(sl[0] * inv_b);
+    loss_out[0] = loss;
+    if (loss_accum) loss_accum[0] += (double)loss;
+    float b = t.bias[0], gb = (float)sg[0];
+    if (o.kind == RB2_OPT_SGD) {
+      sgd_elem(b, gb, o);
+    } else {
+      float m = t.bias[1], v = t.bias[2];
+      adam_elem(b, m, v, gb, o);
+      t.bias[1] = m;
+      t.bias[2] = v;
+    }
+    t.bias[0] = b;
+  }
+}
+
+__global__ void k_zero_parts(FmWs w) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < w.n_parts) { w.loss_part[i] = 0.0; w.gz_part[i] = 0.0; }
+}
+
+}  // namespace
+
+#define RB2_FM_DIM(dim, ...)                                                                  \
+  switch (dim) {                                                                              \
+    case 16: { constexpr int D_ = 16; __VA_ARGS__; } break;                                   \
+    case 32: { constexpr int D_ = 32; __VA_ARGS__; } break;                                   \
+    case 64: { constexpr int D_ = 64; __VA_ARGS__; } break;                                   \
+    case 128: { constexpr int D_ = 128; __VA_ARGS__; } break;                                 \
+    default:                                                                                  \
+      rb2_set_error("FM embedding dim %d not supported (16, 32, 64, 128)", (int)(dim));       \
+      return RB2_EINVAL;                                                                      \
+  }
+
+extern "C" size_t rb2_fm_workspace_bytes(int64_t batch, int32_t n_fields, int32_t dim) {
+  FmWs w;
+  return carve(w, nullptr, batch, n_fields, dim);
+}
+
+extern "C" int rb2_fm_train_step(float *E, float *mE, float *vE, float *W, float *mW, float *vW, float *bias3,
+                                 int64_t n_rows, int32_t dim, const int64_t *ids, const int64_t *offsets,
+                                 int32_t n_fields, const float *label, int64_t batch, const rb2_optim *h_opt,
+                                 float *loss_out, double *loss_accum, void *workspace, size_t workspace_bytes,
+                                 void *stream) {
+  RB2_REQUIRE(E && W && bias3 && ids && offsets && label && h_opt && loss_out && workspace, RB2_EINVAL,
+              "rb2_fm_train_step: null argument");
+  RB2_REQUIRE(batch > 0 && n_fields > 0 && batch * (int64_t)n_fields < ((int64_t)1 << 31), RB2_EINVAL,
+              "rb2_fm_train_step: batch*fields out of range");
+  RB2_REQUIRE(n_rows > 0 && n_rows < ((int64_t)1 << 32) - 1, RB2_EINVAL, "rb2_fm_train_step: table too large");
+  OptScalars o = rb2_opt_scalars(h_opt);
+  RB2_REQUIRE(o.kind == RB2_OPT_SGD || o.kind == RB2_OPT_ADAM, RB2_EINVAL,
+              "rb2_fm_train_step: optimizer kind %d not supported (sgd, adam)", o.kind);
+  if (o.kind != RB2_OPT_SGD) RB2_REQUIRE(mE && vE && mW && vW, RB2_EINVAL, "rb2_fm_train_step: Adam needs m and v");
+  FmWs w;
+  size_t need = carve(w, workspace, batch, n_fields, dim);
+  RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_fm_train_step: workspace %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  FmTables t{E, mE, vE, W, mW, vW, bias3};
+  const int64_t M = batch * n_fields;
+  k_zero_parts<<<(unsigned)((w.n_parts + 255) / 256), 256, 0, st>>>(w);
+  RB2_FM_DIM(dim, {
+    constexpr int LANES = RowCfg<D_>::LANES;
+    int64_t warps = std::min<int64_t>(batch, w.n_parts);
+    warps = std::min<int64_t>(warps, (int64_t)rb2_num_sms() * 64);
+    unsigned fblocks = (unsigned)((warps * 32 + kThreads - 1) / kThreads);
+    if ((int64_t)fblocks * (kThreads / 32) > w.n_parts) fblocks = (unsigned)std::max<int64_t>(1, w.n_parts / (kThreads / 32));
+    {
+      ProfScope prof(RB2_ST_FM_FWD, st, 2);
+      k_fm_forward<D_, true><<<fblocks, kThreads, 0, st>>>(t, ids, offsets, label, batch, n_fields, n_rows,
+                                                           1.f / (float)batch, w, nullptr);
+    }
+    size_t tmp = w.cub_bytes;
+    {
+      ProfScope prof(RB2_ST_SORT_ITEM, st, 2 + (rb2_bits_for(n_rows) + 7) / 8);
+      RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.key, w.key_s, w.val, w.val_s, (int)M, 0,
+                                               rb2_bits_for(n_rows), st));
+    }
+    const int T = rb2_pick_tile(M, LANES);
+    const int64_t nt = (M + T - 1) / T;
+    unsigned blocks = (unsigned)((nt * LANES + kThreads - 1) / kThreads);
+    {
+      ProfScope prof(RB2_ST_FM_UPDATE, st, 3);
+      k_fm_rows<D_><<<blocks, kThreads, 0, st>>>(t, w, M, n_fields, T, nt, o);
+      k_fm_fixup<D_><<<blocks, kThreads, 0, st>>>(t, w, M, T, nt, o);
+      k_fm_bias_loss<<<1, 256, 0, st>>>(t, w, w.n_parts, 1.0 / (double)batch, o, loss_out, loss_accum);
+    }
+  });
+  RB2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int rb2_fm_predict(const float *E, const float *W, const float *bias3, int64_t n_rows, int32_t dim,
+                              const int64_t *ids, const int64_t *offsets, int32_t n_fields, int64_t batch,
+                              float *y_out, void *workspace, size_t workspace_bytes, void *stream) {
+  RB2_REQUIRE(E && W && bias3 && ids && offsets && y_out && workspace, RB2_EINVAL, "rb2_fm_predict: null argument");
+  if (batch <= 0) return 0;
+  FmWs w;
+  size_t need = carve(w, workspace, batch, n_fields, dim);
+  RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_fm_predict: workspace %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  FmTables t{const_cast<float *>(E), nullptr, nullptr, const_cast<float *>(W), nullptr, nullptr,
+             const_cast<float *>(bias3)};
+  RB2_FM_DIM(dim, {
+    int64_t warps = std::min<int64_t>(batch, (int64_t)rb2_num_sms() * 64);
+    unsigned fblocks = (unsigned)((warps * 32 + kThreads - 1) / kThreads);
+    ProfScope prof(RB2_ST_FM_FWD, st);
+    k_fm_forward<D_, false><<<fblocks, kThreads, 0, st>>>(t, ids, offsets, nullptr, batch, n_fields, n_rows, 1.f, w,
+                                                          y_out);
+  });
+  RB2_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -169,6 +169,35 @@ def adam_lazy_flush(P, M, V, last, optim):
                                   _ptr(last, torch.int32), P.shape[0], P.shape[1], ctypes.byref(o), _stream()))
 
 
+def fm_workspace(batch, n_fields, dim, device):
+    return Workspace(lib.rb2_fm_workspace_bytes(int(batch), int(n_fields), int(dim)), device)
+
+
+def fm_train_step(E, W, bias3, state, ids, offsets, label, optim, loss_out, loss_accum, ws):
+    """One fused FM step (rb2_fm_train_step).  state: mE, vE, mW, vW for Adam."""
+    optim.step += 1
+    o = optim.c_struct(E.device)
+    f32 = torch.float32
+    check(lib.rb2_fm_train_step(_ptr(E, f32), _ptr(state.get("mE"), f32, True), _ptr(state.get("vE"), f32, True),
+                                _ptr(W, f32), _ptr(state.get("mW"), f32, True), _ptr(state.get("vW"), f32, True),
+                                _ptr(bias3, f32), E.shape[0], E.shape[1], _ptr(ids, torch.int64),
+                                _ptr(offsets, torch.int64), ids.shape[1], _ptr(label, f32), ids.shape[0],
+                                ctypes.byref(o), _ptr(loss_out, f32), _ptr(loss_accum, torch.float64, True), ws.ptr(),
+                                ws.nbytes, _stream()))
+
+
+def fm_predict(E, W, bias3, ids, offsets, ws=None):
+    B, F = ids.shape
+    if ws is None:
+        ws = fm_workspace(B, F, E.shape[1], E.device)
+    y = torch.empty(B, dtype=torch.float32, device=E.device)
+    f32 = torch.float32
+    check(lib.rb2_fm_predict(_ptr(E, f32), _ptr(W, f32), _ptr(bias3, f32), E.shape[0], E.shape[1],
+                             _ptr(ids, torch.int64), _ptr(offsets, torch.int64), F, B, _ptr(y), ws.ptr(), ws.nbytes,
+                             _stream()))
+    return y
+
+
 def gather_dot(U, V, user, item):
     out = torch.empty(user.numel(), dtype=torch.float32, device=U.device)
     check(lib.rb2_gather_dot(_ptr(U, torch.float32), _ptr(V, torch.float32), U.shape[0], V.shape[0], U.shape[1],

@@ -1,0 +1,119 @@
+"""GPU parity: fused FM training step / predict (through the C ABI) vs the reference goldens and the
+oracle.  Tolerance: loss and updated parameters within 1e-5 relative (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fm as ofm
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def test_fm_steps_vs_reference_golden(golden):
+    """recbole FM + BCELoss + torch.optim.Adam for 2 steps (tests/golden/make_golden.py:g_fm).  Every
+    row of the 70-row table occurs in both batches, so row-sparse Adam == the reference's dense Adam."""
+    from recbole_b200 import ops
+    from gpu_util import rel_err, t
+    g = golden("fm_steps.npz")
+    E = t(g["p0_token_embedding_table.embedding.weight"])
+    W = t(g["p0_first_order_linear.token_embedding_table.embedding.weight"].reshape(-1))
+    bias3 = torch.zeros(3, device=E.device)
+    bias3[0] = float(g["p0_first_order_linear.bias"][0])
+    off = t(g["offsets"].astype(np.int64))
+    st = dict(mE=torch.zeros_like(E), vE=torch.zeros_like(E), mW=torch.zeros_like(W), vW=torch.zeros_like(W))
+    opt = ops.Optim("adam", lr=1e-2)
+    loss = torch.zeros(1, device=E.device)
+    B, F = g["ids0"].shape
+    ws = ops.fm_workspace(B, F, E.shape[1], E.device)
+    touched_all = all(len(np.unique(g["ids%d" % s] + g["offsets"][None, :])) == E.shape[0] for s in range(2))
+    for s in range(2):
+        ids, lab = t(g["ids%d" % s].astype(np.int64)), t(g["label%d" % s])
+        y = ops.fm_predict(E, W, bias3, ids, off, ws).cpu().numpy()
+        assert rel_err(y, g["pred%d" % s]) < TOL
+        ops.fm_train_step(E, W, bias3, st, ids, off, lab, opt, loss, None, ws)
+        ref = float(g["loss%d" % s])
+        assert abs(loss.item() - ref) <= TOL * abs(ref)
+        if touched_all or s == 0:
+            assert rel_err(E.cpu().numpy(), g["p%d_token_embedding_table.embedding.weight" % (s + 1)]) < TOL
+            assert rel_err(W.cpu().numpy(),
+                           g["p%d_first_order_linear.token_embedding_table.embedding.weight" % (s + 1)].reshape(-1)) < TOL
+        assert abs(bias3[0].item() - float(g["p%d_first_order_linear.bias" % (s + 1)][0])) < 1e-6
+    ws.check_flags()
+
+
+@pytest.mark.parametrize("dim,F,B,kind", [(16, 26, 20000, "adam"), (16, 26, 20000, "sgd"), (64, 5, 3000, "adam"),
+                                         (128, 3, 777, "adam"), (32, 40, 512, "sgd")])
+def test_fm_random_vs_oracle(dim, F, B, kind):
+    """Criteo-like: skewed ids, fields with tiny vocabularies (runs of thousands of occurrences that
+    straddle tiles), 3 steps; oracle = row-sparse semantics."""
+    from recbole_b200 import ops
+    from gpu_util import rel_err, t
+    rng = np.random.default_rng(dim + F)
+    dims = rng.choice([3, 7, 30, 500, 5000, 40000], size=F)
+    off = np.concatenate([[0], np.cumsum(dims)[:-1]]).astype(np.int64)
+    rows = int(dims.sum())
+    E0 = (rng.standard_normal((rows, dim)) * 0.1).astype(np.float32)
+    W0 = (rng.standard_normal(rows) * 0.1).astype(np.float32)
+    so = ofm.new_state(E0, W0, 0.05)
+    E, W = t(E0), t(W0)
+    bias3 = torch.tensor([0.05, 0, 0], dtype=torch.float32, device=E.device)
+    st = dict(mE=torch.zeros_like(E), vE=torch.zeros_like(E), mW=torch.zeros_like(W), vW=torch.zeros_like(W)) \
+        if kind == "adam" else {}
+    lr = 2e-3 if kind == "adam" else 0.05
+    opt = ops.Optim(kind, lr=lr)
+    loss = torch.zeros(1, device=E.device)
+    ws = ops.fm_workspace(B, F, dim, E.device)
+    for s in range(3):
+        ids = np.stack([np.minimum((np.exp(rng.random(B) * np.log(d))).astype(np.int64), d - 1) for d in dims], axis=1)
+        lab = (rng.random(B) < 0.25).astype(np.float32)
+        ops.fm_train_step(E, W, bias3, st, t(ids), t(off), t(lab), opt, loss, None, ws)
+        if kind == "adam":
+            lo = ofm.fm_train_step(so, ids + off[None, :], lab, s + 1, dense=False, lr=lr)
+        else:
+            lo, dE, dW, db, _ = ofm.fm_grads(so["E"], so["W"], so["b"][0], ids + off[None, :], lab)
+            so["E"] -= np.float32(lr) * dE
+            so["W"] -= np.float32(lr) * dW
+            so["b"][0] -= np.float32(lr) * db
+        assert abs(loss.item() - lo) <= TOL * abs(lo)
+    ws.check_flags()
+    assert rel_err(E.cpu().numpy(), so["E"]) < TOL
+    assert rel_err(W.cpu().numpy(), so["W"]) < 2e-5
+    assert abs(bias3[0].item() - so["b"][0]) < 2e-6
+
+
+def test_fused_fm_model_mirror(golden):
+    """FusedFM behind the reference's ContextRecommender surface, fed Interaction-style dicts."""
+    from recbole_b200 import FusedFM
+    from gpu_util import rel_err, t
+    g = golden("fm_steps.npz")
+
+    class Cfg(dict):
+        def __getitem__(self, k):
+            return self.get(k)
+
+    names = ["f%d" % i for i in range(len(g["field_dims"]))]
+
+    class DS:
+        field2type = {**{n: "token" for n in names}, "label": "float"}
+
+        def fields(self):
+            return names + ["label"]
+
+        def num(self, f):
+            return int(g["field_dims"][names.index(f)])
+
+    m = FusedFM(Cfg(LABEL_FIELD="label", embedding_size=16, device="cuda"), DS()).to("cuda")
+    assert sorted(m.state_dict()) == ["first_order_linear.bias",
+                                      "first_order_linear.token_embedding_table.embedding.weight",
+                                      "token_embedding_table.embedding.weight"]
+    m.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("p0_")})
+    m.build_optimizer("adam", 1e-2)
+    inter = {n: t(g["ids0"][:, i].astype(np.int64)) for i, n in enumerate(names)}
+    inter["label"] = t(g["label0"])
+    assert rel_err(m.predict(inter).cpu().numpy(), g["pred0"]) < TOL
+    loss = m.train_step(inter)
+    assert abs(loss.item() - float(g["loss0"])) <= TOL * abs(float(g["loss0"]))
+    assert rel_err(m.state_dict()["token_embedding_table.embedding.weight"].cpu().numpy(),
+                   g["p1_token_embedding_table.embedding.weight"]) < TOL
+    assert abs(m.first_order_linear.bias.item() - float(g["p1_first_order_linear.bias"][0])) < 1e-6
