@@ -211,6 +211,21 @@ int rb2_fullsort_topk(const float *query_p, const int64_t *query_ids, int64_t nq
                       int64_t *out_ids, float *out_scores,
                       void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (2c) Full-sort cross-entropy head (SASRec-style, loss_type='CE').  Replaces
+ *   logits = seq_output @ item_emb.weight.T ; nn.CrossEntropyLoss()(logits, pos)
+ * (recbole/model/sequential_recommender/sasrec.py:137-141) and, in the same pass, full_sort_predict +
+ * pad mask + top-k (sasrec.py:152-158, trainer.py:343, evaluators.py:68-72): the [nq, n_items] logits
+ * (16.4 GB at 4096 x 1M) are never written.  The logsumexp runs online over EVERY item incl. the
+ * padding row 0 (it is a class of the CE), the top-k excludes id 0.  Scores are the canonical fp32
+ * chain.  loss_out[0] = mean_r(lse[r] - logit[r, target[r]]) (target == NULL: no loss);
+ * lse_out [nq] optional.
+ * ---------------------------------------------------------------------------------------- */
+size_t rb2_ce_head_workspace_bytes(int64_t nq, int64_t n_items, int32_t dim, int32_t k);
+int rb2_ce_head(const float *x, int64_t nq, const float *item_p, int64_t n_items, int32_t dim,
+                const int64_t *target, int32_t k, float *loss_out, float *lse_out, int64_t *topk_ids,
+                float *topk_scores, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Diagnostic: how many rows of the last RB2_SCORER_TC call failed the certificate and were redone by
  * the fp32 kernel (or nq if the shape is not covered by the MMA tiling: dim not in {64,128}, k > 16). */
 int32_t rb2_fullsort_tc_last_fallback_rows(void);

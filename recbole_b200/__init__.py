@@ -8,7 +8,7 @@ from .data import EvalIndex  # noqa: F401
 from .evaluator import FusedTopKEvaluator  # noqa: F401
 from .interaction import Interaction  # noqa: F401
 from .model import FusedBPR, FusedOptimizer  # noqa: F401
-from .model_fm import FusedFM  # noqa: F401
+from .model_fm import FusedFM, FusedMFSimple  # noqa: F401
 from .sampler import DeviceSampler  # noqa: F401
 from .trainer import FusedTrainer  # noqa: F401
 

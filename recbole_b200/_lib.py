@@ -61,6 +61,8 @@ SIGNATURES = {
     "rb2_fullsort_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32, _i32]),
     "rb2_fullsort_topk": (ctypes.c_int, [_p, _p, _i64, _p, _i64, _i64, _i32, _p, _p, _i32, _i32, _p, _p, _p, _sz,
                                          _p]),
+    "rb2_ce_head_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
+    "rb2_ce_head": (ctypes.c_int, [_p, _i64, _p, _i64, _i32, _p, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "rb2_fullsort_tc_last_fallback_rows": (_i32, []),
     "rb2_fullsort_tc_set_kprime": (ctypes.c_int, [_i32]),
     "rb2_topk_merge": (ctypes.c_int, [_p, _p, _i32, _i64, _i32, _p, _p, _p]),

@@ -79,7 +79,7 @@ struct FsCfg {
   static constexpr int TILE_FLOATS = TI * D;
 };
 
-template <int D>
+template <int D, bool LSE>
 __global__ void __launch_bounds__(kRows) k_fullsort_fp32(const float *__restrict__ query_p,
                                                           const int64_t *__restrict__ query_ids, int64_t nq,
                                                           const float *__restrict__ item_p, int64_t n_local,
@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(kRows) k_fullsort_fp32(const float *__restrict
                                                           const int64_t *__restrict__ hist_indices, int K,
                                                           int64_t items_per_split, int64_t *__restrict__ out_ids,
                                                           float *__restrict__ out_scores,
-                                                          const int32_t *__restrict__ row_map, int scatter_out) {
+                                                          const int32_t *__restrict__ row_map, int scatter_out,
+                                                          float *__restrict__ lse_m, float *__restrict__ lse_s) {
   constexpr int TI = FsCfg<D>::TI;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float *tile0 = reinterpret_cast<float *>(smem_raw);
@@ -128,6 +129,13 @@ __global__ void __launch_bounds__(kRows) k_fullsort_fp32(const float *__restrict
     lid[j * kRows + tid] = -1;
   }
   float tau = -INFINITY;
+  // online logsumexp over EVERY item of the range, pad row included (nn.CrossEntropyLoss over n_items
+  // classes, sasrec.py:139-140): run_m = running max, run_s = sum exp(s - run_m)
+  float run_m = -INFINITY, run_s = 0.f;
+  auto lse_add = [&](float sc) {
+    if (sc > run_m) { run_s = run_s * __expf(run_m - sc) + 1.f; run_m = sc; }
+    else run_s += __expf(sc - run_m);
+  };
   float *my_sc = lsc + tid;
   int *my_id = lid + tid;
 
@@ -174,6 +182,7 @@ __global__ void __launch_bounds__(kRows) k_fullsort_fp32(const float *__restrict
           s2 = fmaf(q[4 * k + 3], c.w, s2); s3 = fmaf(q[4 * k + 3], d.w, s3);
         }
         const int64_t g = item_base + i0 + i;
+        if (LSE) { lse_add(s0); lse_add(s1); lse_add(s2); lse_add(s3); }
         if (s0 > tau) topk_insert(my_sc, my_id, K, s0, g + 0, hist, hlen, tau);
         if (s1 > tau) topk_insert(my_sc, my_id, K, s1, g + 1, hist, hlen, tau);
         if (s2 > tau) topk_insert(my_sc, my_id, K, s2, g + 2, hist, hlen, tau);
@@ -190,6 +199,7 @@ __global__ void __launch_bounds__(kRows) k_fullsort_fp32(const float *__restrict
           s = fmaf(q[4 * k + 2], a.z, s);
           s = fmaf(q[4 * k + 3], a.w, s);
         }
+        if (LSE) lse_add(s);
         if (s > tau) topk_insert(my_sc, my_id, K, s, item_base + i0 + i, hist, hlen, tau);
       }
     }
@@ -202,7 +212,46 @@ __global__ void __launch_bounds__(kRows) k_fullsort_fp32(const float *__restrict
       out_ids[o + j] = (int64_t)my_id[j * kRows];
       out_scores[o + j] = my_sc[j * kRows];
     }
+    if (LSE) {
+      lse_m[(int64_t)blockIdx.y * nq + rc] = run_m;
+      lse_s[(int64_t)blockIdx.y * nq + rc] = run_s;
+    }
   }
+}
+
+// CE head: merge the per-split (max, sum) pairs, subtract the target logit (canonical chain), and
+// leave per-row loss terms for the fixed-order mean
+template <int D>
+__global__ void k_ce_finish(const float *__restrict__ x, const float *__restrict__ item_p, int64_t nq, int64_t n_items,
+                            const int64_t *__restrict__ target, const float *__restrict__ lse_m,
+                            const float *__restrict__ lse_s, int parts, float *__restrict__ lse_out,
+                            float *__restrict__ row_loss) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nq) return;
+  float m = -INFINITY;
+  for (int p = 0; p < parts; ++p) m = fmaxf(m, lse_m[(int64_t)p * nq + r]);
+  float ssum = 0.f;
+  for (int p = 0; p < parts; ++p) ssum += lse_s[(int64_t)p * nq + r] * expf(lse_m[(int64_t)p * nq + r] - m);
+  float lse = m + logf(ssum);
+  if (lse_out) lse_out[r] = lse;
+  int64_t t = target ? min(max(target[r], (int64_t)0), n_items - 1) : 0;
+  const float *q = x + r * D, *v = item_p + t * D;
+  float sc = 0.f;
+  for (int k = 0; k < D; ++k) sc = fmaf(q[k], v[k], sc);
+  row_loss[r] = target ? lse - sc : 0.f;
+}
+
+__global__ void k_mean(const float *__restrict__ v, int64_t n, float *out) {
+  __shared__ double sm[256];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += (double)v[i];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)(sm[0] / (double)n);
 }
 
 // merge `parts` sorted lists per row; order (score desc, id asc); id -1 = empty slot
@@ -374,6 +423,11 @@ FsPlan plan_any(int dim, int64_t nq, int64_t n_local, int K) {
 }  // namespace
 
 size_t rb2_fullsort_fp32_workspace(int64_t nq, int64_t n_items_local, int32_t dim, int32_t k);
+int rb2_fullsort_fp32_lse(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p,
+                          int64_t n_items_local, int64_t item_base, int32_t dim, const int64_t *hist_indptr,
+                          const int64_t *hist_indices, int32_t k, int64_t *out_ids, float *out_scores,
+                          void *workspace, size_t workspace_bytes, cudaStream_t st, const int32_t *row_map,
+                          float *lse_m, float *lse_s, int *parts_out);
 // implemented in fullsort_tc.cu
 size_t rb2_fullsort_tc_workspace_bytes(int64_t nq, int64_t n_items_local, int32_t dim, int32_t k);
 int rb2_fullsort_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p,
@@ -403,7 +457,20 @@ int rb2_fullsort_fp32(const float *query_p, const int64_t *query_ids, int64_t nq
                       int64_t n_items_local, int64_t item_base, int32_t dim, const int64_t *hist_indptr,
                       const int64_t *hist_indices, int32_t k, int64_t *out_ids, float *out_scores, void *workspace,
                       size_t workspace_bytes, cudaStream_t st, const int32_t *row_map) {
+  return rb2_fullsort_fp32_lse(query_p, query_ids, nq, item_p, n_items_local, item_base, dim, hist_indptr,
+                               hist_indices, k, out_ids, out_scores, workspace, workspace_bytes, st, row_map, nullptr,
+                               nullptr, nullptr);
+}
+
+// same, optionally with the per-split logsumexp partials (lse_m / lse_s sized [64, nq]); *parts_out =
+// number of splits used
+int rb2_fullsort_fp32_lse(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p,
+                          int64_t n_items_local, int64_t item_base, int32_t dim, const int64_t *hist_indptr,
+                          const int64_t *hist_indices, int32_t k, int64_t *out_ids, float *out_scores,
+                          void *workspace, size_t workspace_bytes, cudaStream_t st, const int32_t *row_map,
+                          float *lse_m, float *lse_s, int *parts_out) {
   FsPlan p = plan_any(dim, nq, n_items_local, k);
+  if (parts_out) *parts_out = p.n_split;
   RB2_REQUIRE(p.n_split > 0, RB2_EINVAL, "rb2_fullsort_topk: embedding dim %d not supported by the fp32 scorer (16, 32, 64, 128)",
               (int)dim);
   RB2_REQUIRE(p.smem <= 200 * 1024, RB2_EINVAL, "rb2_fullsort_topk: k=%d too large", (int)k);
@@ -416,11 +483,21 @@ int rb2_fullsort_fp32(const float *query_p, const int64_t *query_ids, int64_t nq
   dim3 grid((unsigned)((nq + kRows - 1) / kRows), (unsigned)p.n_split);
 #define RB2_FS(D_)                                                                                              \
   {                                                                                                             \
-    RB2_CUDA(cudaFuncSetAttribute(k_fullsort_fp32<D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem)); \
-    k_fullsort_fp32<D_><<<grid, kRows, p.smem, st>>>(query_p, query_ids, nq, item_p, n_items_local, item_base,  \
-                                                     hist_indptr, hist_indices, k, p.items_per_split,           \
-                                                     direct ? out_ids : part_ids, direct ? out_scores : part_sc, \
-                                                     row_map, direct ? 1 : 0);                                  \
+    if (lse_m) {                                                                                                 \
+      RB2_CUDA(cudaFuncSetAttribute(k_fullsort_fp32<D_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                    (int)p.smem));                                                              \
+      k_fullsort_fp32<D_, true><<<grid, kRows, p.smem, st>>>(                                                   \
+          query_p, query_ids, nq, item_p, n_items_local, item_base, hist_indptr, hist_indices, k,               \
+          p.items_per_split, direct ? out_ids : part_ids, direct ? out_scores : part_sc, row_map, direct ? 1 : 0, \
+          lse_m, lse_s);                                                                                        \
+    } else {                                                                                                    \
+      RB2_CUDA(cudaFuncSetAttribute(k_fullsort_fp32<D_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                    (int)p.smem));                                                              \
+      k_fullsort_fp32<D_, false><<<grid, kRows, p.smem, st>>>(                                                  \
+          query_p, query_ids, nq, item_p, n_items_local, item_base, hist_indptr, hist_indices, k,               \
+          p.items_per_split, direct ? out_ids : part_ids, direct ? out_scores : part_sc, row_map, direct ? 1 : 0, \
+          nullptr, nullptr);                                                                                    \
+    }                                                                                                           \
   }
   {
     ProfScope prof(RB2_ST_FULLSORT, st);
@@ -501,6 +578,49 @@ extern "C" int rb2_topk_metrics(const int64_t *topk_ids, int64_t nq, int32_t k, 
                                                                 discount, idcg, part, hit, ref_idx);
   int n = RB2_NUM_METRICS * k;
   k_metrics_reduce<<<(n + 127) / 128, 128, 0, st>>>(part, blocks, n, sums);
+  RB2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CE head: logits = X . E^T never materialised; loss = mean(logsumexp - logit[target]); top-K of the
+// same pass with the pad column masked.
+extern "C" size_t rb2_ce_head_workspace_bytes(int64_t nq, int64_t n_items, int32_t dim, int32_t k) {
+  Carver c(nullptr);
+  c.take<float>((size_t)64 * nq);
+  c.take<float>((size_t)64 * nq);
+  c.take<float>(nq);
+  return c.off + rb2_fullsort_fp32_workspace(nq, n_items, dim, k) + 256;
+}
+
+extern "C" int rb2_ce_head(const float *x, int64_t nq, const float *item_p, int64_t n_items, int32_t dim,
+                           const int64_t *target, int32_t k, float *loss_out, float *lse_out, int64_t *topk_ids,
+                           float *topk_scores, void *workspace, size_t workspace_bytes, void *stream) {
+  RB2_REQUIRE(x && item_p && topk_ids && topk_scores && workspace, RB2_EINVAL, "rb2_ce_head: null argument");
+  RB2_REQUIRE(k >= 1 && k <= 128, RB2_EINVAL, "rb2_ce_head: k=%d outside 1..128", (int)k);
+  RB2_REQUIRE(!target || loss_out, RB2_EINVAL, "rb2_ce_head: target given without loss_out");
+  if (nq <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver c(workspace);
+  float *lse_m = c.take<float>((size_t)64 * nq);
+  float *lse_s = c.take<float>((size_t)64 * nq);
+  float *row_loss = c.take<float>(nq);
+  size_t fs_bytes = rb2_fullsort_fp32_workspace(nq, n_items, dim, k);
+  void *fs_ws = c.take<char>(fs_bytes);
+  RB2_REQUIRE(c.off <= workspace_bytes, RB2_EWORKSPACE, "rb2_ce_head: workspace %zu < %zu", workspace_bytes, c.off);
+  int parts = 0;
+  int rc = rb2_fullsort_fp32_lse(x, nullptr, nq, item_p, n_items, 0, dim, nullptr, nullptr, k, topk_ids, topk_scores,
+                                 fs_ws, fs_bytes, st, nullptr, lse_m, lse_s, &parts);
+  if (rc) return rc;
+  ProfScope prof(RB2_ST_MISC, st, 2);
+  unsigned blocks = (unsigned)((nq + 127) / 128);
+  switch (dim) {
+    case 16: k_ce_finish<16><<<blocks, 128, 0, st>>>(x, item_p, nq, n_items, target, lse_m, lse_s, parts, lse_out, row_loss); break;
+    case 32: k_ce_finish<32><<<blocks, 128, 0, st>>>(x, item_p, nq, n_items, target, lse_m, lse_s, parts, lse_out, row_loss); break;
+    case 64: k_ce_finish<64><<<blocks, 128, 0, st>>>(x, item_p, nq, n_items, target, lse_m, lse_s, parts, lse_out, row_loss); break;
+    case 128: k_ce_finish<128><<<blocks, 128, 0, st>>>(x, item_p, nq, n_items, target, lse_m, lse_s, parts, lse_out, row_loss); break;
+  }
+  if (loss_out) k_mean<<<1, 256, 0, st>>>(row_loss, nq, loss_out);
   RB2_CUDA(cudaGetLastError());
   return 0;
 }

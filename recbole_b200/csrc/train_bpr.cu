@@ -306,11 +306,29 @@ __global__ void __launch_bounds__(kThreads) k_fixup(float *P, float *M, float *V
   int64_t last_pos = min((tile + 1) * (int64_t)T, n_occ) - 1;
   uint32_t key = keys_sorted[last_pos];
   Row<D> acc = row_ld<D>(tail, tile, lane);
-  for (int64_t j = tile + 1; j < n_tiles; ++j) {
-    uint8_t f = fh[j];
-    if (!f) break;  // cannot happen for a well-formed sort; defensive
-    row_add<D>(acc, row_ld<D>(head, j, lane));
-    if (f != 2) break;
+  // the chain of continuation partials can be thousands of tiles long for a hot row: walk it CH tiles
+  // at a time with all loads in flight (still a fixed summation order)
+  constexpr int CH = 8;
+  bool done = false;
+  for (int64_t j0 = tile + 1; j0 < n_tiles && !done; j0 += CH) {
+    uint8_t f[CH];
+    Row<D> part[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) f[c] = (j0 + c < n_tiles) ? fh[j0 + c] : (uint8_t)0;
+    int cnt = 0;  // partials of this chunk that belong to the chain
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      if (!done) {
+        if (f[c]) ++cnt;
+        if (f[c] != 2) done = true;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+      if (c < cnt) part[c] = row_ld<D>(head, j0 + c, lane);
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+      if (c < cnt) row_add<D>(acc, part[c]);
   }
   if (grad_out) {
     row_st<D>(grad_out, key, lane, acc);

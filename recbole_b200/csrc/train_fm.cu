@@ -95,24 +95,41 @@ __global__ void __launch_bounds__(kThreads) k_fm_forward(FmTables t, const int64
   float loss_local = 0.f, gz_local = 0.f;
   for (int64_t s = warp_global; s < B; s += n_warps) {
     float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
-    float sq = 0.f, first = 0.f;
-    for (int f = g; f < F; f += GROUPS) {
+    float sq = 0.f, first = 0.f, cross = 0.f;
+    auto fetch = [&](int f, float4 &v) {
       int64_t row = ids[s * F + f] + offsets[f];
       if (row < 0 || row >= n_rows) {
         w.hdr->range_error = 1;
         row = min(max(row, (int64_t)0), n_rows - 1);
       }
-      float4 v = __ldg(reinterpret_cast<const float4 *>(t.E + row * D) + gl);
-      S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
-      sq = fmaf(v.x, v.x, sq); sq = fmaf(v.y, v.y, sq); sq = fmaf(v.z, v.z, sq); sq = fmaf(v.w, v.w, sq);
+      v = __ldg(reinterpret_cast<const float4 *>(t.E + row * D) + gl);
       if (gl == 0) first += __ldg(t.W + row);
       if (TRAIN && gl == 0) {
         int64_t o = s * F + f;
         w.key[o] = (uint32_t)row;
         w.val[o] = (uint32_t)o;
       }
+    };
+    if (F == 2) {
+      // two fields = the point-wise "dot" model (fork's MFSimple, mfsimple.py:39-46:
+      // sigmoid(<u,v> + b_u + b_i + b)): take the product directly instead of the
+      // 0.5*[(u+v)^2 - u^2 - v^2] identity, which cancels badly in fp32
+      if (g == 0) {
+        float4 a, b;
+        fetch(0, a);
+        fetch(1, b);
+        S = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        cross = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+      }
+    } else {
+      for (int f = g; f < F; f += GROUPS) {
+        float4 v;
+        fetch(f, v);
+        S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
+        sq = fmaf(v.x, v.x, sq); sq = fmaf(v.y, v.y, sq); sq = fmaf(v.z, v.z, sq); sq = fmaf(v.w, v.w, sq);
+      }
     }
-    // across the lane groups of the warp: S (per lane-in-group), sq and first (everything)
+    // across the lane groups of the warp: S (per lane-in-group), sq / cross / first (everything)
 #pragma unroll
     for (int o = LANES; o < 32; o <<= 1) {
       S.x += __shfl_xor_sync(0xffffffffu, S.x, o);
@@ -123,13 +140,20 @@ __global__ void __launch_bounds__(kThreads) k_fm_forward(FmTables t, const int64
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      cross += __shfl_xor_sync(0xffffffffu, cross, o);
       first += __shfl_xor_sync(0xffffffffu, first, o);
     }
-    // sum_k S_k^2 over the d elements: every group holds the full S after the reduction above
-    float ss = S.x * S.x + S.y * S.y + S.z * S.z + S.w * S.w;
+    float second;
+    if (F == 2) {
+      second = cross;
+    } else {
+      // sum_k S_k^2 over the d elements: every group holds the full S after the reduction above
+      float ss = S.x * S.x + S.y * S.y + S.z * S.z + S.w * S.w;
 #pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float z = first + bias + 0.5f * (ss - sq);      // fm.py:49, layers.py:164-171,1061
+      for (int o = LANES / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      second = 0.5f * (ss - sq);                          // layers.py:164-171
+    }
+    const float z = first + bias + second;                // fm.py:49, layers.py:1061
     const float y = 1.f / (1.f + expf(-z));
     if (y_out && lane == 0) y_out[s] = y;
     if (TRAIN) {
@@ -259,12 +283,30 @@ __global__ void __launch_bounds__(kThreads) k_fm_fixup(FmTables t, FmWs w, int64
   uint32_t key = w.key_s[last_pos];
   Row<D> acc = row_ld<D>(w.tail, tile, lane);
   float zacc = w.tail_z[tile];
-  for (int64_t j = tile + 1; j < n_tiles; ++j) {
-    uint8_t f = w.fh[j];
-    if (!f) break;
-    row_add<D>(acc, row_ld<D>(w.head, j, lane));
-    zacc += w.head_z[j];
-    if (f != 2) break;
+  // hot rows (a field with a handful of values) have chains of thousands of partials: walk them CH at
+  // a time with all loads in flight (fixed summation order)
+  constexpr int CH = 16;
+  bool done = false;
+  for (int64_t j0 = tile + 1; j0 < n_tiles && !done; j0 += CH) {
+    uint8_t f[CH];
+    Row<D> part[CH];
+    float pz[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) f[c] = (j0 + c < n_tiles) ? w.fh[j0 + c] : (uint8_t)0;
+    int cnt = 0;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      if (!done) {
+        if (f[c]) ++cnt;
+        if (f[c] != 2) done = true;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+      if (c < cnt) { part[c] = row_ld<D>(w.head, j0 + c, lane); pz[c] = w.head_z[j0 + c]; }
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+      if (c < cnt) { row_add<D>(acc, part[c]); zacc += pz[c]; }
   }
   fm_row_step<D>(t, key, lane, acc, zacc, o);
 }

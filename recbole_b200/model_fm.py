@@ -124,3 +124,89 @@ class FusedFM(nn.Module):
     def calculate_loss(self, interaction):  # fm.py:52-56 (forward only; training goes through train_step)
         y = self.predict(interaction)
         return nn.functional.binary_cross_entropy(y, interaction[self.LABEL])
+
+
+class FusedMFSimple(nn.Module):
+    """The fork's point-wise "dot" model (recbole/model/general_recommender/mfsimple.py:8-62):
+    ``sigmoid(<u, v> + b_u + b_i + b)`` with ``nn.BCELoss``.  It is exactly a two-field FM
+    (field 0 = user id, field 1 = item id: 0.5[(u+v)^2 - u^2 - v^2] = <u, v>, first-order terms = the
+    biases), so it runs on the fused FM kernels with the two tables stored back to back; the state
+    dict keeps the reference's names (user_embedding.weight, item_embedding.weight, user_bias,
+    item_bias, bias)."""
+    input_type = "pointwise"
+    type = "general"
+
+    def __init__(self, config, dataset):
+        super().__init__()
+        self.USER_ID, self.ITEM_ID = config["USER_ID_FIELD"], config["ITEM_ID_FIELD"]
+        self.LABEL = config["LABEL_FIELD"]
+        self.n_users, self.n_items = dataset.num(self.USER_ID), dataset.num(self.ITEM_ID)
+        self.embedding_dim = config["embedding_dimension"]
+        self.device = config["device"]
+        rows = self.n_users + self.n_items
+        self.table = nn.Parameter(torch.empty(rows, self.embedding_dim).normal_(0.0, 0.01))   # mfsimple.py:35-37
+        self.biases = nn.Parameter(torch.zeros(rows))
+        self.bias = nn.Parameter(torch.zeros(1))
+        self._optim, self._state, self._ws = None, {}, {}
+        self._offsets = self._bias3 = self._loss_out = self._loss_accum = None
+
+    # reference-compatible state dict -------------------------------------------------------------------
+    def state_dict(self, *a, **k):
+        nu = self.n_users
+        return {"user_embedding.weight": self.table.data[:nu], "item_embedding.weight": self.table.data[nu:],
+                "user_bias": self.biases.data[:nu], "item_bias": self.biases.data[nu:], "bias": self.bias.data}
+
+    def load_state_dict(self, sd, strict=True):
+        nu = self.n_users
+        with torch.no_grad():
+            self.table[:nu].copy_(sd["user_embedding.weight"])
+            self.table[nu:].copy_(sd["item_embedding.weight"])
+            self.biases[:nu].copy_(sd["user_bias"])
+            self.biases[nu:].copy_(sd["item_bias"])
+            self.bias.copy_(sd["bias"])
+
+    def _prep(self):
+        dev = self.table.device
+        if self._offsets is None or self._offsets.device != dev:
+            self._offsets = torch.tensor([0, self.n_users], dtype=torch.int64, device=dev)
+            self._bias3 = torch.zeros(3, dtype=torch.float32, device=dev)
+            self._loss_out = torch.zeros(1, dtype=torch.float32, device=dev)
+            self._loss_accum = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._bias3[0:1].copy_(self.bias.data)
+
+    def _workspace(self, batch):
+        key = int(batch)
+        if key not in self._ws:
+            self._ws = {key: ops.fm_workspace(batch, 2, self.embedding_dim, self.table.device)}
+        return self._ws[key]
+
+    def build_optimizer(self, learner="adam", learning_rate=1e-3, weight_decay=0.0):
+        self._optim = ops.Optim(learner.lower(), learning_rate, weight_decay)
+        self._state = {}
+        if learner.lower() == "adam":
+            z = torch.zeros_like
+            self._state = dict(mE=z(self.table.data), vE=z(self.table.data), mW=z(self.biases.data),
+                               vW=z(self.biases.data))
+        self._prep()
+        return self
+
+    def _ids(self, interaction):
+        return torch.stack([interaction[self.USER_ID], interaction[self.ITEM_ID]], dim=1).contiguous()
+
+    def train_step(self, interaction):
+        self._prep()
+        ids = self._ids(interaction)
+        ops.fm_train_step(self.table.data, self.biases.data, self._bias3, self._state, ids, self._offsets,
+                          interaction[self.LABEL].contiguous(), self._optim, self._loss_out, self._loss_accum,
+                          self._workspace(ids.shape[0]))
+        self.bias.data.copy_(self._bias3[0:1])
+        return self._loss_out
+
+    def predict(self, interaction):  # mfsimple.py:59-62
+        self._prep()
+        ids = self._ids(interaction)
+        return ops.fm_predict(self.table.data, self.biases.data, self._bias3, ids, self._offsets,
+                              self._workspace(ids.shape[0]))
+
+    def calculate_loss(self, interaction):  # mfsimple.py:48-57 (forward only)
+        return nn.functional.binary_cross_entropy(self.predict(interaction), interaction[self.LABEL])

@@ -227,6 +227,20 @@ def fullsort_topk(Q, query_ids, V, k, hist_indptr=None, hist_indices=None, item_
     return ids, sc
 
 
+def ce_head(X, E, target, k=10):
+    """Fused full-sort CE head (rb2_ce_head): returns dict(loss 0-dim, lse [nq], ids [nq,k], scores [nq,k])."""
+    nq, dev = X.shape[0], X.device
+    ws = Workspace(lib.rb2_ce_head_workspace_bytes(nq, E.shape[0], E.shape[1], int(k)), dev)
+    loss = torch.zeros(1, dtype=torch.float32, device=dev)
+    lse = torch.empty(nq, dtype=torch.float32, device=dev)
+    ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    check(lib.rb2_ce_head(_ptr(X, torch.float32), nq, _ptr(E, torch.float32), E.shape[0], E.shape[1],
+                          _ptr(target, torch.int64, True), int(k), _ptr(loss), _ptr(lse), _ptr(ids), _ptr(sc),
+                          ws.ptr(), ws.nbytes, _stream()))
+    return dict(loss=loss[0], lse=lse, ids=ids, scores=sc)
+
+
 def topk_merge(ids, scores):
     """[parts, nq, k] sorted lists -> global [nq, k]."""
     parts, nq, k = ids.shape

@@ -1,0 +1,51 @@
+"""GPU parity: fused full-sort CE head (logits never materialised) vs the reference golden
+(sasrec.py:137-141,152-158 expressions) and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ce_head as oce
+
+pytestmark = pytest.mark.gpu
+
+
+def test_ce_head_vs_reference_golden(golden):
+    from recbole_b200 import ops
+    from gpu_util import rel_err, t
+    g = golden("ce_head.npz")
+    out = ops.ce_head(t(g["X"]), t(g["E"]), t(g["pos"]), k=10)
+    assert abs(out["loss"].item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert rel_err(out["lse"].cpu().numpy(), g["lse"]) < 1e-5
+    o_ids, o_sc = oce.full_sort_topk(g["X"], g["E"], 10)
+    np.testing.assert_array_equal(out["ids"].cpu().numpy(), o_ids)          # bit-exact vs the oracle
+    np.testing.assert_array_equal(out["scores"].cpu().numpy(), o_sc)
+    assert (out["ids"].cpu().numpy() != g["topk_ids"]).sum() <= 2           # reference: fp32 near-ties only
+
+
+@pytest.mark.parametrize("nq,N,d", [(4096, 100001, 64), (37, 5000, 128), (1, 3, 16), (300, 70000, 32)])
+def test_ce_head_random_vs_oracle(nq, N, d):
+    from recbole_b200 import ops
+    from gpu_util import rel_err, t
+    rng = np.random.default_rng(nq + N)
+    X = rng.standard_normal((nq, d)).astype(np.float32)
+    X = (X - X.mean(1, keepdims=True)) / X.std(1, keepdims=True)          # layer-normed rows
+    E = (rng.standard_normal((N, d)) * 0.02 * 20).astype(np.float32)
+    E[0] = 0
+    tgt = rng.integers(1, N, nq) if N > 1 else np.zeros(nq, np.int64)
+    out = ops.ce_head(t(X), t(E), t(tgt), k=min(10, N))
+    sub = np.arange(min(nq, 64))
+    loss_sub, lse_sub = oce.ce_loss(X[sub], E, tgt[sub])
+    assert rel_err(out["lse"].cpu().numpy()[sub], lse_sub) < 1e-5
+    o_ids, o_sc = oce.full_sort_topk(X[sub], E, min(10, N))
+    np.testing.assert_array_equal(out["ids"].cpu().numpy()[sub], o_ids)
+    if nq <= 64:
+        assert abs(out["loss"].item() - loss_sub) <= 1e-5 * abs(loss_sub)
+    else:  # loss over all rows = mean(lse - target logit); check through its definition
+        lse = out["lse"].cpu().numpy().astype(np.float64)
+        tl = oracle_pair(X, E, tgt)
+        assert abs(out["loss"].item() - float((lse - tl).mean())) <= 1e-5 * abs(float((lse - tl).mean()))
+
+
+def oracle_pair(X, E, tgt):
+    import oracle
+    return oracle.clib.pair_scores_fma(X, E, np.arange(len(tgt)), tgt).astype(np.float64)

@@ -117,3 +117,38 @@ def test_fused_fm_model_mirror(golden):
     assert rel_err(m.state_dict()["token_embedding_table.embedding.weight"].cpu().numpy(),
                    g["p1_token_embedding_table.embedding.weight"]) < TOL
     assert abs(m.first_order_linear.bias.item() - float(g["p1_first_order_linear.bias"][0])) < 1e-6
+
+
+def test_mfsimple_dot_loss_vs_reference_golden(golden):
+    """The fork's MFSimple (point-wise dot + biases + BCELoss) on the two-field FM kernels: forward,
+    loss and -- through one SGD step -- every gradient the reference's autograd produced."""
+    from recbole_b200 import FusedMFSimple
+    from gpu_util import rel_err, t
+    g = golden("dot_steps.npz")
+
+    class Cfg(dict):
+        def __getitem__(self, k):
+            return self.get(k)
+
+    nu, ni = g["p_user_embedding.weight"].shape[0], g["p_item_embedding.weight"].shape[0]
+
+    class DS:
+        def num(self, f):
+            return {"user_id": nu, "item_id": ni}[f]
+
+    m = FusedMFSimple(Cfg(USER_ID_FIELD="user_id", ITEM_ID_FIELD="item_id", LABEL_FIELD="label", device="cuda",
+                          embedding_dimension=g["p_user_embedding.weight"].shape[1]), DS()).to("cuda")
+    m.load_state_dict({k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("p_")})
+    inter = {"user_id": t(g["user_id"]), "item_id": t(g["item_id"]), "label": t(g["label"])}
+    assert rel_err(m.predict(inter).cpu().numpy(), g["pred"]) < TOL
+    lr = 0.5
+    m.build_optimizer("sgd", lr)
+    loss = m.train_step(inter)
+    assert abs(loss.item() - float(g["loss"])) <= TOL * abs(float(g["loss"]))
+    sd = m.state_dict()
+    for name in ("user_embedding.weight", "item_embedding.weight", "user_bias", "item_bias", "bias"):
+        want = g["p_" + name] - np.float32(lr) * g["g_" + name]
+        assert rel_err(sd[name].cpu().numpy(), want) < TOL, name
+    # the gradient itself (not hidden behind the parameter magnitude)
+    gU = (g["p_user_embedding.weight"] - sd["user_embedding.weight"].cpu().numpy()) / lr
+    assert rel_err(gU, g["g_user_embedding.weight"]) < 1e-4
