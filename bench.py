@@ -158,7 +158,7 @@ def run_ours(args, rank, world, local_rank):
     from recbole_b200.data import EvalIndex
     from recbole_b200.evaluator import FusedTopKEvaluator
 
-    if world > 1:
+    if world > 1 or args.workload == "cfg3":
         return run_ours_multi(args, rank, world, local_rank)
 
     torch.cuda.set_device(local_rank)
@@ -360,6 +360,9 @@ def main():
     ap.add_argument("--eval-reps", type=int, default=3, dest="eval_reps")
     ap.add_argument("--cpu-steps", type=int, default=4, dest="cpu_steps")
     ap.add_argument("--ref-eval-users", type=int, default=4096, dest="ref_eval_users")
+    ap.add_argument("--eval-layout", default="auto", choices=["auto", "replicate", "sharded"], dest="eval_layout")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "dense", "sparse"])
+    ap.add_argument("--scale", type=float, default=1.0, help="cfg3 only: shrink users/items by this factor")
     ap.add_argument("--skip-cpu", action="store_true", dest="skip_cpu", help="profiling runs only")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

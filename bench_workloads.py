@@ -137,3 +137,54 @@ class BprWorkload:
     def describe(self):
         return dict(workload=self.name, desc=self.desc, n_users=self.n_users, n_items=self.n_items, dim=self.dim,
                     interactions=self.n_inter, train_batch=self.batch, eval_users=int(len(self.uid_list)), topk=10)
+
+
+class Cfg3Device:
+    """BASELINE config 3 shape (10M users x 2M items x d=128), generated ON THE DEVICE for the users
+    one rank owns -- never through pandas / numpy.  Per user a sorted list of
+    `per_user` Zipf(1) train items (the CSR the sampler rejects against and the evaluation history),
+    batches = (user, one of its train items, a negative from rb2_neg_sample_hash), test positives =
+    `n_test` further items per user."""
+
+    def __init__(self, rank, world, device, n_users=10_000_001, n_items=2_000_001, dim=128, per_user=64, n_test=8,
+                 batch=1 << 20, n_batches=4, seed=2020, scale=1.0):
+        import torch
+        from recbole_b200 import ops
+        self.name = "cfg3"
+        self.desc = "BPR-MF synthetic 10M users x 2M items x d=128 (device-generated, %d train items/user)" % per_user
+        self.n_users, self.n_items, self.dim, self.batch = int(n_users * scale) | 1, int(n_items * scale) | 1, dim, batch
+        n_users, n_items = self.n_users, self.n_items
+        blk = (n_users + world - 1) // world
+        self.u_lo, self.u_hi = min(rank * blk, n_users), min((rank + 1) * blk, n_users)
+        if rank == 0:
+            self.u_lo_eval = 1          # user 0 is [PAD]
+        nu = self.u_hi - self.u_lo
+        g = torch.Generator(device=device)
+        g.manual_seed(seed + 1000 * rank)
+
+        def zipf_items(shape):
+            u = torch.rand(shape, device=device, generator=g)
+            rank_ = torch.exp(u * float(np.log(n_items - 1))).long().clamp_(1, n_items - 1)
+            return (rank_ * 2654435761 % (n_items - 1)) + 1       # decouple popularity from id order
+
+        # train lists: sorted, duplicates inside a row collapsed by pushing them to distinct ids is not
+        # needed -- duplicates are harmless for a CSR used as a rejection set
+        items = torch.sort(zipf_items((nu, per_user)), dim=1).values
+        self.used_indptr = torch.arange(0, (nu + 1) * per_user, per_user, device=device, dtype=torch.int64)
+        self.used_indices = items.reshape(-1).contiguous()
+        self.per_user = per_user
+        # batches
+        self.batches = []
+        for b in range(n_batches):
+            ul = torch.randint(1 if rank == 0 else 0, nu, (batch,), device=device, generator=g)
+            slot = torch.randint(0, per_user, (batch,), device=device, generator=g)
+            pos = items[ul, slot].contiguous()
+            neg = ops.neg_sample_hash(ul, 1, n_items, self.used_indptr, self.used_indices, seed, b + 1)
+            self.batches.append(((ul + self.u_lo).contiguous(), pos, neg))
+        # evaluation: own users, positives = n_test fresh items
+        self.test_items = torch.sort(zipf_items((nu, n_test)), dim=1).values
+        self.n_test = n_test
+
+    def describe(self):
+        return dict(workload="cfg3", desc=self.desc, n_users=self.n_users, n_items=self.n_items, dim=self.dim,
+                    interactions=int((self.n_users - 1) * self.per_user), train_batch=self.batch, topk=10)

@@ -262,11 +262,39 @@ class ShardedBPR:
         return self.comm.all_gather_equal(self.U)
 
     @torch.no_grad()
-    def evaluate(self, index, evaluator, mode="tc", user_tile=1 << 20):
+    def evaluate(self, index, evaluator, mode="tc", user_tile=1 << 20, layout="auto"):
         """index: ShardedEvalIndex.  Returns the metric dict over ALL evaluated users (identical on
-        every rank)."""
+        every rank).
+
+        layout="replicate": the item table is all-gathered once (p only; 1 GB at 2M x 128) and every
+            rank scores ITS OWN users against all items -- no user-table all-gather, no candidate
+            exchange, and the scorer sees the full item range (long streams keep the tensor pipe fed).
+        layout="sharded": items stay sharded; every rank scores every user against its shard and the
+            per-shard top-K lists are merged at the users' owners (north_star's all-gather merge);
+            needed only when the item table does not fit beside the rest.
+        """
         ops, comm = self.ops, self.comm
         K = evaluator.max_k
+        if layout == "auto":
+            layout = "replicate" if self.n_items * self.dim * 4 <= (8 << 30) else "sharded"
+        if layout == "replicate":
+            V_all = comm.all_gather_equal(self.V)[: self.n_items]
+            n = index.n_own
+            ids = torch.empty((n, K), dtype=torch.int64, device=self.device)
+            local_users = (index.uid_own - self.u_lo).contiguous()
+            for lo in range(0, n, user_tile):
+                hi = min(lo + user_tile, n)
+                ptr = index.own_hist_indptr[lo:hi + 1].contiguous()
+                i, _ = ops.fullsort_topk(self.U, local_users[lo:hi].contiguous(), V_all, K, ptr,
+                                         index.own_hist_indices, mode=mode)
+                ids[lo:hi] = i
+            if n > 0:
+                sums = ops.topk_metrics(ids, index.pos_indptr, index.pos_indices, self.n_items)["sums"]
+            else:
+                sums = torch.zeros((6, K), dtype=torch.float64, device=self.device)
+            comm.all_reduce_sum(sums)
+            self.last_topk = ids
+            return evaluator.result(sums, int(index.uid_all.numel()))
         U_all = self.gather_user_table()
         n = int(index.uid_all.numel())
         ids = torch.empty((n, K), dtype=torch.int64, device=self.device)
@@ -302,11 +330,14 @@ class ShardedEvalIndex:
     """Per-rank evaluation index: every evaluated user's history restricted to this rank's item
     shard, and the positives of the users this rank owns."""
 
-    def __init__(self, uid_all, hist, pos_own, owner_counts, n_own):
+    def __init__(self, uid_all, hist, pos_own, owner_counts, n_own, uid_own=None, hist_own=None):
         self.uid_all = uid_all
-        self.hist_indptr, self.hist_indices = hist
+        self.hist_indptr, self.hist_indices = hist            # all users x my item shard
         self.pos_indptr, self.pos_indices = pos_own
         self.owner_counts, self.n_own = owner_counts, n_own
+        self.uid_own = uid_own                                # my users (global ids)
+        if hist_own is not None:
+            self.own_hist_indptr, self.own_hist_indices = hist_own   # my users x all items
 
     @classmethod
     def from_global(cls, uid_list, hist, pos, user_bounds, item_bounds, rank, device):
@@ -325,6 +356,9 @@ class ShardedEvalIndex:
         pp, pi = np.asarray(pos[0]), np.asarray(pos[1])
         own_ptr = (pp[a:b + 1] - pp[a]).astype(np.int64)
         own_idx = pi[pp[a]:pp[b]]
+        oh_ptr = (hp[a:b + 1] - hp[a]).astype(np.int64)
+        oh_idx = hi[hp[a]:hp[b]]
         t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(device)  # noqa: E731
         return cls(t(uid_list.astype(np.int64)), (t(nhp), t(hi[keep].astype(np.int64))),
-                   (t(own_ptr), t(own_idx.astype(np.int64))), owner_counts, b - a)
+                   (t(own_ptr), t(own_idx.astype(np.int64))), owner_counts, b - a,
+                   uid_own=t(uid_list[a:b].astype(np.int64)), hist_own=(t(oh_ptr), t(oh_idx.astype(np.int64))))

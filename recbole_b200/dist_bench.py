@@ -11,6 +11,8 @@ import torch.distributed as dist
 
 
 def _max_over_ranks(x, dev):
+    if not dist.is_initialized():
+        return float(x)
     t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
@@ -24,21 +26,32 @@ def run(args, rank, world, local_rank, load_peaks, ClockSampler):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    dist.init_process_group("nccl", device_id=dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     comm = Comm()
     peaks = load_peaks()
-    w = bw.BprWorkload(args.workload, batch=args.batch, n_batches=1)
-    B, d = w.batch, w.dim
-    batches = w.rank_batches(rank, world, args.n_batches)
-    model = ShardedBPR(w.n_users, w.n_items, d, comm, dev, U_full=w.U0, V_full=w.V0)
+    big = args.workload == "cfg3"
+    if big:
+        w = bw.Cfg3Device(rank, world, dev, batch=args.batch or (1 << 20), n_batches=args.n_batches,
+                          scale=args.scale)
+        B, d = w.batch, w.dim
+        model = ShardedBPR(w.n_users, w.n_items, d, comm, dev, exchange=args.exchange)
+        resident = w.batches
+        host = [tuple(x.cpu().pin_memory() for x in b) for b in resident]
+    else:
+        w = bw.BprWorkload(args.workload, batch=args.batch, n_batches=1)
+        B, d = w.batch, w.dim
+        batches = w.rank_batches(rank, world, args.n_batches)
+        model = ShardedBPR(w.n_users, w.n_items, d, comm, dev, U_full=w.U0, V_full=w.V0, exchange=args.exchange)
+        host = [tuple(torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in b) for b in batches]
+        resident = [tuple(x.to(dev) for x in b) for b in host]
     model.build_optimizer("adam", 1e-3, 0.0)
-    host = [tuple(torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in b) for b in batches]
-    resident = [tuple(x.to(dev) for x in b) for b in host]
     nb = len(resident)
     GB = B * world
 
     def barrier():
-        dist.barrier()
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
 
     for i in range(args.warmup):
@@ -86,13 +99,29 @@ def run(args, rank, world, local_rank, load_peaks, ClockSampler):
 
     ev = FusedTopKEvaluator(Cfg(metrics=["Recall", "MRR", "NDCG", "Hit", "Precision"], topk=[10],
                                 metric_decimal_place=4))
-    index = ShardedEvalIndex.from_global(w.uid_list, w.hist, w.pos, model.user_bounds, model.item_bounds, rank, dev)
-    nq = len(w.uid_list)
-    model.evaluate(index, ev, mode=args.scorer)
+    if big:
+        nu = w.u_hi - w.u_lo
+        first = 1 if rank == 0 else 0                      # user 0 is [PAD]
+        uid_own = torch.arange(w.u_lo + first, w.u_hi, device=dev, dtype=torch.int64)
+        n_all = w.n_users - 1
+        pos_ptr = torch.arange(0, (nu - first + 1) * w.n_test, w.n_test, device=dev, dtype=torch.int64)
+        hist_ptr = (w.used_indptr[first:] - w.used_indptr[first]).contiguous()
+        index = ShardedEvalIndex(torch.empty(n_all, dtype=torch.int8, device="meta"), (None, None),
+                                 (pos_ptr, w.test_items[first:].reshape(-1).contiguous()), None, nu - first,
+                                 uid_own=uid_own, hist_own=(hist_ptr, w.used_indices[first * w.per_user:].contiguous()))
+        nq = n_all
+        if args.eval_layout == "sharded":
+            raise SystemExit("cfg3 bench evaluates with --eval-layout replicate (own users x all items)")
+        args.eval_layout = "replicate"
+    else:
+        index = ShardedEvalIndex.from_global(w.uid_list, w.hist, w.pos, model.user_bounds, model.item_bounds, rank,
+                                             dev)
+        nq = len(w.uid_list)
+    model.evaluate(index, ev, mode=args.scorer, layout=args.eval_layout)
     barrier()
     e0.record()
     for _ in range(args.eval_reps):
-        result = model.evaluate(index, ev, mode=args.scorer)
+        result = model.evaluate(index, ev, mode=args.scorer, layout=args.eval_layout)
     e1.record()
     barrier()
     eval_ms = _max_over_ranks(e0.elapsed_time(e1), dev) / args.eval_reps
@@ -117,7 +146,7 @@ def run(args, rank, world, local_rank, load_peaks, ClockSampler):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": train_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(w.describe(), train_batch_per_gpu=B, global_batch=GB, optimizer="adam(row-sparse) lr=1e-3",
-                           scorer=args.scorer,
+                           scorer=args.scorer, eval_layout=args.eval_layout, exchange=model.exchange,
                            parallelism="users range-partitioned, item table row-sharded x%d, NCCL all-to-all" % world,
                            l2="no flush: every step reads a different batch"),
             "clocks": clk, "roofline": roofline,
@@ -129,5 +158,6 @@ def run(args, rank, world, local_rank, load_peaks, ClockSampler):
                      "users": nq, "ms": eval_ms, "topk": 10, "result": result},
         }
         print(json.dumps(line), flush=True)
-    dist.barrier()
-    dist.destroy_process_group()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()

@@ -48,7 +48,9 @@ def _rank_fn(rank, world, kind, mode, exchange):
                                 metric_decimal_place=4))
     uid, hist, pos = ofs.eval_index(n_users, pairs, 2)
     idx = ShardedEvalIndex.from_global(uid, hist, pos, m.user_bounds, m.item_bounds, rank, dev)
-    res = m.evaluate(idx, ev, mode=mode)
+    res = m.evaluate(idx, ev, mode=mode, layout="sharded")
+    res2 = m.evaluate(idx, ev, mode=mode, layout="replicate")
+    assert res2 == res
     return dict(losses=losses, U=m.U[: m.u_hi - m.u_lo].cpu().numpy(), V=m.V[: m.i_hi - m.i_lo].cpu().numpy(), res=res,
                 topk=m.last_topk.cpu().numpy(), u_lo=m.u_lo, i_lo=m.i_lo)
 
@@ -73,7 +75,7 @@ def test_two_ranks_equal_single_device_oracle(kind, mode, exchange):
     # evaluation on the tables the ranks actually hold (so that ids can be compared bit for bit)
     uid, hist, pos = ofs.eval_index(U0.shape[0], pairs, 2)
     o_ids, _ = ofs.full_sort_topk(U, V, uid, hist[0], hist[1], 10)
-    got = np.concatenate([out[0]["topk"], out[1]["topk"]])
+    got = np.concatenate([out[0]["topk"], out[1]["topk"]])   # last_topk of the "replicate" layout: own users
     np.testing.assert_array_equal(got, o_ids)
     ref = ofs.evaluate(o_ids, pos[0], pos[1], ["recall", "mrr", "ndcg", "hit", "precision", "map"], [1, 5, 10])
     assert out[0]["res"] == ref and out[1]["res"] == ref
