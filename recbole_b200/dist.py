@@ -159,6 +159,14 @@ def return_grads(comm, G, send_counts, recv_counts):
     return comm.all_to_all(G, send_counts, recv_counts)
 
 
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 class ShardedBPR:
     """BPR-MF with range-partitioned users and a row-sharded item table."""
 
@@ -211,10 +219,35 @@ class ShardedBPR:
             self._ws = {key: self.ops.bpr_workspace(batch, self.dim, self.device)}
         return self._ws[key]
 
-    def train_step(self, user, pos, neg, global_batch=None):
+    def plan(self, user, pos, neg):
+        """Everything of a sparse-exchange step that depends only on the batch IDS (not on the
+        parameters): de-duplication, bucketing by owner, the count exchange and all-to-all of the
+        requested ids.  It contains the step's only host synchronisations, so train_step() runs it for
+        the NEXT batch on a side stream while the current step's kernels execute."""
+        comm = self.comm
+        if not hasattr(self, "_plan_stream"):
+            self._plan_stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        st = self._plan_stream
+        ctx = torch.cuda.stream(st) if st is not None else _NullCtx()
+        if st is not None:
+            st.wait_stream(torch.cuda.current_stream())
+        with ctx:
+            B = int(user.numel())
+            uniq, inv, send_counts = plan_item_exchange(torch.cat([pos, neg]), self.item_bounds)
+            recv_counts = comm.exchange_counts(send_counts)
+            req = comm.all_to_all(uniq, send_counts, recv_counts)      # ids other ranks want from me
+            p = dict(B=B, user_local=(user - self.u_lo).contiguous(), pos_c=inv[:B].contiguous(),
+                     neg_c=inv[B:].contiguous(), n_uniq=int(uniq.numel()), send_counts=send_counts,
+                     recv_counts=recv_counts, local_idx=(req - self.i_lo).contiguous(), ids=(user, pos, neg))
+            p["event"] = torch.cuda.Event() if st is not None else None
+            if st is not None:
+                p["event"].record(st)
+        return p
+
+    def train_step(self, user, pos, neg, global_batch=None, next_batch=None):
         """user/pos/neg: int64 device vectors with GLOBAL ids; every user must belong to this rank.
-        Returns the device scalar holding this rank's share of the global mean loss (after the
-        all-reduce: the global mean loss)."""
+        Returns the device scalar holding the global mean loss.  next_batch=(user, pos, neg) lets the
+        id-only part of the following step overlap with this one (sparse exchange)."""
         ops, comm = self.ops, self.comm
         B = int(user.numel())
         if global_batch is None:
@@ -223,16 +256,23 @@ class ShardedBPR:
         t = self.optim.step
         if self.exchange == "dense":
             return self._train_step_dense(user, pos, neg, global_batch, t)
-        uniq, inv, send_counts = plan_item_exchange(torch.cat([pos, neg]), self.item_bounds)
-        C, local_idx, recv_counts = fetch_rows(comm, uniq, send_counts, lambda idx: self.V.index_select(0, idx),
-                                               self.i_lo)
+        p = getattr(self, "_next_plan", None)
+        if p is None or p["ids"][0] is not user:
+            p = self.plan(user, pos, neg)
+        self._next_plan = None
+        if p["event"] is not None:
+            torch.cuda.current_stream().wait_event(p["event"])
+        # all-to-all #1 (rows): parameters as they are after the previous step
+        rows = self.V.index_select(0, p["local_idx"])
+        C = comm.all_to_all(rows, p["recv_counts"], p["send_counts"])
         G = torch.empty_like(C)
-        user_local = (user - self.u_lo).contiguous()
-        ops.bpr_train_step_sharded(self.U, self.state, C, user_local, inv[:B].contiguous(), inv[B:].contiguous(),
-                                   global_batch, self.optim, self.loss_out, None, G, self._workspace(B), step=t)
-        grads = return_grads(comm, G, send_counts, recv_counts)
+        ops.bpr_train_step_sharded(self.U, self.state, C, p["user_local"], p["pos_c"], p["neg_c"], global_batch,
+                                   self.optim, self.loss_out, None, G, self._workspace(B), step=t)
+        if next_batch is not None:      # enqueue the next plan now: its host syncs overlap with the kernels above
+            self._next_plan = self.plan(*next_batch)
+        grads = return_grads(comm, G, p["send_counts"], p["recv_counts"])
         self._rows_ws = ops.sparse_rows_update(self.V, self.state.get("mV"), self.state.get("vV"), None,
-                                               local_idx.contiguous(), grads, self.optim, self._rows_ws, step=t)
+                                               p["local_idx"], grads, self.optim, self._rows_ws, step=t)
         comm.all_reduce_sum(self.loss_out)
         self.loss_accum += self.loss_out.double()
         return self.loss_out

@@ -54,8 +54,11 @@ def run(args, rank, world, local_rank, load_peaks, ClockSampler):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def nxt(i):
+        return resident[(i + 1) % nb]
+
     for i in range(args.warmup):
-        model.train_step(*resident[i % nb], global_batch=GB)
+        model.train_step(*resident[i % nb], global_batch=GB, next_batch=nxt(i))
     barrier()
     ops.profile_enable(True)
     ops.profile_read()
@@ -65,7 +68,7 @@ def run(args, rank, world, local_rank, load_peaks, ClockSampler):
     barrier()
     e0.record()
     for i in range(args.steps):
-        model.train_step(*resident[(args.warmup + i) % nb], global_batch=GB)
+        model.train_step(*resident[(args.warmup + i) % nb], global_batch=GB, next_batch=nxt(args.warmup + i))
     e1.record()
     barrier()
     ms_total = _max_over_ranks(e0.elapsed_time(e1), dev)
