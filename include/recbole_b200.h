@@ -127,7 +127,19 @@ int rb2_bpr_train_step_sharded(float *user_p, float *user_m, float *user_v, int3
                                const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t batch,
                                int64_t global_batch, const rb2_optim *h_opt, float *loss_out, double *loss_accum,
                                float *item_grad_out, int32_t *item_touched /* nullable: [n_item_rows], set to 1 for
-                               every row written */, void *workspace, size_t workspace_bytes, void *stream);
+                               every row written */, const void *item_plan /* nullable: the plan workspace
+                               rb2_item_plan filled for this batch; its sorted occurrences are reused */,
+                               void *workspace, size_t workspace_bytes, void *stream);
+
+/* The id-only half of a sharded step (what the caller needs before any parameter is read): unique
+ * item ids of the batch in ascending order (= grouped by owner shard), pos / neg rewritten as indices
+ * into that list, and cuts[g] = number of unique ids below shard_bounds[g] (g = 0..world),
+ * cuts[world+1] = number of unique ids.  uniq must hold 2*batch entries.  All outputs on the device;
+ * the caller copies `cuts` (world+2 values) to the host to size the all-to-all. */
+size_t rb2_item_plan_workspace_bytes(int64_t batch);
+int rb2_item_plan(const int64_t *pos, const int64_t *neg, int64_t batch, int64_t n_items,
+                  const int64_t *shard_bounds, int32_t world, int64_t *uniq, int64_t *pos_c, int64_t *neg_c,
+                  int64_t *cuts, void *plan_workspace, size_t plan_workspace_bytes, void *stream);
 
 /* Owner side of the replicated-small-table exchange (all-gather rows, reduce-scatter gradients):
  * rows with touched[row] > 0 take one optimizer step with grads[row, :]. */

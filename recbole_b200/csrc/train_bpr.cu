@@ -18,6 +18,7 @@
 //   k_loss        fixed-order reduction of the per-tile loss partials.
 // Every touched row is read (p, m, v) and written (p, m, v) exactly once per step.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
 
@@ -390,7 +391,8 @@ __global__ void __launch_bounds__(kThreads) k_bpr_loss(const float *__restrict__
 
 template <int D, bool LAZY>
 int launch_step(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, const OptScalars &o, float *loss_out,
-                double *loss_accum, cudaStream_t st, int64_t global_batch) {
+                double *loss_accum, cudaStream_t st, int64_t global_batch, const uint32_t *pre_ikey_s,
+                const uint32_t *pre_ival_s) {
   constexpr int LANES = RowCfg<D>::LANES;
   const int Tu = pick_tile(B, LANES), Ti = pick_tile(2 * B, LANES);
   const int64_t ntu = (B + Tu - 1) / Tu, nti = (2 * B + Ti - 1) / Ti;
@@ -404,7 +406,11 @@ int launch_step(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, 
                                              bits_for(n_users), st));
   }
   tmp = w.cub_bytes;
-  {
+  if (pre_ikey_s) {
+    // rb2_item_plan already sorted the item occurrences (by global id == by compact id)
+    w.ikey_s = const_cast<uint32_t *>(pre_ikey_s);
+    w.ival_s = const_cast<uint32_t *>(pre_ival_s);
+  } else {
     ProfScope prof(RB2_ST_SORT_ITEM, st, 2 + (bits_for(n_items) + 7) / 8);
     RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ikey, w.ikey_s, w.ival, w.ival_s, (int)(2 * B), 0,
                                              bits_for(n_items), st));
@@ -474,12 +480,119 @@ extern "C" size_t rb2_bpr_workspace_bytes(int64_t batch, int32_t dim) {
   return carve(w, nullptr, batch, dim);
 }
 
+// ---------------------------------------------------------------------------------------------
+// rb2_item_plan: the id-only half of a sharded step.  De-duplicates the item ids of a batch on the
+// device (radix sort + head flags + scan), rewrites pos / neg as compact indices, lists the unique
+// ids (ascending = grouped by owner shard) and where each owner's range starts.  The sorted item
+// occurrences stay in the plan workspace and are reused by rb2_bpr_train_step_sharded (the mapping
+// global id -> compact id is monotone, so no second sort).
+namespace {
+struct PlanWs {
+  uint32_t *key, *val, *key_s, *val_s, *ckey_s, *flag, *rank;
+  void *cub_tmp;
+  size_t cub_bytes;
+};
+size_t carve_plan(PlanWs &w, void *base, int64_t B, int want_cub) {
+  Carver c(base);
+  const int64_t M = 2 * B;
+  w.key = c.take<uint32_t>(M);
+  w.val = c.take<uint32_t>(M);
+  w.key_s = c.take<uint32_t>(M);
+  w.val_s = c.take<uint32_t>(M);
+  w.ckey_s = c.take<uint32_t>(M);
+  w.flag = c.take<uint32_t>(M);
+  w.rank = c.take<uint32_t>(M);
+  size_t b1 = 0, b2 = 0;
+  if (want_cub) {
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, (int)M, 0, 32);
+    cub::DeviceScan::InclusiveSum(nullptr, b2, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)M);
+  }
+  w.cub_bytes = b1 > b2 ? b1 : b2;
+  w.cub_tmp = c.take<char>(w.cub_bytes);
+  return c.off;
+}
+__global__ void k_plan_keys(const int64_t *__restrict__ pos, const int64_t *__restrict__ neg, int64_t B,
+                            int64_t n_items, PlanWs w) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B) return;
+  int64_t p = min(max(pos[s], (int64_t)0), n_items - 1), n = min(max(neg[s], (int64_t)0), n_items - 1);
+  w.key[2 * s] = (uint32_t)p;
+  w.val[2 * s] = (uint32_t)(2 * s);
+  w.key[2 * s + 1] = (uint32_t)n;
+  w.val[2 * s + 1] = (uint32_t)(2 * s + 1);
+}
+__global__ void k_plan_flags(PlanWs w, int64_t M) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  w.flag[i] = (i == 0 || w.key_s[i] != w.key_s[i - 1]) ? 1u : 0u;
+}
+__global__ void k_plan_emit(PlanWs w, int64_t M, int64_t *__restrict__ uniq, int64_t *__restrict__ pos_c,
+                            int64_t *__restrict__ neg_c) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  uint32_t c = w.rank[i] - 1u;
+  w.ckey_s[i] = c;
+  if (w.flag[i]) uniq[c] = (int64_t)w.key_s[i];
+  uint32_t o = w.val_s[i];
+  if (o & 1u) neg_c[o >> 1] = (int64_t)c; else pos_c[o >> 1] = (int64_t)c;
+}
+__global__ void k_plan_cuts(PlanWs w, int64_t M, const int64_t *__restrict__ uniq, const int64_t *__restrict__ bounds,
+                            int world, int64_t *__restrict__ cuts) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > world + 1) return;
+  const int64_t n_uniq = (int64_t)w.rank[M - 1];
+  if (g == world + 1) { cuts[g] = n_uniq; return; }
+  const int64_t b = bounds[g];
+  int64_t lo = 0, hi = n_uniq;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (uniq[mid] < b) lo = mid + 1; else hi = mid;
+  }
+  cuts[g] = lo;
+}
+}  // namespace
+
+extern "C" size_t rb2_item_plan_workspace_bytes(int64_t batch) {
+  PlanWs w;
+  return carve_plan(w, nullptr, batch, 1);
+}
+
+extern "C" int rb2_item_plan(const int64_t *pos, const int64_t *neg, int64_t batch, int64_t n_items,
+                             const int64_t *shard_bounds, int32_t world, int64_t *uniq, int64_t *pos_c,
+                             int64_t *neg_c, int64_t *cuts, void *plan_workspace, size_t plan_workspace_bytes,
+                             void *stream) {
+  RB2_REQUIRE(pos && neg && shard_bounds && uniq && pos_c && neg_c && cuts && plan_workspace, RB2_EINVAL,
+              "rb2_item_plan: null argument");
+  RB2_REQUIRE(batch > 0 && batch < ((int64_t)1 << 30) && world >= 1, RB2_EINVAL, "rb2_item_plan: bad sizes");
+  PlanWs w;
+  size_t need = carve_plan(w, plan_workspace, batch, 1);
+  RB2_REQUIRE(plan_workspace_bytes >= need, RB2_EWORKSPACE, "rb2_item_plan: workspace %zu < %zu",
+              plan_workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t M = 2 * batch;
+  ProfScope prof(RB2_ST_MISC, st, 6 + (bits_for(n_items) + 7) / 8);
+  k_plan_keys<<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(pos, neg, batch, n_items, w);
+  size_t tmp = w.cub_bytes;
+  RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.key, w.key_s, w.val, w.val_s, (int)M, 0,
+                                           bits_for(n_items), st));
+  k_plan_flags<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(w, M);
+  tmp = w.cub_bytes;
+  RB2_CUDA(cub::DeviceScan::InclusiveSum(w.cub_tmp, tmp, w.flag, w.rank, (int)M, st));
+  k_plan_emit<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(w, M, uniq, pos_c, neg_c);
+  k_plan_cuts<<<1, 64, 0, st>>>(w, M, uniq, shard_bounds, world, cuts);
+  RB2_REQUIRE(world + 2 <= 64, RB2_EINVAL, "rb2_item_plan: world too large");
+  RB2_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static int bpr_step_impl(float *user_p, float *user_m, float *user_v, int32_t *user_last, float *item_p,
                          float *item_m, float *item_v, int32_t *item_last, int64_t n_users, int64_t n_items,
                          int32_t dim, const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t batch,
                          const rb2_optim *h_opt, float *loss_out, double *loss_accum, void *workspace,
                          size_t workspace_bytes, void *stream, float *item_grad_out, int64_t global_batch,
-                         int32_t *item_touched) {
+                         int32_t *item_touched, const uint32_t *pre_ikey_s = nullptr,
+                         const uint32_t *pre_ival_s = nullptr) {
   RB2_REQUIRE(user_p && item_p && user && pos && neg && h_opt && loss_out && workspace, RB2_EINVAL,
               "rb2_bpr_train_step: null argument");
   RB2_REQUIRE(batch > 0 && batch < ((int64_t)1 << 30), RB2_EINVAL, "rb2_bpr_train_step: batch %lld out of range",
@@ -512,8 +625,10 @@ static int bpr_step_impl(float *user_p, float *user_m, float *user_v, int32_t *u
   RB2_REQUIRE(!(o.kind == RB2_OPT_ADAM_LAZY && item_grad_out), RB2_EINVAL,
               "rb2_bpr_train_step_sharded: adam_lazy is not available on the sharded path");
   RB2_DISPATCH_DIM(dim, {
-    int rc = lazy ? launch_step<D_, true>(t, w, batch, n_users, n_items, o, loss_out, loss_accum, st, global_batch)
-                  : launch_step<D_, false>(t, w, batch, n_users, n_items, o, loss_out, loss_accum, st, global_batch);
+    int rc = lazy ? launch_step<D_, true>(t, w, batch, n_users, n_items, o, loss_out, loss_accum, st, global_batch,
+                                          pre_ikey_s, pre_ival_s)
+                  : launch_step<D_, false>(t, w, batch, n_users, n_items, o, loss_out, loss_accum, st, global_batch,
+                                           pre_ikey_s, pre_ival_s);
     if (rc) return rc;
   });
   return 0;
@@ -534,11 +649,19 @@ extern "C" int rb2_bpr_train_step_sharded(float *user_p, float *user_m, float *u
                                           const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t batch,
                                           int64_t global_batch, const rb2_optim *h_opt, float *loss_out,
                                           double *loss_accum, float *item_grad_out, int32_t *item_touched,
-                                          void *workspace, size_t workspace_bytes, void *stream) {
+                                          const void *item_plan, void *workspace, size_t workspace_bytes,
+                                          void *stream) {
   RB2_REQUIRE(item_grad_out != nullptr, RB2_EINVAL, "rb2_bpr_train_step_sharded: item_grad_out is null");
+  const uint32_t *pk = nullptr, *pv = nullptr;
+  if (item_plan) {  // workspace filled by rb2_item_plan for THIS batch
+    PlanWs pw;
+    carve_plan(pw, const_cast<void *>(item_plan), batch, 1);
+    pk = pw.ckey_s;
+    pv = pw.val_s;
+  }
   return bpr_step_impl(user_p, user_m, user_v, user_last, const_cast<float *>(item_rows), nullptr, nullptr, nullptr,
                        n_users, n_item_rows, dim, user, pos, neg, batch, h_opt, loss_out, loss_accum, workspace,
-                       workspace_bytes, stream, item_grad_out, global_batch, item_touched);
+                       workspace_bytes, stream, item_grad_out, global_batch, item_touched, pk, pv);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -233,12 +233,23 @@ class ShardedBPR:
             st.wait_stream(torch.cuda.current_stream())
         with ctx:
             B = int(user.numel())
-            uniq, inv, send_counts = plan_item_exchange(torch.cat([pos, neg]), self.item_bounds)
+            if not hasattr(self, "_bounds_dev"):
+                self._bounds_dev = torch.as_tensor(self.item_bounds, device=self.device)
+                self._plan_ws = [None, None]
+                self._plan_flip = 0
+            self._plan_flip ^= 1                      # two plans are alive at a time (current + next)
+            ip = self.ops.item_plan(pos, neg, self.n_items, self._bounds_dev, comm.world,
+                                    self._plan_ws[self._plan_flip])
+            self._plan_ws[self._plan_flip] = ip["ws"]
+            cuts = ip["cuts"].tolist()                # the plan's host sync
+            n_uniq = cuts[-1]
+            send_counts = [cuts[g + 1] - cuts[g] for g in range(comm.world)]
+            uniq = ip["uniq"][:n_uniq]
             recv_counts = comm.exchange_counts(send_counts)
             req = comm.all_to_all(uniq, send_counts, recv_counts)      # ids other ranks want from me
-            p = dict(B=B, user_local=(user - self.u_lo).contiguous(), pos_c=inv[:B].contiguous(),
-                     neg_c=inv[B:].contiguous(), n_uniq=int(uniq.numel()), send_counts=send_counts,
-                     recv_counts=recv_counts, local_idx=(req - self.i_lo).contiguous(), ids=(user, pos, neg))
+            p = dict(B=B, user_local=(user - self.u_lo).contiguous(), pos_c=ip["pos_c"], neg_c=ip["neg_c"],
+                     n_uniq=n_uniq, send_counts=send_counts, recv_counts=recv_counts,
+                     local_idx=(req - self.i_lo).contiguous(), ids=(user, pos, neg), plan_ws=ip["ws"])
             p["event"] = torch.cuda.Event() if st is not None else None
             if st is not None:
                 p["event"].record(st)
@@ -267,7 +278,8 @@ class ShardedBPR:
         C = comm.all_to_all(rows, p["recv_counts"], p["send_counts"])
         G = torch.empty_like(C)
         ops.bpr_train_step_sharded(self.U, self.state, C, p["user_local"], p["pos_c"], p["neg_c"], global_batch,
-                                   self.optim, self.loss_out, None, G, self._workspace(B), step=t)
+                                   self.optim, self.loss_out, None, G, self._workspace(B), step=t,
+                                   item_plan=p["plan_ws"])
         if next_batch is not None:      # enqueue the next plan now: its host syncs overlap with the kernels above
             self._next_plan = self.plan(*next_batch)
         grads = return_grads(comm, G, p["send_counts"], p["recv_counts"])

@@ -120,7 +120,7 @@ def bpr_train_step(U, V, state, user, pos, neg, optim, loss_out, loss_accum, ws)
 
 
 def bpr_train_step_sharded(U, state, item_rows, user, pos_c, neg_c, global_batch, optim, loss_out, loss_accum,
-                           item_grad_out, ws, step=None, item_touched=None):
+                           item_grad_out, ws, step=None, item_touched=None, item_plan=None):
     """User side + per-compact-row item gradient sums (rb2_bpr_train_step_sharded).  optim.step is NOT
     incremented here (the owner-side update of the same logical step shares it)."""
     o = optim.c_struct(U.device, step)
@@ -130,7 +130,25 @@ def bpr_train_step_sharded(U, state, item_rows, user, pos_c, neg_c, global_batch
         _ptr(state.get("lastU"), torch.int32, True), _ptr(item_rows, f32), U.shape[0], item_rows.shape[0],
         U.shape[1], _ptr(user, i64), _ptr(pos_c, i64), _ptr(neg_c, i64), user.numel(), int(global_batch),
         ctypes.byref(o), _ptr(loss_out, f32), _ptr(loss_accum, torch.float64, True), _ptr(item_grad_out, f32),
-        _ptr(item_touched, torch.int32, True), ws.ptr(), ws.nbytes, _stream()))
+        _ptr(item_touched, torch.int32, True), item_plan.ptr() if item_plan is not None else None,
+        ws.ptr(), ws.nbytes, _stream()))
+
+
+def item_plan(pos, neg, n_items, bounds_dev, world, plan_ws=None):
+    """rb2_item_plan: returns dict(uniq [2B] (first n_uniq valid), pos_c, neg_c, cuts [world+2] on the
+    device, ws = the plan workspace to hand to bpr_train_step_sharded)."""
+    B, dev = int(pos.numel()), pos.device
+    need = lib.rb2_item_plan_workspace_bytes(B)
+    if plan_ws is None or plan_ws.nbytes < need:
+        plan_ws = Workspace(need, dev)
+    uniq = torch.empty(2 * B, dtype=torch.int64, device=dev)
+    pos_c = torch.empty(B, dtype=torch.int64, device=dev)
+    neg_c = torch.empty(B, dtype=torch.int64, device=dev)
+    cuts = torch.empty(world + 2, dtype=torch.int64, device=dev)
+    check(lib.rb2_item_plan(_ptr(pos, torch.int64), _ptr(neg, torch.int64), B, int(n_items),
+                            _ptr(bounds_dev, torch.int64), int(world), _ptr(uniq), _ptr(pos_c), _ptr(neg_c),
+                            _ptr(cuts), plan_ws.ptr(), plan_ws.nbytes, _stream()))
+    return dict(uniq=uniq, pos_c=pos_c, neg_c=neg_c, cuts=cuts, ws=plan_ws)
 
 
 def dense_rows_update(P, M, V, grads, touched, optim, step=None):
