@@ -297,7 +297,7 @@ def run_ours(args, rank, world, local_rank):
                          "note": "whole fused step vs the no-duplicate algorithmic bytes; at this shape a batch of "
                                  "2^20 triples touches each user row ~8x and each item row ~78x, so the bytes that "
                                  "really reach DRAM are far below the algorithmic count (see traffic)"},
-                "stages_ms": {k: v[0] / max(v[1], 1) for k, v in stages.items()}}
+                "stages_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()}}
     if roofline["achieved"]:
         roofline["frac"] = roofline["achieved"] / peaks["hbm"]
     fs_stage = "tc_score" if args.scorer == "tc" else "fullsort"

@@ -141,7 +141,7 @@ def run(args, rank, world, local_rank, load_peaks, ClockSampler):
                     "step": {"achieved_all_gpus": alg_step / (train_ms * 1e-3) / 1e9,
                              "frac_of_n_gpu_peak": alg_step / (train_ms * 1e-3) / 1e9 / (peaks["hbm"] * world),
                              "bytes_per_sample": 72 * d + 24},
-                    "stages_ms_rank0": {k: v[0] / max(v[1], 1) for k, v in stages.items()}}
+                    "stages_ms_per_step_rank0": {k: v[0] / args.steps for k, v in stages.items()}}
         if roofline["achieved"]:
             roofline["frac"] = roofline["achieved"] / peaks["hbm"]
         line = {
