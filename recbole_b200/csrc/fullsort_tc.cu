@@ -54,7 +54,7 @@ constexpr int BK = 64;        // bf16 elements per 128-byte swizzle row
 constexpr int UNIT_BYTES = BN * BK * 2;   // one B ring slot: 256 items x 64 k
 constexpr int A_KB_BYTES = BM * BK * 2;
 constexpr int kThreadsTc = 320;          // producer warp + MMA warp + 2 x 4 epilogue warps
-constexpr int BLOOM_WORDS = 64;          // 2048 bits per row, 2 hashes
+constexpr int BLOOM_WORDS = 32;          // 1024 bits per row, 2 hashes
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -175,12 +175,11 @@ struct TcSmem {
   static constexpr size_t A_BYTES = (size_t)KB * A_KB_BYTES;
   static constexpr size_t B_BYTES = (size_t)NSTAGE * UNIT_BYTES;
   static constexpr size_t BLOOM_BYTES = (size_t)BLOOM_WORDS * BM * 4;
-  static constexpr size_t STAGE_BYTES = 32 * 256 * 4;
-  static constexpr size_t TOTAL = 1024 /*align slack*/ + A_BYTES + B_BYTES + BLOOM_BYTES + STAGE_BYTES + 256 /*barriers*/;
+  static constexpr size_t TOTAL = 1024 /*align slack*/ + A_BYTES + B_BYTES + BLOOM_BYTES + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ uint32_t bloom_h1(uint32_t x) { return (x * 0x9E3779B1u) >> 21; }
-__device__ __forceinline__ uint32_t bloom_h2(uint32_t x) { return (x * 0x85EBCA77u) >> 21; }
+__device__ __forceinline__ uint32_t bloom_h1(uint32_t x) { return (x * 0x9E3779B1u) >> 22; }
+__device__ __forceinline__ uint32_t bloom_h2(uint32_t x) { return (x * 0x85EBCA77u) >> 22; }
 
 // sorted (descending) candidate list in registers; precondition s > ls[KP-1].  Branch-free bubble:
 // the new entry replaces the tail and climbs while it is strictly greater than its neighbour.
@@ -198,6 +197,21 @@ __device__ __forceinline__ void list_insert(float (&ls)[KP], int (&li)[KP], floa
     li[i] = sw ? ib : ia;
     li[i + 1] = sw ? ia : ib;
   }
+}
+
+// v[j] for a run-time j without local memory: select tree over the bits of j (31 SELs)
+__device__ __forceinline__ float pick32(const uint32_t (&v)[32], int j) {
+  uint32_t a[16], b[8], c[4], d[2];
+  const bool b0 = j & 1, b1 = j & 2, b2 = j & 4, b3 = j & 8, b4 = j & 16;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = b0 ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = b1 ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = b2 ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) d[i] = b3 ? c[2 * i + 1] : c[2 * i];
+  return __uint_as_float(b4 ? d[1] : d[0]);
 }
 
 __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
@@ -218,8 +232,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   unsigned char *sA = smem;                                  // [KB][128 rows][128 B]
   unsigned char *sB = sA + TcSmem<KB, NSTAGE>::A_BYTES;      // [NSTAGE][256 rows][128 B]
   uint32_t *bloom = reinterpret_cast<uint32_t *>(sB + TcSmem<KB, NSTAGE>::B_BYTES);  // [BLOOM_WORDS][BM]
-  float *stage_buf = reinterpret_cast<float *>(bloom + BLOOM_WORDS * BM);            // [32][256]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(stage_buf + 32 * 256);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(bloom + BLOOM_WORDS * BM);
   uint64_t *full = bars;                 // [NSTAGE]
   uint64_t *empty = bars + NSTAGE;       // [NSTAGE]
   uint64_t *a_full = bars + 2 * NSTAGE;  // [1]
@@ -322,7 +335,6 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int quarter = warp & 3;                 // TMEM lanes this warp may touch: [32*quarter, +32)
     const int t = quarter * 32 + lane;            // row inside the tile
     uint32_t *my_bloom = bloom + t;               // word i at my_bloom[i * BM]
-    float *my_stage = stage_buf + (ws * BM + t);  // score j of the current chunk at my_stage[j * 256]
     uint32_t tcount = 0;
     for (int w = cluster_id; w < n_work; w += n_clusters) {
       const int ut = 2 * (w % n_utp) + crank, sp = w / n_utp;
@@ -381,18 +393,15 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           TC_LD32(taddr + c0, v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (max32(v) > tau) {
-            // rare path, kept compact (one copy of the insert): stage the 32 scores in shared memory
-            // so that the passing ones can be fetched by a run-time index
+            // rare path, kept compact (one copy of the insert): bit mask of the passing scores, each
+            // fetched from its register by a 5-level select tree on the run-time index
             uint32_t mask = 0u;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              my_stage[j * 256] = __uint_as_float(v[j]);
-              mask |= (__uint_as_float(v[j]) > tau ? 1u : 0u) << j;
-            }
+            for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) > tau ? 1u : 0u) << j;
             while (mask) {
               const int j = __ffs(mask) - 1;
               mask &= mask - 1;
-              const float s = my_stage[j * 256];
+              const float s = pick32(v, j);
               if (s > tau) consider(s, g0 + c0 + j);
             }
           }
@@ -650,7 +659,7 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
            int64_t item_base, const int64_t *hist_indptr, const int64_t *hist_indices, int k, int64_t *out_ids,
            float *out_scores, void *workspace, size_t workspace_bytes, cudaStream_t st) {
   constexpr int KB = D / BK;
-  constexpr int NSTAGE = 4;
+  constexpr int NSTAGE = (KB == 1) ? 6 : 5;   // B ring depth: what fits beside A, the Bloom filters and the barriers
   TcWs w;
   size_t need = carve_tc(w, workspace, nq, n_local, D, k);
   RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_fullsort_topk(tc): workspace %zu < %zu", workspace_bytes, need);
