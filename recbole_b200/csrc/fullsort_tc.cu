@@ -39,6 +39,12 @@ size_t rb2_fullsort_fp32_workspace(int64_t nq, int64_t n_items_local, int32_t di
 // number of rows the last RB2_SCORER_TC call had to redo in fp32 (diagnostic for bench / tests)
 static int32_t g_last_tc_fallback_rows = 0;
 static int32_t g_tc_kprime = 0;  // 0 = automatic, 16 or 32 = forced (rb2_fullsort_tc_set_kprime)
+static int32_t g_tc_variant = 0; // 0 / 2 = CTA-pair MMA (cta_group::2), 1 = per-CTA MMA with multicast B
+extern "C" int rb2_fullsort_tc_set_variant(int32_t v) {
+  if (v < 0 || v > 2) return RB2_EINVAL;
+  g_tc_variant = v;
+  return 0;
+}
 extern "C" int rb2_fullsort_tc_set_kprime(int32_t kp) {
   if (kp != 0 && kp != 16 && kp != 32) return RB2_EINVAL;
   g_tc_kprime = kp;
@@ -102,6 +108,45 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t cta_mask) {
                "h"(cta_mask)
                : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: one MMA spans both SMs (M = 256), each CTA keeps its own
+// 128 query rows and HALF of every B slot in shared memory ----
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in CTA 0
+__device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *map, int c0, int c1,
+                                                uint32_t leader_bar_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(leader_bar_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t *bar) {   // arrives on `bar` in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)0x3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta0(uint64_t *bar) {   // arrive on CTA 0's copy of `bar`
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -170,10 +215,10 @@ struct TcParams {
   float *cand_sc;     // approximate (bf16) scores, each list sorted descending
 };
 
-template <int KB, int NSTAGE>
+template <int KB, int NSTAGE, bool TWO_SM = false>
 struct TcSmem {
   static constexpr size_t A_BYTES = (size_t)KB * A_KB_BYTES;
-  static constexpr size_t B_BYTES = (size_t)NSTAGE * UNIT_BYTES;
+  static constexpr size_t B_BYTES = (size_t)NSTAGE * (TWO_SM ? UNIT_BYTES / 2 : UNIT_BYTES);
   static constexpr size_t BLOOM_BYTES = (size_t)BLOOM_WORDS * BM * 4;
   static constexpr size_t TOTAL = 1024 /*align slack*/ + A_BYTES + B_BYTES + BLOOM_BYTES + 256 /*barriers*/;
 };
@@ -224,14 +269,20 @@ __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
   return fmaxf(fmaxf(fmaxf(a, b), c), fmaxf(m[9], m[10]));
 }
 
-template <int KB, int NSTAGE, int KP>
+// TWO_SM = false: cta_group::1, each CTA runs its own M=128 MMAs on a full B slot that the pair loads by
+//                 halves and multicasts (NSTAGE slots of 32 KB).
+// TWO_SM = true : cta_group::2, one M=256 MMA per k-step issued by CTA 0 for the pair; each CTA keeps only
+//                 its half of every B slot (NSTAGE slots of 16 KB: twice the tiles in flight, half the
+//                 shared-memory operand traffic per SM).
+template <int KB, int NSTAGE, int KP, bool TWO_SM>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+  constexpr int SLOT_BYTES = TWO_SM ? UNIT_BYTES / 2 : UNIT_BYTES;
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char *sA = smem;                                  // [KB][128 rows][128 B]
-  unsigned char *sB = sA + TcSmem<KB, NSTAGE>::A_BYTES;      // [NSTAGE][256 rows][128 B]
-  uint32_t *bloom = reinterpret_cast<uint32_t *>(sB + TcSmem<KB, NSTAGE>::B_BYTES);  // [BLOOM_WORDS][BM]
+  unsigned char *sB = sA + TcSmem<KB, NSTAGE, TWO_SM>::A_BYTES;      // [NSTAGE][256 (or 128) rows][128 B]
+  uint32_t *bloom = reinterpret_cast<uint32_t *>(sB + TcSmem<KB, NSTAGE, TWO_SM>::B_BYTES);  // [BLOOM_WORDS][BM]
   uint64_t *bars = reinterpret_cast<uint64_t *>(bloom + BLOOM_WORDS * BM);
   uint64_t *full = bars;                 // [NSTAGE]
   uint64_t *empty = bars + NSTAGE;       // [NSTAGE]
@@ -251,18 +302,25 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int n_tiles_all = (int)((p.n_local + BN - 1) / BN);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }  // empty: both CTAs' MMAs
+    // empty: 1-SM variant = both CTAs' MMA threads commit to it; 2-SM variant = one multicast commit
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], TWO_SM ? 1 : 2); }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
     mbar_init(&t_full[0], 1); mbar_init(&t_full[1], 1);
-    mbar_init(&t_empty[0], 128); mbar_init(&t_empty[1], 128);
+    // accumulator drained: 2-SM variant = both CTAs' epilogue warp sets arrive on CTA 0's barrier
+    mbar_init(&t_empty[0], TWO_SM ? 256 : 128); mbar_init(&t_empty[1], TWO_SM ? 256 : 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
   if (warp == 1) {  // TMEM: all 512 columns (two 256-column accumulator stages)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (TWO_SM) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -278,25 +336,38 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       for (int w = cluster_id; w < n_work; w += n_clusters) {
         const int ut = 2 * (w % n_utp) + crank, sp = w / n_utp;
         mbar_wait(a_empty, a_phase ^ 1);
-        mbar_expect_tx(a_full, KB * A_KB_BYTES);
-        for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * A_KB_BYTES, &tmA, kb * BK, ut * BM, a_full);
+        if (TWO_SM) {
+          // both CTAs' A tiles report to CTA 0's barrier (the MMA issuer lives there)
+          if (crank == 0) mbar_expect_tx(a_full, 2 * KB * A_KB_BYTES);
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_2d_2sm(sA + kb * A_KB_BYTES, &tmA, kb * BK, ut * BM, smem_u32(a_full) & kPeerBitMask);
+        } else {
+          mbar_expect_tx(a_full, KB * A_KB_BYTES);
+          for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * A_KB_BYTES, &tmA, kb * BK, ut * BM, a_full);
+        }
         a_phase ^= 1;
         const int t0 = sp * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, n_tiles_all);
         for (int it = t0; it < t1; ++it) {
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);       // both CTAs are done reading this slot
-            mbar_expect_tx(&full[stage], UNIT_BYTES);  // my half + the peer's half
-            tma_load_2d_mc(sB + (size_t)stage * UNIT_BYTES + (size_t)crank * (UNIT_BYTES / 2), &tmB, kb * BK,
-                           it * BN + crank * (BN / 2), &full[stage], (uint16_t)0x3);
+            if (TWO_SM) {
+              if (crank == 0) mbar_expect_tx(&full[stage], UNIT_BYTES);   // my half + the peer's half
+              tma_load_2d_2sm(sB + (size_t)stage * SLOT_BYTES, &tmB, kb * BK, it * BN + crank * (BN / 2),
+                              smem_u32(&full[stage]) & kPeerBitMask);
+            } else {
+              mbar_expect_tx(&full[stage], UNIT_BYTES);  // my half + the peer's half
+              tma_load_2d_mc(sB + (size_t)stage * UNIT_BYTES + (size_t)crank * (UNIT_BYTES / 2), &tmB, kb * BK,
+                             it * BN + crank * (BN / 2), &full[stage], (uint16_t)0x3);
+            }
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (one thread; in the 2-SM variant only CTA 0's) =====================
+    if (lane == 0 && (!TWO_SM || crank == 0)) {
       int stage = 0;
       uint32_t phase = 0, a_phase = 0, tcount = 0;
       for (int w = cluster_id; w < n_work; w += n_clusters) {
@@ -314,19 +385,24 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             mbar_wait(&full[stage], phase);
             tc_fence_after();
             const uint64_t adesc = make_smem_desc(smem_u32(sA + kb * A_KB_BYTES));
-            const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)stage * UNIT_BYTES));
+            const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)stage * SLOT_BYTES));
 #pragma unroll
             for (int k4 = 0; k4 < BK / 16; ++k4) {
               // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in 16-byte units
-              tc_mma_bf16(tmem_d, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), kIdesc,
-                          (kb | k4) ? 1u : 0u);
+              if (TWO_SM)
+                tc_mma_bf16_2sm(tmem_d, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), kIdesc2,
+                                (kb | k4) ? 1u : 0u);
+              else
+                tc_mma_bf16(tmem_d, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), kIdesc,
+                            (kb | k4) ? 1u : 0u);
             }
-            tc_commit_mc(&empty[stage], (uint16_t)0x3);   // tell both producers this CTA is done with the slot
+            // the slot is free for both producers once these MMAs have read it
+            if (TWO_SM) tc_commit_2sm(&empty[stage]); else tc_commit_mc(&empty[stage], (uint16_t)0x3);
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
-          tc_commit(&t_full[acc]);      // accumulator stage complete
+          if (TWO_SM) tc_commit_2sm(&t_full[acc]); else tc_commit(&t_full[acc]);      // accumulator stage complete
         }
-        tc_commit(a_empty);             // every MMA that reads this A tile has completed
+        if (TWO_SM) tc_commit_2sm(a_empty); else tc_commit(a_empty);   // every MMA reading this A tile completed
       }
     }
   } else {
@@ -407,7 +483,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           }
         }
         tc_fence_before();
-        mbar_arrive(&t_empty[acc]);
+        if (TWO_SM) mbar_arrive_cta0(&t_empty[acc]); else mbar_arrive(&t_empty[acc]);
       }
       if (active) {
         int64_t o = (((int64_t)sp * 2 + ws) * p.nq + r) * KP;
@@ -425,7 +501,8 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   cluster_sync_all();   // nobody leaves while the peer may still write into this CTA's smem / barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (TWO_SM) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -654,12 +731,13 @@ int make_map(CUtensorMap *m, void *base, int64_t rows, int dim, int box_rows) {
   return 0;
 }
 
-template <int D, int KP>
+template <int D, int KP, bool TWO_SM>
 int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p, int64_t n_local,
            int64_t item_base, const int64_t *hist_indptr, const int64_t *hist_indices, int k, int64_t *out_ids,
            float *out_scores, void *workspace, size_t workspace_bytes, cudaStream_t st) {
   constexpr int KB = D / BK;
-  constexpr int NSTAGE = (KB == 1) ? 6 : 5;   // B ring depth: what fits beside A, the Bloom filters and the barriers
+  // B ring depth: what fits beside A, the Bloom filters and the barriers (2-SM slots are half the size)
+  constexpr int NSTAGE = TWO_SM ? ((KB == 1) ? 12 : 10) : ((KB == 1) ? 6 : 5);
   TcWs w;
   size_t need = carve_tc(w, workspace, nq, n_local, D, k);
   RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_fullsort_topk(tc): workspace %zu < %zu", workspace_bytes, need);
@@ -687,10 +765,10 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
   p.n_ut = pl.n_ut; p.n_split = pl.n_split; p.tiles_per_split = pl.tiles_per_split;
   p.hist_indptr = hist_indptr; p.hist_indices = hist_indices;
   p.cand_ids = w.cand_ids; p.cand_sc = w.cand_sc;
-  const size_t smem = TcSmem<KB, NSTAGE>::TOTAL;
+  const size_t smem = TcSmem<KB, NSTAGE, TWO_SM>::TOTAL;
   {
     ProfScope prof(RB2_ST_TC_SCORE, st);
-    RB2_CUDA(cudaFuncSetAttribute(k_fullsort_tc<KB, NSTAGE, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RB2_CUDA(cudaFuncSetAttribute(k_fullsort_tc<KB, NSTAGE, KP, TWO_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)pl.grid);
@@ -704,7 +782,7 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RB2_CUDA(cudaLaunchKernelEx(&cfg, k_fullsort_tc<KB, NSTAGE, KP>, tmA, tmB, p));
+    RB2_CUDA(cudaLaunchKernelEx(&cfg, k_fullsort_tc<KB, NSTAGE, KP, TWO_SM>, tmA, tmB, p));
     RB2_CUDA(cudaGetLastError());
   }
   {
@@ -751,8 +829,11 @@ int rb2_fullsort_tc(const float *query_p, const int64_t *query_ids, int64_t nq, 
   // caller merges shards: the global K-th score sits far above a shard's 16th), 32 otherwise
   const bool small_list = (g_tc_kprime == 16) || (g_tc_kprime == 0 && k <= 8);
 #define RB2_TC(D_, KP_)                                                                                        \
-  return run_tc<D_, KP_>(query_p, query_ids, nq, item_p, n_items_local, item_base, hist_indptr, hist_indices, k, \
-                         out_ids, out_scores, workspace, workspace_bytes, st)
+  return (g_tc_variant == 1)                                                                                   \
+             ? run_tc<D_, KP_, false>(query_p, query_ids, nq, item_p, n_items_local, item_base, hist_indptr,   \
+                                      hist_indices, k, out_ids, out_scores, workspace, workspace_bytes, st)    \
+             : run_tc<D_, KP_, true>(query_p, query_ids, nq, item_p, n_items_local, item_base, hist_indptr,    \
+                                     hist_indices, k, out_ids, out_scores, workspace, workspace_bytes, st)
   if (dim == 64) {
     if (small_list) RB2_TC(64, 16);
     RB2_TC(64, 32);

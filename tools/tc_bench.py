@@ -20,6 +20,9 @@ def timeit(fn, warm=1, it=3):
 
 
 def main():
+    if len(sys.argv) > 1:
+        lib.rb2_fullsort_tc_set_variant(int(sys.argv[1]))
+        print("variant", sys.argv[1])
     dev = torch.device("cuda:0")
     gen = torch.Generator(device=dev)
     gen.manual_seed(0)
