@@ -245,8 +245,9 @@ int32_t rb2_fullsort_tc_last_fallback_rows(void);
  * when k <= 8).  More candidates = looser certificate, more epilogue work.  The result is exact either
  * way. */
 int rb2_fullsort_tc_set_kprime(int32_t kprime);
-/* MMA variant of RB2_SCORER_TC: 0 or 2 = CTA pair (tcgen05 cta_group::2, M = 256 across two SMs, each SM
- * holds half of every item slot), 1 = per-CTA M = 128 MMAs on item slots multicast to the pair. */
+/* MMA variant of RB2_SCORER_TC: 0 or 1 = per-CTA M = 128 MMAs (cta_group::1) on item slots that a CTA pair
+ * loads by halves and multicasts (default, measured faster); 2 = CTA-pair MMA (tcgen05 cta_group::2, M = 256
+ * across two SMs, each SM holds half of every item slot). */
 int rb2_fullsort_tc_set_variant(int32_t variant);
 
 /* Merge `parts` per-shard top-K lists ([parts, nq, k], each sorted) into the global top-K

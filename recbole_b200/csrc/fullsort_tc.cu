@@ -39,7 +39,7 @@ size_t rb2_fullsort_fp32_workspace(int64_t nq, int64_t n_items_local, int32_t di
 // number of rows the last RB2_SCORER_TC call had to redo in fp32 (diagnostic for bench / tests)
 static int32_t g_last_tc_fallback_rows = 0;
 static int32_t g_tc_kprime = 0;  // 0 = automatic, 16 or 32 = forced (rb2_fullsort_tc_set_kprime)
-static int32_t g_tc_variant = 0; // 0 / 2 = CTA-pair MMA (cta_group::2), 1 = per-CTA MMA with multicast B
+static int32_t g_tc_variant = 0; // 0 / 1 = per-CTA MMA with multicast B (measured faster), 2 = CTA-pair MMA (cta_group::2)
 extern "C" int rb2_fullsort_tc_set_variant(int32_t v) {
   if (v < 0 || v > 2) return RB2_EINVAL;
   g_tc_variant = v;
@@ -463,33 +463,25 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
         const int64_t g0 = p.item_base + (int64_t)it * BN;
-        // TMEM -> registers 8 columns at a time, ONE load in flight per warp: measured on B200
-        // (tools/tmem_ld_microbench.cu) tcgen05.ld.32x32b.x8 + wait sustains ~42 B/clk per warp and
-        // ~250 B/clk per SM over 8 warps, whereas x16 / x32 (or several x8 in flight) collapse to
-        // ~30 B/clk per SM -- which made the accumulator drain, not the MMA, the bottleneck.
+        // Draining the accumulators (128 KB of fp32 per tile) is what bounds this kernel, not the MMA:
+        // tools/mma_microbench*.cu / tmem_ld_microbench.cu measure 128.0 cycles per 128x256x16 MMA (100 % of
+        // peak) even with TMA and tcgen05.ld traffic running, but a streaming tcgen05.ld drain sustains only
+        // ~30-55 B/clk per SM whatever the shape (x8 ... x32) -- ~2400 cycles per tile against 1024 of MMA.
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 8) {
-          uint32_t v[8];
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                       : "r"(taddr + c0));
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          TC_LD32(taddr + c0, v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const float m = fmaxf(fmaxf(fmaxf(fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), __uint_as_float(v[2])),
-                                      fmaxf(fmaxf(__uint_as_float(v[3]), __uint_as_float(v[4])), __uint_as_float(v[5]))),
-                                fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7])));
-          if (m > tau) {
+          if (max32(v) > tau) {
             // rare path, kept compact (one copy of the insert): bit mask of the passing scores, each
-            // fetched from its register by a select tree on the run-time index
+            // fetched from its register by a 5-level select tree on the run-time index
             uint32_t mask = 0u;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) mask |= (__uint_as_float(v[j]) > tau ? 1u : 0u) << j;
+            for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) > tau ? 1u : 0u) << j;
             while (mask) {
               const int j = __ffs(mask) - 1;
               mask &= mask - 1;
-              const uint32_t a0 = (j & 1) ? v[1] : v[0], a1 = (j & 1) ? v[3] : v[2], a2 = (j & 1) ? v[5] : v[4],
-                             a3 = (j & 1) ? v[7] : v[6];
-              const uint32_t b0 = (j & 2) ? a1 : a0, b1 = (j & 2) ? a3 : a2;
-              const float s = __uint_as_float((j & 4) ? b1 : b0);
+              const float s = pick32(v, j);
               if (s > tau) consider(s, g0 + c0 + j);
             }
           }
@@ -841,7 +833,7 @@ int rb2_fullsort_tc(const float *query_p, const int64_t *query_ids, int64_t nq, 
   // caller merges shards: the global K-th score sits far above a shard's 16th), 32 otherwise
   const bool small_list = (g_tc_kprime == 16) || (g_tc_kprime == 0 && k <= 8);
 #define RB2_TC(D_, KP_)                                                                                        \
-  return (g_tc_variant == 1)                                                                                   \
+  return (g_tc_variant != 2)                                                                                   \
              ? run_tc<D_, KP_, false>(query_p, query_ids, nq, item_p, n_items_local, item_base, hist_indptr,   \
                                       hist_indices, k, out_ids, out_scores, workspace, workspace_bytes, st)    \
              : run_tc<D_, KP_, true>(query_p, query_ids, nq, item_p, n_items_local, item_base, hist_indptr,    \

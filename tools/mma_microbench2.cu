@@ -31,7 +31,7 @@ __device__ __forceinline__ void mma(uint32_t tmem_d, uint64_t a, uint64_t b, uin
       : "r"(taddr))
 
 // flags: bit0 = TMEM readers on, bit1 = bulk copies on, bit2 = readers do ALU work (max tree)
-__global__ void __launch_bounds__(192, 1) k_bench(int iters, int flags, const unsigned char *gsrc, long long *out,
+__global__ void __launch_bounds__(320, 1) k_bench(int iters, int flags, const unsigned char *gsrc, long long *out,
                                                   float *sink) {
   extern __shared__ unsigned char raw[];
   unsigned char *smem = (unsigned char *)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
@@ -113,8 +113,18 @@ __global__ void __launch_bounds__(192, 1) k_bench(int iters, int flags, const un
     long long n = 0;
     while (!done) {
       uint32_t v[32];
+      if (flags & 32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(v[8*q+0]),"=r"(v[8*q+1]),"=r"(v[8*q+2]),"=r"(v[8*q+3]),"=r"(v[8*q+4]),"=r"(v[8*q+5]),"=r"(v[8*q+6]),"=r"(v[8*q+7])
+                       : "r"(taddr + (uint32_t)((n & 7) * 32 + 8 * q)));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+      } else {
       TC_LD32(taddr + (uint32_t)((n & 7) * 32), v);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      }
       if (flags & 4) {
         float m = __uint_as_float(v[0]);
 #pragma unroll
@@ -145,18 +155,22 @@ int main() {
   const char *names[] = {"MMA alone", "MMA + 4 warps tcgen05.ld (other stage)", "MMA + bulk copies into smem",
                          "MMA + tcgen05.ld + bulk copies", "", "MMA + tcgen05.ld + max-tree ALU", "",
                          "MMA + tcgen05.ld + ALU + bulk copies"};
-  for (int flags : {0, 1, 2, 3, 5, 7, 9, 13, 17, 11}) {
+  for (int flags : {1, 33, 9, 41, 17, 49}) {
+   for (int threads : {192, 320}) {
     int iters = 4000;
     cudaMemset(d, 0, 64);
-    k_bench<<<148, 192, smem>>>(iters, flags, gsrc, d, sink);
+    k_bench<<<148, threads, smem>>>(iters, flags, gsrc, d, sink);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[3] = {0, 0, 0};
     cudaMemcpy(h, d, 24, cudaMemcpyDeviceToHost);
     double per = (double)h[0] / (iters * 8.0);
-    const char *nm = flags < 8 ? names[flags] : (flags == 9 ? "no MMA: 4 warps tcgen05.ld" : flags == 13 ? "no MMA: tcgen05.ld + ALU" : flags == 17 ? "MMA 50% duty + tcgen05.ld" : "no MMA: tcgen05.ld + bulk copies");
-    printf("%-42s %.1f cycles/MMA (%.0f%% of peak); bulk copies %lld (%.1f B/clk), tmem loads/warp %lld (%.1f B/clk/warp) [%s]\n",
-           nm, per, 100.0 * 128.0 / per, h[1], h[1] * 32768.0 / (double)h[0], h[2], h[2] * 4096.0 / (double)h[0],
+    char nmbuf[128];
+    snprintf(nmbuf, sizeof(nmbuf), "%s%s, %d reader warps, %s", (flags & 8) ? "no MMA" : (flags & 16) ? "MMA 50% duty" : "MMA 100%", "", (threads - 64) / 32, (flags & 32) ? "x8+wait" : "x32");
+    const char *nm = nmbuf; const char *unused = flags < 8 ? names[flags] : (flags == 9 ? "no MMA: 4 warps tcgen05.ld" : flags == 13 ? "no MMA: tcgen05.ld + ALU" : flags == 17 ? "MMA 50% duty + tcgen05.ld" : "no MMA: tcgen05.ld + bulk copies");
+    printf("%-42s %.1f cycles/MMA (%.0f%% of peak); bulk copies %lld (%.1f B/clk), tmem loads/warp %lld (%.1f B/clk per SM) [%s]\n",
+           nm, per, 100.0 * 128.0 / per, h[1], h[1] * 32768.0 / (double)h[0], h[2], h[2] * 4096.0 / (double)h[0] * ((threads - 64) / 32),
            cudaGetErrorString(e));
+   }
   }
   return 0;
 }
