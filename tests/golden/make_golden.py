@@ -18,6 +18,8 @@ modified or copied.  Every array saved here is an INPUT or an OUTPUT of referenc
   sampler.npz    recbole.sampler.Sampler.sample_by_user_ids with its random_list / random_pr state
   fm_steps.npz   recbole FM (token fields) + BCELoss + Adam, 2 steps
   ce_head.npz    the SASRec head expressions of sasrec.py:137-141,152-158
+  cfg1_train.npz BASELINE config 1: the reference pipeline on ml-100k, 2 epochs of Trainer._train_epoch
+                 (every batch recorded) + Trainer.evaluate
 """
 import os
 import sys
@@ -290,6 +292,66 @@ def g_fullsort_ml100k(out, out_sampler):
     print("ml-100k:", _fullsort(config, train, test, out, seed=2020, scale=1.0, extra=extra, train_epochs=8))
 
 
+def g_cfg1_train(out):
+    """BASELINE config 1 trajectory: the reference's own pipeline on ml-100k (BPR, d=64, Adam 1e-3,
+    B=2048), 2 epochs through Trainer._train_epoch, then Trainer.evaluate on the test split.  Saves
+    the initial tables, every batch the reference's dataloader + sampler produced, the final tables
+    and the result dict."""
+    from recbole.model.general_recommender.bpr import BPR
+    from recbole.trainer import Trainer
+    cfg = {
+        "model": "BPR", "dataset": "ml-100k", "data_path": os.path.join(REF, "dataset"),
+        "load_col": {"inter": ["user_id", "item_id"]}, "use_gpu": False,
+        "topk": [10], "metrics": ["Recall", "MRR", "NDCG", "Hit", "Precision"],
+    }
+    config, train, valid, test = _pipeline(cfg)
+    torch.manual_seed(2020)
+    model = BPR(config, train).to(config["device"])
+    cwd = os.getcwd()
+    os.makedirs("/tmp/rb2_golden_scratch", exist_ok=True)
+    os.chdir("/tmp/rb2_golden_scratch")
+    try:
+        trainer = Trainer(config, model)
+    finally:
+        os.chdir(cwd)
+    d = dict(U0=model.user_embedding.weight.detach().numpy().copy(),
+             V0=model.item_embedding.weight.detach().numpy().copy())
+    # record the batches by wrapping the model's loss function (trainer.py:151: loss_func argument)
+    rec = []
+
+    def loss_func(interaction):
+        rec.append(np.stack([interaction["user_id"].numpy(), interaction["item_id"].numpy(),
+                             interaction["neg_item_id"].numpy()]).astype(np.int32))
+        return model.calculate_loss(interaction)
+
+    losses = []
+    for ep in range(2):
+        losses.append(trainer._train_epoch(train, ep, loss_func=loss_func))
+    d["epoch_loss"] = np.array(losses, dtype=np.float64)
+    d["batch_sizes"] = np.array([b.shape[1] for b in rec], dtype=np.int64)
+    d["batches"] = np.concatenate(rec, axis=1)
+    d["U"] = model.user_embedding.weight.detach().numpy().copy()
+    d["V"] = model.item_embedding.weight.detach().numpy().copy()
+    with torch.no_grad():
+        result = trainer.evaluate(test, load_best_model=False)
+    d["result_keys"] = np.array(list(result.keys()))
+    d["result_vals"] = np.array(list(result.values()), dtype=np.float64)
+    ds = test.dataset
+    d["pos_user"] = ds.inter_feat[ds.uid_field].numpy()
+    d["pos_item"] = ds.inter_feat[ds.iid_field].numpy()
+    used = test.sampler.used_ids
+    uu, ii = [], []
+    for u in range(len(used)):
+        for i in sorted(used[u]):
+            uu.append(u)
+            ii.append(i)
+    d["used_user"], d["used_item"] = np.array(uu, dtype=np.int32), np.array(ii, dtype=np.int32)
+    d["uid_list"] = np.asarray(test.uid_list)
+    d["n_items"] = ds.item_num
+    print("cfg1 train:", losses, result)
+    np.savez_compressed(out, **d)
+
+
 def g_fm(out):
     from recbole.model.context_aware_recommender.fm import FM
     from recbole.utils import FeatureType
@@ -356,6 +418,7 @@ if __name__ == "__main__":
     g_ce(o("ce_head.npz"))
     g_fullsort_small(o("fullsort_small.npz"))
     g_fullsort_ml100k(o("fullsort_ml100k.npz"), o("sampler.npz"))
+    g_cfg1_train(o("cfg1_train.npz"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
