@@ -125,16 +125,19 @@ struct Tables {
 
 __device__ __forceinline__ void bpr_sample(float x, float inv_b, float &loss_term, float &g) {
   // loss.py:48   -log(gamma + sigmoid(x)) ;  d/dx = -sig*(1-sig)/(gamma+sig), times 1/B for the mean
-  float sig = 1.f / (1.f + expf(-x));
+  // MUFU-based exp / log / reciprocal: ~1e-7 relative, two orders inside the 1e-5 parity tolerance; the
+  // optimizer arithmetic (common.cuh) keeps IEEE sqrt and division.
+  float e = __expf(-x);
+  float sig = __fdividef(1.f, 1.f + e);
   float den = kGamma + sig;
-  loss_term = -logf(den);
-  g = -inv_b * sig * (1.f - sig) / den;
+  loss_term = -__logf(den);
+  g = -inv_b * __fdividef(sig * (1.f - sig), den);
 }
 
 // ---------------------------------------------------------------------------------------------
 // user side
 template <int D, bool LAZY>
-__global__ void __launch_bounds__(kThreads) k_user_side(Tables t, BprWs w, int64_t B, int T, int64_t n_tiles,
+__global__ void __launch_bounds__(kThreads, (D <= 128 && !LAZY) ? 3 : 1) k_user_side(Tables t, BprWs w, int64_t B, int T, int64_t n_tiles,
                                                          float inv_b, OptScalars o) {
   constexpr int LANES = RowCfg<D>::LANES;
   constexpr int UNR = 4;
@@ -187,7 +190,9 @@ __global__ void __launch_bounds__(kThreads) k_user_side(Tables t, BprWs w, int64
         int2 pn = w.pn[s[j]];
         a[j] = row_ld_effective<D, LAZY>(t.ip, t.im, t.iv, t.il, pn.x, lane, o);
         b[j] = row_ld_effective<D, LAZY>(t.ip, t.im, t.iv, t.il, pn.y, lane, o);
-        ur[j] = row_ld_effective<D, LAZY>(t.up, t.um, t.uv, t.ul, k[j], lane, o);
+        // the user row is only needed where a run starts (a batch hits the same user many times)
+        const uint32_t before = (j == 0) ? cur : k[j > 0 ? j - 1 : 0];
+        if (k[j] != before) ur[j] = row_ld_effective<D, LAZY>(t.up, t.um, t.uv, t.ul, k[j], lane, o);
       }
     }
 #pragma unroll
@@ -200,11 +205,10 @@ __global__ void __launch_bounds__(kThreads) k_user_side(Tables t, BprWs w, int64
         acc = row_zero<D>();
         started_before = (base + j == lo) && (cur == prev_key);
       }
-      // x = <u, vi> - <u, vj>   (bpr.py:81: two dots, then the difference)
-      float ps = group_sum<LANES>(row_dot_lane<D>(u, a[j]), gmask);
-      float ns = group_sum<LANES>(row_dot_lane<D>(u, b[j]), gmask);
+      // x = <u, vi> - <u, vj>   (bpr.py:81); the two per-lane partial dots share one shuffle reduction
+      float x = group_sum<LANES>(row_dot_lane<D>(u, a[j]) - row_dot_lane<D>(u, b[j]), gmask);
       float lt, g;
-      bpr_sample(ps - ns, inv_b, lt, g);
+      bpr_sample(x, inv_b, lt, g);
       loss_local += lt;
       row_fma<D>(acc, g, a[j]);    // du += g*vi - g*vj
       row_fma<D>(acc, -g, b[j]);
@@ -380,10 +384,9 @@ __global__ void __launch_bounds__(kThreads) k_bpr_loss(const float *__restrict__
       n = min(max(n, (int64_t)0), n_items - 1);
     }
     Row<D> ur = row_ldg<D>(up, u, lane), a = row_ldg<D>(ip, p, lane), b = row_ldg<D>(ip, n, lane);
-    float ps = group_sum<LANES>(row_dot_lane<D>(ur, a), gmask);
-    float ns = group_sum<LANES>(row_dot_lane<D>(ur, b), gmask);
+    float x = group_sum<LANES>(row_dot_lane<D>(ur, a) - row_dot_lane<D>(ur, b), gmask);
     float lt, g;
-    bpr_sample(ps - ns, 1.f, lt, g);
+    bpr_sample(x, 1.f, lt, g);
     local += lt;
   }
   if (lane == 0 && gid < ngroups) part[gid] = (double)local;
