@@ -53,7 +53,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -94,7 +94,7 @@ class ClockSampler:
 # the reference's CPU path (oracle/torch_port.py) -- cpu_baseline leg and --impl reference arm
 # -------------------------------------------------------------------------------------------------
 
-def cpu_reference(w, train_steps, warmup_steps, eval_users, threads):
+def cpu_reference(w, train_steps, warmup_steps, eval_users, threads, budget_s=120.0):
     import torch
     from oracle import torch_port
     torch.set_num_threads(threads)
@@ -106,9 +106,19 @@ def cpu_reference(w, train_steps, warmup_steps, eval_users, threads):
     opt = torch_port.build_optimizer(model, "adam", 1e-3, 0.0)
     batches = [tuple(torch.from_numpy(np.ascontiguousarray(x)) for x in b) for b in w.batches]
     nb = len(batches)
-    torch_port.train_steps(model, opt, [batches[i % nb] for i in range(warmup_steps)])
+    # bounded sample: if the whole run would exceed `budget_s`, every step processes only the first
+    # `per_step` triples of its batch (same arithmetic, same metric)
+    per_step = w.batch
     t0 = time.perf_counter()
-    loss = torch_port.train_steps(model, opt, [batches[(warmup_steps + i) % nb] for i in range(train_steps)])
+    torch_port.train_steps(model, opt, [batches[0]])
+    t1 = time.perf_counter() - t0
+    total_steps = max(warmup_steps - 1, 0) + train_steps
+    if t1 * total_steps > budget_s:
+        per_step = max(1024, int(w.batch * budget_s / (t1 * total_steps)))
+    cut = lambda b: tuple(x[:per_step] for x in b)  # noqa: E731
+    torch_port.train_steps(model, opt, [cut(batches[i % nb]) for i in range(1, warmup_steps)])
+    t0 = time.perf_counter()
+    loss = torch_port.train_steps(model, opt, [cut(batches[(warmup_steps + i) % nb]) for i in range(train_steps)])
     t_train = time.perf_counter() - t0
     ne = min(eval_users, len(w.uid_list))
     hist = (w.hist[0][:ne + 1], w.hist[1])
@@ -116,7 +126,8 @@ def cpu_reference(w, train_steps, warmup_steps, eval_users, threads):
     t0 = time.perf_counter()
     res, _ = torch_port.full_sort_eval(model, w.uid_list[:ne], hist, pos, w.n_items, topk=(10,))
     t_eval = time.perf_counter() - t0
-    return dict(train_samples_per_s=train_steps * w.batch / t_train, train_s=t_train, train_steps=train_steps,
+    return dict(train_samples_per_s=train_steps * per_step / t_train, train_s=t_train, train_steps=train_steps,
+                per_step=per_step,
                 eval_users_per_s=ne / t_eval, eval_s=t_eval, eval_users=ne, loss=loss, result=res)
 
 
@@ -127,8 +138,8 @@ def run_reference(args, rank, world):
     w = bw.BprWorkload(args.workload, batch=args.batch, n_batches=args.n_batches)
     threads = os.cpu_count() or 1
     r = cpu_reference(w, args.steps, args.warmup, args.ref_eval_users, threads)
-    sample = "%d warm-up + %d timed steps of %d triples (torch CPU, dense grads + dense Adam); eval of the first %d test users" % (
-        args.warmup, args.steps, w.batch, r["eval_users"])
+    sample = "%d warm-up + %d timed steps of %d triples each (of the %d-triple batch; torch CPU, dense grads + dense Adam); eval of the first %d test users" % (
+        args.warmup, args.steps, r["per_step"], w.batch, r["eval_users"])
     line = {
         "impl": "reference", "metric": "bpr_train_samples_per_s", "value": r["train_samples_per_s"], "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -350,8 +361,8 @@ def run_ours_multi(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--batch", type=int, default=None)
