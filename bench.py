@@ -299,8 +299,13 @@ def run_ours(args, rank, world, local_rank):
     alg_step = B * (72 * d + 24)                      # bytes per triple, row-sparse Adam
     alg_user = B * (32 * d + 24)                      # the share k_user_side must move
     step_kernels_ms = sum(v[0] for v in stages.values()) / args.steps
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tp) and args.workload == "cfg2" and B == (1 << 20):
+        traffic = json.load(open(tp)).get("k_user_side@cfg2")     # bytes per launch, from the committed ncu capture
     roofline = {"bound": "hbm", "kernel": "k_user_side", "achieved": alg_user / (us_ms * 1e-3) / 1e9 if us_ms else None,
-                "peak": peaks["hbm"], "unit": "GB/s", "frac": None, "traffic": None,
+                "peak": peaks["hbm"], "unit": "GB/s", "frac": None, "traffic": traffic,
+                "algorithmic_bytes_per_launch": alg_user,
                 "peak_source": peaks["source"], "ms_per_launch": us_ms,
                 "share_of_step": us_ms / step_kernels_ms if step_kernels_ms else None,
                 "step": {"achieved": alg_step / (train_ms * 1e-3) / 1e9, "frac": alg_step / (train_ms * 1e-3) / 1e9 / peaks["hbm"],

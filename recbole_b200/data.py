@@ -132,3 +132,35 @@ def split_by_ratio(user, item, ratios=(0.8, 0.1, 0.1), seed=0):
     a, b = ratios[0], ratios[0] + ratios[1]
     m0, m1, m2 = r < a, (r >= a) & (r < b), r >= b
     return [(user[m], item[m]) for m in (m0, m1, m2)]
+
+
+class DeviceTrainLoader:
+    """Device-resident replacement for the training side of ``GeneralNegSampleDataLoader``
+    (recbole/data/dataloader/general_dataloader.py:212-241) + ``Dataset.shuffle``
+    (recbole/data/interaction.py:272-276) + ``Interaction.to(device)`` (trainer.py:158-159): the
+    interactions live in HBM, an epoch is a device-side permutation, negatives come from the sampler
+    kernel, and every batch is already an on-device ``Interaction`` with the reference's field names
+    (pair-wise format: user, item, neg_item).  SURVEY.md 8f rank 1."""
+
+    def __init__(self, user, item, sampler, batch_size, uid_field="user_id", iid_field="item_id", neg_prefix="neg_",
+                 shuffle=True, seed=2020):
+        from .interaction import Interaction
+        self._Interaction = Interaction
+        self.user = torch.as_tensor(user, dtype=torch.int64, device=sampler.device).contiguous()
+        self.item = torch.as_tensor(item, dtype=torch.int64, device=sampler.device).contiguous()
+        self.sampler, self.batch_size, self.shuffle = sampler, int(batch_size), shuffle
+        self.uid_field, self.iid_field, self.neg_field = uid_field, iid_field, neg_prefix + iid_field
+        self.gen = torch.Generator(device=sampler.device)
+        self.gen.manual_seed(int(seed))
+
+    def __len__(self):
+        return (self.user.numel() + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        n = self.user.numel()
+        perm = torch.randperm(n, device=self.user.device, generator=self.gen) if self.shuffle else None
+        for lo in range(0, n, self.batch_size):
+            idx = perm[lo:lo + self.batch_size] if perm is not None else slice(lo, lo + self.batch_size)
+            u = self.user[idx].contiguous()
+            yield self._Interaction({self.uid_field: u, self.iid_field: self.item[idx].contiguous(),
+                                     self.neg_field: self.sampler.sample_by_user_ids(u, 1)})
