@@ -124,6 +124,9 @@ class FusedBPR(nn.Module):
 
     # ---- the reference's plugin API -------------------------------------------------------------
     def calculate_loss(self, interaction):  # bpr.py:74-83
+        # adam_lazy: the forward-only kernel reads the raw tables, so bring every row up to date first
+        # (O(table), what the reference's dense Adam costs anyway; train_step() does not need this)
+        self.flush()
         user, pos, neg = self._ids(interaction)
         return _RecordBatch.apply(self.user_embedding.weight, self, user, pos, neg)
 
