@@ -137,7 +137,7 @@ __device__ __forceinline__ void bpr_sample(float x, float inv_b, float &loss_ter
 // ---------------------------------------------------------------------------------------------
 // user side
 template <int D, bool LAZY>
-__global__ void __launch_bounds__(kThreads, (D <= 64 && !LAZY) ? 3 : 1) k_user_side(Tables t, BprWs w, int64_t B, int T, int64_t n_tiles,
+__global__ void __launch_bounds__(kThreads, LAZY ? 1 : (D <= 64 ? 3 : (D == 128 ? 2 : 1))) k_user_side(Tables t, BprWs w, int64_t B, int T, int64_t n_tiles,
                                                          float inv_b, OptScalars o) {
   constexpr int LANES = RowCfg<D>::LANES;
   constexpr int UNR = 4;
