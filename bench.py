@@ -382,6 +382,11 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", dest="skip_cpu", help="profiling runs only")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.workload in ("cfg4", "cfg5"):
+        if rank == 0 and args.impl != "reference":
+            import bench_extra
+            (bench_extra.run_cfg4 if args.workload == "cfg4" else bench_extra.run_cfg5)(args, load_peaks, ClockSampler)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -130,3 +130,55 @@ def sampler_draw(random_list, random_pr, used_sets, user_ids, num):
         check = np.array([i for i, used, v in zip(check, used_sets[key_ids[check]], value_ids[check]) if v in used],
                          dtype=np.int64)
     return value_ids, pr
+
+
+class RefFM(nn.Module):
+    """FM on TOKEN fields restated with the reference's own torch calls:
+    FMEmbedding (layers.py:121-144), BaseFactorizationMachine (layers.py:147-171), FMFirstOrderLinear token
+    part + bias (layers.py:1021-1061), FM.forward / calculate_loss (fm.py:47-56)."""
+
+    def __init__(self, field_dims, dim):
+        super().__init__()
+        rows = int(sum(field_dims))
+        self.offsets = torch.as_tensor(np.array((0, *np.cumsum(field_dims)[:-1]), dtype=np.int64))
+        self.embedding = nn.Embedding(rows, dim)
+        self.first_order = nn.Embedding(rows, 1)
+        self.bias = nn.Parameter(torch.zeros((1,)))
+        nn.init.xavier_normal_(self.embedding.weight.data)
+        nn.init.xavier_normal_(self.first_order.weight.data)
+        self.loss = nn.BCELoss()
+
+    def forward(self, ids):  # ids int64 [B, F]
+        x = ids + self.offsets.unsqueeze(0)                       # layers.py:142
+        e = self.embedding(x)                                     # [B, F, d]
+        square_of_sum = torch.sum(e, dim=1) ** 2                  # layers.py:165-166
+        sum_of_square = torch.sum(e ** 2, dim=1)
+        fm = 0.5 * torch.sum(square_of_sum - sum_of_square, dim=1, keepdim=True)
+        first = torch.sum(self.first_order(x), dim=1) + self.bias  # layers.py:1021-1061
+        return torch.sigmoid(first + fm).squeeze()                # fm.py:49-50
+
+    def calculate_loss(self, ids, label):
+        return self.loss(self.forward(ids), label)                # fm.py:52-56
+
+
+def fm_train_steps(model, optimizer, batches):
+    model.train()
+    total = 0.0
+    for ids, label in batches:
+        optimizer.zero_grad()
+        loss = model.calculate_loss(ids, label)
+        total += loss.item()
+        loss.backward()
+        optimizer.step()
+    return total
+
+
+@torch.no_grad()
+def ce_head(X, E, target, k=10):
+    """sasrec.py:137-141 (CE branch) + 152-158 / trainer.py:343 / evaluators.py:72 on one chunk."""
+    logits = torch.matmul(X, E.transpose(0, 1))
+    loss = nn.functional.cross_entropy(logits, target)
+    scores = logits.clone()
+    scores[:, 0] = -np.inf
+    _, idx = torch.topk(scores, k, dim=-1)
+    return loss, idx
