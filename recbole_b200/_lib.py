@@ -68,6 +68,7 @@ SIGNATURES = {
     "rb2_fullsort_tc_last_fallback_rows": (_i32, []),
     "rb2_fullsort_tc_set_kprime": (ctypes.c_int, [_i32]),
     "rb2_fullsort_tc_set_variant": (ctypes.c_int, [_i32]),
+    "rb2_fullsort_tc_set_trace": (ctypes.c_int, [_p]),
     "rb2_topk_merge": (ctypes.c_int, [_p, _p, _i32, _i64, _i32, _p, _p, _p]),
     "rb2_topk_metrics_workspace_bytes": (_sz, [_i64, _i32]),
     "rb2_topk_metrics": (ctypes.c_int, [_p, _i64, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),

@@ -25,6 +25,7 @@
 //                    compacted and redone by the fp32 kernel, so the result is always exact.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -39,9 +40,11 @@ size_t rb2_fullsort_fp32_workspace(int64_t nq, int64_t n_items_local, int32_t di
 // number of rows the last RB2_SCORER_TC call had to redo in fp32 (diagnostic for bench / tests)
 static int32_t g_last_tc_fallback_rows = 0;
 static int32_t g_tc_kprime = 0;  // 0 = automatic, 16 or 32 = forced (rb2_fullsort_tc_set_kprime)
-static int32_t g_tc_variant = 0; // 0 / 1 = per-CTA MMA with multicast B (measured faster), 2 = CTA-pair MMA (cta_group::2)
+// 0 / 1 = per-CTA MMA with multicast B, bf16 operands, fp32 accumulators; 2 = CTA-pair MMA (cta_group::2);
+// 3 = per-CTA MMA, fp16 operands (rows rescaled by powers of two), FP16 accumulators drained with .pack::16b
+static int32_t g_tc_variant = 0;
 extern "C" int rb2_fullsort_tc_set_variant(int32_t v) {
-  if (v < 0 || v > 2) return RB2_EINVAL;
+  if (v < 0 || v > 3) return RB2_EINVAL;
   g_tc_variant = v;
   return 0;
 }
@@ -51,6 +54,13 @@ extern "C" int rb2_fullsort_tc_set_kprime(int32_t kp) {
   return 0;
 }
 extern "C" int32_t rb2_fullsort_tc_last_fallback_rows(void) { return g_last_tc_fallback_rows; }
+// diagnostics: device buffer of 16 int64 per CTA that k_fullsort_tc fills with the cycles its producer / MMA /
+// epilogue roles spent waiting on each barrier (nullptr = off)
+static long long *g_tc_trace = nullptr;
+extern "C" int rb2_fullsort_tc_set_trace(void *device_buffer) {
+  g_tc_trace = static_cast<long long *>(device_buffer);
+  return 0;
+}
 
 namespace {
 
@@ -187,6 +197,22 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // instruction descriptor: c=f32, a=b=bf16, both K-major, N=256, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
+// fp16 operands, FP16 accumulator (c_format = a_format = b_format = 0): one 16-bit score in the low half of
+// every 32-bit TMEM column (tools/mma_f16acc_check.cu)
+constexpr uint32_t kIdescH16 = ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// 64 columns of 16-bit cells -> 32 registers (low half = even column, high half = odd column)
+#define TC_LD32P(taddr, v)                                                                                      \
+  asm volatile(                                                                                                 \
+      "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, " \
+      "%13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"  \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),       \
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), \
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),           \
+        "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),           \
+        "=r"(v[30]), "=r"(v[31])                                                                               \
+      : "r"(taddr))
+
 #define TC_LD32(taddr, v)                                                                                       \
   asm volatile(                                                                                                 \
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, " \
@@ -213,7 +239,18 @@ struct TcParams {
   const int64_t *hist_indptr, *hist_indices;
   int *cand_ids;      // [n_split * 2][nq][KP]   (x2: one list per epilogue warp set)
   float *cand_sc;     // approximate (bf16) scores, each list sorted descending
+  long long *trace;   // diagnostics (rb2_fullsort_tc_set_trace), usually nullptr
 };
+#define TC_TIMED(slot, stmt)                          \
+  do {                                                \
+    if (p.trace) {                                    \
+      long long t_ = clock64();                       \
+      stmt;                                           \
+      tr[slot] += clock64() - t_;                     \
+    } else {                                          \
+      stmt;                                           \
+    }                                                 \
+  } while (0)
 
 template <int KB, int NSTAGE, bool TWO_SM = false>
 struct TcSmem {
@@ -269,12 +306,28 @@ __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
   return fmaxf(fmaxf(fmaxf(a, b), c), fmaxf(m[9], m[10]));
 }
 
+__device__ __forceinline__ __half2 as_h2(uint32_t w) { return *reinterpret_cast<__half2 *>(&w); }
+// max over the 64 fp16 scores packed in 32 registers (HMNMX2 tree)
+__device__ __forceinline__ float max64h(const uint32_t (&v)[32]) {
+  __half2 m[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) m[i] = __hmax2(as_h2(v[2 * i]), as_h2(v[2 * i + 1]));
+#pragma unroll
+  for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+    for (int i = 0; i < w; ++i) m[i] = __hmax2(m[i], m[i + w]);
+  return fmaxf(__low2float(m[0]), __high2float(m[0]));
+}
+__device__ __forceinline__ uint32_t pick32u(const uint32_t (&v)[32], int j) {
+  return __float_as_uint(pick32(v, j));
+}
+
 // TWO_SM = false: cta_group::1, each CTA runs its own M=128 MMAs on a full B slot that the pair loads by
 //                 halves and multicasts (NSTAGE slots of 32 KB).
 // TWO_SM = true : cta_group::2, one M=256 MMA per k-step issued by CTA 0 for the pair; each CTA keeps only
 //                 its half of every B slot (NSTAGE slots of 16 KB: twice the tiles in flight, half the
 //                 shared-memory operand traffic per SM).
-template <int KB, int NSTAGE, int KP, bool TWO_SM>
+template <int KB, int NSTAGE, int KP, bool TWO_SM, bool H16>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
   constexpr int SLOT_BYTES = TWO_SM ? UNIT_BYTES / 2 : UNIT_BYTES;
@@ -333,9 +386,10 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
+      long long tr[16] = {0}, t_begin = clock64();
       for (int w = cluster_id; w < n_work; w += n_clusters) {
         const int ut = 2 * (w % n_utp) + crank, sp = w / n_utp;
-        mbar_wait(a_empty, a_phase ^ 1);
+        TC_TIMED(1, mbar_wait(a_empty, a_phase ^ 1));
         if (TWO_SM) {
           // both CTAs' A tiles report to CTA 0's barrier (the MMA issuer lives there)
           if (crank == 0) mbar_expect_tx(a_full, 2 * KB * A_KB_BYTES);
@@ -350,7 +404,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const int t1 = min(t0 + p.tiles_per_split, n_tiles_all);
         for (int it = t0; it < t1; ++it) {
           for (int kb = 0; kb < KB; ++kb) {
-            mbar_wait(&empty[stage], phase ^ 1);       // both CTAs are done reading this slot
+            TC_TIMED(0, mbar_wait(&empty[stage], phase ^ 1));       // both CTAs are done reading this slot
             if (TWO_SM) {
               if (crank == 0) mbar_expect_tx(&full[stage], UNIT_BYTES);   // my half + the peer's half
               tma_load_2d_2sm(sB + (size_t)stage * SLOT_BYTES, &tmB, kb * BK, it * BN + crank * (BN / 2),
@@ -364,25 +418,33 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           }
         }
       }
+      if (p.trace) {
+        long long *o = p.trace + (size_t)blockIdx.x * 16;
+        o[0] = tr[0]; o[1] = tr[1]; o[11] = clock64() - t_begin;
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread; in the 2-SM variant only CTA 0's) =====================
     if (lane == 0 && (!TWO_SM || crank == 0)) {
       int stage = 0;
       uint32_t phase = 0, a_phase = 0, tcount = 0;
+      long long tr[16] = {0}, t_begin = clock64();
       for (int w = cluster_id; w < n_work; w += n_clusters) {
         const int sp = w / n_utp;
-        mbar_wait(a_full, a_phase);
+        TC_TIMED(4, mbar_wait(a_full, a_phase));
         a_phase ^= 1;
         const int t0 = sp * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, n_tiles_all);
         for (int it = t0; it < t1; ++it, ++tcount) {
           const int acc = tcount & 1;
-          mbar_wait(&t_empty[acc], ((tcount >> 1) & 1) ^ 1);
+          TC_TIMED(3, mbar_wait(&t_empty[acc], ((tcount >> 1) & 1) ^ 1));
           tc_fence_after();
+          long long *ev = (p.trace && blockIdx.x == 0 && tcount >= 1000u && tcount < 1064u)
+                              ? p.trace + 148 * 16 + (size_t)(tcount - 1000u) * 16 : nullptr;
+          if (ev) ev[0] = clock64();
           const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
           for (int kb = 0; kb < KB; ++kb) {
-            mbar_wait(&full[stage], phase);
+            TC_TIMED(2, mbar_wait(&full[stage], phase));
             tc_fence_after();
             const uint64_t adesc = make_smem_desc(smem_u32(sA + kb * A_KB_BYTES));
             const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)stage * SLOT_BYTES));
@@ -393,7 +455,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 tc_mma_bf16_2sm(tmem_d, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), kIdesc2,
                                 (kb | k4) ? 1u : 0u);
               else
-                tc_mma_bf16(tmem_d, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), kIdesc,
+                tc_mma_bf16(tmem_d, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), H16 ? kIdescH16 : kIdesc,
                             (kb | k4) ? 1u : 0u);
             }
             // the slot is free for both producers once these MMAs have read it
@@ -401,8 +463,13 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
           if (TWO_SM) tc_commit_2sm(&t_full[acc]); else tc_commit(&t_full[acc]);      // accumulator stage complete
+          if (ev) ev[1] = clock64();
         }
         if (TWO_SM) tc_commit_2sm(a_empty); else tc_commit(a_empty);   // every MMA reading this A tile completed
+      }
+      if (p.trace) {
+        long long *o = p.trace + (size_t)blockIdx.x * 16;
+        o[2] = tr[2]; o[3] = tr[3]; o[4] = tr[4]; o[5] = clock64() - t_begin; o[10] = tcount;
       }
     }
   } else {
@@ -412,6 +479,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int t = quarter * 32 + lane;            // row inside the tile
     uint32_t *my_bloom = bloom + t;               // word i at my_bloom[i * BM]
     uint32_t tcount = 0;
+    long long tr[16] = {0};
     for (int w = cluster_id; w < n_work; w += n_clusters) {
       const int ut = 2 * (w % n_utp) + crank, sp = w / n_utp;
       const int64_t r = (int64_t)ut * BM + t;
@@ -459,19 +527,52 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       for (int it = t0; it < t1; ++it, ++tcount) {
         const int acc = tcount & 1;
         if (acc != ws) continue;
-        mbar_wait(&t_full[acc], (tcount >> 1) & 1);
+        TC_TIMED(6, mbar_wait(&t_full[acc], (tcount >> 1) & 1));
         tc_fence_after();
+        const long long t_drain = p.trace ? clock64() : 0;
+        long long *ev = (p.trace && blockIdx.x == 0 && quarter == 0 && lane == 0 && tcount >= 1000u && tcount < 1064u)
+                            ? p.trace + 148 * 16 + (size_t)(tcount - 1000u) * 16 : nullptr;
+        if (ev) ev[2] = t_drain;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
         const int64_t g0 = p.item_base + (int64_t)it * BN;
         // Draining the accumulators (128 KB of fp32 per tile) is what bounds this kernel, not the MMA:
         // tools/mma_microbench*.cu / tmem_ld_microbench.cu measure 128.0 cycles per 128x256x16 MMA (100 % of
         // peak) even with TMA and tcgen05.ld traffic running, but a streaming tcgen05.ld drain sustains only
         // ~30-55 B/clk per SM whatever the shape (x8 ... x32) -- ~2400 cycles per tile against 1024 of MMA.
+        if (H16) {
+          // FP16 accumulators: half the registers to move per score (the drain is paid per destination
+          // register, tools/tmem_ld_microbench.cu), 64 columns per load
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 64) {
+            uint32_t v[32];
+            TC_LD32P(taddr + c0, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (ev) ev[4 + c0 / 64] = clock64();
+            if (max64h(v) > tau) {
+              uint32_t mlo = 0u, mhi = 0u;   // passing scores in the even / odd columns
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                mlo |= (__low2float(as_h2(v[j])) > tau ? 1u : 0u) << j;
+                mhi |= (__high2float(as_h2(v[j])) > tau ? 1u : 0u) << j;
+              }
+              while (mlo | mhi) {             // ascending column order
+                const int jl = mlo ? __ffs(mlo) - 1 : 32, jh = mhi ? __ffs(mhi) - 1 : 32;
+                const bool odd = jh < jl;
+                const int j = odd ? jh : jl;
+                if (odd) mhi &= mhi - 1; else mlo &= mlo - 1;
+                const __half2 h = as_h2(pick32u(v, j));
+                const float s = odd ? __high2float(h) : __low2float(h);
+                if (s > tau) consider(s, g0 + c0 + 2 * j + (odd ? 1 : 0));
+              }
+            }
+          }
+        } else {
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t v[32];
           TC_LD32(taddr + c0, v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (ev) ev[4 + c0 / 32] = clock64();
           if (max32(v) > tau) {
             // rare path, kept compact (one copy of the insert): bit mask of the passing scores, each
             // fetched from its register by a 5-level select tree on the run-time index
@@ -486,8 +587,11 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             }
           }
         }
+        }
         tc_fence_before();
         if (TWO_SM) mbar_arrive_cta0(&t_empty[acc]); else mbar_arrive(&t_empty[acc]);
+        if (p.trace) tr[7] += clock64() - t_drain;
+        if (ev) ev[3] = clock64();
       }
       if (active) {
         int64_t o = (((int64_t)sp * 2 + ws) * p.nq + r) * KP;
@@ -497,6 +601,10 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           p.cand_sc[o + j] = ls[j];
         }
       }
+    }
+    if (p.trace && quarter == 0 && lane == 0) {   // one thread of each epilogue warp set
+      long long *o = p.trace + (size_t)blockIdx.x * 16 + 6 + 2 * ws;
+      o[0] = tr[6]; o[1] = tr[7];
     }
   }
 
@@ -511,37 +619,89 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 }
 
 // ---------------------------------------------------------------------------------------------
-// fp32 -> bf16 rows (+ norms).  One lane group per row.
+// fp32 -> 16-bit rows (+ norms).  One lane group per row.
+//   H16 = false: bf16, no scaling.
+//   H16 = true : fp16 after an exact power-of-two rescale so that every score fits the FP16 accumulator:
+//                queries by their own 2^-e (||u * scale|| in [0.5, 1)), items by the table-wide `*gscale`
+//                (max ||v * scale|| in [0.5, 1)).  Norms are those of the SCALED rows.  row_acc[r] =
+//                sum over the d/16 MMA k-steps of ||h(u)[0 : 16 j]|| bounds the sum of the partial
+//                accumulations the tensor core rounds to fp16.
+__device__ __forceinline__ float pow2_scale(float norm) {
+  if (!(norm > 0.f) || !isfinite(norm)) return 1.f;
+  int e;
+  frexpf(norm, &e);                 // norm = m * 2^e, m in [0.5, 1)
+  e = max(min(e, 120), -120);
+  return ldexpf(1.f, -e);
+}
+
 template <int D>
+__global__ void __launch_bounds__(256) k_rows_max_sqnorm(const float *__restrict__ src, int64_t rows,
+                                                          float *__restrict__ out_max_sq) {
+  constexpr int LANES = RowCfg<D>::LANES;
+  const int lane = threadIdx.x % LANES;
+  const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x % 32) / LANES * LANES));
+  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  if (r >= rows) return;
+  Row<D> x = row_ldg<D>(src, r, lane);
+  float n2 = group_sum<LANES>(row_dot_lane<D>(x, x), gmask);
+  if (lane == 0) atomicMax(reinterpret_cast<int *>(out_max_sq), __float_as_int(n2));   // non-negative (NaN sorts on top)
+}
+__global__ void k_item_scale(float *maxes) { maxes[2] = pow2_scale(sqrtf(maxes[3])); }
+
+template <int D, bool H16>
 __global__ void __launch_bounds__(256) k_convert_rows(const float *__restrict__ src, const int64_t *__restrict__ ids,
-                                                       int64_t rows, int64_t src_rows, __nv_bfloat16 *__restrict__ dst,
+                                                       int64_t rows, int64_t src_rows, uint16_t *__restrict__ dst,
                                                        float *__restrict__ row_norm, float *__restrict__ row_dnorm,
-                                                       float *__restrict__ max_bnorm, float *__restrict__ max_dnorm) {
+                                                       float *__restrict__ max_bnorm, float *__restrict__ max_dnorm,
+                                                       const float *__restrict__ gscale, float *__restrict__ row_scale,
+                                                       float *__restrict__ row_acc) {
   constexpr int LANES = RowCfg<D>::LANES;
   constexpr int VPL = RowCfg<D>::VPL;
+  static_assert(!H16 || VPL == 1, "the fp16 path covers d <= 128");
   const int lane = threadIdx.x % LANES;
   const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x % 32) / LANES * LANES));
   int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
   if (r >= rows) return;
   int64_t sr = ids ? min(max(ids[r], (int64_t)0), src_rows - 1) : r;
   Row<D> x = row_ldg<D>(src, sr, lane);
+  float scale = 1.f;
+  if (H16) scale = gscale ? *gscale : pow2_scale(sqrtf(group_sum<LANES>(row_dot_lane<D>(x, x), gmask)));
   float n2 = 0.f, d2 = 0.f, b2 = 0.f;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    float f[4] = {x.v[i].x, x.v[i].y, x.v[i].z, x.v[i].w};
-    __nv_bfloat16 h[4];
+    float f[4] = {x.v[i].x * scale, x.v[i].y * scale, x.v[i].z * scale, x.v[i].w * scale};
+    uint16_t h[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      h[e] = __float2bfloat16_rn(f[e]);
-      float back = __bfloat162float(h[e]);
+      float back;
+      if (H16) {
+        __half hh = __float2half_rn(f[e]);
+        h[e] = __half_as_ushort(hh);
+        back = __half2float(hh);
+      } else {
+        __nv_bfloat16 hb = __float2bfloat16_rn(f[e]);
+        h[e] = __bfloat16_as_ushort(hb);
+        back = __bfloat162float(hb);
+      }
       n2 = fmaf(f[e], f[e], n2);
       b2 = fmaf(back, back, b2);
       d2 = fmaf(f[e] - back, f[e] - back, d2);
     }
     uint2 packed;
-    packed.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
-    packed.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+    packed.x = (uint32_t)h[0] | ((uint32_t)h[1] << 16);
+    packed.y = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
     reinterpret_cast<uint2 *>(dst + r * D)[i * LANES + lane] = packed;
+  }
+  float acc = 0.f;
+  if (H16 && row_acc) {
+    // prefix sums of ||h(u)||^2 over the lanes (4 lanes = one K=16 MMA step)
+    float pre = b2;
+#pragma unroll
+    for (int o = 1; o < LANES; o <<= 1) {
+      float t = __shfl_up_sync(gmask, pre, o, LANES);
+      if (lane >= o) pre += t;
+    }
+    acc = group_sum<LANES>((lane % 4 == 3) ? sqrtf(pre) * 1.0001f : 0.f, gmask);
   }
   n2 = group_sum<LANES>(n2, gmask);
   d2 = group_sum<LANES>(d2, gmask);
@@ -551,6 +711,8 @@ __global__ void __launch_bounds__(256) k_convert_rows(const float *__restrict__ 
     float nn = sqrtf(n2) * 1.0001f, dd = sqrtf(d2) * 1.0001f, bb = sqrtf(b2) * 1.0001f;
     if (row_norm) row_norm[r] = nn;
     if (row_dnorm) row_dnorm[r] = dd;
+    if (row_scale) row_scale[r] = scale;
+    if (row_acc) row_acc[r] = acc;
     if (max_bnorm) atomicMax(reinterpret_cast<int *>(max_bnorm), __float_as_int(bb));   // non-negative floats
     if (max_dnorm) atomicMax(reinterpret_cast<int *>(max_dnorm), __float_as_int(dd));
   }
@@ -559,12 +721,13 @@ __global__ void __launch_bounds__(256) k_convert_rows(const float *__restrict__ 
 // ---------------------------------------------------------------------------------------------
 // exact re-score + order + certificate.  One warp per query row; `parts` sorted lists of KP
 // candidates each (parts * KP <= 1024).
-template <int D, int KP>
+template <int D, int KP, bool H16>
 __global__ void __launch_bounds__(128) k_refine(const float *__restrict__ query_p, const int64_t *__restrict__ query_ids,
                                                  int64_t nq, const float *__restrict__ item_p, int64_t item_base,
                                                  const int *__restrict__ cand_ids, const float *__restrict__ cand_sc,
                                                  int parts, int K, const float *__restrict__ qnorm,
                                                  const float *__restrict__ qdnorm, const float *__restrict__ maxes,
+                                                 const float *__restrict__ qscale, const float *__restrict__ qacc,
                                                  int64_t *__restrict__ out_ids, float *__restrict__ out_scores,
                                                  int32_t *__restrict__ fail_rows, int32_t *__restrict__ fail_count) {
   constexpr int MAXC = 32;  // candidates per lane
@@ -642,7 +805,15 @@ __global__ void __launch_bounds__(128) k_refine(const float *__restrict__ query_
   if (lane == 0 && any_full) {
     // |approx - exact| <= ||du||*max||bv|| + ||u||*max||dv||  (+ fp32 accumulation slack)
     float E = qdnorm[r] * maxes[0] + qnorm[r] * maxes[1] + 1.6e-5f * qnorm[r] * maxes[0];
-    bool ok = (found == K) && (kth > tau_max + E);
+    float kth_s = kth;
+    if (H16) {
+      // scores live in the rescaled domain (exact powers of two).  Every K=16 MMA rounds the running sum
+      // to fp16 (round-to-nearest, bit-checked by tools/mma_f16acc_check.cu): |err_j| <= 2^-11 |acc_j|,
+      // |acc_j| <= ||h(u)[0:16j]|| * max||h(v)||; the constant adds the subnormal / second-order slack
+      kth_s = kth * qscale[r] * maxes[2];
+      E += 1.03f * 4.8828125e-4f * qacc[r] * maxes[0] + 3e-5f;
+    }
+    bool ok = (found == K) && (kth_s > tau_max + E);
     if (!ok) {
       int slot = atomicAdd(fail_count, 1);
       fail_rows[slot] = (int32_t)r;
@@ -651,8 +822,9 @@ __global__ void __launch_bounds__(128) k_refine(const float *__restrict__ query_
 }
 
 struct TcWs {
-  __nv_bfloat16 *qb, *vb;
-  float *qnorm, *qdnorm, *maxes;  // maxes[0] = max ||bf16(v)||, maxes[1] = max ||v - bf16(v)||
+  uint16_t *qb, *vb;              // bf16 or fp16 rows
+  float *qnorm, *qdnorm, *qscale, *qacc;
+  float *maxes;  // [0] = max ||16bit(v)||, [1] = max ||v - 16bit(v)||, [2] = item scale, [3] = max ||v||^2
   int *cand_ids;
   float *cand_sc;
   int32_t *fail_rows, *fail_count;
@@ -690,10 +862,12 @@ size_t carve_tc(TcWs &w, void *base, int64_t nq, int64_t n_local, int dim, int k
   Carver c(base);
   TcPlan pl = make_plan(nq, n_local);
   int64_t nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM);
-  w.qb = c.take<__nv_bfloat16>(nq_pad * dim);
-  w.vb = c.take<__nv_bfloat16>(n_local * dim);
+  w.qb = c.take<uint16_t>(nq_pad * dim);
+  w.vb = c.take<uint16_t>(n_local * dim);
   w.qnorm = c.take<float>(nq);
   w.qdnorm = c.take<float>(nq);
+  w.qscale = c.take<float>(nq);
+  w.qacc = c.take<float>(nq);
   w.maxes = c.take<float>(4);
   w.cand_ids = c.take<int>((size_t)pl.n_split * 2 * nq * KP_MAX);
   w.cand_sc = c.take<float>((size_t)pl.n_split * 2 * nq * KP_MAX);
@@ -722,20 +896,20 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_map(CUtensorMap *m, void *base, int64_t rows, int dim, int box_rows) {
+int make_map(CUtensorMap *m, void *base, int64_t rows, int dim, int box_rows, bool half) {
   EncodeTiledFn fn = get_encode_fn();
   RB2_REQUIRE(fn != nullptr, RB2_EINVAL, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)dim * 2};
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult rc = fn(m, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   RB2_REQUIRE(rc == CUDA_SUCCESS, RB2_EINVAL, "cuTensorMapEncodeTiled failed with %d", (int)rc);
   return 0;
 }
 
-template <int D, int KP, bool TWO_SM>
+template <int D, int KP, bool TWO_SM, bool H16>
 int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p, int64_t n_local,
            int64_t item_base, const int64_t *hist_indptr, const int64_t *hist_indices, int k, int64_t *out_ids,
            float *out_scores, void *workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -749,30 +923,36 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
   constexpr int LANES = RowCfg<D>::LANES;
   const int64_t nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM);
   {
-    ProfScope prof(RB2_ST_TC_CONVERT, st, 4);
+    ProfScope prof(RB2_ST_TC_CONVERT, st, H16 ? 6 : 4);
     RB2_CUDA(cudaMemsetAsync(w.maxes, 0, 4 * sizeof(float), st));
     RB2_CUDA(cudaMemsetAsync(w.fail_count, 0, 4 * sizeof(int32_t), st));
     if (nq_pad > nq) RB2_CUDA(cudaMemsetAsync(w.qb + nq * D, 0, (size_t)(nq_pad - nq) * D * 2, st));
-    k_convert_rows<D><<<(unsigned)((nq * LANES + 255) / 256), 256, 0, st>>>(query_p, query_ids, nq, INT64_MAX, w.qb,
-                                                                            w.qnorm, w.qdnorm, nullptr, nullptr);
-    k_convert_rows<D><<<(unsigned)((n_local * LANES + 255) / 256), 256, 0, st>>>(item_p, nullptr, n_local, n_local,
-                                                                                 w.vb, nullptr, nullptr, w.maxes,
-                                                                                 w.maxes + 1);
+    const unsigned item_blocks = (unsigned)((n_local * LANES + 255) / 256);
+    if (H16) {
+      k_rows_max_sqnorm<D><<<item_blocks, 256, 0, st>>>(item_p, n_local, w.maxes + 3);
+      k_item_scale<<<1, 1, 0, st>>>(w.maxes);
+    }
+    k_convert_rows<D, H16><<<(unsigned)((nq * LANES + 255) / 256), 256, 0, st>>>(
+        query_p, query_ids, nq, INT64_MAX, w.qb, w.qnorm, w.qdnorm, nullptr, nullptr, nullptr, w.qscale, w.qacc);
+    k_convert_rows<D, H16><<<item_blocks, 256, 0, st>>>(item_p, nullptr, n_local, n_local, w.vb, nullptr, nullptr,
+                                                        w.maxes, w.maxes + 1, H16 ? w.maxes + 2 : nullptr, nullptr,
+                                                        nullptr);
   }
   CUtensorMap tmA, tmB;
-  int rc = make_map(&tmA, w.qb, nq_pad, D, BM);
+  int rc = make_map(&tmA, w.qb, nq_pad, D, BM, H16);
   if (rc) return rc;
-  rc = make_map(&tmB, w.vb, n_local, D, BN / 2);   // each CTA of the pair loads half a slot
+  rc = make_map(&tmB, w.vb, n_local, D, BN / 2, H16);   // each CTA of the pair loads half a slot
   if (rc) return rc;
   TcParams p;
   p.nq = nq; p.n_local = n_local; p.item_base = item_base;
   p.n_ut = pl.n_ut; p.n_split = pl.n_split; p.tiles_per_split = pl.tiles_per_split;
   p.hist_indptr = hist_indptr; p.hist_indices = hist_indices;
   p.cand_ids = w.cand_ids; p.cand_sc = w.cand_sc;
+  p.trace = g_tc_trace;
   const size_t smem = TcSmem<KB, NSTAGE, TWO_SM>::TOTAL;
   {
     ProfScope prof(RB2_ST_TC_SCORE, st);
-    RB2_CUDA(cudaFuncSetAttribute(k_fullsort_tc<KB, NSTAGE, KP, TWO_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RB2_CUDA(cudaFuncSetAttribute(k_fullsort_tc<KB, NSTAGE, KP, TWO_SM, H16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)pl.grid);
@@ -786,15 +966,14 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RB2_CUDA(cudaLaunchKernelEx(&cfg, k_fullsort_tc<KB, NSTAGE, KP, TWO_SM>, tmA, tmB, p));
+    RB2_CUDA(cudaLaunchKernelEx(&cfg, k_fullsort_tc<KB, NSTAGE, KP, TWO_SM, H16>, tmA, tmB, p));
     RB2_CUDA(cudaGetLastError());
   }
   {
     ProfScope prof(RB2_ST_TC_REFINE, st);
-    k_refine<D, KP><<<(unsigned)((nq * 32 + 127) / 128), 128, 0, st>>>(query_p, query_ids, nq, item_p, item_base,
-                                                                  w.cand_ids, w.cand_sc, pl.n_split * 2, k, w.qnorm,
-                                                                  w.qdnorm, w.maxes, out_ids, out_scores, w.fail_rows,
-                                                                  w.fail_count);
+    k_refine<D, KP, H16><<<(unsigned)((nq * 32 + 127) / 128), 128, 0, st>>>(
+        query_p, query_ids, nq, item_p, item_base, w.cand_ids, w.cand_sc, pl.n_split * 2, k, w.qnorm, w.qdnorm, w.maxes,
+        w.qscale, w.qacc, out_ids, out_scores, w.fail_rows, w.fail_count);
     RB2_CUDA(cudaGetLastError());
   }
   // rows whose certificate failed: redo exactly (one small D2H per call)
@@ -832,12 +1011,13 @@ int rb2_fullsort_tc(const float *query_p, const int64_t *query_ids, int64_t nq, 
   // K' = 16 candidates per list when the item range is a shard of a larger table (item_base > 0 or the
   // caller merges shards: the global K-th score sits far above a shard's 16th), 32 otherwise
   const bool small_list = (g_tc_kprime == 16) || (g_tc_kprime == 0 && k <= 8);
-#define RB2_TC(D_, KP_)                                                                                        \
-  return (g_tc_variant != 2)                                                                                   \
-             ? run_tc<D_, KP_, false>(query_p, query_ids, nq, item_p, n_items_local, item_base, hist_indptr,   \
-                                      hist_indices, k, out_ids, out_scores, workspace, workspace_bytes, st)    \
-             : run_tc<D_, KP_, true>(query_p, query_ids, nq, item_p, n_items_local, item_base, hist_indptr,    \
-                                     hist_indices, k, out_ids, out_scores, workspace, workspace_bytes, st)
+#define RB2_TC_ARGS                                                                                           \
+  (query_p, query_ids, nq, item_p, n_items_local, item_base, hist_indptr, hist_indices, k, out_ids, out_scores, \
+   workspace, workspace_bytes, st)
+#define RB2_TC(D_, KP_)                                                      \
+  return (g_tc_variant == 3)   ? run_tc<D_, KP_, false, true> RB2_TC_ARGS    \
+         : (g_tc_variant == 2) ? run_tc<D_, KP_, true, false> RB2_TC_ARGS    \
+                               : run_tc<D_, KP_, false, false> RB2_TC_ARGS
   if (dim == 64) {
     if (small_list) RB2_TC(64, 16);
     RB2_TC(64, 32);

@@ -56,6 +56,12 @@ __device__ __forceinline__ float do_load(uint32_t taddr, int lane) {
                    : "=r"(v[8*q+0]),"=r"(v[8*q+1]),"=r"(v[8*q+2]),"=r"(v[8*q+3]),"=r"(v[8*q+4]),"=r"(v[8*q+5]),"=r"(v[8*q+6]),"=r"(v[8*q+7]) : "r"(taddr + 8 * q));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     r = __uint_as_float(v[lane]) + __uint_as_float(v[32 + lane]);
+  } else if (MODE == 8) {  // 32x32b.x32 with .pack::16b: 64 columns of 16-bit cells -> 32 registers
+    uint32_t v[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]),"=r"(v[1]),"=r"(v[2]),"=r"(v[3]),"=r"(v[4]),"=r"(v[5]),"=r"(v[6]),"=r"(v[7]),"=r"(v[8]),"=r"(v[9]),"=r"(v[10]),"=r"(v[11]),"=r"(v[12]),"=r"(v[13]),"=r"(v[14]),"=r"(v[15]),"=r"(v[16]),"=r"(v[17]),"=r"(v[18]),"=r"(v[19]),"=r"(v[20]),"=r"(v[21]),"=r"(v[22]),"=r"(v[23]),"=r"(v[24]),"=r"(v[25]),"=r"(v[26]),"=r"(v[27]),"=r"(v[28]),"=r"(v[29]),"=r"(v[30]),"=r"(v[31]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    r = __uint_as_float(v[lane]);
   } else if (MODE == 4) {  // 32x32b.x1
     uint32_t v;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
@@ -112,6 +118,7 @@ int main() {
   run<6>("4 x 32x32b.x8 in flight", 4096);
   run<7>("8 x 32x32b.x8 in flight", 8192);
   run<0>("32x32b.x32", 4096);
+  run<8>("32x32b.x32.pack::16b (64 col)", 8192);
 
   return 0;
 }
