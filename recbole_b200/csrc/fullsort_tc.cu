@@ -40,11 +40,11 @@ size_t rb2_fullsort_fp32_workspace(int64_t nq, int64_t n_items_local, int32_t di
 // number of rows the last RB2_SCORER_TC call had to redo in fp32 (diagnostic for bench / tests)
 static int32_t g_last_tc_fallback_rows = 0;
 static int32_t g_tc_kprime = 0;  // 0 = automatic, 16 or 32 = forced (rb2_fullsort_tc_set_kprime)
-// 0 / 1 = per-CTA MMA with multicast B, bf16 operands, fp32 accumulators; 2 = CTA-pair MMA (cta_group::2);
-// 3 = per-CTA MMA, fp16 operands (rows rescaled by powers of two), FP16 accumulators drained with .pack::16b
+// 0 = default (= 3); 1 = bf16 operands, fp32 accumulators; 3 = fp16 operands (rows rescaled by powers of
+// two), FP16 accumulators drained with .pack::16b.  (2 was a cta_group::2 experiment: slower, removed.)
 static int32_t g_tc_variant = 0;
 extern "C" int rb2_fullsort_tc_set_variant(int32_t v) {
-  if (v < 0 || v > 3) return RB2_EINVAL;
+  if (v != 0 && v != 1 && v != 3) return RB2_EINVAL;
   g_tc_variant = v;
   return 0;
 }
@@ -65,12 +65,15 @@ extern "C" int rb2_fullsort_tc_set_trace(void *device_buffer) {
 namespace {
 
 constexpr int BM = 128;       // query rows per CTA tile (= TMEM lanes)
-constexpr int BN = 256;       // items per accumulator stage (= MMA N)
+constexpr int BN = 256;       // items per tile = per B ring slot
+constexpr int HN = 128;       // columns of every accumulator stage that one epilogue warp set drains
+constexpr int NACC = 2;       // accumulator stages in TMEM (2 x 256 columns)
 constexpr int BK = 64;        // bf16 elements per 128-byte swizzle row
 constexpr int UNIT_BYTES = BN * BK * 2;   // one B ring slot: 256 items x 64 k
 constexpr int A_KB_BYTES = BM * BK * 2;
 constexpr int kThreadsTc = 320;          // producer warp + MMA warp + 2 x 4 epilogue warps
 constexpr int BLOOM_WORDS = 32;          // 1024 bits per row, 2 hashes
+constexpr int CAPB = 16;                 // per-row append buffer (entries) in front of the candidate list
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -118,45 +121,6 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t cta_mask) {
                "h"(cta_mask)
                : "memory");
 }
-// ---- CTA-pair (cta_group::2) variants: one MMA spans both SMs (M = 256), each CTA keeps its own
-// 128 query rows and HALF of every B slot in shared memory ----
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in CTA 0
-__device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *map, int c0, int c1,
-                                                uint32_t leader_bar_addr) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
-      "[%2];" ::"r"(smem_u32(dst)),
-      "l"(map), "r"(leader_bar_addr), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                                uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_2sm(uint64_t *bar) {   // arrives on `bar` in BOTH CTAs
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"((uint16_t)0x3)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cta0(uint64_t *bar) {   // arrive on CTA 0's copy of `bar`
-  asm volatile(
-      "{\n"
-      ".reg .b32 ra;\n"
-      "mapa.shared::cluster.u32 ra, %0, 0;\n"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
-      "}\n" ::"r"(smem_u32(bar))
-      : "memory");
-}
-constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
-
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -252,34 +216,59 @@ struct TcParams {
     }                                                 \
   } while (0)
 
-template <int KB, int NSTAGE, bool TWO_SM = false>
+template <int KB, int NSTAGE>
 struct TcSmem {
   static constexpr size_t A_BYTES = (size_t)KB * A_KB_BYTES;
-  static constexpr size_t B_BYTES = (size_t)NSTAGE * (TWO_SM ? UNIT_BYTES / 2 : UNIT_BYTES);
+  static constexpr size_t B_BYTES = (size_t)NSTAGE * UNIT_BYTES;
   static constexpr size_t BLOOM_BYTES = (size_t)BLOOM_WORDS * BM * 4;
-  static constexpr size_t TOTAL = 1024 /*align slack*/ + A_BYTES + B_BYTES + BLOOM_BYTES + 256 /*barriers*/;
+  static constexpr size_t CBUF_BYTES = (size_t)2 * CAPB * BM * 8;   // two warp sets x (score, id)
+  static constexpr size_t TAU_BYTES = (size_t)2 * BM * 4;            // thresholds the two warp sets publish
+  static constexpr size_t TOTAL =
+      1024 /*align slack*/ + A_BYTES + B_BYTES + BLOOM_BYTES + CBUF_BYTES + TAU_BYTES + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ uint32_t bloom_h1(uint32_t x) { return (x * 0x9E3779B1u) >> 22; }
 __device__ __forceinline__ uint32_t bloom_h2(uint32_t x) { return (x * 0x85EBCA77u) >> 22; }
 
-// sorted (descending) candidate list in registers; precondition s > ls[KP-1].  Branch-free bubble:
-// the new entry replaces the tail and climbs while it is strictly greater than its neighbour.
+// minimum of the (unsorted) candidate list and the slot that holds it: (value, slot) tournament tree
 template <int KP>
-__device__ __forceinline__ void list_insert(float (&ls)[KP], int (&li)[KP], float s, int id) {
-  ls[KP - 1] = s;
-  li[KP - 1] = id;
+__device__ __forceinline__ void list_min(const float (&ls)[KP], float &mn, int &amin) {
+  float m[KP / 2];
+  int a[KP / 2];
 #pragma unroll
-  for (int i = KP - 2; i >= 0; --i) {
-    const bool sw = ls[i + 1] > ls[i];
-    const float a = ls[i], b = ls[i + 1];
-    const int ia = li[i], ib = li[i + 1];
-    ls[i] = sw ? b : a;
-    ls[i + 1] = sw ? a : b;
-    li[i] = sw ? ib : ia;
-    li[i + 1] = sw ? ia : ib;
+  for (int i = 0; i < KP / 2; ++i) {
+    const bool lt = ls[2 * i + 1] < ls[2 * i];
+    m[i] = lt ? ls[2 * i + 1] : ls[2 * i];
+    a[i] = lt ? 2 * i + 1 : 2 * i;
   }
+#pragma unroll
+  for (int w = KP / 4; w > 0; w >>= 1)
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const bool lt = m[i + w] < m[i];
+      m[i] = lt ? m[i + w] : m[i];
+      a[i] = lt ? a[i + w] : a[i];
+    }
+  mn = m[0];
+  amin = a[0];
 }
+
+// bit j of `m` |= (x > tau): FSETP + predicated LOP3
+#define TC_MASK_GT_F32(m, x, tau, bit) \
+  asm("{\n.reg .pred p;\nsetp.gt.f32 p, %1, %2;\n@p or.b32 %0, %0, %3;\n}\n" : "+r"(m) : "r"(x), "f"(tau), "r"(bit))
+// packed pair: bit of `mlo` |= (low half > tau), bit of `mhi` |= (high half > tau)
+#define TC_MASK_GT_F16X2(mlo, mhi, x, tau2, bit)                                                              \
+  asm("{\n.reg .pred p, q;\nsetp.gt.f16x2 p|q, %2, %3;\n@p or.b32 %0, %0, %4;\n@q or.b32 %1, %1, %4;\n}\n" \
+      : "+r"(mlo), "+r"(mhi) : "r"(x), "r"(tau2), "r"(bit))
+
+// the registers a tcgen05.ld wrote are defined only after tcgen05.wait::ld: pin their first use behind it
+#define TC_REGS_AFTER_WAIT(v)                                                                                    \
+  asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), \
+                    "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]),      \
+                    "+r"(v[15]));                                                                                 \
+  asm volatile("" : "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]),    \
+                    "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]),    \
+                    "+r"(v[30]), "+r"(v[31]))
 
 // v[j] for a run-time j without local memory: select tree over the bits of j (31 SELs)
 __device__ __forceinline__ float pick32(const uint32_t (&v)[32], int j) {
@@ -322,32 +311,33 @@ __device__ __forceinline__ uint32_t pick32u(const uint32_t (&v)[32], int j) {
   return __float_as_uint(pick32(v, j));
 }
 
-// TWO_SM = false: cta_group::1, each CTA runs its own M=128 MMAs on a full B slot that the pair loads by
-//                 halves and multicasts (NSTAGE slots of 32 KB).
-// TWO_SM = true : cta_group::2, one M=256 MMA per k-step issued by CTA 0 for the pair; each CTA keeps only
-//                 its half of every B slot (NSTAGE slots of 16 KB: twice the tiles in flight, half the
-//                 shared-memory operand traffic per SM).
-template <int KB, int NSTAGE, int KP, bool TWO_SM, bool H16>
+// One CTA = 128 query rows; CTAs run as pairs (cluster of 2) that walk the same item tiles for two query
+// tiles: each loads half of every B slot and multicasts it to both.  Two 256-column accumulator stages;
+// warp set h drains columns [128 h, +128) of EVERY tile and hands the stage back to the MMA issuer as soon
+// as its scores sit in registers, before they are examined (barrier-wait traces, tools/tc_trace.py: when a
+// set owned a whole stage and released it after the examination, the tile time was drain + signalling
+// latency, 2200-2500 cycles against 1024 of MMA).
+template <int KB, int NSTAGE, int KP, bool H16>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
-  constexpr int SLOT_BYTES = TWO_SM ? UNIT_BYTES / 2 : UNIT_BYTES;
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char *sA = smem;                                  // [KB][128 rows][128 B]
-  unsigned char *sB = sA + TcSmem<KB, NSTAGE, TWO_SM>::A_BYTES;      // [NSTAGE][256 (or 128) rows][128 B]
-  uint32_t *bloom = reinterpret_cast<uint32_t *>(sB + TcSmem<KB, NSTAGE, TWO_SM>::B_BYTES);  // [BLOOM_WORDS][BM]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(bloom + BLOOM_WORDS * BM);
+  unsigned char *sB = sA + TcSmem<KB, NSTAGE>::A_BYTES;      // [NSTAGE][256 rows][128 B]
+  uint32_t *bloom = reinterpret_cast<uint32_t *>(sB + TcSmem<KB, NSTAGE>::B_BYTES);  // [BLOOM_WORDS][BM]
+  float *cbuf_s = reinterpret_cast<float *>(bloom + BLOOM_WORDS * BM);                          // [2][CAPB][BM]
+  int *cbuf_i = reinterpret_cast<int *>(cbuf_s + 2 * CAPB * BM);                                // [2][CAPB][BM]
+  volatile float *tau_pub = reinterpret_cast<float *>(cbuf_i + 2 * CAPB * BM);                  // [2][BM]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(const_cast<float *>(tau_pub) + 2 * BM);
   uint64_t *full = bars;                 // [NSTAGE]
   uint64_t *empty = bars + NSTAGE;       // [NSTAGE]
   uint64_t *a_full = bars + 2 * NSTAGE;  // [1]
   uint64_t *a_empty = a_full + 1;        // [1]
-  uint64_t *t_full = a_empty + 1;        // [2]
-  uint64_t *t_empty = t_full + 2;        // [2]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
+  uint64_t *t_full = a_empty + 1;        // [NACC]
+  uint64_t *t_empty = t_full + NACC;     // [NACC]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + NACC);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  // CTA pair (cluster of 2): both CTAs walk the same item tiles for two different query tiles; each
-  // loads half of every B slot and multicasts it to both, halving the L2 -> SM traffic per FLOP
   const int crank = (int)cluster_ctarank();
   const int n_utp = (p.n_ut + 1) / 2;                 // query-tile pairs
   const int n_work = n_utp * p.n_split;               // work items per CLUSTER
@@ -355,25 +345,18 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int n_tiles_all = (int)((p.n_local + BN - 1) / BN);
 
   if (threadIdx.x == 0) {
-    // empty: 1-SM variant = both CTAs' MMA threads commit to it; 2-SM variant = one multicast commit
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], TWO_SM ? 1 : 2); }
+    // empty: both CTAs' MMA threads commit to it (in both CTAs)
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
-    mbar_init(&t_full[0], 1); mbar_init(&t_full[1], 1);
-    // accumulator drained: 2-SM variant = both CTAs' epilogue warp sets arrive on CTA 0's barrier
-    mbar_init(&t_empty[0], TWO_SM ? 256 : 128); mbar_init(&t_empty[1], TWO_SM ? 256 : 128);
+    for (int q = 0; q < NACC; ++q) { mbar_init(&t_full[q], 1); mbar_init(&t_empty[q], 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
   if (warp == 1) {  // TMEM: all 512 columns (two 256-column accumulator stages)
-    if (TWO_SM) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -390,30 +373,17 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       for (int w = cluster_id; w < n_work; w += n_clusters) {
         const int ut = 2 * (w % n_utp) + crank, sp = w / n_utp;
         TC_TIMED(1, mbar_wait(a_empty, a_phase ^ 1));
-        if (TWO_SM) {
-          // both CTAs' A tiles report to CTA 0's barrier (the MMA issuer lives there)
-          if (crank == 0) mbar_expect_tx(a_full, 2 * KB * A_KB_BYTES);
-          for (int kb = 0; kb < KB; ++kb)
-            tma_load_2d_2sm(sA + kb * A_KB_BYTES, &tmA, kb * BK, ut * BM, smem_u32(a_full) & kPeerBitMask);
-        } else {
-          mbar_expect_tx(a_full, KB * A_KB_BYTES);
-          for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * A_KB_BYTES, &tmA, kb * BK, ut * BM, a_full);
-        }
+        mbar_expect_tx(a_full, KB * A_KB_BYTES);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * A_KB_BYTES, &tmA, kb * BK, ut * BM, a_full);
         a_phase ^= 1;
         const int t0 = sp * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, n_tiles_all);
         for (int it = t0; it < t1; ++it) {
           for (int kb = 0; kb < KB; ++kb) {
             TC_TIMED(0, mbar_wait(&empty[stage], phase ^ 1));       // both CTAs are done reading this slot
-            if (TWO_SM) {
-              if (crank == 0) mbar_expect_tx(&full[stage], UNIT_BYTES);   // my half + the peer's half
-              tma_load_2d_2sm(sB + (size_t)stage * SLOT_BYTES, &tmB, kb * BK, it * BN + crank * (BN / 2),
-                              smem_u32(&full[stage]) & kPeerBitMask);
-            } else {
-              mbar_expect_tx(&full[stage], UNIT_BYTES);  // my half + the peer's half
-              tma_load_2d_mc(sB + (size_t)stage * UNIT_BYTES + (size_t)crank * (UNIT_BYTES / 2), &tmB, kb * BK,
-                             it * BN + crank * (BN / 2), &full[stage], (uint16_t)0x3);
-            }
+            mbar_expect_tx(&full[stage], UNIT_BYTES);  // my half + the peer's half
+            tma_load_2d_mc(sB + (size_t)stage * UNIT_BYTES + (size_t)crank * (UNIT_BYTES / 2), &tmB, kb * BK,
+                           it * BN + crank * (BN / 2), &full[stage], (uint16_t)0x3);
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
         }
@@ -424,8 +394,8 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread; in the 2-SM variant only CTA 0's) =====================
-    if (lane == 0 && (!TWO_SM || crank == 0)) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, a_phase = 0, tcount = 0;
       long long tr[16] = {0}, t_begin = clock64();
@@ -436,36 +406,32 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const int t0 = sp * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, n_tiles_all);
         for (int it = t0; it < t1; ++it, ++tcount) {
-          const int acc = tcount & 1;
-          TC_TIMED(3, mbar_wait(&t_empty[acc], ((tcount >> 1) & 1) ^ 1));
-          tc_fence_after();
           long long *ev = (p.trace && blockIdx.x == 0 && tcount >= 1000u && tcount < 1064u)
                               ? p.trace + 148 * 16 + (size_t)(tcount - 1000u) * 16 : nullptr;
+          const int q = (int)(tcount & 1u);
+          TC_TIMED(3, mbar_wait(&t_empty[q], ((tcount >> 1) & 1) ^ 1));
+          tc_fence_after();
           if (ev) ev[0] = clock64();
-          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+          const uint32_t tmem_d = tmem_base + (uint32_t)(q * BN);
           for (int kb = 0; kb < KB; ++kb) {
             TC_TIMED(2, mbar_wait(&full[stage], phase));
             tc_fence_after();
             const uint64_t adesc = make_smem_desc(smem_u32(sA + kb * A_KB_BYTES));
-            const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)stage * SLOT_BYTES));
+            const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)stage * UNIT_BYTES));
 #pragma unroll
             for (int k4 = 0; k4 < BK / 16; ++k4) {
-              // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in 16-byte units
-              if (TWO_SM)
-                tc_mma_bf16_2sm(tmem_d, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), kIdesc2,
-                                (kb | k4) ? 1u : 0u);
-              else
-                tc_mma_bf16(tmem_d, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), H16 ? kIdescH16 : kIdesc,
-                            (kb | k4) ? 1u : 0u);
+              // advance 16 elements = 32 bytes inside the swizzle row: +2 in 16-byte units
+              tc_mma_bf16(tmem_d, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), H16 ? kIdescH16 : kIdesc,
+                          (kb | k4) ? 1u : 0u);
             }
             // the slot is free for both producers once these MMAs have read it
-            if (TWO_SM) tc_commit_2sm(&empty[stage]); else tc_commit_mc(&empty[stage], (uint16_t)0x3);
+            tc_commit_mc(&empty[stage], (uint16_t)0x3);
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
-          if (TWO_SM) tc_commit_2sm(&t_full[acc]); else tc_commit(&t_full[acc]);      // accumulator stage complete
-          if (ev) ev[1] = clock64();
+          tc_commit(&t_full[q]);      // accumulator stage complete
+          if (ev) ev[2] = clock64();
         }
-        if (TWO_SM) tc_commit_2sm(a_empty); else tc_commit(a_empty);   // every MMA reading this A tile completed
+        tc_commit(a_empty);   // every MMA reading this A tile completed
       }
       if (p.trace) {
         long long *o = p.trace + (size_t)blockIdx.x * 16;
@@ -474,7 +440,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
   } else {
     // ===================== epilogue: 2 warp sets x 4 warps; thread <-> TMEM lane <-> query row ========
-    const int ws = (warp - 2) >> 2;               // warp set = accumulator stage it drains
+    const int ws = (warp - 2) >> 2;               // warp set = the half of every tile it drains
     const int quarter = warp & 3;                 // TMEM lanes this warp may touch: [32*quarter, +32)
     const int t = quarter * 32 + lane;            // row inside the tile
     uint32_t *my_bloom = bloom + t;               // word i at my_bloom[i * BM]
@@ -491,8 +457,28 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         hlen = p.hist_indptr[r + 1] - h0;
         hist = p.hist_indices + h0;
       }
-      // everyone is done with the previous work item's filter
+      // Candidate list: KP (score, id) pairs in registers, UNSORTED; `tau_list` = its minimum, held in slot
+      // `amin` (-inf while the list is not full).  A score above the filter threshold `tau` is only
+      // APPENDED to a small per-row buffer in shared memory (a few instructions; 32 rows share a warp, so
+      // whatever one row does here stalls the other 31); the buffers are folded into the lists by all
+      // lanes together when one of them is full.  tau is therefore a little stale (low) between two folds
+      // -- more appends, each far cheaper than keeping the list exact.  The two warp sets hold separate
+      // lists for the same rows (the two halves of every tile) and publish their list minima: k_refine's
+      // certificate cuts at the MAXIMUM over a row's lists anyway, so each set filters with the larger of
+      // the two and the pair behaves like one list.  Everything ever dropped had approx <= that maximum.
+      float ls[KP];
+      int li[KP];
+#pragma unroll
+      for (int j = 0; j < KP; ++j) { ls[j] = -INFINITY; li[j] = -1; }
+      float tau = active ? -INFINITY : INFINITY;   // inactive rows never append
+      float tau_list = -INFINITY;
+      int amin = 0, cnt = 0;
+      float *cb_s = cbuf_s + (size_t)ws * CAPB * BM + t;   // entry e at [e * BM]
+      int *cb_i = cbuf_i + (size_t)ws * CAPB * BM + t;
+      volatile float *tau_mine = tau_pub + ws * BM + t, *tau_other = tau_pub + (ws ^ 1) * BM + t;
+      // everyone is done with the previous work item's filter and thresholds
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      *tau_mine = -INFINITY;
       if (ws == 0) {
         for (int i = 0; i < BLOOM_WORDS; ++i) my_bloom[i * BM] = 0u;
         for (int64_t h = 0; h < hlen; ++h) {
@@ -503,102 +489,132 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-
-      float ls[KP];
-      int li[KP];
-#pragma unroll
-      for (int j = 0; j < KP; ++j) { ls[j] = -INFINITY; li[j] = -1; }
-      float tau = active ? -INFINITY : INFINITY;   // inactive rows never insert
       const int64_t item_limit = p.item_base + p.n_local;
       const int t0 = sp * p.tiles_per_split;
       const int t1 = min(t0 + p.tiles_per_split, n_tiles_all);
 
-      auto consider = [&](float s, int64_t item) {
-        if (item == 0 || item >= item_limit) return;            // [PAD] / zero-filled rows past the table
+      auto valid = [&](int64_t item) -> bool {
+        if (item == 0 || item >= item_limit) return false;      // [PAD] / zero-filled rows past the table
         if (hlen > 0) {
           uint32_t x = (uint32_t)item, a = bloom_h1(x), b = bloom_h2(x);
           bool maybe = ((my_bloom[(a >> 5) * BM] >> (a & 31)) & (my_bloom[(b >> 5) * BM] >> (b & 31)) & 1u) != 0u;
-          if (maybe && csr_has(hist, hlen, item)) return;       // trainer.py:344-345
+          if (maybe && csr_has(hist, hlen, item)) return false; // trainer.py:344-345
         }
-        list_insert<KP>(ls, li, s, (int)item);
-        tau = ls[KP - 1];
+        return true;
+      };
+      auto fold = [&]() {
+        for (int e = 0; e < cnt; ++e) {
+          const float s = cb_s[e * BM];
+          const int id = cb_i[e * BM];
+          if (s > tau && valid((int64_t)id)) {
+#pragma unroll
+            for (int j = 0; j < KP; ++j) {   // replace the minimum
+              const bool hit = j == amin;
+              ls[j] = hit ? s : ls[j];
+              li[j] = hit ? id : li[j];
+            }
+            list_min<KP>(ls, tau_list, amin);
+            tau = fmaxf(tau, tau_list);
+          }
+        }
+        cnt = 0;
+        *tau_mine = tau_list;
+      };
+      // one chunk of scores in registers: 32 fp32 columns, or 64 fp16 columns packed two per register
+      auto process = [&](const uint32_t (&v)[32], int64_t gbase) {
+        const float m = H16 ? max64h(v) : max32(v);
+        if (!__any_sync(0xffffffffu, m > tau)) return;           // the common case
+        uint32_t mlo = 0u, mhi = 0u;                             // passing scores (even / odd columns for fp16)
+        if (m > tau) {
+          uint32_t ma = 0u, mb = 0u, mc = 0u, md = 0u;
+          if (H16) {
+            const __half2 th = __float2half2_rn(tau);            // exact: tau is +-inf or an fp16 score
+            const uint32_t t2 = *reinterpret_cast<const uint32_t *>(&th);
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              TC_MASK_GT_F16X2(ma, mb, v[j], t2, 1u << j);
+              TC_MASK_GT_F16X2(mc, md, v[j + 1], t2, 1u << (j + 1));
+            }
+            mlo = ma | mc;
+            mhi = mb | md;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              TC_MASK_GT_F32(ma, v[j], tau, 1u << j);
+              TC_MASK_GT_F32(mb, v[j + 1], tau, 1u << (j + 1));
+              TC_MASK_GT_F32(mc, v[j + 2], tau, 1u << (j + 2));
+              TC_MASK_GT_F32(md, v[j + 3], tau, 1u << (j + 3));
+            }
+            mlo = (ma | mb) | (mc | md);
+          }
+        }
+        for (;;) {
+          bool overflow = false;
+          while (mlo | mhi) {                                     // ascending column order
+            const int jl = mlo ? __ffs(mlo) - 1 : 32, jh = mhi ? __ffs(mhi) - 1 : 32;
+            const bool odd = H16 && jh < jl;
+            const int j = odd ? jh : jl;
+            if (cnt == CAPB) { overflow = true; break; }        // keep the bit: resumed after the fold
+            const uint32_t wv = pick32u(v, j);
+            cb_s[cnt * BM] = H16 ? (odd ? __high2float(as_h2(wv)) : __low2float(as_h2(wv))) : __uint_as_float(wv);
+            cb_i[cnt * BM] = (int)(gbase + (H16 ? 2 * j + (odd ? 1 : 0) : j));
+            ++cnt;
+            if (odd) mhi &= mhi - 1; else mlo &= mlo - 1;
+          }
+          if (!__any_sync(0xffffffffu, overflow)) break;
+          fold();                                                 // every lane folds what it has
+        }
       };
 
       for (int it = t0; it < t1; ++it, ++tcount) {
-        const int acc = tcount & 1;
-        if (acc != ws) continue;
-        TC_TIMED(6, mbar_wait(&t_full[acc], (tcount >> 1) & 1));
+        const int q = (int)(tcount & 1u);
+        TC_TIMED(6, mbar_wait(&t_full[q], (tcount >> 1) & 1));
         tc_fence_after();
+        tau = fmaxf(tau, *tau_other);
         const long long t_drain = p.trace ? clock64() : 0;
-        long long *ev = (p.trace && blockIdx.x == 0 && quarter == 0 && lane == 0 && tcount >= 1000u && tcount < 1064u)
+        long long *ev = (p.trace && blockIdx.x == 0 && ws == 0 && quarter == 0 && lane == 0 && tcount >= 1000u && tcount < 1064u)
                             ? p.trace + 148 * 16 + (size_t)(tcount - 1000u) * 16 : nullptr;
-        if (ev) ev[2] = t_drain;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-        const int64_t g0 = p.item_base + (int64_t)it * BN;
-        // Draining the accumulators (128 KB of fp32 per tile) is what bounds this kernel, not the MMA:
-        // tools/mma_microbench*.cu / tmem_ld_microbench.cu measure 128.0 cycles per 128x256x16 MMA (100 % of
-        // peak) even with TMA and tcgen05.ld traffic running, but a streaming tcgen05.ld drain sustains only
-        // ~30-55 B/clk per SM whatever the shape (x8 ... x32) -- ~2400 cycles per tile against 1024 of MMA.
-        if (H16) {
-          // FP16 accumulators: half the registers to move per score (the drain is paid per destination
-          // register, tools/tmem_ld_microbench.cu), 64 columns per load
+        if (ev) ev[4] = t_drain;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(q * BN + ws * HN);
+        const int64_t g0 = p.item_base + (int64_t)it * BN + ws * HN;
+        constexpr int CH = H16 ? 64 : 32;      // accumulator columns per load
+        constexpr int NCH = HN / CH;           // 2 (fp16: the whole stage sits in registers) or 4
+        uint32_t va[32], vb[32];
+        if (H16) { TC_LD32P(taddr, va); TC_LD32P(taddr + CH, vb); } else { TC_LD32(taddr, va); TC_LD32(taddr + CH, vb); }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        TC_REGS_AFTER_WAIT(va);
+        TC_REGS_AFTER_WAIT(vb);
 #pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += 64) {
-            uint32_t v[32];
-            TC_LD32P(taddr + c0, v);
+        for (int c = 0; c < NCH; c += 2) {
+          if (c + 2 >= NCH) {
+            // the rest of the stage is in registers: hand it back before looking at the scores
+            tc_fence_before();
+            mbar_arrive(&t_empty[q]);
+            if (ev) ev[5] = clock64();
+          }
+          process(va, g0 + c * CH);
+          if (c + 2 < NCH) TC_LD32(taddr + (c + 2) * CH, va);
+          process(vb, g0 + (c + 1) * CH);
+          if (c + 2 < NCH) {
+            TC_LD32(taddr + (c + 3) * CH, vb);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (ev) ev[4 + c0 / 64] = clock64();
-            if (max64h(v) > tau) {
-              uint32_t mlo = 0u, mhi = 0u;   // passing scores in the even / odd columns
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                mlo |= (__low2float(as_h2(v[j])) > tau ? 1u : 0u) << j;
-                mhi |= (__high2float(as_h2(v[j])) > tau ? 1u : 0u) << j;
-              }
-              while (mlo | mhi) {             // ascending column order
-                const int jl = mlo ? __ffs(mlo) - 1 : 32, jh = mhi ? __ffs(mhi) - 1 : 32;
-                const bool odd = jh < jl;
-                const int j = odd ? jh : jl;
-                if (odd) mhi &= mhi - 1; else mlo &= mlo - 1;
-                const __half2 h = as_h2(pick32u(v, j));
-                const float s = odd ? __high2float(h) : __low2float(h);
-                if (s > tau) consider(s, g0 + c0 + 2 * j + (odd ? 1 : 0));
-              }
-            }
-          }
-        } else {
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          TC_LD32(taddr + c0, v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (ev) ev[4 + c0 / 32] = clock64();
-          if (max32(v) > tau) {
-            // rare path, kept compact (one copy of the insert): bit mask of the passing scores, each
-            // fetched from its register by a 5-level select tree on the run-time index
-            uint32_t mask = 0u;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) > tau ? 1u : 0u) << j;
-            while (mask) {
-              const int j = __ffs(mask) - 1;
-              mask &= mask - 1;
-              const float s = pick32(v, j);
-              if (s > tau) consider(s, g0 + c0 + j);
-            }
+            TC_REGS_AFTER_WAIT(va);
+            TC_REGS_AFTER_WAIT(vb);
           }
         }
-        }
-        tc_fence_before();
-        if (TWO_SM) mbar_arrive_cta0(&t_empty[acc]); else mbar_arrive(&t_empty[acc]);
         if (p.trace) tr[7] += clock64() - t_drain;
-        if (ev) ev[3] = clock64();
+        if (ev) ev[6] = clock64();
       }
+      __syncwarp();
+      fold();
       if (active) {
+        // slot KP-1 of the output holds the list minimum (k_refine reads the cut-off there)
         int64_t o = (((int64_t)sp * 2 + ws) * p.nq + r) * KP;
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
-          p.cand_ids[o + j] = li[j];
-          p.cand_sc[o + j] = ls[j];
+          const int pos = (j == amin) ? KP - 1 : ((j == KP - 1) ? amin : j);
+          p.cand_ids[o + pos] = li[j];
+          p.cand_sc[o + pos] = ls[j];
         }
       }
     }
@@ -613,8 +629,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   cluster_sync_all();   // nobody leaves while the peer may still write into this CTA's smem / barriers
   if (warp == 1) {
     tc_fence_after();
-    if (TWO_SM) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -909,13 +924,13 @@ int make_map(CUtensorMap *m, void *base, int64_t rows, int dim, int box_rows, bo
   return 0;
 }
 
-template <int D, int KP, bool TWO_SM, bool H16>
+template <int D, int KP, bool H16>
 int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p, int64_t n_local,
            int64_t item_base, const int64_t *hist_indptr, const int64_t *hist_indices, int k, int64_t *out_ids,
            float *out_scores, void *workspace, size_t workspace_bytes, cudaStream_t st) {
   constexpr int KB = D / BK;
   // B ring depth: what fits beside A, the Bloom filters and the barriers (2-SM slots are half the size)
-  constexpr int NSTAGE = TWO_SM ? ((KB == 1) ? 12 : 10) : ((KB == 1) ? 6 : 5);
+  constexpr int NSTAGE = (KB == 1) ? 5 : 4;
   TcWs w;
   size_t need = carve_tc(w, workspace, nq, n_local, D, k);
   RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_fullsort_topk(tc): workspace %zu < %zu", workspace_bytes, need);
@@ -949,10 +964,10 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
   p.hist_indptr = hist_indptr; p.hist_indices = hist_indices;
   p.cand_ids = w.cand_ids; p.cand_sc = w.cand_sc;
   p.trace = g_tc_trace;
-  const size_t smem = TcSmem<KB, NSTAGE, TWO_SM>::TOTAL;
+  const size_t smem = TcSmem<KB, NSTAGE>::TOTAL;
   {
     ProfScope prof(RB2_ST_TC_SCORE, st);
-    RB2_CUDA(cudaFuncSetAttribute(k_fullsort_tc<KB, NSTAGE, KP, TWO_SM, H16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RB2_CUDA(cudaFuncSetAttribute(k_fullsort_tc<KB, NSTAGE, KP, H16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)pl.grid);
@@ -966,7 +981,7 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RB2_CUDA(cudaLaunchKernelEx(&cfg, k_fullsort_tc<KB, NSTAGE, KP, TWO_SM, H16>, tmA, tmB, p));
+    RB2_CUDA(cudaLaunchKernelEx(&cfg, k_fullsort_tc<KB, NSTAGE, KP, H16>, tmA, tmB, p));
     RB2_CUDA(cudaGetLastError());
   }
   {
@@ -1014,10 +1029,8 @@ int rb2_fullsort_tc(const float *query_p, const int64_t *query_ids, int64_t nq, 
 #define RB2_TC_ARGS                                                                                           \
   (query_p, query_ids, nq, item_p, n_items_local, item_base, hist_indptr, hist_indices, k, out_ids, out_scores, \
    workspace, workspace_bytes, st)
-#define RB2_TC(D_, KP_)                                                      \
-  return (g_tc_variant == 3)   ? run_tc<D_, KP_, false, true> RB2_TC_ARGS    \
-         : (g_tc_variant == 2) ? run_tc<D_, KP_, true, false> RB2_TC_ARGS    \
-                               : run_tc<D_, KP_, false, false> RB2_TC_ARGS
+#define RB2_TC(D_, KP_) \
+  return (g_tc_variant == 1) ? run_tc<D_, KP_, false> RB2_TC_ARGS : run_tc<D_, KP_, true> RB2_TC_ARGS
   if (dim == 64) {
     if (small_list) RB2_TC(64, 16);
     RB2_TC(64, 32);

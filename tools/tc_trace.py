@@ -13,15 +13,15 @@ NAMES = ["producer: wait empty slot", "producer: wait A free", "mma: wait full s
 
 def show_events(ev):
     base = int(ev[0, 0])
-    print("  CTA 0, tiles 1000..: cycles relative to the first event")
-    print("  tile  mma_start mma_issued | drain_start  loads done ...  drain_end")
+    print("  CTA 0, tiles 1000..: cycles relative to the first event (epilogue columns: warp set 0, lane quarter 0)")
+    print("  tile  mma_start mma_issued | stage_full  released  examined")
     for i in range(12):
         e = [int(x) - base if int(x) else -1 for x in ev[i]]
-        print("  %4d  %9d %10d | %10d  %s  %9d" % (1000 + i, e[0], e[1], e[2], " ".join("%6d" % x for x in e[4:12] if x >= 0), e[3]))
+        print("  %4d  %9d %10d | %10d %9d %9d" % (1000 + i, e[0], e[2], e[4], e[5], e[6]))
 
 
 def main():
-    variant = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+    variant = int(sys.argv[1]) if len(sys.argv) > 1 else 3
     nq, N, d = (int(a) for a in sys.argv[2:5]) if len(sys.argv) > 4 else (131072, 2_000_001, 128)
     lib.rb2_fullsort_tc_set_variant(variant)
     dev = torch.device("cuda:0")
