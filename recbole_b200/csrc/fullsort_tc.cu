@@ -40,11 +40,12 @@ size_t rb2_fullsort_fp32_workspace(int64_t nq, int64_t n_items_local, int32_t di
 // number of rows the last RB2_SCORER_TC call had to redo in fp32 (diagnostic for bench / tests)
 static int32_t g_last_tc_fallback_rows = 0;
 static int32_t g_tc_kprime = 0;  // 0 = automatic, 16 or 32 = forced (rb2_fullsort_tc_set_kprime)
-// 0 = default (= 3); 1 = bf16 operands, fp32 accumulators; 3 = fp16 operands (rows rescaled by powers of
-// two), FP16 accumulators drained with .pack::16b.  (2 was a cta_group::2 experiment: slower, removed.)
+// 0 = default (= 3); 1 = bf16 operands, fp32 accumulators, per-CTA MMAs; 3 = fp16 operands (rows rescaled by
+// powers of two), FP16 accumulators drained with .pack::16b, per-CTA MMAs; 2 = as 3 with CTA-pair MMAs
+// (cta_group::2)
 static int32_t g_tc_variant = 0;
 extern "C" int rb2_fullsort_tc_set_variant(int32_t v) {
-  if (v != 0 && v != 1 && v != 3) return RB2_EINVAL;
+  if (v < 0 || v > 3) return RB2_EINVAL;
   g_tc_variant = v;
   return 0;
 }
@@ -73,7 +74,7 @@ constexpr int UNIT_BYTES = BN * BK * 2;   // one B ring slot: 256 items x 64 k
 constexpr int A_KB_BYTES = BM * BK * 2;
 constexpr int kThreadsTc = 320;          // producer warp + MMA warp + 2 x 4 epilogue warps
 constexpr int BLOOM_WORDS = 32;          // 1024 bits per row, 2 hashes
-constexpr int CAPB = 16;                 // per-row append buffer (entries) in front of the candidate list
+constexpr int CAPB = 8;                  // per-row append buffer (entries) in front of the candidate list
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -121,6 +122,43 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t cta_mask) {
                "h"(cta_mask)
                : "memory");
 }
+// ---- CTA-pair (cta_group::2) MMAs: one M = 256 MMA spans both SMs, each CTA keeps its own 128 query rows
+// and HALF of every B slot in shared memory (half the operand traffic per SM) ----
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in CTA 0
+__device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *map, int c0, int c1,
+                                                uint32_t leader_bar_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(leader_bar_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t *bar) {   // arrives on `bar` in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)0x3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta0(uint64_t *bar) {   // arrive on CTA 0's copy of `bar`
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -161,9 +199,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // instruction descriptor: c=f32, a=b=bf16, both K-major, N=256, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
+constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 // fp16 operands, FP16 accumulator (c_format = a_format = b_format = 0): one 16-bit score in the low half of
 // every 32-bit TMEM column (tools/mma_f16acc_check.cu)
 constexpr uint32_t kIdescH16 = ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t kIdesc2H16 = ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 
 // 64 columns of 16-bit cells -> 32 registers (low half = even column, high half = odd column)
 #define TC_LD32P(taddr, v)                                                                                      \
@@ -216,10 +256,10 @@ struct TcParams {
     }                                                 \
   } while (0)
 
-template <int KB, int NSTAGE>
+template <int KB, int NSTAGE, bool TWO_SM>
 struct TcSmem {
   static constexpr size_t A_BYTES = (size_t)KB * A_KB_BYTES;
-  static constexpr size_t B_BYTES = (size_t)NSTAGE * UNIT_BYTES;
+  static constexpr size_t B_BYTES = (size_t)NSTAGE * (TWO_SM ? UNIT_BYTES / 2 : UNIT_BYTES);
   static constexpr size_t BLOOM_BYTES = (size_t)BLOOM_WORDS * BM * 4;
   static constexpr size_t CBUF_BYTES = (size_t)2 * CAPB * BM * 8;   // two warp sets x (score, id)
   static constexpr size_t TAU_BYTES = (size_t)2 * BM * 4;            // thresholds the two warp sets publish
@@ -317,14 +357,21 @@ __device__ __forceinline__ uint32_t pick32u(const uint32_t (&v)[32], int j) {
 // as its scores sit in registers, before they are examined (barrier-wait traces, tools/tc_trace.py: when a
 // set owned a whole stage and released it after the examination, the tile time was drain + signalling
 // latency, 2200-2500 cycles against 1024 of MMA).
-template <int KB, int NSTAGE, int KP, bool H16>
+//   TWO_SM = false: cta_group::1, each CTA issues its own M = 128 MMAs on full B slots (32 KB) that the pair
+//                   loads by halves and multicasts.
+//   TWO_SM = true : cta_group::2, CTA 0 issues one M = 256 MMA per k-step for the pair; each CTA keeps only
+//                   its half of every B slot (16 KB).  The per-CTA MMAs read and write every B byte through
+//                   shared memory once per 1024 MMA-cycles (~128 B/clk, the whole shared-memory bandwidth);
+//                   splitting B halves that.
+template <int KB, int NSTAGE, int KP, bool H16, bool TWO_SM>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+  constexpr int SLOT_BYTES = TWO_SM ? UNIT_BYTES / 2 : UNIT_BYTES;
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char *sA = smem;                                  // [KB][128 rows][128 B]
-  unsigned char *sB = sA + TcSmem<KB, NSTAGE>::A_BYTES;      // [NSTAGE][256 rows][128 B]
-  uint32_t *bloom = reinterpret_cast<uint32_t *>(sB + TcSmem<KB, NSTAGE>::B_BYTES);  // [BLOOM_WORDS][BM]
+  unsigned char *sB = sA + TcSmem<KB, NSTAGE, TWO_SM>::A_BYTES;      // [NSTAGE][256 rows][128 B]
+  uint32_t *bloom = reinterpret_cast<uint32_t *>(sB + TcSmem<KB, NSTAGE, TWO_SM>::B_BYTES);  // [BLOOM_WORDS][BM]
   float *cbuf_s = reinterpret_cast<float *>(bloom + BLOOM_WORDS * BM);                          // [2][CAPB][BM]
   int *cbuf_i = reinterpret_cast<int *>(cbuf_s + 2 * CAPB * BM);                                // [2][CAPB][BM]
   volatile float *tau_pub = reinterpret_cast<float *>(cbuf_i + 2 * CAPB * BM);                  // [2][BM]
@@ -346,17 +393,23 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
   if (threadIdx.x == 0) {
     // empty: both CTAs' MMA threads commit to it (in both CTAs)
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }
+    // (2-SM: one multicast commit from CTA 0; both CTAs' epilogue threads arrive on CTA 0's t_empty)
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], TWO_SM ? 1 : 2); }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
-    for (int q = 0; q < NACC; ++q) { mbar_init(&t_full[q], 1); mbar_init(&t_empty[q], 256); }
+    for (int q = 0; q < NACC; ++q) { mbar_init(&t_full[q], 1); mbar_init(&t_empty[q], TWO_SM ? 512 : 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
   if (warp == 1) {  // TMEM: all 512 columns (two 256-column accumulator stages)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (TWO_SM) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -373,17 +426,30 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       for (int w = cluster_id; w < n_work; w += n_clusters) {
         const int ut = 2 * (w % n_utp) + crank, sp = w / n_utp;
         TC_TIMED(1, mbar_wait(a_empty, a_phase ^ 1));
-        mbar_expect_tx(a_full, KB * A_KB_BYTES);
-        for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * A_KB_BYTES, &tmA, kb * BK, ut * BM, a_full);
+        if (TWO_SM) {
+          // both CTAs' A tiles report to CTA 0's barrier (the MMA issuer lives there)
+          if (crank == 0) mbar_expect_tx(a_full, 2 * KB * A_KB_BYTES);
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_2d_2sm(sA + kb * A_KB_BYTES, &tmA, kb * BK, ut * BM, smem_u32(a_full) & kPeerBitMask);
+        } else {
+          mbar_expect_tx(a_full, KB * A_KB_BYTES);
+          for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * A_KB_BYTES, &tmA, kb * BK, ut * BM, a_full);
+        }
         a_phase ^= 1;
         const int t0 = sp * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, n_tiles_all);
         for (int it = t0; it < t1; ++it) {
           for (int kb = 0; kb < KB; ++kb) {
             TC_TIMED(0, mbar_wait(&empty[stage], phase ^ 1));       // both CTAs are done reading this slot
-            mbar_expect_tx(&full[stage], UNIT_BYTES);  // my half + the peer's half
-            tma_load_2d_mc(sB + (size_t)stage * UNIT_BYTES + (size_t)crank * (UNIT_BYTES / 2), &tmB, kb * BK,
-                           it * BN + crank * (BN / 2), &full[stage], (uint16_t)0x3);
+            if (TWO_SM) {
+              if (crank == 0) mbar_expect_tx(&full[stage], UNIT_BYTES);   // my half + the peer's half
+              tma_load_2d_2sm(sB + (size_t)stage * SLOT_BYTES, &tmB, kb * BK, it * BN + crank * (BN / 2),
+                              smem_u32(&full[stage]) & kPeerBitMask);
+            } else {
+              mbar_expect_tx(&full[stage], UNIT_BYTES);  // my half + the peer's half
+              tma_load_2d_mc(sB + (size_t)stage * UNIT_BYTES + (size_t)crank * (UNIT_BYTES / 2), &tmB, kb * BK,
+                             it * BN + crank * (BN / 2), &full[stage], (uint16_t)0x3);
+            }
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
         }
@@ -394,8 +460,8 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (one thread; 2-SM: only CTA 0's) =====================
+    if (lane == 0 && (!TWO_SM || crank == 0)) {
       int stage = 0;
       uint32_t phase = 0, a_phase = 0, tcount = 0;
       long long tr[16] = {0}, t_begin = clock64();
@@ -417,21 +483,25 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             TC_TIMED(2, mbar_wait(&full[stage], phase));
             tc_fence_after();
             const uint64_t adesc = make_smem_desc(smem_u32(sA + kb * A_KB_BYTES));
-            const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)stage * UNIT_BYTES));
+            const uint64_t bdesc = make_smem_desc(smem_u32(sB + (size_t)stage * SLOT_BYTES));
 #pragma unroll
             for (int k4 = 0; k4 < BK / 16; ++k4) {
               // advance 16 elements = 32 bytes inside the swizzle row: +2 in 16-byte units
-              tc_mma_bf16(tmem_d, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), H16 ? kIdescH16 : kIdesc,
-                          (kb | k4) ? 1u : 0u);
+              if (TWO_SM)
+                tc_mma_2sm(tmem_d, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), H16 ? kIdesc2H16 : kIdesc2,
+                           (kb | k4) ? 1u : 0u);
+              else
+                tc_mma_bf16(tmem_d, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), H16 ? kIdescH16 : kIdesc,
+                            (kb | k4) ? 1u : 0u);
             }
             // the slot is free for both producers once these MMAs have read it
-            tc_commit_mc(&empty[stage], (uint16_t)0x3);
+            if (TWO_SM) tc_commit_2sm(&empty[stage]); else tc_commit_mc(&empty[stage], (uint16_t)0x3);
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
-          tc_commit(&t_full[q]);      // accumulator stage complete
+          if (TWO_SM) tc_commit_2sm(&t_full[q]); else tc_commit(&t_full[q]);      // accumulator stage complete
           if (ev) ev[2] = clock64();
         }
-        tc_commit(a_empty);   // every MMA reading this A tile completed
+        if (TWO_SM) tc_commit_2sm(a_empty); else tc_commit(a_empty);   // every MMA reading this A tile completed
       }
       if (p.trace) {
         long long *o = p.trace + (size_t)blockIdx.x * 16;
@@ -520,46 +590,68 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         cnt = 0;
         *tau_mine = tau_list;
       };
-      // one chunk of scores in registers: 32 fp32 columns, or 64 fp16 columns packed two per register
+      // one chunk of scores in registers: 32 fp32 columns, or 64 fp16 columns packed two per register.
+      // Latency matters more than throughput here (the stage cannot be refilled before every warp has
+      // fetched its share of the NEXT one): the flags of the passing scores are gathered with two
+      // instructions per register over four independent accumulators, and the usual case -- exactly one
+      // passing score, which is the maximum already known -- skips the register select tree.
       auto process = [&](const uint32_t (&v)[32], int64_t gbase) {
         const float m = H16 ? max64h(v) : max32(v);
         if (!__any_sync(0xffffffffu, m > tau)) return;           // the common case
-        uint32_t mlo = 0u, mhi = 0u;                             // passing scores (even / odd columns for fp16)
+        // fp16: fa = registers 0-15, fb = registers 16-31; bit j = even column of register j, bit 16 + j =
+        // odd column.  fp32: fa bit j = column j.
+        uint32_t fa = 0u, fb = 0u;
         if (m > tau) {
-          uint32_t ma = 0u, mb = 0u, mc = 0u, md = 0u;
+          uint32_t f0 = 0u, f1 = 0u, f2 = 0u, f3 = 0u;
           if (H16) {
             const __half2 th = __float2half2_rn(tau);            // exact: tau is +-inf or an fp16 score
-            const uint32_t t2 = *reinterpret_cast<const uint32_t *>(&th);
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              TC_MASK_GT_F16X2(ma, mb, v[j], t2, 1u << j);
-              TC_MASK_GT_F16X2(mc, md, v[j + 1], t2, 1u << (j + 1));
+            for (int j = 0; j < 16; j += 2) {
+              f0 |= __hgt2_mask(as_h2(v[j]), th) & (0x00010001u << j);
+              f1 |= __hgt2_mask(as_h2(v[j + 1]), th) & (0x00010001u << (j + 1));
+              f2 |= __hgt2_mask(as_h2(v[16 + j]), th) & (0x00010001u << j);
+              f3 |= __hgt2_mask(as_h2(v[17 + j]), th) & (0x00010001u << (j + 1));
             }
-            mlo = ma | mc;
-            mhi = mb | md;
+            fa = f0 | f1;
+            fb = f2 | f3;
           } else {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              TC_MASK_GT_F32(ma, v[j], tau, 1u << j);
-              TC_MASK_GT_F32(mb, v[j + 1], tau, 1u << (j + 1));
-              TC_MASK_GT_F32(mc, v[j + 2], tau, 1u << (j + 2));
-              TC_MASK_GT_F32(md, v[j + 3], tau, 1u << (j + 3));
+              TC_MASK_GT_F32(f0, v[j], tau, 1u << j);
+              TC_MASK_GT_F32(f1, v[j + 1], tau, 1u << (j + 1));
+              TC_MASK_GT_F32(f2, v[j + 2], tau, 1u << (j + 2));
+              TC_MASK_GT_F32(f3, v[j + 3], tau, 1u << (j + 3));
             }
-            mlo = (ma | mb) | (mc | md);
+            fa = (f0 | f1) | (f2 | f3);
           }
         }
+        const bool single = (__popc(fa) + __popc(fb)) == 1;
         for (;;) {
           bool overflow = false;
-          while (mlo | mhi) {                                     // ascending column order
-            const int jl = mlo ? __ffs(mlo) - 1 : 32, jh = mhi ? __ffs(mhi) - 1 : 32;
-            const bool odd = H16 && jh < jl;
-            const int j = odd ? jh : jl;
-            if (cnt == CAPB) { overflow = true; break; }        // keep the bit: resumed after the fold
-            const uint32_t wv = pick32u(v, j);
-            cb_s[cnt * BM] = H16 ? (odd ? __high2float(as_h2(wv)) : __low2float(as_h2(wv))) : __uint_as_float(wv);
-            cb_i[cnt * BM] = (int)(gbase + (H16 ? 2 * j + (odd ? 1 : 0) : j));
+          while (fa | fb) {
+            if (cnt == CAPB) { overflow = true; break; }        // keep the flag: resumed after the fold
+            const bool second = fa == 0u;
+            const int bit = __ffs(second ? fb : fa) - 1;
+            int col;
+            float sc;
+            if (H16) {
+              const int reg = (bit & 15) + (second ? 16 : 0);
+              const bool odd = bit >= 16;
+              col = 2 * reg + (odd ? 1 : 0);
+              if (single) {
+                sc = m;
+              } else {
+                const uint32_t wv = pick32u(v, reg);
+                sc = odd ? __high2float(as_h2(wv)) : __low2float(as_h2(wv));
+              }
+            } else {
+              col = bit;
+              sc = single ? m : pick32(v, bit);
+            }
+            cb_s[cnt * BM] = sc;
+            cb_i[cnt * BM] = (int)(gbase + col);
             ++cnt;
-            if (odd) mhi &= mhi - 1; else mlo &= mlo - 1;
+            if (second) fb &= fb - 1; else fa &= fa - 1;
           }
           if (!__any_sync(0xffffffffu, overflow)) break;
           fold();                                                 // every lane folds what it has
@@ -589,7 +681,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           if (c + 2 >= NCH) {
             // the rest of the stage is in registers: hand it back before looking at the scores
             tc_fence_before();
-            mbar_arrive(&t_empty[q]);
+            if (TWO_SM) mbar_arrive_cta0(&t_empty[q]); else mbar_arrive(&t_empty[q]);
             if (ev) ev[5] = clock64();
           }
           process(va, g0 + c * CH);
@@ -629,7 +721,8 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   cluster_sync_all();   // nobody leaves while the peer may still write into this CTA's smem / barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (TWO_SM) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -924,13 +1017,13 @@ int make_map(CUtensorMap *m, void *base, int64_t rows, int dim, int box_rows, bo
   return 0;
 }
 
-template <int D, int KP, bool H16>
+template <int D, int KP, bool H16, bool TWO_SM>
 int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p, int64_t n_local,
            int64_t item_base, const int64_t *hist_indptr, const int64_t *hist_indices, int k, int64_t *out_ids,
            float *out_scores, void *workspace, size_t workspace_bytes, cudaStream_t st) {
   constexpr int KB = D / BK;
   // B ring depth: what fits beside A, the Bloom filters and the barriers (2-SM slots are half the size)
-  constexpr int NSTAGE = (KB == 1) ? 5 : 4;
+  constexpr int NSTAGE = TWO_SM ? ((KB == 1) ? 10 : 9) : 5;
   TcWs w;
   size_t need = carve_tc(w, workspace, nq, n_local, D, k);
   RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_fullsort_topk(tc): workspace %zu < %zu", workspace_bytes, need);
@@ -964,10 +1057,10 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
   p.hist_indptr = hist_indptr; p.hist_indices = hist_indices;
   p.cand_ids = w.cand_ids; p.cand_sc = w.cand_sc;
   p.trace = g_tc_trace;
-  const size_t smem = TcSmem<KB, NSTAGE>::TOTAL;
+  const size_t smem = TcSmem<KB, NSTAGE, TWO_SM>::TOTAL;
   {
     ProfScope prof(RB2_ST_TC_SCORE, st);
-    RB2_CUDA(cudaFuncSetAttribute(k_fullsort_tc<KB, NSTAGE, KP, H16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RB2_CUDA(cudaFuncSetAttribute(k_fullsort_tc<KB, NSTAGE, KP, H16, TWO_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)pl.grid);
@@ -981,7 +1074,7 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RB2_CUDA(cudaLaunchKernelEx(&cfg, k_fullsort_tc<KB, NSTAGE, KP, H16>, tmA, tmB, p));
+    RB2_CUDA(cudaLaunchKernelEx(&cfg, k_fullsort_tc<KB, NSTAGE, KP, H16, TWO_SM>, tmA, tmB, p));
     RB2_CUDA(cudaGetLastError());
   }
   {
@@ -1029,8 +1122,10 @@ int rb2_fullsort_tc(const float *query_p, const int64_t *query_ids, int64_t nq, 
 #define RB2_TC_ARGS                                                                                           \
   (query_p, query_ids, nq, item_p, n_items_local, item_base, hist_indptr, hist_indices, k, out_ids, out_scores, \
    workspace, workspace_bytes, st)
-#define RB2_TC(D_, KP_) \
-  return (g_tc_variant == 1) ? run_tc<D_, KP_, false> RB2_TC_ARGS : run_tc<D_, KP_, true> RB2_TC_ARGS
+#define RB2_TC(D_, KP_)                                                        \
+  return (g_tc_variant == 1)   ? run_tc<D_, KP_, false, false> RB2_TC_ARGS     \
+         : (g_tc_variant == 2) ? run_tc<D_, KP_, true, true> RB2_TC_ARGS       \
+                               : run_tc<D_, KP_, true, false> RB2_TC_ARGS
   if (dim == 64) {
     if (small_list) RB2_TC(64, 16);
     RB2_TC(64, 32);
