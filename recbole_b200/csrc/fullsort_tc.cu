@@ -72,7 +72,7 @@ constexpr int NACC = 2;       // accumulator stages in TMEM (2 x 256 columns)
 constexpr int BK = 64;        // bf16 elements per 128-byte swizzle row
 constexpr int UNIT_BYTES = BN * BK * 2;   // one B ring slot: 256 items x 64 k
 constexpr int A_KB_BYTES = BM * BK * 2;
-constexpr int kThreadsTc = 320;          // producer warp + MMA warp + 2 x 4 epilogue warps
+constexpr int kThreadsTc = 384;          // warp group 0: producer warp, MMA warp, 2 idle; warp groups 1, 2: epilogue sets
 constexpr int BLOOM_WORDS = 32;          // 1024 bits per row, 2 hashes
 constexpr int CAPB = 8;                  // per-row append buffer (entries) in front of the candidate list
 
@@ -247,7 +247,7 @@ struct TcParams {
 };
 #define TC_TIMED(slot, stmt)                          \
   do {                                                \
-    if (p.trace) {                                    \
+    if (TRACE) {                                      \
       long long t_ = clock64();                       \
       stmt;                                           \
       tr[slot] += clock64() - t_;                     \
@@ -363,7 +363,7 @@ __device__ __forceinline__ uint32_t pick32u(const uint32_t (&v)[32], int j) {
 //                   its half of every B slot (16 KB).  The per-CTA MMAs read and write every B byte through
 //                   shared memory once per 1024 MMA-cycles (~128 B/clk, the whole shared-memory bandwidth);
 //                   splitting B halves that.
-template <int KB, int NSTAGE, int KP, bool H16, bool TWO_SM>
+template <int KB, int NSTAGE, int KP, bool H16, bool TWO_SM, bool TRACE>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
   constexpr int SLOT_BYTES = TWO_SM ? UNIT_BYTES / 2 : UNIT_BYTES;
@@ -417,12 +417,16 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // registers move from the producer / MMA warp group to the two epilogue warp groups (candidate list +
+  // two chunks of scores per thread): 4 x 56 + 8 x 224 registers per lane <= 64 K
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
-      long long tr[16] = {0}, t_begin = clock64();
+      long long tr[16] = {0}, t_begin = TRACE ? clock64() : 0;
       for (int w = cluster_id; w < n_work; w += n_clusters) {
         const int ut = 2 * (w % n_utp) + crank, sp = w / n_utp;
         TC_TIMED(1, mbar_wait(a_empty, a_phase ^ 1));
@@ -454,7 +458,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           }
         }
       }
-      if (p.trace) {
+      if (TRACE) {
         long long *o = p.trace + (size_t)blockIdx.x * 16;
         o[0] = tr[0]; o[1] = tr[1]; o[11] = clock64() - t_begin;
       }
@@ -464,7 +468,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (lane == 0 && (!TWO_SM || crank == 0)) {
       int stage = 0;
       uint32_t phase = 0, a_phase = 0, tcount = 0;
-      long long tr[16] = {0}, t_begin = clock64();
+      long long tr[16] = {0}, t_begin = TRACE ? clock64() : 0;
       for (int w = cluster_id; w < n_work; w += n_clusters) {
         const int sp = w / n_utp;
         TC_TIMED(4, mbar_wait(a_full, a_phase));
@@ -472,7 +476,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const int t0 = sp * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, n_tiles_all);
         for (int it = t0; it < t1; ++it, ++tcount) {
-          long long *ev = (p.trace && blockIdx.x == 0 && tcount >= 1000u && tcount < 1064u)
+          long long *ev = (TRACE && blockIdx.x == 0 && tcount >= 1000u && tcount < 1064u)
                               ? p.trace + 148 * 16 + (size_t)(tcount - 1000u) * 16 : nullptr;
           const int q = (int)(tcount & 1u);
           TC_TIMED(3, mbar_wait(&t_empty[q], ((tcount >> 1) & 1) ^ 1));
@@ -503,14 +507,16 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
         if (TWO_SM) tc_commit_2sm(a_empty); else tc_commit(a_empty);   // every MMA reading this A tile completed
       }
-      if (p.trace) {
+      if (TRACE) {
         long long *o = p.trace + (size_t)blockIdx.x * 16;
         o[2] = tr[2]; o[3] = tr[3]; o[4] = tr[4]; o[5] = clock64() - t_begin; o[10] = tcount;
       }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
     // ===================== epilogue: 2 warp sets x 4 warps; thread <-> TMEM lane <-> query row ========
-    const int ws = (warp - 2) >> 2;               // warp set = the half of every tile it drains
+    const int ws = (warp - 4) >> 2;               // warp set = the half of every tile it drains
     const int quarter = warp & 3;                 // TMEM lanes this warp may touch: [32*quarter, +32)
     const int t = quarter * 32 + lane;            // row inside the tile
     uint32_t *my_bloom = bloom + t;               // word i at my_bloom[i * BM]
@@ -663,8 +669,8 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         TC_TIMED(6, mbar_wait(&t_full[q], (tcount >> 1) & 1));
         tc_fence_after();
         tau = fmaxf(tau, *tau_other);
-        const long long t_drain = p.trace ? clock64() : 0;
-        long long *ev = (p.trace && blockIdx.x == 0 && ws == 0 && quarter == 0 && lane == 0 && tcount >= 1000u && tcount < 1064u)
+        const long long t_drain = TRACE ? clock64() : 0;
+        long long *ev = (TRACE && blockIdx.x == 0 && ws == 0 && quarter == 0 && lane == 0 && tcount >= 1000u && tcount < 1064u)
                             ? p.trace + 148 * 16 + (size_t)(tcount - 1000u) * 16 : nullptr;
         if (ev) ev[4] = t_drain;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(q * BN + ws * HN);
@@ -694,7 +700,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             TC_REGS_AFTER_WAIT(vb);
           }
         }
-        if (p.trace) tr[7] += clock64() - t_drain;
+        if (TRACE) tr[7] += clock64() - t_drain;
         if (ev) ev[6] = clock64();
       }
       __syncwarp();
@@ -710,7 +716,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
       }
     }
-    if (p.trace && quarter == 0 && lane == 0) {   // one thread of each epilogue warp set
+    if (TRACE && quarter == 0 && lane == 0) {   // one thread of each epilogue warp set
       long long *o = p.trace + (size_t)blockIdx.x * 16 + 6 + 2 * ws;
       o[0] = tr[6]; o[1] = tr[7];
     }
@@ -1017,7 +1023,7 @@ int make_map(CUtensorMap *m, void *base, int64_t rows, int dim, int box_rows, bo
   return 0;
 }
 
-template <int D, int KP, bool H16, bool TWO_SM>
+template <int D, int KP, bool H16, bool TWO_SM, bool TRACE = false>
 int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p, int64_t n_local,
            int64_t item_base, const int64_t *hist_indptr, const int64_t *hist_indices, int k, int64_t *out_ids,
            float *out_scores, void *workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -1060,7 +1066,7 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
   const size_t smem = TcSmem<KB, NSTAGE, TWO_SM>::TOTAL;
   {
     ProfScope prof(RB2_ST_TC_SCORE, st);
-    RB2_CUDA(cudaFuncSetAttribute(k_fullsort_tc<KB, NSTAGE, KP, H16, TWO_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RB2_CUDA(cudaFuncSetAttribute(k_fullsort_tc<KB, NSTAGE, KP, H16, TWO_SM, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)pl.grid);
@@ -1074,7 +1080,7 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RB2_CUDA(cudaLaunchKernelEx(&cfg, k_fullsort_tc<KB, NSTAGE, KP, H16, TWO_SM>, tmA, tmB, p));
+    RB2_CUDA(cudaLaunchKernelEx(&cfg, k_fullsort_tc<KB, NSTAGE, KP, H16, TWO_SM, TRACE>, tmA, tmB, p));
     RB2_CUDA(cudaGetLastError());
   }
   {
@@ -1131,6 +1137,10 @@ int rb2_fullsort_tc(const float *query_p, const int64_t *query_ids, int64_t nq, 
     RB2_TC(64, 32);
   }
   if (small_list) RB2_TC(128, 16);
+  if (g_tc_trace) {   // the instrumented build exists for d = 128, K' = 32 only (tools/tc_trace.py)
+    if (g_tc_variant == 2) return run_tc<128, 32, true, true, true> RB2_TC_ARGS;
+    if (g_tc_variant != 1) return run_tc<128, 32, true, false, true> RB2_TC_ARGS;
+  }
   RB2_TC(128, 32);
 #undef RB2_TC
 }
