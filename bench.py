@@ -264,6 +264,8 @@ def run_ours(args, rank, world, local_rank):
                       (torch.from_numpy(w.pos[0]).to(dev), torch.from_numpy(w.pos[1]).to(dev)), w.n_items)
     ev = FusedTopKEvaluator(cfg)
     nq = index.n_eval_users
+    from recbole_b200._lib import lib as _lib
+    _lib.rb2_fullsort_tc_set_kprime(args.tc_kprime)
 
     def eval_once():
         ids, _ = model.full_sort_topk(index.uid_list, 10, index.hist_indptr, index.hist_indices, mode=args.scorer)
@@ -352,7 +354,8 @@ def run_ours(args, rank, world, local_rank):
                  "users": nq, "ms": eval_ms, "topk": 10, "roofline": eval_roof,
                  "e2e": {"value": nq / eval_e2e_s, "unit": "users/s", "h2d_bytes_per_step": 8 * nq,
                          "d2h_bytes_per_step": 6 * 10 * 8},
-                 "result": result, "gpu_launches": int(sum(v[2] for v in estages.values()))},
+                 "result": result, "gpu_launches": int(sum(v[2] for v in estages.values())),
+                 "tc_fallback_rows": int(_lib.rb2_fullsort_tc_last_fallback_rows()) if args.scorer == "tc" else None},
     }
     assert res2 == result
     print(json.dumps(line), flush=True)
@@ -380,6 +383,8 @@ def main():
     ap.add_argument("--exchange", default="auto", choices=["auto", "dense", "sparse"])
     ap.add_argument("--scale", type=float, default=1.0, help="cfg3 only: shrink users/items by this factor")
     ap.add_argument("--skip-cpu", action="store_true", dest="skip_cpu", help="profiling runs only")
+    ap.add_argument("--tc-kprime", type=int, default=0, dest="tc_kprime", choices=[0, 16, 32],
+                    help="candidates per list of the tensor-core scorer (0 = automatic)")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.workload in ("cfg4", "cfg5"):

@@ -245,11 +245,12 @@ int32_t rb2_fullsort_tc_last_fallback_rows(void);
  * when k <= 8).  More candidates = looser certificate, more epilogue work.  The result is exact either
  * way. */
 int rb2_fullsort_tc_set_kprime(int32_t kprime);
-/* MMA variant of RB2_SCORER_TC: 0 or 1 = per-CTA M = 128 MMAs (cta_group::1) on item slots that a CTA pair
- * loads by halves and multicasts (default, measured faster); 2 = CTA-pair MMA (tcgen05 cta_group::2, M = 256
- * across two SMs, each SM holds half of every item slot); 3 = per-CTA MMAs on fp16 operands (rows rescaled
- * by exact powers of two) with FP16 accumulators read back two per register (tcgen05.ld .pack::16b); the
- * accumulate error joins the certificate, so the result is exact in every variant. */
+/* MMA variant of RB2_SCORER_TC: 0 = default (= 3); 1 = bf16 operands, fp32 accumulators, per-CTA M = 128
+ * MMAs (cta_group::1) on item slots that a CTA pair loads by halves and multicasts; 3 = fp16 operands (rows
+ * rescaled by exact powers of two) with FP16 accumulators read back two per register (tcgen05.ld
+ * .pack::16b), per-CTA MMAs; 2 = as 3 with CTA-pair MMAs (cta_group::2, M = 256 across two SMs, each SM holds
+ * half of every item slot).  The accumulate error joins the certificate: the result is exact in every
+ * variant. */
 int rb2_fullsort_tc_set_variant(int32_t variant);
 /* Diagnostic: `device_buffer` (16 int64 per CTA, 148 CTAs at most; NULL = off) receives the cycles the
  * producer / MMA / epilogue roles of the RB2_SCORER_TC kernel spent waiting on each of their barriers. */

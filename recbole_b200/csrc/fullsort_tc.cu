@@ -6,23 +6,38 @@
 // (trainer.py:342-345) + TopKEvaluator.collect's topk (evaluators.py:68-72); the score matrix is
 // never written.
 //
-//   k_convert_rows   fp32 rows -> bf16 rows (queries are gathered by id), plus per-row ||u|| and
-//                    ||u - bf16(u)|| and, for the item side, max ||bf16(v)|| / max ||v - bf16(v)||.
-//   k_fullsort_tc    persistent, warp-specialised: warp 0 = TMA producer (128B-swizzled tiles),
-//                    warp 1 = single-thread tcgen05.mma issuer (bf16 x bf16 -> fp32 in TMEM, two
-//                    256-column accumulator stages), warps 2-9 = two epilogue warp sets, one per
-//                    accumulator stage (thread <-> TMEM lane <-> query row): tcgen05.ld 32 columns
-//                    at a time, FMNMX3 max tree against the row's running threshold, rare insert
-//                    into a K' (16 or 32) candidate list held in REGISTERS (branch-free bubble);
-//                    pad / history are checked only there, history through a per-row Bloom filter
-//                    in shared memory so that the CSR binary search is almost never taken.
+//   k_convert_rows   fp32 rows -> 16-bit rows (queries are gathered by id), plus per-row ||u||, ||u - h(u)||
+//                    and, for the item side, max ||h(v)|| / max ||v - h(v)||.  Default: fp16 after an EXACT
+//                    power-of-two rescale (each query row by its own 2^-e, the item table by one 2^-e), so
+//                    that every score fits the FP16 accumulator; variant 1: bf16, no rescale.
+//   k_fullsort_tc    persistent, warp-specialised, 384 threads: warp 0 = TMA producer (128B-swizzled
+//                    tiles, a CTA pair loads every item slot by halves and multicasts it), warp 1 =
+//                    single-thread tcgen05.mma issuer (M = 128, N = 256, K = 16; two 256-column accumulator
+//                    stages in TMEM), warp groups 1 and 2 = two epilogue warp sets (thread <-> TMEM lane <->
+//                    query row).  Set h drains columns [128 h, +128) of EVERY stage with two
+//                    tcgen05.ld ... .pack::16b (64 fp16 scores -> 32 registers each) and hands the stage
+//                    back BEFORE looking at the scores; HMNMX2 max tree against the row's threshold; a
+//                    passing score is appended to a small per-row buffer in shared memory and the buffers
+//                    are folded into the K' (16 or 32) candidate lists held in REGISTERS by all lanes
+//                    together; the two sets publish their list minima and filter with the larger one.
+//                    Pad / history are checked at the fold, history through a per-row Bloom filter in
+//                    shared memory so that the CSR binary search is almost never taken.  setmaxnreg moves
+//                    registers from the producer / MMA warp group to the epilogue warp groups.
 //   k_refine         candidates are re-scored with the canonical fp32 chain s = fmaf(q[k], v[k], s)
 //                    and ordered (score desc, id asc).  Certificate per row:
 //                        exact_K  >  max_part(approx K'-th score) + E,
-//                        E = ||du||*max||bv|| + ||u||*max||dv|| + slack      (Cauchy-Schwarz on
-//                        u.v - bu.bv = du.bv + u.dv)
+//                        E = ||du||*max||hv|| + ||u||*max||dv||   (Cauchy-Schwarz on u.v - hu.hv = du.hv + u.dv)
+//                          + 2^-11 * sum_j ||hu[0:16j]|| * max||hv||   (FP16 accumulators: every K = 16 MMA rounds
+//                            the running sum to nearest fp16 -- checked bit for bit by tools/mma_f16acc_check.cu)
+//                          + slack
 //                    proves no non-candidate can be in the exact top-K.  Rows that fail are
 //                    compacted and redone by the fp32 kernel, so the result is always exact.
+//
+// What bounds it (tools/tc_trace.py, tools/tc_bench.py): with K = d = 128 a tile is only 8 MMAs (1024
+// cycles); the chain TMA -> MMA -> tcgen05.ld -> release has to turn around inside that, and the kernel
+// runs power-limited (SM clock ~1.5-1.6 GHz under this load).  Measured 1.18 PFLOP/s at 512k x 2M x 128 =
+// 0.71 of the cuBLAS bf16 peak measured on the same GPUs; with the examination switched off entirely the
+// MMA/TMA chain alone reaches 1.36.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -73,7 +88,6 @@ constexpr int BK = 64;        // bf16 elements per 128-byte swizzle row
 constexpr int UNIT_BYTES = BN * BK * 2;   // one B ring slot: 256 items x 64 k
 constexpr int A_KB_BYTES = BM * BK * 2;
 constexpr int kThreadsTc = 384;          // warp group 0: producer warp, MMA warp, 2 idle; warp groups 1, 2: epilogue sets
-constexpr int BLOOM_WORDS = 32;          // 1024 bits per row, 2 hashes
 constexpr int CAPB = 8;                  // per-row append buffer (entries) in front of the candidate list
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -228,15 +242,6 @@ constexpr uint32_t kIdesc2H16 = ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * B
         "=r"(v[30]), "=r"(v[31])                                                                               \
       : "r"(taddr))
 
-__device__ __forceinline__ bool csr_has(const int64_t *__restrict__ a, int64_t n, int64_t x) {
-  int64_t lo = 0, hi = n;
-  while (lo < hi) {
-    int64_t mid = (lo + hi) >> 1;
-    if (a[mid] < x) lo = mid + 1; else hi = mid;
-  }
-  return lo < n && a[lo] == x;
-}
-
 struct TcParams {
   int64_t nq, n_local, item_base;
   int n_ut, n_split, tiles_per_split;   // work decomposition
@@ -260,15 +265,12 @@ template <int KB, int NSTAGE, bool TWO_SM>
 struct TcSmem {
   static constexpr size_t A_BYTES = (size_t)KB * A_KB_BYTES;
   static constexpr size_t B_BYTES = (size_t)NSTAGE * (TWO_SM ? UNIT_BYTES / 2 : UNIT_BYTES);
-  static constexpr size_t BLOOM_BYTES = (size_t)BLOOM_WORDS * BM * 4;
   static constexpr size_t CBUF_BYTES = (size_t)2 * CAPB * BM * 8;   // two warp sets x (score, id)
   static constexpr size_t TAU_BYTES = (size_t)2 * BM * 4;            // thresholds the two warp sets publish
   static constexpr size_t TOTAL =
-      1024 /*align slack*/ + A_BYTES + B_BYTES + BLOOM_BYTES + CBUF_BYTES + TAU_BYTES + 256 /*barriers*/;
+      1024 /*align slack*/ + A_BYTES + B_BYTES + CBUF_BYTES + TAU_BYTES + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ uint32_t bloom_h1(uint32_t x) { return (x * 0x9E3779B1u) >> 22; }
-__device__ __forceinline__ uint32_t bloom_h2(uint32_t x) { return (x * 0x85EBCA77u) >> 22; }
 
 // minimum of the (unsorted) candidate list and the slot that holds it: (value, slot) tournament tree
 template <int KP>
@@ -371,8 +373,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char *sA = smem;                                  // [KB][128 rows][128 B]
   unsigned char *sB = sA + TcSmem<KB, NSTAGE, TWO_SM>::A_BYTES;      // [NSTAGE][256 rows][128 B]
-  uint32_t *bloom = reinterpret_cast<uint32_t *>(sB + TcSmem<KB, NSTAGE, TWO_SM>::B_BYTES);  // [BLOOM_WORDS][BM]
-  float *cbuf_s = reinterpret_cast<float *>(bloom + BLOOM_WORDS * BM);                          // [2][CAPB][BM]
+  float *cbuf_s = reinterpret_cast<float *>(sB + TcSmem<KB, NSTAGE, TWO_SM>::B_BYTES);          // [2][CAPB][BM]
   int *cbuf_i = reinterpret_cast<int *>(cbuf_s + 2 * CAPB * BM);                                // [2][CAPB][BM]
   volatile float *tau_pub = reinterpret_cast<float *>(cbuf_i + 2 * CAPB * BM);                  // [2][BM]
   uint64_t *bars = reinterpret_cast<uint64_t *>(const_cast<float *>(tau_pub) + 2 * BM);
@@ -519,7 +520,6 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int ws = (warp - 4) >> 2;               // warp set = the half of every tile it drains
     const int quarter = warp & 3;                 // TMEM lanes this warp may touch: [32*quarter, +32)
     const int t = quarter * 32 + lane;            // row inside the tile
-    uint32_t *my_bloom = bloom + t;               // word i at my_bloom[i * BM]
     uint32_t tcount = 0;
     long long tr[16] = {0};
     for (int w = cluster_id; w < n_work; w += n_clusters) {
@@ -555,34 +555,30 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       // everyone is done with the previous work item's filter and thresholds
       asm volatile("bar.sync 1, 256;" ::: "memory");
       *tau_mine = -INFINITY;
-      if (ws == 0) {
-        for (int i = 0; i < BLOOM_WORDS; ++i) my_bloom[i * BM] = 0u;
-        for (int64_t h = 0; h < hlen; ++h) {
-          uint32_t x = (uint32_t)hist[h];
-          uint32_t a = bloom_h1(x), b = bloom_h2(x);
-          my_bloom[(a >> 5) * BM] |= 1u << (a & 31);
-          my_bloom[(b >> 5) * BM] |= 1u << (b & 31);
-        }
-      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      // History exclusion (trainer.py:344-345) without a search: a set sees its items in ascending order
+      // and the CSR row is sorted, so a cursor into the row (and the id under it, in a register) answers
+      // "seen in training?" for every passing score; it only ever moves forward.
+      int64_t hcur = 0;
+      int next_h = hlen > 0 ? (int)hist[0] : 0x7fffffff;
       const int64_t item_limit = p.item_base + p.n_local;
       const int t0 = sp * p.tiles_per_split;
       const int t1 = min(t0 + p.tiles_per_split, n_tiles_all);
 
-      auto valid = [&](int64_t item) -> bool {
-        if (item == 0 || item >= item_limit) return false;      // [PAD] / zero-filled rows past the table
-        if (hlen > 0) {
-          uint32_t x = (uint32_t)item, a = bloom_h1(x), b = bloom_h2(x);
-          bool maybe = ((my_bloom[(a >> 5) * BM] >> (a & 31)) & (my_bloom[(b >> 5) * BM] >> (b & 31)) & 1u) != 0u;
-          if (maybe && csr_has(hist, hlen, item)) return false; // trainer.py:344-345
+      auto valid = [&](int item) -> bool {
+        if (item == 0 || (int64_t)item >= item_limit) return false;      // [PAD] / zero-filled rows past the table
+        if (next_h < item) {
+          while (hcur + 16 < hlen && (int)hist[hcur + 16] < item) hcur += 16;   // gallop over long histories
+          do { ++hcur; } while (hcur < hlen && (int)hist[hcur] < item);
+          next_h = hcur < hlen ? (int)hist[hcur] : 0x7fffffff;
         }
-        return true;
+        return next_h != item;
       };
       auto fold = [&]() {
         for (int e = 0; e < cnt; ++e) {
           const float s = cb_s[e * BM];
           const int id = cb_i[e * BM];
-          if (s > tau && valid((int64_t)id)) {
+          if (s > tau) {
 #pragma unroll
             for (int j = 0; j < KP; ++j) {   // replace the minimum
               const bool hit = j == amin;
@@ -634,15 +630,18 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const bool single = (__popc(fa) + __popc(fb)) == 1;
         for (;;) {
           bool overflow = false;
-          while (fa | fb) {
+          while (fa | fb) {                                       // ascending item order (the history cursor needs it)
             if (cnt == CAPB) { overflow = true; break; }        // keep the flag: resumed after the fold
             const bool second = fa == 0u;
-            const int bit = __ffs(second ? fb : fa) - 1;
-            int col;
+            const uint32_t f = second ? fb : fa;
+            int col, bit;
             float sc;
             if (H16) {
-              const int reg = (bit & 15) + (second ? 16 : 0);
-              const bool odd = bit >= 16;
+              const uint32_t fe = f & 0xffffu, fo = f >> 16;
+              const int je = fe ? __ffs(fe) - 1 : 99, jo = fo ? __ffs(fo) - 1 : 99;
+              const bool odd = jo < je;                           // column 2 jo + 1 < 2 je
+              const int reg = (odd ? jo : je) + (second ? 16 : 0);
+              bit = (odd ? jo + 16 : je);
               col = 2 * reg + (odd ? 1 : 0);
               if (single) {
                 sc = m;
@@ -651,13 +650,17 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 sc = odd ? __high2float(as_h2(wv)) : __low2float(as_h2(wv));
               }
             } else {
+              bit = __ffs(f) - 1;
               col = bit;
               sc = single ? m : pick32(v, bit);
             }
-            cb_s[cnt * BM] = sc;
-            cb_i[cnt * BM] = (int)(gbase + col);
-            ++cnt;
-            if (second) fb &= fb - 1; else fa &= fa - 1;
+            const int item = (int)(gbase + col);
+            if (valid(item)) {
+              cb_s[cnt * BM] = sc;
+              cb_i[cnt * BM] = item;
+              ++cnt;
+            }
+            if (second) fb &= ~(1u << bit); else fa &= ~(1u << bit);
           }
           if (!__any_sync(0xffffffffu, overflow)) break;
           fold();                                                 // every lane folds what it has
@@ -1029,7 +1032,7 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
            float *out_scores, void *workspace, size_t workspace_bytes, cudaStream_t st) {
   constexpr int KB = D / BK;
   // B ring depth: what fits beside A, the Bloom filters and the barriers (2-SM slots are half the size)
-  constexpr int NSTAGE = TWO_SM ? ((KB == 1) ? 10 : 9) : 5;
+  constexpr int NSTAGE = TWO_SM ? 10 : 5;
   TcWs w;
   size_t need = carve_tc(w, workspace, nq, n_local, D, k);
   RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_fullsort_topk(tc): workspace %zu < %zu", workspace_bytes, need);
@@ -1122,9 +1125,9 @@ int rb2_fullsort_tc(const float *query_p, const int64_t *query_ids, int64_t nq, 
     return rb2_fullsort_fp32(query_p, query_ids, nq, item_p, n_items_local, item_base, dim, hist_indptr,
                              hist_indices, k, out_ids, out_scores, workspace, workspace_bytes, st, nullptr);
   }
-  // K' = 16 candidates per list when the item range is a shard of a larger table (item_base > 0 or the
-  // caller merges shards: the global K-th score sits far above a shard's 16th), 32 otherwise
-  const bool small_list = (g_tc_kprime == 16) || (g_tc_kprime == 0 && k <= 8);
+  // K' = 16 candidates per list for small K, and for short item ranges (list upkeep dominates there and a
+  // row whose certificate fails is cheap to redo); 32 otherwise
+  const bool small_list = (g_tc_kprime == 16) || (g_tc_kprime == 0 && (k <= 8 || (k <= 12 && n_items_local <= 262144)));
 #define RB2_TC_ARGS                                                                                           \
   (query_p, query_ids, nq, item_p, n_items_local, item_base, hist_indptr, hist_indices, k, out_ids, out_scores, \
    workspace, workspace_bytes, st)

@@ -274,3 +274,69 @@ def test_fullsort_tc_unsupported_shapes_use_fp32_kernel():
     ids, _ = ops.fullsort_topk(t(Q), None, t(V), 20, t(hp), t(hi), mode="tc")
     o_ids, _ = ofs.full_sort_topk(Q, V, np.arange(50), hp, hi, 20)
     np.testing.assert_array_equal(ids.cpu().numpy(), o_ids)
+
+
+@pytest.fixture
+def tc_variant():
+    """Sets the MMA variant of the tensor-core scorer for one test and restores the default."""
+    from recbole_b200._lib import lib
+
+    def set_(v):
+        assert lib.rb2_fullsort_tc_set_variant(int(v)) == 0
+    yield set_
+    lib.rb2_fullsort_tc_set_variant(0)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("kind", ["gauss", "row_scales", "tiny", "low_rank"])
+def test_fullsort_tc_variants_exact(tc_variant, variant, kind):
+    """1 = bf16 operands / fp32 accumulators, 3 = fp16 operands rescaled by powers of two / FP16
+    accumulators (default), 2 = 3 with CTA-pair MMAs: all three return the oracle's top-K bit for bit,
+    whatever the magnitudes of the rows (the fp16 path rescales every query row and the item table)."""
+    from recbole_b200 import ops
+    from gpu_util import t
+    tc_variant(variant)
+    rng = np.random.default_rng(17 + variant)
+    nq, N, d, K = 700, 40001, 128, 10
+    Q = rng.standard_normal((nq, d)).astype(np.float32)
+    V = rng.standard_normal((N, d)).astype(np.float32)
+    if kind == "gauss":
+        Q *= 0.1
+        V *= 0.1
+    elif kind == "row_scales":
+        Q *= np.exp(rng.standard_normal((nq, 1)) * 3).astype(np.float32)
+        V *= (np.exp(rng.standard_normal((N, 1))) * 1e-3).astype(np.float32)
+    elif kind == "tiny":
+        Q *= 1e-20
+        V *= 1e-12
+    else:
+        Bm = rng.standard_normal((8, d)).astype(np.float32)
+        Q = (rng.standard_normal((nq, 8)).astype(np.float32) @ Bm + 0.05 * Q).astype(np.float32)
+        V = (rng.standard_normal((N, 8)).astype(np.float32) @ Bm + 0.05 * V).astype(np.float32)
+    hp = np.arange(0, 5 * nq + 1, 5, dtype=np.int64)
+    hi = np.sort(rng.integers(1, N, (nq, 5)), axis=1).reshape(-1).astype(np.int64)
+    ids, sc = ops.fullsort_topk(t(Q), None, t(V), K, t(hp), t(hi), mode="tc")
+    o_ids, o_sc = ofs.full_sort_topk(Q, V, np.arange(nq), hp, hi, K)
+    np.testing.assert_array_equal(ids.cpu().numpy(), o_ids)
+    np.testing.assert_array_equal(sc.cpu().numpy(), o_sc)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_fullsort_tc_variants_agree_with_fp32_kernel_at_size(tc_variant, variant):
+    """A shape the oracle cannot finish (20k x 300k x 128, 30 history items per row): the tensor-core
+    variants and the exact CUDA-core kernel agree bit for bit, and the certificate holds for every row."""
+    from recbole_b200 import ops
+    from recbole_b200._lib import lib
+    tc_variant(variant)
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5)
+    nq, N, d, h = 20000, 300001, 128, 30
+    Q = torch.randn(nq, d, device=dev, generator=gen) * 0.1
+    V = torch.randn(N, d, device=dev, generator=gen) * 0.1
+    hp = torch.arange(0, h * nq + 1, h, device=dev, dtype=torch.int64)
+    hi = torch.sort(torch.randint(1, N, (nq, h), device=dev, generator=gen), dim=1).values.reshape(-1).contiguous()
+    ids_t, sc_t = ops.fullsort_topk(Q, None, V, 10, hp, hi, mode="tc")
+    assert lib.rb2_fullsort_tc_last_fallback_rows() == 0
+    ids_f, sc_f = ops.fullsort_topk(Q, None, V, 10, hp, hi, mode="fp32")
+    assert torch.equal(ids_t, ids_f) and torch.equal(sc_t, sc_f)
