@@ -838,7 +838,7 @@ __global__ void __launch_bounds__(256) k_convert_rows(const float *__restrict__ 
 // ---------------------------------------------------------------------------------------------
 // exact re-score + order + certificate.  One warp per query row; `parts` sorted lists of KP
 // candidates each (parts * KP <= 1024).
-template <int D, int KP, bool H16>
+template <int D, int KP, bool H16, int MAXC>
 __global__ void __launch_bounds__(128) k_refine(const float *__restrict__ query_p, const int64_t *__restrict__ query_ids,
                                                  int64_t nq, const float *__restrict__ item_p, int64_t item_base,
                                                  const int *__restrict__ cand_ids, const float *__restrict__ cand_sc,
@@ -847,7 +847,7 @@ __global__ void __launch_bounds__(128) k_refine(const float *__restrict__ query_
                                                  const float *__restrict__ qscale, const float *__restrict__ qacc,
                                                  int64_t *__restrict__ out_ids, float *__restrict__ out_scores,
                                                  int32_t *__restrict__ fail_rows, int32_t *__restrict__ fail_count) {
-  constexpr int MAXC = 32;  // candidates per lane
+  // MAXC = candidates per lane (parts * KP <= 32 * MAXC)
   const int lane = threadIdx.x % 32;
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
   if (r >= nq) return;
@@ -1088,9 +1088,17 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
   }
   {
     ProfScope prof(RB2_ST_TC_REFINE, st);
-    k_refine<D, KP, H16><<<(unsigned)((nq * 32 + 127) / 128), 128, 0, st>>>(
-        query_p, query_ids, nq, item_p, item_base, w.cand_ids, w.cand_sc, pl.n_split * 2, k, w.qnorm, w.qdnorm, w.maxes,
-        w.qscale, w.qacc, out_ids, out_scores, w.fail_rows, w.fail_count);
+    const int total = pl.n_split * 2 * KP;
+#define RB2_REFINE(MAXC_)                                                                                          \
+  k_refine<D, KP, H16, MAXC_><<<(unsigned)((nq * 32 + 127) / 128), 128, 0, st>>>(                                   \
+      query_p, query_ids, nq, item_p, item_base, w.cand_ids, w.cand_sc, pl.n_split * 2, k, w.qnorm, w.qdnorm, w.maxes, \
+      w.qscale, w.qacc, out_ids, out_scores, w.fail_rows, w.fail_count)
+    if (total <= 32) RB2_REFINE(1);
+    else if (total <= 64) RB2_REFINE(2);
+    else if (total <= 128) RB2_REFINE(4);
+    else if (total <= 256) RB2_REFINE(8);
+    else RB2_REFINE(32);
+#undef RB2_REFINE
     RB2_CUDA(cudaGetLastError());
   }
   // rows whose certificate failed: redo exactly (one small D2H per call)
