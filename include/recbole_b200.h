@@ -238,6 +238,11 @@ int rb2_ce_head(const float *x, int64_t nq, const float *item_p, int64_t n_items
                 const int64_t *target, int32_t k, float *loss_out, float *lse_out, int64_t *topk_ids,
                 float *topk_scores, void *workspace, size_t workspace_bytes, void *stream);
 
+/* rb2_ce_head runs on the tensor cores where covered (dim == 64, k <= 16): bf16 hi/lo split operands, one
+ * K = 192 GEMM with fp32 accumulators (logits good to ~2^-16 ||x|| ||e||), online logsumexp in the epilogue,
+ * certified exact top-k as RB2_SCORER_TC.  mode 1 forces the CUDA-core fp32 kernel, 0 = automatic. */
+int rb2_ce_head_set_scorer(int32_t mode);
+
 /* Diagnostic: how many rows of the last RB2_SCORER_TC call failed the certificate and were redone by
  * the fp32 kernel (or nq if the shape is not covered by the MMA tiling: dim not in {64,128}, k > 16). */
 int32_t rb2_fullsort_tc_last_fallback_rows(void);

@@ -65,6 +65,7 @@ SIGNATURES = {
                                          _p]),
     "rb2_ce_head_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "rb2_ce_head": (ctypes.c_int, [_p, _i64, _p, _i64, _i32, _p, _i32, _p, _p, _p, _p, _p, _sz, _p]),
+    "rb2_ce_head_set_scorer": (ctypes.c_int, [_i32]),
     "rb2_fullsort_tc_last_fallback_rows": (_i32, []),
     "rb2_fullsort_tc_set_kprime": (ctypes.c_int, [_i32]),
     "rb2_fullsort_tc_set_variant": (ctypes.c_int, [_i32]),

@@ -582,6 +582,18 @@ extern "C" int rb2_topk_metrics(const int64_t *topk_ids, int64_t nq, int32_t k, 
   return 0;
 }
 
+// tensor-core form (fullsort_tc.cu), dim == 64 and k <= 16
+size_t rb2_fullsort_tc_lse_workspace_bytes(int64_t nq, int64_t n_items, int32_t dim, int32_t k);
+int rb2_fullsort_tc_lse(const float *x, int64_t nq, const float *item_p, int64_t n_items, int32_t dim, int32_t k,
+                        int64_t *out_ids, float *out_scores, void *workspace, size_t workspace_bytes, cudaStream_t st,
+                        float *lse_m, float *lse_s, int *parts_out);
+static int32_t g_ce_scorer = 0;   // 0 = tensor cores where covered, 1 = CUDA-core fp32 kernel
+extern "C" int rb2_ce_head_set_scorer(int32_t mode) {
+  if (mode != 0 && mode != 1) return RB2_EINVAL;
+  g_ce_scorer = mode;
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // CE head: logits = X . E^T never materialised; loss = mean(logsumexp - logit[target]); top-K of the
 // same pass with the pad column masked.
@@ -590,7 +602,8 @@ extern "C" size_t rb2_ce_head_workspace_bytes(int64_t nq, int64_t n_items, int32
   c.take<float>((size_t)64 * nq);
   c.take<float>((size_t)64 * nq);
   c.take<float>(nq);
-  return c.off + rb2_fullsort_fp32_workspace(nq, n_items, dim, k) + 256;
+  size_t fs = rb2_fullsort_fp32_workspace(nq, n_items, dim, k), tc = rb2_fullsort_tc_lse_workspace_bytes(nq, n_items, dim, k);
+  return c.off + (fs > tc ? fs : tc) + 256;
 }
 
 extern "C" int rb2_ce_head(const float *x, int64_t nq, const float *item_p, int64_t n_items, int32_t dim,
@@ -606,11 +619,16 @@ extern "C" int rb2_ce_head(const float *x, int64_t nq, const float *item_p, int6
   float *lse_s = c.take<float>((size_t)64 * nq);
   float *row_loss = c.take<float>(nq);
   size_t fs_bytes = rb2_fullsort_fp32_workspace(nq, n_items, dim, k);
+  size_t tc_bytes = rb2_fullsort_tc_lse_workspace_bytes(nq, n_items, dim, k);
+  const bool use_tc = g_ce_scorer == 0 && tc_bytes > 0;
+  if (use_tc && tc_bytes > fs_bytes) fs_bytes = tc_bytes;
   void *fs_ws = c.take<char>(fs_bytes);
   RB2_REQUIRE(c.off <= workspace_bytes, RB2_EWORKSPACE, "rb2_ce_head: workspace %zu < %zu", workspace_bytes, c.off);
   int parts = 0;
-  int rc = rb2_fullsort_fp32_lse(x, nullptr, nq, item_p, n_items, 0, dim, nullptr, nullptr, k, topk_ids, topk_scores,
-                                 fs_ws, fs_bytes, st, nullptr, lse_m, lse_s, &parts);
+  int rc = use_tc ? rb2_fullsort_tc_lse(x, nq, item_p, n_items, dim, k, topk_ids, topk_scores, fs_ws, fs_bytes, st, lse_m,
+                                        lse_s, &parts)
+                  : rb2_fullsort_fp32_lse(x, nullptr, nq, item_p, n_items, 0, dim, nullptr, nullptr, k, topk_ids,
+                                          topk_scores, fs_ws, fs_bytes, st, nullptr, lse_m, lse_s, &parts);
   if (rc) return rc;
   ProfScope prof(RB2_ST_MISC, st, 2);
   unsigned blocks = (unsigned)((nq + 127) / 128);

@@ -249,6 +249,7 @@ struct TcParams {
   int *cand_ids;      // [n_split * 2][nq][KP]   (x2: one list per epilogue warp set)
   float *cand_sc;     // approximate (bf16) scores, each list sorted descending
   long long *trace;   // diagnostics (rb2_fullsort_tc_set_trace), usually nullptr
+  float *lse_m, *lse_s;   // LSE kernels: per (list, row) running max and sum of exp   [n_split * 2][nq]
 };
 #define TC_TIMED(slot, stmt)                          \
   do {                                                \
@@ -338,6 +339,11 @@ __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
 }
 
 __device__ __forceinline__ __half2 as_h2(uint32_t w) { return *reinterpret_cast<__half2 *>(&w); }
+__device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2; ex2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // max over the 64 fp16 scores packed in 32 registers (HMNMX2 tree)
 __device__ __forceinline__ float max64h(const uint32_t (&v)[32]) {
   __half2 m[16];
@@ -365,7 +371,7 @@ __device__ __forceinline__ uint32_t pick32u(const uint32_t (&v)[32], int j) {
 //                   its half of every B slot (16 KB).  The per-CTA MMAs read and write every B byte through
 //                   shared memory once per 1024 MMA-cycles (~128 B/clk, the whole shared-memory bandwidth);
 //                   splitting B halves that.
-template <int KB, int NSTAGE, int KP, bool H16, bool TWO_SM, bool TRACE>
+template <int KB, int NSTAGE, int KP, bool H16, bool TWO_SM, bool TRACE, bool LSE = false>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
   constexpr int SLOT_BYTES = TWO_SM ? UNIT_BYTES / 2 : UNIT_BYTES;
@@ -549,6 +555,7 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       float tau = active ? -INFINITY : INFINITY;   // inactive rows never append
       float tau_list = -INFINITY;
       int amin = 0, cnt = 0;
+      float run_m = -INFINITY, run_s = 0.f;        // LSE: online logsumexp over EVERY column of my half tiles
       float *cb_s = cbuf_s + (size_t)ws * CAPB * BM + t;   // entry e at [e * BM]
       int *cb_i = cbuf_i + (size_t)ws * CAPB * BM + t;
       volatile float *tau_mine = tau_pub + ws * BM + t, *tau_other = tau_pub + (ws ^ 1) * BM + t;
@@ -597,8 +604,34 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       // fetched its share of the NEXT one): the flags of the passing scores are gathered with two
       // instructions per register over four independent accumulators, and the usual case -- exactly one
       // passing score, which is the maximum already known -- skips the register select tree.
-      auto process = [&](const uint32_t (&v)[32], int64_t gbase) {
+      auto process = [&](uint32_t (&v)[32], int64_t gbase) {
+        if (LSE) {
+          // zero-filled rows past the end of the table are not classes of the softmax
+          const int64_t n_ok = item_limit - gbase;
+          if (n_ok < 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j >= n_ok) v[j] = 0xff800000u;   // -inf
+          }
+        }
         const float m = H16 ? max64h(v) : max32(v);
+        if (LSE && m != -INFINITY) {
+          constexpr float kLog2e = 1.4426950408889634f;
+          if (m > run_m) {   // rare after the first tiles
+            run_s *= exp2f((run_m - m) * kLog2e);
+            run_m = m;
+          }
+          const float mb = run_m * kLog2e;
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            a0 += ex2_approx(fmaf(__uint_as_float(v[j]), kLog2e, -mb));
+            a1 += ex2_approx(fmaf(__uint_as_float(v[j + 1]), kLog2e, -mb));
+            a2 += ex2_approx(fmaf(__uint_as_float(v[j + 2]), kLog2e, -mb));
+            a3 += ex2_approx(fmaf(__uint_as_float(v[j + 3]), kLog2e, -mb));
+          }
+          run_s += (a0 + a1) + (a2 + a3);
+        }
         if (!__any_sync(0xffffffffu, m > tau)) return;           // the common case
         // fp16: fa = registers 0-15, fb = registers 16-31; bit j = even column of register j, bit 16 + j =
         // odd column.  fp32: fa bit j = column j.
@@ -708,6 +741,10 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
       __syncwarp();
       fold();
+      if (LSE && active) {
+        p.lse_m[((int64_t)sp * 2 + ws) * p.nq + r] = run_m;
+        p.lse_s[((int64_t)sp * 2 + ws) * p.nq + r] = run_s;
+      }
       if (active) {
         // slot KP-1 of the output holds the list minimum (k_refine reads the cut-off there)
         int64_t o = (((int64_t)sp * 2 + ws) * p.nq + r) * KP;
@@ -743,6 +780,28 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 //                (max ||v * scale|| in [0.5, 1)).  Norms are those of the SCALED rows.  row_acc[r] =
 //                sum over the d/16 MMA k-steps of ||h(u)[0 : 16 j]|| bounds the sum of the partial
 //                accumulations the tensor core rounds to fp16.
+// maxima of non-negative floats, compared as integers (a NaN stays on top and fails every certificate):
+// warp shuffle, shared-memory atomic, ONE global atomic per block.  Every thread of the block calls this.
+__device__ __forceinline__ void block_max3(int a, int b, int c, float *ga, float *gb, float *gc) {
+  __shared__ int sm[3];
+  if (threadIdx.x == 0) sm[0] = sm[1] = sm[2] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a = max(a, __shfl_xor_sync(0xffffffffu, a, o));
+    b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+    c = max(c, __shfl_xor_sync(0xffffffffu, c, o));
+  }
+  if (threadIdx.x % 32 == 0) { atomicMax(&sm[0], a); atomicMax(&sm[1], b); atomicMax(&sm[2], c); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (ga) atomicMax(reinterpret_cast<int *>(ga), sm[0]);
+    if (gb) atomicMax(reinterpret_cast<int *>(gb), sm[1]);
+    if (gc) atomicMax(reinterpret_cast<int *>(gc), sm[2]);
+  }
+}
+constexpr int kConvertBlocks = 148 * 16;
+
 __device__ __forceinline__ float pow2_scale(float norm) {
   if (!(norm > 0.f) || !isfinite(norm)) return 1.f;
   int e;
@@ -757,11 +816,14 @@ __global__ void __launch_bounds__(256) k_rows_max_sqnorm(const float *__restrict
   constexpr int LANES = RowCfg<D>::LANES;
   const int lane = threadIdx.x % LANES;
   const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x % 32) / LANES * LANES));
-  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
-  if (r >= rows) return;
-  Row<D> x = row_ldg<D>(src, r, lane);
-  float n2 = group_sum<LANES>(row_dot_lane<D>(x, x), gmask);
-  if (lane == 0) atomicMax(reinterpret_cast<int *>(out_max_sq), __float_as_int(n2));   // non-negative (NaN sorts on top)
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x / LANES;
+  int mx = 0;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES; r < rows; r += stride) {
+    Row<D> x = row_ldg<D>(src, r, lane);
+    float n2 = group_sum<LANES>(row_dot_lane<D>(x, x), gmask);
+    mx = max(mx, __float_as_int(n2));
+  }
+  block_max3(mx, 0, 0, out_max_sq, nullptr, nullptr);
 }
 __global__ void k_item_scale(float *maxes) { maxes[2] = pow2_scale(sqrtf(maxes[3])); }
 
@@ -777,8 +839,9 @@ __global__ void __launch_bounds__(256) k_convert_rows(const float *__restrict__ 
   static_assert(!H16 || VPL == 1, "the fp16 path covers d <= 128");
   const int lane = threadIdx.x % LANES;
   const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x % 32) / LANES * LANES));
-  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
-  if (r >= rows) return;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x / LANES;
+  int mx_b = 0, mx_d = 0;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES; r < rows; r += stride) {
   int64_t sr = ids ? min(max(ids[r], (int64_t)0), src_rows - 1) : r;
   Row<D> x = row_ldg<D>(src, sr, lane);
   float scale = 1.f;
@@ -830,15 +893,76 @@ __global__ void __launch_bounds__(256) k_convert_rows(const float *__restrict__ 
     if (row_dnorm) row_dnorm[r] = dd;
     if (row_scale) row_scale[r] = scale;
     if (row_acc) row_acc[r] = acc;
-    if (max_bnorm) atomicMax(reinterpret_cast<int *>(max_bnorm), __float_as_int(bb));   // non-negative floats
-    if (max_dnorm) atomicMax(reinterpret_cast<int *>(max_dnorm), __float_as_int(dd));
+    mx_b = max(mx_b, __float_as_int(bb));
+    mx_d = max(mx_d, __float_as_int(dd));
   }
+  }
+  if (max_bnorm) block_max3(mx_b, mx_d, 0, max_bnorm, max_dnorm, nullptr);   // (uniform: a kernel argument)
+}
+
+// ---------------------------------------------------------------------------------------------
+// Split-precision operands for the CE head: x = hi + lo + dd with hi = bf16(x), lo = bf16(x - hi).  A row of
+// d = 64 becomes three 64-wide k-blocks -- queries [hi | hi | lo], items [hi | lo | hi] -- so that ONE
+// K = 192 GEMM with fp32 accumulators yields hi.hi + hi.lo + lo.hi = x.e - (lo.lo + dd.e + x.dd'), i.e.
+// logits good to ~2^-16 of ||x|| ||e|| (the logsumexp needs 1e-5).  Norms for the certificate:
+// row_norm = ||x||, row_lo = ||lo||, row_dd = ||x - hi - lo||; items: maxima of the same three.
+template <int D>
+__global__ void __launch_bounds__(256) k_convert_split(const float *__restrict__ src, int64_t rows, bool item_side,
+                                                        uint16_t *__restrict__ dst, float *__restrict__ row_norm,
+                                                        float *__restrict__ row_lo, float *__restrict__ row_dd,
+                                                        float *__restrict__ maxes) {
+  constexpr int LANES = RowCfg<D>::LANES;
+  static_assert(RowCfg<D>::VPL == 1, "d <= 128");
+  const int lane = threadIdx.x % LANES;
+  const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x % 32) / LANES * LANES));
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x / LANES;
+  int mx_n = 0, mx_d = 0, mx_l = 0;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES; r < rows; r += stride) {
+  Row<D> x = row_ldg<D>(src, r, lane);
+  float f[4] = {x.v[0].x, x.v[0].y, x.v[0].z, x.v[0].w};
+  uint16_t hi[4], lo[4];
+  float n2 = 0.f, l2 = 0.f, d2 = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat16 h = __float2bfloat16_rn(f[e]);
+    float hb = __bfloat162float(h);
+    __nv_bfloat16 l = __float2bfloat16_rn(f[e] - hb);
+    float lb = __bfloat162float(l);
+    float dd = (f[e] - hb) - lb;
+    hi[e] = __bfloat16_as_ushort(h);
+    lo[e] = __bfloat16_as_ushort(l);
+    n2 = fmaf(f[e], f[e], n2);
+    l2 = fmaf(lb, lb, l2);
+    d2 = fmaf(dd, dd, d2);
+  }
+  uint2 ph, pl;
+  ph.x = (uint32_t)hi[0] | ((uint32_t)hi[1] << 16); ph.y = (uint32_t)hi[2] | ((uint32_t)hi[3] << 16);
+  pl.x = (uint32_t)lo[0] | ((uint32_t)lo[1] << 16); pl.y = (uint32_t)lo[2] | ((uint32_t)lo[3] << 16);
+  uint2 *o = reinterpret_cast<uint2 *>(dst + r * (3 * D));
+  o[lane] = ph;
+  o[LANES + lane] = item_side ? pl : ph;
+  o[2 * LANES + lane] = item_side ? ph : pl;
+  n2 = group_sum<LANES>(n2, gmask);
+  l2 = group_sum<LANES>(l2, gmask);
+  d2 = group_sum<LANES>(d2, gmask);
+  if (lane == 0) {
+    float nn = sqrtf(n2) * 1.0001f, ll = sqrtf(l2) * 1.0001f, dd = sqrtf(d2) * 1.0001f;   // rounded up
+    if (row_norm) { row_norm[r] = nn; row_lo[r] = ll; row_dd[r] = dd; }
+    mx_n = max(mx_n, __float_as_int(nn));
+    mx_d = max(mx_d, __float_as_int(dd));
+    mx_l = max(mx_l, __float_as_int(ll));
+  }
+  }
+  if (maxes) block_max3(mx_n, mx_d, mx_l, maxes, maxes + 1, maxes + 2);
 }
 
 // ---------------------------------------------------------------------------------------------
 // exact re-score + order + certificate.  One warp per query row; `parts` sorted lists of KP
 // candidates each (parts * KP <= 1024).
-template <int D, int KP, bool H16, int MAXC>
+// EMODE: 0 = bf16 operands / fp32 accumulators, 1 = rescaled fp16 operands / FP16 accumulators,
+//        2 = split bf16 operands (k_convert_split): qscale = ||lo(u)||, qacc = ||dd(u)||, qdnorm unused,
+//            maxes = {max ||v||, max ||dd(v)||, max ||lo(v)||}
+template <int D, int KP, int EMODE, int MAXC>
 __global__ void __launch_bounds__(128) k_refine(const float *__restrict__ query_p, const int64_t *__restrict__ query_ids,
                                                  int64_t nq, const float *__restrict__ item_p, int64_t item_base,
                                                  const int *__restrict__ cand_ids, const float *__restrict__ cand_sc,
@@ -921,9 +1045,13 @@ __global__ void __launch_bounds__(128) k_refine(const float *__restrict__ query_
   }
   if (lane == 0 && any_full) {
     // |approx - exact| <= ||du||*max||bv|| + ||u||*max||dv||  (+ fp32 accumulation slack)
-    float E = qdnorm[r] * maxes[0] + qnorm[r] * maxes[1] + 1.6e-5f * qnorm[r] * maxes[0];
+    float E = (EMODE == 2) ? 0.f : qdnorm[r] * maxes[0] + qnorm[r] * maxes[1] + 1.6e-5f * qnorm[r] * maxes[0];
     float kth_s = kth;
-    if (H16) {
+    if (EMODE == 2) {
+      // x.e - (hi.hi + hi.lo + lo.hi) = lo.lo' + dd.e + x.dd' (+ the K = 192 fp32 accumulation of the tensor core)
+      E = qscale[r] * maxes[2] + qacc[r] * maxes[0] + qnorm[r] * maxes[1] + 3e-5f * qnorm[r] * maxes[0];
+    }
+    if (EMODE == 1) {
       // scores live in the rescaled domain (exact powers of two).  Every K=16 MMA rounds the running sum
       // to fp16 (round-to-nearest, bit-checked by tools/mma_f16acc_check.cu): |err_j| <= 2^-11 |acc_j|,
       // |acc_j| <= ||h(u)[0:16j]|| * max||h(v)||; the constant adds the subnormal / second-order slack
@@ -958,17 +1086,25 @@ struct TcPlan {
 TcPlan make_plan(int64_t nq, int64_t n_local) {
   TcPlan pl;
   pl.n_ut = (int)((nq + BM - 1) / BM);
-  int n_tiles = (int)((n_local + BN - 1) / BN);
-  int sms = rb2_num_sms();
-  int want = (2 * (sms / 2) + (pl.n_ut + 1) / 2 - 1) / ((pl.n_ut + 1) / 2);   // >= 2 work items per CTA pair
-  if (want < 1) want = 1;
-  if (want > 16) want = 16;
-  if (want > (n_tiles + 1) / 2) want = (n_tiles + 1) / 2;   // at least two tiles per work item (two warp sets)
-  if (want < 1) want = 1;
-  pl.tiles_per_split = (n_tiles + want - 1) / want;
+  const int n_tiles = (int)((n_local + BN - 1) / BN);
+  const int pairs = (pl.n_ut + 1) / 2, clusters = rb2_num_sms() / 2;
+  // Split the item range into `want` pieces so that the work items (query-tile pair x piece) fill the CTA
+  // pairs in whole rounds: cost = rounds x (tiles per piece + the cost of starting a work item: every piece
+  // warms its thresholds up again, K' ln(n / K') slow-path events per row ~ 150 tiles' worth of time).  Few
+  // query tiles need many pieces; many need one.
+  int best = 1;
+  long best_cost = -1;
+  for (int want = 1; want <= 16 && want <= n_tiles; ++want) {
+    int tps = (n_tiles + want - 1) / want;
+    int n_split = (n_tiles + tps - 1) / tps;
+    long work = (long)pairs * n_split;
+    long rounds = (work + clusters - 1) / clusters;
+    long cost = rounds * (tps + 150);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = want; }
+  }
+  pl.tiles_per_split = (n_tiles + best - 1) / best;
   pl.n_split = (n_tiles + pl.tiles_per_split - 1) / pl.tiles_per_split;
-  int work = ((pl.n_ut + 1) / 2) * pl.n_split;       // work items per CTA pair
-  int clusters = sms / 2;
+  int work = pairs * pl.n_split;       // work items per CTA pair
   pl.grid = 2 * (work < clusters ? work : clusters);
   return pl;
 }
@@ -1044,12 +1180,12 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
     RB2_CUDA(cudaMemsetAsync(w.maxes, 0, 4 * sizeof(float), st));
     RB2_CUDA(cudaMemsetAsync(w.fail_count, 0, 4 * sizeof(int32_t), st));
     if (nq_pad > nq) RB2_CUDA(cudaMemsetAsync(w.qb + nq * D, 0, (size_t)(nq_pad - nq) * D * 2, st));
-    const unsigned item_blocks = (unsigned)((n_local * LANES + 255) / 256);
+    const unsigned item_blocks = (unsigned)min((int64_t)kConvertBlocks, (n_local * LANES + 255) / 256);
     if (H16) {
       k_rows_max_sqnorm<D><<<item_blocks, 256, 0, st>>>(item_p, n_local, w.maxes + 3);
       k_item_scale<<<1, 1, 0, st>>>(w.maxes);
     }
-    k_convert_rows<D, H16><<<(unsigned)((nq * LANES + 255) / 256), 256, 0, st>>>(
+    k_convert_rows<D, H16><<<(unsigned)min((int64_t)kConvertBlocks, (nq * LANES + 255) / 256), 256, 0, st>>>(
         query_p, query_ids, nq, INT64_MAX, w.qb, w.qnorm, w.qdnorm, nullptr, nullptr, nullptr, w.qscale, w.qacc);
     k_convert_rows<D, H16><<<item_blocks, 256, 0, st>>>(item_p, nullptr, n_local, n_local, w.vb, nullptr, nullptr,
                                                         w.maxes, w.maxes + 1, H16 ? w.maxes + 2 : nullptr, nullptr,
@@ -1090,7 +1226,7 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
     ProfScope prof(RB2_ST_TC_REFINE, st);
     const int total = pl.n_split * 2 * KP;
 #define RB2_REFINE(MAXC_)                                                                                          \
-  k_refine<D, KP, H16, MAXC_><<<(unsigned)((nq * 32 + 127) / 128), 128, 0, st>>>(                                   \
+  k_refine<D, KP, H16 ? 1 : 0, MAXC_><<<(unsigned)((nq * 32 + 127) / 128), 128, 0, st>>>(                                   \
       query_p, query_ids, nq, item_p, item_base, w.cand_ids, w.cand_sc, pl.n_split * 2, k, w.qnorm, w.qdnorm, w.maxes, \
       w.qscale, w.qacc, out_ids, out_scores, w.fail_rows, w.fail_count)
     if (total <= 32) RB2_REFINE(1);
@@ -1109,6 +1245,116 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
   if (n_fail > 0) {
     rc = rb2_fullsort_fp32(query_p, query_ids, n_fail, item_p, n_local, item_base, D, hist_indptr, hist_indices, k,
                            out_ids, out_scores, w.fp32_ws, w.fp32_bytes, st, w.fail_rows);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// ---- CE head on the tensor cores (d = 64, k <= 16): split-precision logits, online logsumexp -------------
+struct TcLseWs {
+  uint16_t *qb, *vb;
+  float *qnorm, *qlo, *qdd, *maxes;
+  int *cand_ids;
+  float *cand_sc;
+  int32_t *fail_rows, *fail_count;
+  void *fp32_ws;
+  size_t fp32_bytes;
+};
+size_t carve_tc_lse(TcLseWs &w, void *base, int64_t nq, int64_t n_items, int k) {
+  Carver c(base);
+  TcPlan pl = make_plan(nq, n_items);
+  int64_t nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM);
+  w.qb = c.take<uint16_t>(nq_pad * 192);
+  w.vb = c.take<uint16_t>(n_items * 192);
+  w.qnorm = c.take<float>(nq);
+  w.qlo = c.take<float>(nq);
+  w.qdd = c.take<float>(nq);
+  w.maxes = c.take<float>(4);
+  w.cand_ids = c.take<int>((size_t)pl.n_split * 2 * nq * KP_MAX);
+  w.cand_sc = c.take<float>((size_t)pl.n_split * 2 * nq * KP_MAX);
+  w.fail_rows = c.take<int32_t>(nq);
+  w.fail_count = c.take<int32_t>(4);
+  w.fp32_bytes = rb2_fullsort_fp32_workspace(nq, n_items, 64, k);
+  w.fp32_ws = c.take<char>(w.fp32_bytes);
+  return c.off;
+}
+
+template <int KP>
+int run_tc_lse(const float *x, int64_t nq, const float *item_p, int64_t n_items, int k, int64_t *out_ids,
+               float *out_scores, void *workspace, size_t workspace_bytes, cudaStream_t st, float *lse_m, float *lse_s,
+               int *parts_out) {
+  constexpr int D = 64, KB = 3, NSTAGE = 5;
+  TcLseWs w;
+  size_t need = carve_tc_lse(w, workspace, nq, n_items, k);
+  RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_ce_head(tc): workspace %zu < %zu", workspace_bytes, need);
+  TcPlan pl = make_plan(nq, n_items);
+  RB2_REQUIRE(pl.n_split * 2 <= 64, RB2_EINVAL, "rb2_ce_head(tc): %d logsumexp parts > 64", pl.n_split * 2);
+  constexpr int LANES = RowCfg<D>::LANES;
+  const int64_t nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM);
+  {
+    ProfScope prof(RB2_ST_TC_CONVERT, st, 5);
+    RB2_CUDA(cudaMemsetAsync(w.maxes, 0, 4 * sizeof(float), st));
+    RB2_CUDA(cudaMemsetAsync(w.fail_count, 0, 4 * sizeof(int32_t), st));
+    if (nq_pad > nq) RB2_CUDA(cudaMemsetAsync(w.qb + nq * 192, 0, (size_t)(nq_pad - nq) * 192 * 2, st));
+    k_convert_split<D><<<(unsigned)min((int64_t)kConvertBlocks, (nq * LANES + 255) / 256), 256, 0, st>>>(x, nq, false, w.qb, w.qnorm, w.qlo, w.qdd, nullptr);
+    k_convert_split<D><<<(unsigned)min((int64_t)kConvertBlocks, (n_items * LANES + 255) / 256), 256, 0, st>>>(item_p, n_items, true, w.vb, nullptr,
+                                                                                 nullptr, nullptr, w.maxes);
+  }
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, w.qb, nq_pad, 192, BM, false);
+  if (rc) return rc;
+  rc = make_map(&tmB, w.vb, n_items, 192, BN / 2, false);
+  if (rc) return rc;
+  TcParams p;
+  p.nq = nq; p.n_local = n_items; p.item_base = 0;
+  p.n_ut = pl.n_ut; p.n_split = pl.n_split; p.tiles_per_split = pl.tiles_per_split;
+  p.hist_indptr = nullptr; p.hist_indices = nullptr;
+  p.cand_ids = w.cand_ids; p.cand_sc = w.cand_sc;
+  p.trace = nullptr;
+  p.lse_m = lse_m; p.lse_s = lse_s;
+  *parts_out = pl.n_split * 2;
+  const size_t smem = TcSmem<KB, NSTAGE, false>::TOTAL;
+  {
+    ProfScope prof(RB2_ST_TC_SCORE, st);
+    auto kern = k_fullsort_tc<KB, NSTAGE, KP, false, false, false, true>;
+    RB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)pl.grid);
+    cfg.blockDim = dim3(kThreadsTc);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RB2_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+    RB2_CUDA(cudaGetLastError());
+  }
+  {
+    ProfScope prof(RB2_ST_TC_REFINE, st);
+    const int total = pl.n_split * 2 * KP;
+#define RB2_REFINE(MAXC_)                                                                                         \
+  k_refine<D, KP, 2, MAXC_><<<(unsigned)((nq * 32 + 127) / 128), 128, 0, st>>>(                                    \
+      x, nullptr, nq, item_p, 0, w.cand_ids, w.cand_sc, pl.n_split * 2, k, w.qnorm, nullptr, w.maxes, w.qlo, w.qdd, \
+      out_ids, out_scores, w.fail_rows, w.fail_count)
+    if (total <= 32) RB2_REFINE(1);
+    else if (total <= 64) RB2_REFINE(2);
+    else if (total <= 128) RB2_REFINE(4);
+    else if (total <= 256) RB2_REFINE(8);
+    else RB2_REFINE(32);
+#undef RB2_REFINE
+    RB2_CUDA(cudaGetLastError());
+  }
+  int32_t n_fail = 0;
+  RB2_CUDA(cudaMemcpyAsync(&n_fail, w.fail_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  RB2_CUDA(cudaStreamSynchronize(st));
+  g_last_tc_fallback_rows = n_fail;
+  if (n_fail > 0) {
+    rc = rb2_fullsort_fp32(x, nullptr, n_fail, item_p, n_items, 0, D, nullptr, nullptr, k, out_ids, out_scores, w.fp32_ws,
+                           w.fp32_bytes, st, w.fail_rows);
     if (rc) return rc;
   }
   return 0;
@@ -1154,4 +1400,19 @@ int rb2_fullsort_tc(const float *query_p, const int64_t *query_ids, int64_t nq, 
   }
   RB2_TC(128, 32);
 #undef RB2_TC
+}
+
+// CE head (fullsort.cu: rb2_ce_head) on the tensor cores: top-k as rb2_fullsort_tc plus the per-part
+// (max, sum exp) pairs of the logsumexp over ALL items.  Covers dim == 64, k <= 16; returns 1 otherwise.
+size_t rb2_fullsort_tc_lse_workspace_bytes(int64_t nq, int64_t n_items, int32_t dim, int32_t k) {
+  if (dim != 64 || k > 16) return 0;
+  TcLseWs w;
+  return carve_tc_lse(w, nullptr, nq, n_items, k) + 256;
+}
+int rb2_fullsort_tc_lse(const float *x, int64_t nq, const float *item_p, int64_t n_items, int32_t dim, int32_t k,
+                        int64_t *out_ids, float *out_scores, void *workspace, size_t workspace_bytes, cudaStream_t st,
+                        float *lse_m, float *lse_s, int *parts_out) {
+  if (dim != 64 || k > 16) return 1;
+  if (k <= 8) return run_tc_lse<16>(x, nq, item_p, n_items, k, out_ids, out_scores, workspace, workspace_bytes, st, lse_m, lse_s, parts_out);
+  return run_tc_lse<32>(x, nq, item_p, n_items, k, out_ids, out_scores, workspace, workspace_bytes, st, lse_m, lse_s, parts_out);
 }

@@ -245,9 +245,11 @@ def fullsort_topk(Q, query_ids, V, k, hist_indptr=None, hist_indices=None, item_
     return ids, sc
 
 
-def ce_head(X, E, target, k=10):
-    """Fused full-sort CE head (rb2_ce_head): returns dict(loss 0-dim, lse [nq], ids [nq,k], scores [nq,k])."""
+def ce_head(X, E, target, k=10, scorer="auto"):
+    """Fused full-sort CE head (rb2_ce_head): returns dict(loss 0-dim, lse [nq], ids [nq,k], scores [nq,k]).
+    scorer: "auto" = tensor cores where covered (dim 64, k <= 16), "fp32" = the CUDA-core kernel."""
     nq, dev = X.shape[0], X.device
+    check(lib.rb2_ce_head_set_scorer({"auto": 0, "tc": 0, "fp32": 1}[scorer]))
     ws = Workspace(lib.rb2_ce_head_workspace_bytes(nq, E.shape[0], E.shape[1], int(k)), dev)
     loss = torch.zeros(1, dtype=torch.float32, device=dev)
     lse = torch.empty(nq, dtype=torch.float32, device=dev)

@@ -49,3 +49,30 @@ def test_ce_head_random_vs_oracle(nq, N, d):
 def oracle_pair(X, E, tgt):
     import oracle
     return oracle.clib.pair_scores_fma(X, E, np.arange(len(tgt)), tgt).astype(np.float64)
+
+
+@pytest.mark.parametrize("scale", [0.02, 1.0])
+def test_ce_head_tensor_core_vs_fp32_kernel_at_cfg4_size(scale):
+    """BASELINE config 4 shape (4096 x 1,000,001 x 64): the tensor-core CE head (bf16 hi/lo split
+    operands, K = 192, online logsumexp in the epilogue) against the exact CUDA-core kernel: identical
+    top-k, logsumexp and loss within 1e-5 (measured ~1e-6); `scale` 1.0 gives logits of +-40."""
+    from recbole_b200 import ops
+    from recbole_b200._lib import lib
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4)
+    nq, N, d = 4096, 1_000_001, 64
+    X = torch.randn(nq, d, device=dev, generator=gen)
+    X = (X - X.mean(1, keepdim=True)) / X.std(1, keepdim=True)
+    E = torch.randn(N, d, device=dev, generator=gen) * scale
+    E[0] = 0
+    tgt = torch.randint(1, N, (nq,), device=dev, generator=gen)
+    a = ops.ce_head(X, E, tgt, 10, scorer="tc")
+    fb = lib.rb2_fullsort_tc_last_fallback_rows()
+    b = ops.ce_head(X, E, tgt, 10, scorer="fp32")
+    assert torch.equal(a["ids"], b["ids"]) and torch.equal(a["scores"], b["scores"])
+    assert fb <= nq // 100
+    rel = ((a["lse"] - b["lse"]).abs() / b["lse"].abs()).max().item()
+    assert rel < 1e-5, rel
+    assert abs(a["loss"].item() - b["loss"].item()) <= 1e-5 * abs(b["loss"].item())
+    ops.ce_head(X[:8], E[:100], tgt[:8] % 100, 10, scorer="auto")   # leaves the knob at its default
