@@ -355,6 +355,7 @@ def run_ours(args, rank, world, local_rank):
                  "e2e": {"value": nq / eval_e2e_s, "unit": "users/s", "h2d_bytes_per_step": 8 * nq,
                          "d2h_bytes_per_step": 6 * 10 * 8},
                  "result": result, "gpu_launches": int(sum(v[2] for v in estages.values())),
+                 "tc_pass2_rows": int(_lib.rb2_fullsort_tc_last_pass2_rows()) if args.scorer == "tc" else None,
                  "tc_fallback_rows": int(_lib.rb2_fullsort_tc_last_fallback_rows()) if args.scorer == "tc" else None},
     }
     assert res2 == result

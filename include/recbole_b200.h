@@ -246,6 +246,10 @@ int rb2_ce_head_set_scorer(int32_t mode);
 /* Diagnostic: how many rows of the last RB2_SCORER_TC call failed the certificate and were redone by
  * the fp32 kernel (or nq if the shape is not covered by the MMA tiling: dim not in {64,128}, k > 16). */
 int32_t rb2_fullsort_tc_last_fallback_rows(void);
+/* Diagnostic: rows of the last RB2_SCORER_TC call whose first (FP16-accumulator) certificate failed and that
+ * were re-scored by the second tensor-core pass (same fp16 operands, fp32 accumulators, ~10x tighter error
+ * bound); only what fails there too reaches the fp32 kernel (rb2_fullsort_tc_last_fallback_rows). */
+int32_t rb2_fullsort_tc_last_pass2_rows(void);
 /* Tuning knob of RB2_SCORER_TC: candidates kept per (row, list): 16, 32, or 0 = automatic (32, or 16
  * when k <= 8).  More candidates = looser certificate, more epilogue work.  The result is exact either
  * way. */

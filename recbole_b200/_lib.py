@@ -67,6 +67,7 @@ SIGNATURES = {
     "rb2_ce_head": (ctypes.c_int, [_p, _i64, _p, _i64, _i32, _p, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "rb2_ce_head_set_scorer": (ctypes.c_int, [_i32]),
     "rb2_fullsort_tc_last_fallback_rows": (_i32, []),
+    "rb2_fullsort_tc_last_pass2_rows": (_i32, []),
     "rb2_fullsort_tc_set_kprime": (ctypes.c_int, [_i32]),
     "rb2_fullsort_tc_set_variant": (ctypes.c_int, [_i32]),
     "rb2_fullsort_tc_set_trace": (ctypes.c_int, [_p]),

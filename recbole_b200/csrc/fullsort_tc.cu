@@ -54,6 +54,7 @@ size_t rb2_fullsort_fp32_workspace(int64_t nq, int64_t n_items_local, int32_t di
 
 // number of rows the last RB2_SCORER_TC call had to redo in fp32 (diagnostic for bench / tests)
 static int32_t g_last_tc_fallback_rows = 0;
+static int32_t g_last_tc_pass2_rows = 0;   // rows the last call sent through the second (fp32-accumulator) tensor pass
 static int32_t g_tc_kprime = 0;  // 0 = automatic, 16 or 32 = forced (rb2_fullsort_tc_set_kprime)
 // 0 = default (= 3); 1 = bf16 operands, fp32 accumulators, per-CTA MMAs; 3 = fp16 operands (rows rescaled by
 // powers of two), FP16 accumulators drained with .pack::16b, per-CTA MMAs; 2 = as 3 with CTA-pair MMAs
@@ -70,6 +71,7 @@ extern "C" int rb2_fullsort_tc_set_kprime(int32_t kp) {
   return 0;
 }
 extern "C" int32_t rb2_fullsort_tc_last_fallback_rows(void) { return g_last_tc_fallback_rows; }
+extern "C" int32_t rb2_fullsort_tc_last_pass2_rows(void) { return g_last_tc_pass2_rows; }
 // diagnostics: device buffer of 16 int64 per CTA that k_fullsort_tc fills with the cycles its producer / MMA /
 // epilogue roles spent waiting on each barrier (nullptr = off)
 static long long *g_tc_trace = nullptr;
@@ -213,6 +215,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // instruction descriptor: c=f32, a=b=bf16, both K-major, N=256, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
+// (c format: F32 = 1 << 4 / F16 = 0; a and b formats: BF16 = 1 << 7 | 1 << 10 / F16 = 0; N >> 3 at bit 17; M >> 4 at bit 24)
+constexpr uint32_t make_idesc(bool acc_f32, bool in_bf16, int m) {
+  return (acc_f32 ? (1u << 4) : 0u) | (in_bf16 ? ((1u << 7) | (1u << 10)) : 0u) | ((uint32_t)(BN >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
 constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 // fp16 operands, FP16 accumulator (c_format = a_format = b_format = 0): one 16-bit score in the low half of
 // every 32-bit TMEM column (tools/mma_f16acc_check.cu)
@@ -250,6 +257,7 @@ struct TcParams {
   float *cand_sc;     // approximate (bf16) scores, each list sorted descending
   long long *trace;   // diagnostics (rb2_fullsort_tc_set_trace), usually nullptr
   float *lse_m, *lse_s;   // LSE kernels: per (list, row) running max and sum of exp   [n_split * 2][nq]
+  const int32_t *row_map; // second pass over the rows whose certificate failed: row of this pass -> caller's row
 };
 #define TC_TIMED(slot, stmt)                          \
   do {                                                \
@@ -371,7 +379,7 @@ __device__ __forceinline__ uint32_t pick32u(const uint32_t (&v)[32], int j) {
 //                   its half of every B slot (16 KB).  The per-CTA MMAs read and write every B byte through
 //                   shared memory once per 1024 MMA-cycles (~128 B/clk, the whole shared-memory bandwidth);
 //                   splitting B halves that.
-template <int KB, int NSTAGE, int KP, bool H16, bool TWO_SM, bool TRACE, bool LSE = false>
+template <int KB, int NSTAGE, int KP, bool H16, bool TWO_SM, bool TRACE, bool LSE = false, bool F16IN = H16>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
   constexpr int SLOT_BYTES = TWO_SM ? UNIT_BYTES / 2 : UNIT_BYTES;
@@ -499,11 +507,11 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             for (int k4 = 0; k4 < BK / 16; ++k4) {
               // advance 16 elements = 32 bytes inside the swizzle row: +2 in 16-byte units
               if (TWO_SM)
-                tc_mma_2sm(tmem_d, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), H16 ? kIdesc2H16 : kIdesc2,
-                           (kb | k4) ? 1u : 0u);
+                tc_mma_2sm(tmem_d, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4),
+                           make_idesc(!H16, !F16IN, 2 * BM), (kb | k4) ? 1u : 0u);
               else
-                tc_mma_bf16(tmem_d, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4), H16 ? kIdescH16 : kIdesc,
-                            (kb | k4) ? 1u : 0u);
+                tc_mma_bf16(tmem_d, adesc + (uint64_t)(2 * k4), bdesc + (uint64_t)(2 * k4),
+                            make_idesc(!H16, !F16IN, BM), (kb | k4) ? 1u : 0u);
             }
             // the slot is free for both producers once these MMAs have read it
             if (TWO_SM) tc_commit_2sm(&empty[stage]); else tc_commit_mc(&empty[stage], (uint16_t)0x3);
@@ -535,8 +543,9 @@ k_fullsort_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const int64_t *hist = nullptr;
       int64_t hlen = 0;
       if (active && p.hist_indptr) {
-        int64_t h0 = p.hist_indptr[r];
-        hlen = p.hist_indptr[r + 1] - h0;
+        const int64_t ro = p.row_map ? (int64_t)p.row_map[r] : r;
+        int64_t h0 = p.hist_indptr[ro];
+        hlen = p.hist_indptr[ro + 1] - h0;
         hist = p.hist_indices + h0;
       }
       // Candidate list: KP (score, id) pairs in registers, UNSORTED; `tau_list` = its minimum, held in slot
@@ -829,7 +838,8 @@ __global__ void k_item_scale(float *maxes) { maxes[2] = pow2_scale(sqrtf(maxes[3
 
 template <int D, bool H16>
 __global__ void __launch_bounds__(256) k_convert_rows(const float *__restrict__ src, const int64_t *__restrict__ ids,
-                                                       int64_t rows, int64_t src_rows, uint16_t *__restrict__ dst,
+                                                       const int32_t *__restrict__ row_map, int64_t rows,
+                                                       int64_t src_rows, uint16_t *__restrict__ dst,
                                                        float *__restrict__ row_norm, float *__restrict__ row_dnorm,
                                                        float *__restrict__ max_bnorm, float *__restrict__ max_dnorm,
                                                        const float *__restrict__ gscale, float *__restrict__ row_scale,
@@ -842,7 +852,8 @@ __global__ void __launch_bounds__(256) k_convert_rows(const float *__restrict__ 
   const int64_t stride = (int64_t)gridDim.x * blockDim.x / LANES;
   int mx_b = 0, mx_d = 0;
   for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES; r < rows; r += stride) {
-  int64_t sr = ids ? min(max(ids[r], (int64_t)0), src_rows - 1) : r;
+  const int64_t rr = row_map ? (int64_t)row_map[r] : r;
+  int64_t sr = ids ? min(max(ids[rr], (int64_t)0), src_rows - 1) : rr;
   Row<D> x = row_ldg<D>(src, sr, lane);
   float scale = 1.f;
   if (H16) scale = gscale ? *gscale : pow2_scale(sqrtf(group_sum<LANES>(row_dot_lane<D>(x, x), gmask)));
@@ -960,6 +971,7 @@ __global__ void __launch_bounds__(256) k_convert_split(const float *__restrict__
 // exact re-score + order + certificate.  One warp per query row; `parts` sorted lists of KP
 // candidates each (parts * KP <= 1024).
 // EMODE: 0 = bf16 operands / fp32 accumulators, 1 = rescaled fp16 operands / FP16 accumulators,
+//        3 = rescaled fp16 operands / fp32 accumulators (second pass: no accumulate term in E),
 //        2 = split bf16 operands (k_convert_split): qscale = ||lo(u)||, qacc = ||dd(u)||, qdnorm unused,
 //            maxes = {max ||v||, max ||dd(v)||, max ||lo(v)||}
 template <int D, int KP, int EMODE, int MAXC>
@@ -969,13 +981,14 @@ __global__ void __launch_bounds__(128) k_refine(const float *__restrict__ query_
                                                  int parts, int K, const float *__restrict__ qnorm,
                                                  const float *__restrict__ qdnorm, const float *__restrict__ maxes,
                                                  const float *__restrict__ qscale, const float *__restrict__ qacc,
-                                                 int64_t *__restrict__ out_ids, float *__restrict__ out_scores,
+                                                 const int32_t *__restrict__ row_map, int64_t *__restrict__ out_ids, float *__restrict__ out_scores,
                                                  int32_t *__restrict__ fail_rows, int32_t *__restrict__ fail_count) {
   // MAXC = candidates per lane (parts * KP <= 32 * MAXC)
   const int lane = threadIdx.x % 32;
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
   if (r >= nq) return;
-  const int64_t qrow = query_ids ? query_ids[r] : r;
+  const int64_t ro = row_map ? (int64_t)row_map[r] : r;        // the caller's row (outputs, query id)
+  const int64_t qrow = query_ids ? query_ids[ro] : ro;
   const float4 *q4 = reinterpret_cast<const float4 *>(query_p + qrow * D);
   const int total = parts * KP;
   float cs[MAXC];
@@ -1038,8 +1051,8 @@ __global__ void __launch_bounds__(128) k_refine(const float *__restrict__ query_
     for (int c = 0; c < MAXC; ++c)
       if (ci[c] == wi) ci[c] = -1;  // remove the winner everywhere (an id may sit in two lists of one row? no: lists partition the items)
     if (lane == 0) {
-      out_ids[r * K + j] = have ? (int64_t)wi : -1;
-      out_scores[r * K + j] = have ? wsc : -INFINITY;
+      out_ids[ro * K + j] = have ? (int64_t)wi : -1;
+      out_scores[ro * K + j] = have ? wsc : -INFINITY;
     }
     if (have) { kth = wsc; ++found; }
   }
@@ -1051,6 +1064,7 @@ __global__ void __launch_bounds__(128) k_refine(const float *__restrict__ query_
       // x.e - (hi.hi + hi.lo + lo.hi) = lo.lo' + dd.e + x.dd' (+ the K = 192 fp32 accumulation of the tensor core)
       E = qscale[r] * maxes[2] + qacc[r] * maxes[0] + qnorm[r] * maxes[1] + 3e-5f * qnorm[r] * maxes[0];
     }
+    if (EMODE == 3) kth_s = kth * qscale[r] * maxes[2];         // rescaled fp16 operands, fp32 accumulators
     if (EMODE == 1) {
       // scores live in the rescaled domain (exact powers of two).  Every K=16 MMA rounds the running sum
       // to fp16 (round-to-nearest, bit-checked by tools/mma_f16acc_check.cu): |err_j| <= 2^-11 |acc_j|,
@@ -1061,7 +1075,7 @@ __global__ void __launch_bounds__(128) k_refine(const float *__restrict__ query_
     bool ok = (found == K) && (kth_s > tau_max + E);
     if (!ok) {
       int slot = atomicAdd(fail_count, 1);
-      fail_rows[slot] = (int32_t)r;
+      fail_rows[slot] = (int32_t)ro;
     }
   }
 }
@@ -1072,18 +1086,19 @@ struct TcWs {
   float *maxes;  // [0] = max ||16bit(v)||, [1] = max ||v - 16bit(v)||, [2] = item scale, [3] = max ||v||^2
   int *cand_ids;
   float *cand_sc;
-  int32_t *fail_rows, *fail_count;
+  int32_t *fail_rows, *fail_rows2, *fail_count;
   int64_t *fb_ids;
   float *fb_sc;
   void *fp32_ws;
   size_t fp32_bytes;
+  int64_t cand_lists;             // capacity of cand_ids / cand_sc in lists of KP_MAX
 };
 
 struct TcPlan {
   int n_ut, n_split, tiles_per_split, grid;
 };
 
-TcPlan make_plan(int64_t nq, int64_t n_local) {
+TcPlan make_plan(int64_t nq, int64_t n_local, int max_split = 16) {
   TcPlan pl;
   pl.n_ut = (int)((nq + BM - 1) / BM);
   const int n_tiles = (int)((n_local + BN - 1) / BN);
@@ -1094,7 +1109,7 @@ TcPlan make_plan(int64_t nq, int64_t n_local) {
   // query tiles need many pieces; many need one.
   int best = 1;
   long best_cost = -1;
-  for (int want = 1; want <= 16 && want <= n_tiles; ++want) {
+  for (int want = 1; want <= max_split && want <= n_tiles; ++want) {
     int tps = (n_tiles + want - 1) / want;
     int n_split = (n_tiles + tps - 1) / tps;
     long work = (long)pairs * n_split;
@@ -1122,9 +1137,11 @@ size_t carve_tc(TcWs &w, void *base, int64_t nq, int64_t n_local, int dim, int k
   w.qscale = c.take<float>(nq);
   w.qacc = c.take<float>(nq);
   w.maxes = c.take<float>(4);
-  w.cand_ids = c.take<int>((size_t)pl.n_split * 2 * nq * KP_MAX);
-  w.cand_sc = c.take<float>((size_t)pl.n_split * 2 * nq * KP_MAX);
+  w.cand_lists = (int64_t)pl.n_split * 2 * nq;
+  w.cand_ids = c.take<int>((size_t)w.cand_lists * KP_MAX);
+  w.cand_sc = c.take<float>((size_t)w.cand_lists * KP_MAX);
   w.fail_rows = c.take<int32_t>(nq);
+  w.fail_rows2 = c.take<int32_t>(nq);
   w.fail_count = c.take<int32_t>(4);
   w.fb_ids = c.take<int64_t>(nq * k);
   w.fb_sc = c.take<float>(nq * k);
@@ -1162,39 +1179,47 @@ int make_map(CUtensorMap *m, void *base, int64_t rows, int dim, int box_rows, bo
   return 0;
 }
 
-template <int D, int KP, bool H16, bool TWO_SM, bool TRACE = false>
-int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p, int64_t n_local,
-           int64_t item_base, const int64_t *hist_indptr, const int64_t *hist_indices, int k, int64_t *out_ids,
-           float *out_scores, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+// One tensor-core pass over `nq` rows (the caller's rows row_map[0..nq) when row_map is given): conversion of the
+// queries (and of the item shard unless a previous pass left it in w.vb / w.maxes), scorer, refine.  Rows whose
+// certificate fails are appended (caller's numbering) to fail_rows / *fail_count.
+template <int D, int KP, bool F16IN, bool H16, bool TWO_SM, bool TRACE>
+int tc_pass(const TcWs &w, const float *query_p, const int64_t *query_ids, const int32_t *row_map, int64_t nq,
+            bool convert_items, const float *item_p, int64_t n_local, int64_t item_base, const int64_t *hist_indptr,
+            const int64_t *hist_indices, int k, int64_t *out_ids, float *out_scores, int32_t *fail_rows,
+            int32_t *fail_count, cudaStream_t st) {
   constexpr int KB = D / BK;
-  // B ring depth: what fits beside A, the Bloom filters and the barriers (2-SM slots are half the size)
-  constexpr int NSTAGE = TWO_SM ? 10 : 5;
-  TcWs w;
-  size_t need = carve_tc(w, workspace, nq, n_local, D, k);
-  RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_fullsort_topk(tc): workspace %zu < %zu", workspace_bytes, need);
-  TcPlan pl = make_plan(nq, n_local);
+  constexpr int NSTAGE = TWO_SM ? 10 : 5;   // B ring depth: what fits beside A, the append buffers and the barriers
+  constexpr int EMODE = F16IN ? (H16 ? 1 : 3) : 0;
+  static_assert(F16IN || !H16, "FP16 accumulators need the rescaled fp16 operands");
+  // the candidate buffers were sized for the first pass: a later pass over fewer rows may not split finer
+  int max_split = (int)(w.cand_lists / (2 * nq));
+  if (max_split > 16) max_split = 16;
+  if (max_split < 1) max_split = 1;
+  TcPlan pl = make_plan(nq, n_local, max_split);
   constexpr int LANES = RowCfg<D>::LANES;
   const int64_t nq_pad = (nq + 2 * BM - 1) / (2 * BM) * (2 * BM);
   {
-    ProfScope prof(RB2_ST_TC_CONVERT, st, H16 ? 6 : 4);
-    RB2_CUDA(cudaMemsetAsync(w.maxes, 0, 4 * sizeof(float), st));
-    RB2_CUDA(cudaMemsetAsync(w.fail_count, 0, 4 * sizeof(int32_t), st));
+    ProfScope prof(RB2_ST_TC_CONVERT, st, 6);
     if (nq_pad > nq) RB2_CUDA(cudaMemsetAsync(w.qb + nq * D, 0, (size_t)(nq_pad - nq) * D * 2, st));
     const unsigned item_blocks = (unsigned)min((int64_t)kConvertBlocks, (n_local * LANES + 255) / 256);
-    if (H16) {
-      k_rows_max_sqnorm<D><<<item_blocks, 256, 0, st>>>(item_p, n_local, w.maxes + 3);
-      k_item_scale<<<1, 1, 0, st>>>(w.maxes);
+    if (convert_items) {
+      RB2_CUDA(cudaMemsetAsync(w.maxes, 0, 4 * sizeof(float), st));
+      if (F16IN) {
+        k_rows_max_sqnorm<D><<<item_blocks, 256, 0, st>>>(item_p, n_local, w.maxes + 3);
+        k_item_scale<<<1, 1, 0, st>>>(w.maxes);
+      }
     }
-    k_convert_rows<D, H16><<<(unsigned)min((int64_t)kConvertBlocks, (nq * LANES + 255) / 256), 256, 0, st>>>(
-        query_p, query_ids, nq, INT64_MAX, w.qb, w.qnorm, w.qdnorm, nullptr, nullptr, nullptr, w.qscale, w.qacc);
-    k_convert_rows<D, H16><<<item_blocks, 256, 0, st>>>(item_p, nullptr, n_local, n_local, w.vb, nullptr, nullptr,
-                                                        w.maxes, w.maxes + 1, H16 ? w.maxes + 2 : nullptr, nullptr,
-                                                        nullptr);
+    k_convert_rows<D, F16IN><<<(unsigned)min((int64_t)kConvertBlocks, (nq * LANES + 255) / 256), 256, 0, st>>>(
+        query_p, query_ids, row_map, nq, INT64_MAX, w.qb, w.qnorm, w.qdnorm, nullptr, nullptr, nullptr, w.qscale, w.qacc);
+    if (convert_items)
+      k_convert_rows<D, F16IN><<<item_blocks, 256, 0, st>>>(item_p, nullptr, nullptr, n_local, n_local, w.vb, nullptr,
+                                                            nullptr, w.maxes, w.maxes + 1,
+                                                            F16IN ? w.maxes + 2 : nullptr, nullptr, nullptr);
   }
   CUtensorMap tmA, tmB;
-  int rc = make_map(&tmA, w.qb, nq_pad, D, BM, H16);
+  int rc = make_map(&tmA, w.qb, nq_pad, D, BM, F16IN);
   if (rc) return rc;
-  rc = make_map(&tmB, w.vb, n_local, D, BN / 2, H16);   // each CTA of the pair loads half a slot
+  rc = make_map(&tmB, w.vb, n_local, D, BN / 2, F16IN);   // each CTA of the pair loads half a slot
   if (rc) return rc;
   TcParams p;
   p.nq = nq; p.n_local = n_local; p.item_base = item_base;
@@ -1202,11 +1227,13 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
   p.hist_indptr = hist_indptr; p.hist_indices = hist_indices;
   p.cand_ids = w.cand_ids; p.cand_sc = w.cand_sc;
   p.trace = g_tc_trace;
+  p.lse_m = nullptr; p.lse_s = nullptr;
+  p.row_map = row_map;
   const size_t smem = TcSmem<KB, NSTAGE, TWO_SM>::TOTAL;
   {
     ProfScope prof(RB2_ST_TC_SCORE, st);
-    RB2_CUDA(cudaFuncSetAttribute(k_fullsort_tc<KB, NSTAGE, KP, H16, TWO_SM, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
+    auto kern = k_fullsort_tc<KB, NSTAGE, KP, H16, TWO_SM, TRACE, false, F16IN>;
+    RB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)pl.grid);
     cfg.blockDim = dim3(kThreadsTc);
@@ -1219,16 +1246,16 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RB2_CUDA(cudaLaunchKernelEx(&cfg, k_fullsort_tc<KB, NSTAGE, KP, H16, TWO_SM, TRACE>, tmA, tmB, p));
+    RB2_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
     RB2_CUDA(cudaGetLastError());
   }
   {
     ProfScope prof(RB2_ST_TC_REFINE, st);
     const int total = pl.n_split * 2 * KP;
-#define RB2_REFINE(MAXC_)                                                                                          \
-  k_refine<D, KP, H16 ? 1 : 0, MAXC_><<<(unsigned)((nq * 32 + 127) / 128), 128, 0, st>>>(                                   \
+#define RB2_REFINE(MAXC_)                                                                                             \
+  k_refine<D, KP, EMODE, MAXC_><<<(unsigned)((nq * 32 + 127) / 128), 128, 0, st>>>(                                    \
       query_p, query_ids, nq, item_p, item_base, w.cand_ids, w.cand_sc, pl.n_split * 2, k, w.qnorm, w.qdnorm, w.maxes, \
-      w.qscale, w.qacc, out_ids, out_scores, w.fail_rows, w.fail_count)
+      w.qscale, w.qacc, row_map, out_ids, out_scores, fail_rows, fail_count)
     if (total <= 32) RB2_REFINE(1);
     else if (total <= 64) RB2_REFINE(2);
     else if (total <= 128) RB2_REFINE(4);
@@ -1237,14 +1264,44 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
 #undef RB2_REFINE
     RB2_CUDA(cudaGetLastError());
   }
-  // rows whose certificate failed: redo exactly (one small D2H per call)
+  return 0;
+}
+
+// The cascade: (1) all rows through the fast pass; (2) the rows whose certificate failed, again, with fp32
+// accumulators -- same fp16 operands, an error bound ~10x tighter (the FP16-accumulate term dominates E) at
+// ~85 % of the speed; (3) what still fails goes to the exact CUDA-core kernel.  Trained tables (a few popular
+// items with large norms inflate max||v||) fail 2-3 % of the rows in (1) and ~10x fewer in (2).
+template <int D, int KP, bool H16, bool TWO_SM, bool TRACE = false>
+int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p, int64_t n_local,
+           int64_t item_base, const int64_t *hist_indptr, const int64_t *hist_indices, int k, int64_t *out_ids,
+           float *out_scores, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+  TcWs w;
+  size_t need = carve_tc(w, workspace, nq, n_local, D, k);
+  RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_fullsort_topk(tc): workspace %zu < %zu", workspace_bytes, need);
+  RB2_CUDA(cudaMemsetAsync(w.fail_count, 0, 4 * sizeof(int32_t), st));
+  int rc = tc_pass<D, KP, H16, H16, TWO_SM, TRACE>(w, query_p, query_ids, nullptr, nq, true, item_p, n_local, item_base,
+                                                   hist_indptr, hist_indices, k, out_ids, out_scores, w.fail_rows,
+                                                   w.fail_count, st);
+  if (rc) return rc;
   int32_t n_fail = 0;
   RB2_CUDA(cudaMemcpyAsync(&n_fail, w.fail_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   RB2_CUDA(cudaStreamSynchronize(st));
+  g_last_tc_pass2_rows = 0;
+  const int32_t *final_rows = w.fail_rows;
+  if (H16 && n_fail > 0) {
+    g_last_tc_pass2_rows = n_fail;
+    rc = tc_pass<D, KP, true, false, false, false>(w, query_p, query_ids, w.fail_rows, n_fail, false, item_p, n_local,
+                                                   item_base, hist_indptr, hist_indices, k, out_ids, out_scores,
+                                                   w.fail_rows2, w.fail_count + 1, st);
+    if (rc) return rc;
+    RB2_CUDA(cudaMemcpyAsync(&n_fail, w.fail_count + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RB2_CUDA(cudaStreamSynchronize(st));
+    final_rows = w.fail_rows2;
+  }
   g_last_tc_fallback_rows = n_fail;
-  if (n_fail > 0) {
+  if (n_fail > 0) {   // redo exactly
     rc = rb2_fullsort_fp32(query_p, query_ids, n_fail, item_p, n_local, item_base, D, hist_indptr, hist_indices, k,
-                           out_ids, out_scores, w.fp32_ws, w.fp32_bytes, st, w.fail_rows);
+                           out_ids, out_scores, w.fp32_ws, w.fp32_bytes, st, final_rows);
     if (rc) return rc;
   }
   return 0;
@@ -1312,11 +1369,12 @@ int run_tc_lse(const float *x, int64_t nq, const float *item_p, int64_t n_items,
   p.cand_ids = w.cand_ids; p.cand_sc = w.cand_sc;
   p.trace = nullptr;
   p.lse_m = lse_m; p.lse_s = lse_s;
+  p.row_map = nullptr;
   *parts_out = pl.n_split * 2;
   const size_t smem = TcSmem<KB, NSTAGE, false>::TOTAL;
   {
     ProfScope prof(RB2_ST_TC_SCORE, st);
-    auto kern = k_fullsort_tc<KB, NSTAGE, KP, false, false, false, true>;
+    auto kern = k_fullsort_tc<KB, NSTAGE, KP, false, false, false, true, false>;
     RB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)pl.grid);
@@ -1339,7 +1397,7 @@ int run_tc_lse(const float *x, int64_t nq, const float *item_p, int64_t n_items,
 #define RB2_REFINE(MAXC_)                                                                                         \
   k_refine<D, KP, 2, MAXC_><<<(unsigned)((nq * 32 + 127) / 128), 128, 0, st>>>(                                    \
       x, nullptr, nq, item_p, 0, w.cand_ids, w.cand_sc, pl.n_split * 2, k, w.qnorm, nullptr, w.maxes, w.qlo, w.qdd, \
-      out_ids, out_scores, w.fail_rows, w.fail_count)
+      nullptr, out_ids, out_scores, w.fail_rows, w.fail_count)
     if (total <= 32) RB2_REFINE(1);
     else if (total <= 64) RB2_REFINE(2);
     else if (total <= 128) RB2_REFINE(4);

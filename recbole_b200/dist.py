@@ -219,7 +219,7 @@ class ShardedBPR:
             self._ws = {key: self.ops.bpr_workspace(batch, self.dim, self.device)}
         return self._ws[key]
 
-    def plan(self, user, pos, neg):
+    def plan(self, user, pos, neg, ids_ready=False):
         """Everything of a sparse-exchange step that depends only on the batch IDS (not on the
         parameters): de-duplication, bucketing by owner, the count exchange and all-to-all of the
         requested ids.  It contains the step's only host synchronisations, so train_step() runs it for
@@ -229,15 +229,20 @@ class ShardedBPR:
             self._plan_stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
         st = self._plan_stream
         ctx = torch.cuda.stream(st) if st is not None else _NullCtx()
+        if not hasattr(self, "_bounds_dev"):
+            self._bounds_dev = torch.as_tensor(self.item_bounds, device=self.device)
+            self._plan_ws = [None, None]
+            self._plan_free = [None, None]            # event: the step that used this buffer has finished
+            self._plan_flip = 0
+        self._plan_flip ^= 1                          # two plans are alive at a time (current + next)
         if st is not None:
-            st.wait_stream(torch.cuda.current_stream())
+            if not ids_ready:
+                st.wait_stream(torch.cuda.current_stream())
+            elif self._plan_free[self._plan_flip] is not None:
+                # the ids are complete already: only the step that read this plan buffer (two plans ago) must be over
+                st.wait_event(self._plan_free[self._plan_flip])
         with ctx:
             B = int(user.numel())
-            if not hasattr(self, "_bounds_dev"):
-                self._bounds_dev = torch.as_tensor(self.item_bounds, device=self.device)
-                self._plan_ws = [None, None]
-                self._plan_flip = 0
-            self._plan_flip ^= 1                      # two plans are alive at a time (current + next)
             ip = self.ops.item_plan(pos, neg, self.n_items, self._bounds_dev, comm.world,
                                     self._plan_ws[self._plan_flip])
             self._plan_ws[self._plan_flip] = ip["ws"]
@@ -249,7 +254,8 @@ class ShardedBPR:
             req = comm.all_to_all(uniq, send_counts, recv_counts)      # ids other ranks want from me
             p = dict(B=B, user_local=(user - self.u_lo).contiguous(), pos_c=ip["pos_c"], neg_c=ip["neg_c"],
                      n_uniq=n_uniq, send_counts=send_counts, recv_counts=recv_counts,
-                     local_idx=(req - self.i_lo).contiguous(), ids=(user, pos, neg), plan_ws=ip["ws"])
+                     local_idx=(req - self.i_lo).contiguous(), ids=(user, pos, neg), plan_ws=ip["ws"],
+                     flip=self._plan_flip)
             p["event"] = torch.cuda.Event() if st is not None else None
             if st is not None:
                 p["event"].record(st)
@@ -271,23 +277,63 @@ class ShardedBPR:
         if p is None or p["ids"][0] is not user:
             p = self.plan(user, pos, neg)
         self._next_plan = None
+        mark = self._phase_mark
+        mark("start")
         if p["event"] is not None:
             torch.cuda.current_stream().wait_event(p["event"])
+            for k in ("user_local", "local_idx"):     # allocated on the plan stream, read on this one
+                p[k].record_stream(torch.cuda.current_stream())
+        mark("wait_plan")
         # all-to-all #1 (rows): parameters as they are after the previous step
         rows = self.V.index_select(0, p["local_idx"])
+        mark("gather_rows")
         C = comm.all_to_all(rows, p["recv_counts"], p["send_counts"])
+        mark("a2a_rows")
         G = torch.empty_like(C)
         ops.bpr_train_step_sharded(self.U, self.state, C, p["user_local"], p["pos_c"], p["neg_c"], global_batch,
                                    self.optim, self.loss_out, None, G, self._workspace(B), step=t,
                                    item_plan=p["plan_ws"])
+        mark("kernels")
         if next_batch is not None:      # enqueue the next plan now: its host syncs overlap with the kernels above
-            self._next_plan = self.plan(*next_batch)
+            self._next_plan = self.plan(*next_batch, ids_ready=self.ids_ready)
         grads = return_grads(comm, G, p["send_counts"], p["recv_counts"])
+        mark("a2a_grads")
         self._rows_ws = ops.sparse_rows_update(self.V, self.state.get("mV"), self.state.get("vV"), None,
                                                p["local_idx"], grads, self.optim, self._rows_ws, step=t)
+        mark("rows_update")
         comm.all_reduce_sum(self.loss_out)
         self.loss_accum += self.loss_out.double()
+        mark("loss")
+        if self.device.type == "cuda":
+            done = torch.cuda.Event()
+            done.record()
+            self._plan_free[p["flip"]] = done
         return self.loss_out
+
+    # ---- optional per-phase timing of the sparse-exchange step (bench diagnostics) -----------------------------
+    phase_timing = False
+    ids_ready = False     # True: next_batch tensors are already complete (resident batches): the plan stream need not
+                          # wait for the training stream
+
+    def _phase_mark(self, name):
+        if not self.phase_timing:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self._phase_events = getattr(self, "_phase_events", [])
+        self._phase_events.append((name, ev))
+
+    def phase_report(self):
+        """ms per phase averaged over the recorded steps (call after a synchronize)."""
+        evs = getattr(self, "_phase_events", [])
+        tot, cnt = {}, {}
+        for (n0, e0), (n1, e1) in zip(evs[:-1], evs[1:]):
+            if n1 == "start":
+                continue
+            tot[n1] = tot.get(n1, 0.0) + e0.elapsed_time(e1)
+            cnt[n1] = cnt.get(n1, 0) + 1
+        self._phase_events = []
+        return {k: tot[k] / cnt[k] for k in tot}
 
     def _train_step_dense(self, user, pos, neg, global_batch, t):
         ops, comm = self.ops, self.comm
@@ -334,12 +380,17 @@ class ShardedBPR:
             n = index.n_own
             ids = torch.empty((n, K), dtype=torch.int64, device=self.device)
             local_users = (index.uid_own - self.u_lo).contiguous()
+            self.last_eval_fallback_rows = 0
+            self.last_eval_pass2_rows = 0
             for lo in range(0, n, user_tile):
                 hi = min(lo + user_tile, n)
                 ptr = index.own_hist_indptr[lo:hi + 1].contiguous()
                 i, _ = ops.fullsort_topk(self.U, local_users[lo:hi].contiguous(), V_all, K, ptr,
                                          index.own_hist_indices, mode=mode)
                 ids[lo:hi] = i
+                if mode == "tc":
+                    self.last_eval_fallback_rows += int(ops.lib.rb2_fullsort_tc_last_fallback_rows())
+                    self.last_eval_pass2_rows += int(ops.lib.rb2_fullsort_tc_last_pass2_rows())
             if n > 0:
                 sums = ops.topk_metrics(ids, index.pos_indptr, index.pos_indices, self.n_items)["sums"]
             else:
