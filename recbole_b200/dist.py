@@ -195,6 +195,10 @@ class ShardedBPR:
         # "dense": all-gather the item rows, reduce-scatter their gradients (no data-dependent sizes,
         #          no host sync; right when the table is small next to the batch).
         # "sparse": all-to-all of the de-duplicated rows the batch touches (large tables).
+        # "auto": dense (all-gather rows + reduce-scatter gradients, no plan, no host sync) for small tables and
+        # whenever a rank's batch covers most of the item table anyway (B >= n_items: >= 86 % of the rows are
+        # touched, measured at cfg3 on 8 GPUs: 7.9 ms dense vs 15.7 ms sparse at B = 2^22, 4.8 vs 4.1 at 2^20)
+        self.exchange_auto = exchange == "auto"
         if exchange == "auto":
             exchange = "dense" if n_items * dim * 4 <= (64 << 20) else "sparse"
         self.exchange = exchange
@@ -271,8 +275,10 @@ class ShardedBPR:
             global_batch = B * comm.world
         self.optim.step += 1
         t = self.optim.step
-        if self.exchange == "dense":
+        if self.exchange == "dense" or (self.exchange_auto and B >= self.n_items):
+            self.last_exchange = "dense"
             return self._train_step_dense(user, pos, neg, global_batch, t)
+        self.last_exchange = "sparse"
         p = getattr(self, "_next_plan", None)
         if p is None or p["ids"][0] is not user:
             p = self.plan(user, pos, neg)

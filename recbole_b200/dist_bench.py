@@ -76,7 +76,7 @@ def run(args, rank, world, local_rank, load_peaks, ClockSampler):
     stages = ops.profile_read()
     ops.profile_enable(False)
     phases = None
-    if world > 1 and getattr(model, "exchange", "") != "dense":
+    if world > 1 and getattr(model, "last_exchange", "") != "dense":
         # second, instrumented pass (events between the phases perturb nothing but are kept out of the timed one)
         model.phase_timing = True
         for i in range(min(args.steps, 6)):
@@ -159,7 +159,7 @@ def run(args, rank, world, local_rank, load_peaks, ClockSampler):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": train_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(w.describe(), train_batch_per_gpu=B, global_batch=GB, optimizer="adam(row-sparse) lr=1e-3",
-                           scorer=args.scorer, eval_layout=args.eval_layout, exchange=model.exchange,
+                           scorer=args.scorer, eval_layout=args.eval_layout, exchange=getattr(model, "last_exchange", model.exchange),
                            parallelism="users range-partitioned, item table row-sharded x%d, NCCL all-to-all" % world,
                            l2="no flush: every step reads a different batch"),
             "clocks": clk, "roofline": roofline,
