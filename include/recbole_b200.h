@@ -188,6 +188,21 @@ int rb2_fm_predict(const float *E, const float *W, const float *bias3, int64_t n
                    const int64_t *ids, const int64_t *offsets, int32_t n_fields, int64_t batch, float *y_out,
                    void *workspace, size_t workspace_bytes, void *stream);
 
+/* Row-sharded FM (one 33M-row table sharded over the GPUs, batch split by rows; no reference
+ * counterpart).  rb2_fm_grad_step is the local part of a step: rows_e [n_rows, dim] / rows_w [n_rows] are the
+ * FETCHED copies of the rows this rank's samples touch (ids index them; same workspace as rb2_fm_train_step); on
+ * return every row holds its summed gradient for loss = sum over the GLOBAL batch / global_batch, loss2[0] = this
+ * rank's share of the loss, loss2[1] = its share of d loss / d bias.  The owners then step their rows:
+ * rb2_sparse_rows_update for the [rows, dim] table, rb2_scalar_rows_update for the d = 1 table (duplicate ids
+ * summed in a fixed order), rb2_scalar_step for the replicated (bias, m, v) block after an all-reduce. */
+int rb2_fm_grad_step(float *rows_e, float *rows_w, const float *bias3, int64_t n_rows, int32_t dim,
+                     const int64_t *ids, const int64_t *offsets, int32_t n_fields, const float *label, int64_t batch,
+                     int64_t global_batch, float *loss2, void *workspace, size_t workspace_bytes, void *stream);
+size_t rb2_scalar_rows_update_workspace_bytes(int64_t m);
+int rb2_scalar_rows_update(float *p, float *m, float *v, int64_t n_rows, const int64_t *ids, const float *grads,
+                           int64_t M, const rb2_optim *h_opt, void *workspace, size_t workspace_bytes, void *stream);
+int rb2_scalar_step(float *p3, const float *grad, const rb2_optim *h_opt, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * (1b) Gather-dot for explicit (user, item) pairs.  Replaces BPR.predict (bpr.py:85-89).
  * ---------------------------------------------------------------------------------------- */

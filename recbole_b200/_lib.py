@@ -59,6 +59,10 @@ SIGNATURES = {
     "rb2_fm_train_step": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _i32, _p, _i64,
                                          ctypes.POINTER(RB2Optim), _p, _p, _p, _sz, _p]),
     "rb2_fm_predict": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _i32, _i64, _p, _p, _sz, _p]),
+    "rb2_fm_grad_step": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _i32, _p, _i64, _i64, _p, _p, _sz, _p]),
+    "rb2_scalar_rows_update_workspace_bytes": (_sz, [_i64]),
+    "rb2_scalar_rows_update": (ctypes.c_int, [_p, _p, _p, _i64, _p, _p, _i64, ctypes.POINTER(RB2Optim), _p, _sz, _p]),
+    "rb2_scalar_step": (ctypes.c_int, [_p, _p, ctypes.POINTER(RB2Optim), _p]),
     "rb2_gather_dot": (ctypes.c_int, [_p, _p, _i64, _i64, _i32, _p, _p, _i64, _p, _p]),
     "rb2_fullsort_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32, _i32]),
     "rb2_fullsort_topk": (ctypes.c_int, [_p, _p, _i64, _p, _i64, _i64, _i32, _p, _p, _i32, _i32, _p, _p, _p, _sz,

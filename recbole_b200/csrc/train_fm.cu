@@ -70,6 +70,10 @@ size_t carve(FmWs &w, void *base, int64_t B, int F, int dim) {
   return c.off;
 }
 
+// internal optimizer kind of rb2_fm_grad_step: the row's summed gradient REPLACES the row (the tables are the
+// fetched copies of a sharded step; every row is processed exactly once, after the forward has read it)
+constexpr int kOptGradOut = 99;
+
 struct FmTables {
   float *E, *mE, *vE;   // [rows, D]
   float *W, *mW, *vW;   // [rows]
@@ -185,6 +189,11 @@ __device__ __forceinline__ void fm_row_step(const FmTables &t, int64_t row, int 
   Row<D> p = row_ld<D>(t.E, row, lane);
   Row<D> g = gsum;
   row_fma<D>(g, -zsum, p);
+  if (o.kind == kOptGradOut) {
+    row_st<D>(t.E, row, lane, g);
+    if (lane == 0) t.W[row] = zsum;
+    return;
+  }
   row_update<D>(t.E, t.mE, t.vE, row, lane, p, g, o);
   if (lane == 0) {
     float pw = t.W[row];
@@ -329,6 +338,10 @@ __global__ void k_fm_bias_loss(FmTables t, FmWs w, int64_t n_parts, double inv_b
     loss_out[0] = loss;
     if (loss_accum) loss_accum[0] += (double)loss;
     float b = t.bias[0], gb = (float)sg[0];
+    if (o.kind == kOptGradOut) {
+      loss_out[1] = gb;          // this rank's share of d loss / d bias
+      return;
+    }
     if (o.kind == RB2_OPT_SGD) {
       sgd_elem(b, gb, o);
     } else {
@@ -364,25 +377,15 @@ extern "C" size_t rb2_fm_workspace_bytes(int64_t batch, int32_t n_fields, int32_
   return carve(w, nullptr, batch, n_fields, dim);
 }
 
-extern "C" int rb2_fm_train_step(float *E, float *mE, float *vE, float *W, float *mW, float *vW, float *bias3,
-                                 int64_t n_rows, int32_t dim, const int64_t *ids, const int64_t *offsets,
-                                 int32_t n_fields, const float *label, int64_t batch, const rb2_optim *h_opt,
-                                 float *loss_out, double *loss_accum, void *workspace, size_t workspace_bytes,
-                                 void *stream) {
-  RB2_REQUIRE(E && W && bias3 && ids && offsets && label && h_opt && loss_out && workspace, RB2_EINVAL,
-              "rb2_fm_train_step: null argument");
+static int fm_step(FmTables t, int64_t n_rows, int32_t dim, const int64_t *ids, const int64_t *offsets, int32_t n_fields,
+                   const float *label, int64_t batch, double norm_batch, OptScalars o, float *loss_out,
+                   double *loss_accum, void *workspace, size_t workspace_bytes, cudaStream_t st, const char *who) {
   RB2_REQUIRE(batch > 0 && n_fields > 0 && batch * (int64_t)n_fields < ((int64_t)1 << 31), RB2_EINVAL,
-              "rb2_fm_train_step: batch*fields out of range");
-  RB2_REQUIRE(n_rows > 0 && n_rows < ((int64_t)1 << 32) - 1, RB2_EINVAL, "rb2_fm_train_step: table too large");
-  OptScalars o = rb2_opt_scalars(h_opt);
-  RB2_REQUIRE(o.kind == RB2_OPT_SGD || o.kind == RB2_OPT_ADAM, RB2_EINVAL,
-              "rb2_fm_train_step: optimizer kind %d not supported (sgd, adam)", o.kind);
-  if (o.kind != RB2_OPT_SGD) RB2_REQUIRE(mE && vE && mW && vW, RB2_EINVAL, "rb2_fm_train_step: Adam needs m and v");
+              "%s: batch*fields out of range", who);
+  RB2_REQUIRE(n_rows > 0 && n_rows < ((int64_t)1 << 32) - 1, RB2_EINVAL, "%s: table too large", who);
   FmWs w;
   size_t need = carve(w, workspace, batch, n_fields, dim);
-  RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_fm_train_step: workspace %zu < %zu", workspace_bytes, need);
-  cudaStream_t st = (cudaStream_t)stream;
-  FmTables t{E, mE, vE, W, mW, vW, bias3};
+  RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "%s: workspace %zu < %zu", who, workspace_bytes, need);
   const int64_t M = batch * n_fields;
   k_zero_parts<<<(unsigned)((w.n_parts + 255) / 256), 256, 0, st>>>(w);
   RB2_FM_DIM(dim, {
@@ -394,7 +397,7 @@ extern "C" int rb2_fm_train_step(float *E, float *mE, float *vE, float *W, float
     {
       ProfScope prof(RB2_ST_FM_FWD, st, 2);
       k_fm_forward<D_, true><<<fblocks, kThreads, 0, st>>>(t, ids, offsets, label, batch, n_fields, n_rows,
-                                                           1.f / (float)batch, w, nullptr);
+                                                           (float)(1.0 / norm_batch), w, nullptr);
     }
     size_t tmp = w.cub_bytes;
     {
@@ -409,9 +412,130 @@ extern "C" int rb2_fm_train_step(float *E, float *mE, float *vE, float *W, float
       ProfScope prof(RB2_ST_FM_UPDATE, st, 3);
       k_fm_rows<D_><<<blocks, kThreads, 0, st>>>(t, w, M, n_fields, T, nt, o);
       k_fm_fixup<D_><<<blocks, kThreads, 0, st>>>(t, w, M, T, nt, o);
-      k_fm_bias_loss<<<1, 256, 0, st>>>(t, w, w.n_parts, 1.0 / (double)batch, o, loss_out, loss_accum);
+      k_fm_bias_loss<<<1, 256, 0, st>>>(t, w, w.n_parts, 1.0 / norm_batch, o, loss_out, loss_accum);
     }
   });
+  RB2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int rb2_fm_train_step(float *E, float *mE, float *vE, float *W, float *mW, float *vW, float *bias3,
+                                 int64_t n_rows, int32_t dim, const int64_t *ids, const int64_t *offsets,
+                                 int32_t n_fields, const float *label, int64_t batch, const rb2_optim *h_opt,
+                                 float *loss_out, double *loss_accum, void *workspace, size_t workspace_bytes,
+                                 void *stream) {
+  RB2_REQUIRE(E && W && bias3 && ids && offsets && label && h_opt && loss_out && workspace, RB2_EINVAL,
+              "rb2_fm_train_step: null argument");
+  OptScalars o = rb2_opt_scalars(h_opt);
+  RB2_REQUIRE(o.kind == RB2_OPT_SGD || o.kind == RB2_OPT_ADAM, RB2_EINVAL,
+              "rb2_fm_train_step: optimizer kind %d not supported (sgd, adam)", o.kind);
+  if (o.kind != RB2_OPT_SGD) RB2_REQUIRE(mE && vE && mW && vW, RB2_EINVAL, "rb2_fm_train_step: Adam needs m and v");
+  FmTables t{E, mE, vE, W, mW, vW, bias3};
+  return fm_step(t, n_rows, dim, ids, offsets, n_fields, label, batch, (double)batch, o, loss_out, loss_accum, workspace,
+                 workspace_bytes, (cudaStream_t)stream, "rb2_fm_train_step");
+}
+
+// Sharded step, the local part: rows_e [n_rows, dim] / rows_w [n_rows] are the FETCHED copies of the rows this
+// rank's samples touch (ids index them, offsets may be all zero); on return every row holds its summed
+// gradient (d loss / d row with loss = sum over the GLOBAL batch / global_batch), loss2[0] = this rank's share of
+// the loss and loss2[1] = its share of d loss / d bias.  Nothing is stepped here.
+extern "C" int rb2_fm_grad_step(float *rows_e, float *rows_w, const float *bias3, int64_t n_rows, int32_t dim,
+                                const int64_t *ids, const int64_t *offsets, int32_t n_fields, const float *label,
+                                int64_t batch, int64_t global_batch, float *loss2, void *workspace,
+                                size_t workspace_bytes, void *stream) {
+  RB2_REQUIRE(rows_e && rows_w && bias3 && ids && offsets && label && loss2 && workspace, RB2_EINVAL,
+              "rb2_fm_grad_step: null argument");
+  RB2_REQUIRE(global_batch >= batch, RB2_EINVAL, "rb2_fm_grad_step: global_batch < batch");
+  OptScalars o = {};
+  o.kind = kOptGradOut;
+  FmTables t{rows_e, nullptr, nullptr, rows_w, nullptr, nullptr, const_cast<float *>(bias3)};
+  return fm_step(t, n_rows, dim, ids, offsets, n_fields, label, batch, (double)global_batch, o, loss2, nullptr, workspace,
+                 workspace_bytes, (cudaStream_t)stream, "rb2_fm_grad_step");
+}
+
+// ---- owner side of the d = 1 table: (ids[M], grads[M]) with duplicates -> sum per row (fixed order), one step
+namespace {
+__global__ void k_scalar_keys(const int64_t *__restrict__ ids, int64_t M, int64_t n_rows, uint32_t *key, uint32_t *val) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  int64_t r = ids[i];
+  key[i] = (uint32_t)min(max(r, (int64_t)0), n_rows - 1);
+  val[i] = (uint32_t)i;
+}
+__global__ void k_scalar_rows(float *P, float *Mm, float *V, const uint32_t *__restrict__ key_s,
+                              const uint32_t *__restrict__ val_s, const float *__restrict__ grads, int64_t M,
+                              OptScalars o) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const uint32_t k = key_s[i];
+  if (i > 0 && key_s[i - 1] == k) return;          // not the head of its run
+  float g = 0.f;
+  for (int64_t j = i; j < M && key_s[j] == k; ++j) g += grads[val_s[j]];   // runs are short (<= senders)
+  float p = P[k];
+  if (o.kind == RB2_OPT_SGD) {
+    sgd_elem(p, g, o);
+  } else {
+    float m = Mm[k], v = V[k];
+    adam_elem(p, m, v, g, o);
+    Mm[k] = m;
+    V[k] = v;
+  }
+  P[k] = p;
+}
+__global__ void k_scalar_step(float *p3, const float *grad, OptScalars o) {
+  float p = p3[0], g = grad[0];
+  if (o.kind == RB2_OPT_SGD) {
+    sgd_elem(p, g, o);
+  } else {
+    float m = p3[1], v = p3[2];
+    adam_elem(p, m, v, g, o);
+    p3[1] = m;
+    p3[2] = v;
+  }
+  p3[0] = p;
+}
+}  // namespace
+
+extern "C" size_t rb2_scalar_rows_update_workspace_bytes(int64_t m) {
+  Carver c(nullptr);
+  c.take<uint32_t>(m); c.take<uint32_t>(m); c.take<uint32_t>(m); c.take<uint32_t>(m);
+  size_t b = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                  (uint32_t *)nullptr, (int)m, 0, 32);
+  c.take<char>(b);
+  return c.off + 256;
+}
+extern "C" int rb2_scalar_rows_update(float *p, float *m, float *v, int64_t n_rows, const int64_t *ids,
+                                      const float *grads, int64_t M, const rb2_optim *h_opt, void *workspace,
+                                      size_t workspace_bytes, void *stream) {
+  RB2_REQUIRE(p && ids && grads && h_opt && workspace, RB2_EINVAL, "rb2_scalar_rows_update: null argument");
+  RB2_REQUIRE(M >= 0 && M < ((int64_t)1 << 31) && n_rows > 0 && n_rows < ((int64_t)1 << 32) - 1, RB2_EINVAL,
+              "rb2_scalar_rows_update: sizes out of range");
+  if (M == 0) return 0;
+  OptScalars o = rb2_opt_scalars(h_opt);
+  RB2_REQUIRE(o.kind == RB2_OPT_SGD || o.kind == RB2_OPT_ADAM, RB2_EINVAL, "rb2_scalar_rows_update: sgd or adam");
+  if (o.kind != RB2_OPT_SGD) RB2_REQUIRE(m && v, RB2_EINVAL, "rb2_scalar_rows_update: Adam needs m and v");
+  RB2_REQUIRE(workspace_bytes >= rb2_scalar_rows_update_workspace_bytes(M) - 256, RB2_EWORKSPACE,
+              "rb2_scalar_rows_update: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver c(workspace);
+  uint32_t *key = c.take<uint32_t>(M), *key_s = c.take<uint32_t>(M), *val = c.take<uint32_t>(M), *val_s = c.take<uint32_t>(M);
+  size_t b = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b, key, key_s, val, val_s, (int)M, 0, 32);
+  char *tmp = c.take<char>(b);
+  unsigned blocks = (unsigned)((M + 255) / 256);
+  k_scalar_keys<<<blocks, 256, 0, st>>>(ids, M, n_rows, key, val);
+  RB2_CUDA(cub::DeviceRadixSort::SortPairs(tmp, b, key, key_s, val, val_s, (int)M, 0, rb2_bits_for(n_rows), st));
+  k_scalar_rows<<<blocks, 256, 0, st>>>(p, m, v, key_s, val_s, grads, M, o);
+  RB2_CUDA(cudaGetLastError());
+  return 0;
+}
+/* one optimizer step of a 3-float parameter block (value, m, v) with the gradient read from the device */
+extern "C" int rb2_scalar_step(float *p3, const float *grad, const rb2_optim *h_opt, void *stream) {
+  RB2_REQUIRE(p3 && grad && h_opt, RB2_EINVAL, "rb2_scalar_step: null argument");
+  OptScalars o = rb2_opt_scalars(h_opt);
+  RB2_REQUIRE(o.kind == RB2_OPT_SGD || o.kind == RB2_OPT_ADAM, RB2_EINVAL, "rb2_scalar_step: sgd or adam");
+  k_scalar_step<<<1, 1, 0, (cudaStream_t)stream>>>(p3, grad, o);
   RB2_CUDA(cudaGetLastError());
   return 0;
 }

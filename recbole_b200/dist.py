@@ -471,3 +471,95 @@ class ShardedEvalIndex:
         return cls(t(uid_list.astype(np.int64)), (t(nhp), t(hi[keep].astype(np.int64))),
                    (t(own_ptr), t(own_idx.astype(np.int64))), owner_counts, b - a,
                    uid_own=t(uid_list[a:b].astype(np.int64)), hist_own=(t(oh_ptr), t(oh_idx.astype(np.int64))))
+
+
+class ShardedFM:
+    """Row-sharded FM (BASELINE config 5 "across 8 B200"): the [sum(field_dims), d] table, the d = 1
+    first-order table and their Adam moments are row-sharded in equal contiguous blocks; the batch is split by
+    rows; the scalar bias is replicated.  One step = de-duplicate the batch's rows (rb2_item_plan) -> all-to-all
+    ids out / rows back -> rb2_fm_grad_step on the fetched copies (forward, BCE loss, per-row gradient sums) ->
+    all-to-all gradients to the owners -> rb2_sparse_rows_update / rb2_scalar_rows_update step exactly the touched
+    rows -> all-reduce of (loss, d bias) and the bias step.  Same arithmetic as the single-GPU rb2_fm_train_step
+    on the concatenated batch (mean loss over the GLOBAL batch); duplicate rows are summed in a fixed order."""
+
+    def __init__(self, field_dims, dim, comm, device, E_full=None, W_full=None, bias=0.0, seed=2020):
+        from . import ops
+        self.ops, self.comm, self.device, self.dim = ops, comm, device, int(dim)
+        self.field_dims = [int(x) for x in field_dims]
+        self.n_fields = len(self.field_dims)
+        self.rows = int(sum(self.field_dims))
+        off = np.concatenate([[0], np.cumsum(self.field_dims)[:-1]]).astype(np.int64)
+        self.offsets = torch.from_numpy(off).to(device)
+        self.zero_offsets = torch.zeros(self.n_fields, dtype=torch.int64, device=device)
+        self.bounds = shard_bounds(self.rows, comm.world)
+        self.blk = self.bounds[1] - self.bounds[0]
+        self.lo, self.hi = self.bounds[comm.rank], self.bounds[comm.rank + 1]
+        n_loc = self.hi - self.lo
+        self.E = torch.zeros((self.blk, self.dim), dtype=torch.float32, device=device)
+        self.W = torch.zeros(self.blk, dtype=torch.float32, device=device)
+        if E_full is not None:
+            self.E[:n_loc] = torch.as_tensor(E_full[self.lo:self.hi]).to(device)
+            self.W[:n_loc] = torch.as_tensor(W_full[self.lo:self.hi]).to(device)
+        elif n_loc > 0:
+            g = torch.Generator(device=device)
+            g.manual_seed(seed + 7919 * comm.rank)
+            self.E[:n_loc] = torch.randn(n_loc, self.dim, device=device, generator=g) * (2.0 / (self.rows + self.dim)) ** 0.5
+            self.W[:n_loc] = torch.randn(n_loc, device=device, generator=g) * (2.0 / (self.rows + 1)) ** 0.5
+        self.bias3 = torch.tensor([float(bias), 0.0, 0.0], dtype=torch.float32, device=device)
+        self.state = {}
+        self.loss2 = torch.zeros(2, dtype=torch.float32, device=device)
+        self._bounds_dev = torch.as_tensor(self.bounds, device=device)
+        self._plan_ws = self._ws = self._rows_ws = self._w_ws = None
+        self.optim = None
+
+    def build_optimizer(self, kind="adam", lr=1e-3, weight_decay=0.0):
+        self.optim = self.ops.Optim(kind, lr=lr, weight_decay=weight_decay)
+        if kind != "sgd":
+            self.state = dict(mE=torch.zeros_like(self.E), vE=torch.zeros_like(self.E), mW=torch.zeros_like(self.W),
+                              vW=torch.zeros_like(self.W))
+        return self.optim
+
+    def train_step(self, ids, label, global_batch=None):
+        """ids int64 [B, F] raw per-field ids of THIS rank's samples, label fp32 [B].  Returns the device scalar
+        holding the global mean loss."""
+        ops, comm = self.ops, self.comm
+        B, F = int(ids.shape[0]), int(ids.shape[1])
+        if global_batch is None:
+            global_batch = B * comm.world
+        self.optim.step += 1
+        t = self.optim.step
+        rows = (ids + self.offsets).reshape(-1)
+        M = int(rows.numel())
+        if M % 2:                                           # rb2_item_plan takes two id vectors of equal length
+            rows = torch.cat([rows, rows[-1:]])
+        half = int(rows.numel()) // 2
+        ip = ops.item_plan(rows[:half], rows[half:], self.rows, self._bounds_dev, comm.world, self._plan_ws)
+        self._plan_ws = ip["ws"]
+        cuts = ip["cuts"].tolist()
+        n_uniq = cuts[-1]
+        send_counts = [cuts[g + 1] - cuts[g] for g in range(comm.world)]
+        recv_counts = comm.exchange_counts(send_counts)
+        req = comm.all_to_all(ip["uniq"][:n_uniq], send_counts, recv_counts)      # rows other ranks want from me
+        local_idx = (req - self.lo).contiguous()
+        C_E = comm.all_to_all(self.E.index_select(0, local_idx), recv_counts, send_counts)   # rows in uniq order
+        C_W = comm.all_to_all(self.W.index_select(0, local_idx), recv_counts, send_counts)
+        compact = torch.cat([ip["pos_c"], ip["neg_c"]])[:M].view(B, F)
+        if self._ws is None or self._ws_key != (B, F):
+            self._ws, self._ws_key = ops.fm_workspace(B, F, self.dim, self.device), (B, F)
+        C_E, C_W = C_E.contiguous(), C_W.contiguous()
+        ops.fm_grad_step(C_E, C_W, self.bias3, compact, self.zero_offsets, label, global_batch, self.loss2, self._ws)
+        gE = comm.all_to_all(C_E, send_counts, recv_counts)
+        gW = comm.all_to_all(C_W, send_counts, recv_counts)
+        self._rows_ws = ops.sparse_rows_update(self.E, self.state.get("mE"), self.state.get("vE"), None, local_idx, gE,
+                                               self.optim, self._rows_ws, step=t)
+        self._w_ws = ops.scalar_rows_update(self.W, self.state.get("mW"), self.state.get("vW"), local_idx, gW, self.optim,
+                                            self._w_ws, step=t)
+        comm.all_reduce_sum(self.loss2)
+        ops.scalar_step(self.bias3, self.loss2[1:], self.optim, step=t)
+        return self.loss2[0]
+
+    def gather_tables(self):
+        """(E [rows, d], W [rows]) assembled on every rank (tests)."""
+        E = self.comm.all_gather_equal(self.E)[: self.rows]
+        W = self.comm.all_gather_equal(self.W.unsqueeze(1))[: self.rows, 0]
+        return E, W

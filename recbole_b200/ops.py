@@ -204,6 +204,35 @@ def fm_train_step(E, W, bias3, state, ids, offsets, label, optim, loss_out, loss
                                 ws.nbytes, _stream()))
 
 
+def fm_grad_step(rows_e, rows_w, bias3, ids, offsets, label, global_batch, loss2, ws):
+    """Local part of a row-sharded FM step (rb2_fm_grad_step): the fetched rows are replaced by their gradients."""
+    f32 = torch.float32
+    check(lib.rb2_fm_grad_step(_ptr(rows_e, f32), _ptr(rows_w, f32), _ptr(bias3, f32), rows_e.shape[0], rows_e.shape[1],
+                               _ptr(ids, torch.int64), _ptr(offsets, torch.int64), ids.shape[1], _ptr(label, f32),
+                               ids.shape[0], int(global_batch), _ptr(loss2, f32), ws.ptr(), ws.nbytes, _stream()))
+
+
+def scalar_rows_update(P, M, V, ids, grads, optim, ws=None, step=None):
+    """d = 1 table: sum duplicate ids' gradients (fixed order), one optimizer step per touched row."""
+    o = optim.c_struct(P.device, step)
+    n = int(ids.numel())
+    if n == 0:
+        return ws
+    need = lib.rb2_scalar_rows_update_workspace_bytes(n)
+    if ws is None or ws.nbytes < need:
+        ws = Workspace(need, P.device)
+    f32 = torch.float32
+    check(lib.rb2_scalar_rows_update(_ptr(P, f32), _ptr(M, f32, True), _ptr(V, f32, True), P.shape[0],
+                                     _ptr(ids, torch.int64), _ptr(grads, f32), n, ctypes.byref(o), ws.ptr(), ws.nbytes,
+                                     _stream()))
+    return ws
+
+
+def scalar_step(p3, grad, optim, step=None):
+    o = optim.c_struct(p3.device, step)
+    check(lib.rb2_scalar_step(_ptr(p3, torch.float32), _ptr(grad, torch.float32), ctypes.byref(o), _stream()))
+
+
 def fm_predict(E, W, bias3, ids, offsets, ws=None):
     B, F = ids.shape
     if ws is None:

@@ -79,3 +79,65 @@ def test_two_ranks_equal_single_device_oracle(kind, mode, exchange):
     np.testing.assert_array_equal(got, o_ids)
     ref = ofs.evaluate(o_ids, pos[0], pos[1], ["recall", "mrr", "ndcg", "hit", "precision", "map"], [1, 5, 10])
     assert out[0]["res"] == ref and out[1]["res"] == ref
+
+
+# ---- row-sharded FM (BASELINE config 5 across GPUs) ------------------------------------------------------------
+FM_DIMS = [7, 300, 3, 41, 1000, 2, 90, 513]
+
+
+def _fm_case(seed=5, B=2048, steps=3, d=16):
+    rng = np.random.default_rng(seed)
+    rows = int(sum(FM_DIMS))
+    E0 = (rng.standard_normal((rows, d)) * 0.1).astype(np.float32)
+    W0 = (rng.standard_normal(rows) * 0.1).astype(np.float32)
+    batches = []
+    for _ in range(steps):
+        ids = np.stack([np.minimum(np.exp(rng.random(B) * np.log(n)).astype(np.int64), n - 1) for n in FM_DIMS], axis=1)
+        batches.append((ids, (rng.random(B) < 0.3).astype(np.float32)))
+    return E0, W0, batches
+
+
+def _fm_rank_fn(rank, world, kind):
+    from recbole_b200.dist import Comm, ShardedFM
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda:0")
+    E0, W0, batches = _fm_case()
+    comm = Comm(staged=True)
+    m = ShardedFM(FM_DIMS, E0.shape[1], comm, dev, E_full=E0, W_full=W0, bias=0.05)
+    m.build_optimizer(kind, lr=0.05 if kind == "sgd" else 2e-3)
+    losses = []
+    for ids, lab in batches:
+        B = ids.shape[0]
+        lo, hi = rank * B // world, (rank + 1) * B // world          # the batch is split by rows
+        loss = m.train_step(torch.from_numpy(ids[lo:hi]).to(dev), torch.from_numpy(lab[lo:hi]).to(dev), global_batch=B)
+        losses.append(float(loss.item()))
+    E, W = m.gather_tables()
+    return dict(losses=losses, E=E.cpu().numpy(), W=W.cpu().numpy(), b=float(m.bias3[0].item()))
+
+
+@pytest.mark.parametrize("world,kind", [(2, "adam"), (3, "adam"), (2, "sgd")])
+def test_sharded_fm_equals_single_device_oracle(world, kind):
+    """The table row-sharded over `world` ranks, the batch split by rows: losses, both tables and the bias match the
+    oracle's single-device row-sparse step on the whole batch to 1e-5."""
+    from oracle import fm as ofm
+    from oracle import optim as oopt
+    out = run_ranks(_fm_rank_fn, world, kind, timeout=300)
+    E0, W0, batches = _fm_case()
+    st = ofm.new_state(E0, W0, 0.05)
+    off = np.concatenate([[0], np.cumsum(FM_DIMS)[:-1]]).astype(np.int64)
+    lr = 0.05 if kind == "sgd" else 2e-3
+    for s, (ids, lab) in enumerate(batches):
+        rows = ids + off[None, :]
+        if kind == "adam":
+            lo = ofm.fm_train_step(st, rows, lab, s + 1, dense=False, lr=lr)
+        else:
+            lo, dE, dW, db, _ = ofm.fm_grads(st["E"], st["W"], st["b"][0], rows, lab)
+            st["E"] -= np.float32(lr) * dE
+            st["W"] -= np.float32(lr) * dW
+            st["b"] -= np.float32(lr) * db
+        for r in range(world):
+            assert abs(out[r]["losses"][s] - lo) <= 1e-5 * abs(lo), (s, out[r]["losses"][s], lo)
+    for r in range(world):
+        assert np.abs(out[r]["E"] - st["E"]).max() <= 1e-5 * np.abs(st["E"]).max()
+        assert np.abs(out[r]["W"] - st["W"]).max() <= 1e-5 * np.abs(st["W"]).max()
+        assert abs(out[r]["b"] - float(st["b"][0])) <= 1e-5 * abs(float(st["b"][0]))
