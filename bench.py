@@ -388,6 +388,10 @@ def main():
                     help="candidates per list of the tensor-core scorer (0 = automatic)")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.workload == "cfg5" and world > 1 and args.impl != "reference":
+        import bench_extra
+        bench_extra.run_cfg5_multi(args, rank, world, local_rank, load_peaks, ClockSampler)
+        return
     if args.workload in ("cfg4", "cfg5"):
         if rank == 0 and args.impl != "reference":
             import bench_extra

@@ -214,3 +214,90 @@ def run_cfg4(args, load_peaks, ClockSampler):
         "gpu_launches": int(sum(v[2] for v in st_ce.values())), "loss": float(host_loss),
     }
     print(json.dumps(line), flush=True)
+
+
+def run_cfg5_multi(args, rank, world, local_rank, load_peaks, ClockSampler):
+    """cfg5 across N GPUs: the 33.76M-row table row-sharded, the batch split by rows (every rank feeds
+    `train_batch` samples per step: weak scaling), NCCL all-to-all of rows and gradients."""
+    import torch
+    import torch.distributed as dist
+    from recbole_b200 import ops
+    from recbole_b200.dist import Comm, ShardedFM
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    comm = Comm()
+    peaks = load_peaks()
+    card, d, F = CRITEO_CARD, 16, 26
+    B = args.batch or (1 << 18)
+    m = ShardedFM(card.tolist(), d, comm, dev, seed=2020)
+    m.build_optimizer("adam", 1e-3)
+    m.ids_ready = True                  # resident batches
+    batches = fm_batches(card, B, args.n_batches, seed=2020 + rank)
+    host = [(torch.from_numpy(i).pin_memory(), torch.from_numpy(l).pin_memory()) for i, l in batches]
+    res = [(i.to(dev), l.to(dev)) for i, l in host]
+    nb, GB = len(res), B * world
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def mx(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(args.warmup):
+        m.train_step(*res[i % nb], global_batch=GB, next_batch=res[(i + 1) % nb][0])
+    barrier()
+    ops.profile_enable(True)
+    ops.profile_read()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    e0, e1 = _events(torch)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        m.train_step(*res[(args.warmup + i) % nb], global_batch=GB, next_batch=res[(args.warmup + i + 1) % nb][0])
+    e1.record()
+    barrier()
+    ms = mx(e0.elapsed_time(e1)) / args.steps
+    stages = ops.profile_read()
+    ops.profile_enable(False)
+    loss_host = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        ids, lab = host[(args.warmup + i) % nb]
+        lo = m.train_step(ids.to(dev, non_blocking=True), lab.to(dev, non_blocking=True), global_batch=GB)
+        loss_host[i:i + 1].copy_(lo.reshape(1), non_blocking=True)
+    barrier()
+    e2e_s = mx(time.perf_counter() - t0)
+    clk = clocks.stop()
+    if rank == 0:
+        bytes_per_sample = F * (24 * d + 24) + 8 * F + 4
+        upd = stages.get("fm_update", (0.0, 1, 0))
+        line = {
+            "metric": "fm_train_samples_per_s", "value": GB / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg5", "desc": "FM CTR, synthetic Criteo shape: 26 categorical fields, 33.76M total vocab, "
+                       "d=16, Adam; table row-sharded x%d, batch split by rows, NCCL all-to-all of rows and gradients" % world,
+                       "fields": F, "rows": int(card.sum()), "dim": d, "train_batch_per_gpu": B, "global_batch": GB,
+                       "l2": "no flush: every step reads a different batch"},
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": "k_fm_rows(+fixup) on the fetched rows",
+                         "achieved": None, "peak": peaks["hbm"], "unit": "GB/s", "frac": None, "traffic": None,
+                         "peak_source": peaks["source"], "ms_per_launch": upd[0] / max(upd[1], 1),
+                         "step": {"achieved_all_gpus": GB * bytes_per_sample / (ms * 1e-3) / 1e9,
+                                  "frac_of_n_gpu_peak": GB * bytes_per_sample / (ms * 1e-3) / 1e9 / (world * peaks["hbm"]),
+                                  "bytes_per_sample": bytes_per_sample},
+                         "stages_ms_per_step_rank0": {k: v[0] / args.steps for k, v in stages.items()}},
+            "cpu_baseline": None,
+            "e2e": {"value": GB * args.steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": GB * (8 * F + 4),
+                    "d2h_bytes_per_step": 4 * world},
+            "gpu_launches": int(sum(v[2] for v in stages.values())), "loss": float(m.loss2[0].item()),
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

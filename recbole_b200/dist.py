@@ -519,35 +519,75 @@ class ShardedFM:
                               vW=torch.zeros_like(self.W))
         return self.optim
 
-    def train_step(self, ids, label, global_batch=None):
+    ids_ready = False     # True: next_batch tensors are complete when passed (resident batches)
+
+    def plan(self, ids, ids_ready=False):
+        """The part of a step that depends only on the batch ids (de-duplication, bucketing by owner, count
+        exchange, all-to-all of the requested row ids): run for the NEXT batch on a side stream, its host
+        synchronisations overlap with the current step's kernels."""
+        ops, comm = self.ops, self.comm
+        cuda = self.device.type == "cuda"
+        if not hasattr(self, "_plan_stream"):
+            self._plan_stream = torch.cuda.Stream(device=self.device) if cuda else None
+            self._plan_bufs = [None, None]
+            self._plan_free = [None, None]
+            self._plan_flip = 0
+        st = self._plan_stream
+        self._plan_flip ^= 1
+        if st is not None:
+            if not ids_ready:
+                st.wait_stream(torch.cuda.current_stream())
+            elif self._plan_free[self._plan_flip] is not None:
+                st.wait_event(self._plan_free[self._plan_flip])
+        with (torch.cuda.stream(st) if st is not None else _NullCtx()):
+            B, F = int(ids.shape[0]), int(ids.shape[1])
+            rows = (ids + self.offsets).reshape(-1)
+            M = int(rows.numel())
+            if M % 2:                                           # rb2_item_plan takes two id vectors of equal length
+                rows = torch.cat([rows, rows[-1:]])
+            half = int(rows.numel()) // 2
+            ip = ops.item_plan(rows[:half], rows[half:], self.rows, self._bounds_dev, comm.world,
+                               self._plan_bufs[self._plan_flip])
+            self._plan_bufs[self._plan_flip] = ip["ws"]
+            cuts = ip["cuts"].tolist()                          # host sync
+            n_uniq = cuts[-1]
+            send_counts = [cuts[g + 1] - cuts[g] for g in range(comm.world)]
+            recv_counts = comm.exchange_counts(send_counts)
+            req = comm.all_to_all(ip["uniq"][:n_uniq], send_counts, recv_counts)      # rows other ranks want from me
+            p = dict(ids=ids, B=B, F=F, send_counts=send_counts, recv_counts=recv_counts,
+                     local_idx=(req - self.lo).contiguous(),
+                     compact=torch.cat([ip["pos_c"], ip["neg_c"]])[:M].view(B, F).contiguous(), flip=self._plan_flip,
+                     event=None)
+            if st is not None:
+                p["event"] = torch.cuda.Event()
+                p["event"].record(st)
+        return p
+
+    def train_step(self, ids, label, global_batch=None, next_batch=None):
         """ids int64 [B, F] raw per-field ids of THIS rank's samples, label fp32 [B].  Returns the device scalar
-        holding the global mean loss."""
+        holding the global mean loss.  next_batch = the ids of the following step (its plan overlaps this step)."""
         ops, comm = self.ops, self.comm
         B, F = int(ids.shape[0]), int(ids.shape[1])
         if global_batch is None:
             global_batch = B * comm.world
         self.optim.step += 1
         t = self.optim.step
-        rows = (ids + self.offsets).reshape(-1)
-        M = int(rows.numel())
-        if M % 2:                                           # rb2_item_plan takes two id vectors of equal length
-            rows = torch.cat([rows, rows[-1:]])
-        half = int(rows.numel()) // 2
-        ip = ops.item_plan(rows[:half], rows[half:], self.rows, self._bounds_dev, comm.world, self._plan_ws)
-        self._plan_ws = ip["ws"]
-        cuts = ip["cuts"].tolist()
-        n_uniq = cuts[-1]
-        send_counts = [cuts[g + 1] - cuts[g] for g in range(comm.world)]
-        recv_counts = comm.exchange_counts(send_counts)
-        req = comm.all_to_all(ip["uniq"][:n_uniq], send_counts, recv_counts)      # rows other ranks want from me
-        local_idx = (req - self.lo).contiguous()
-        C_E = comm.all_to_all(self.E.index_select(0, local_idx), recv_counts, send_counts)   # rows in uniq order
-        C_W = comm.all_to_all(self.W.index_select(0, local_idx), recv_counts, send_counts)
-        compact = torch.cat([ip["pos_c"], ip["neg_c"]])[:M].view(B, F)
+        p = getattr(self, "_next_plan", None)
+        if p is None or p["ids"] is not ids:
+            p = self.plan(ids)
+        self._next_plan = None
+        if p["event"] is not None:
+            torch.cuda.current_stream().wait_event(p["event"])
+            for k in ("local_idx", "compact"):
+                p[k].record_stream(torch.cuda.current_stream())
+        send_counts, recv_counts, local_idx = p["send_counts"], p["recv_counts"], p["local_idx"]
+        C_E = comm.all_to_all(self.E.index_select(0, local_idx), recv_counts, send_counts).contiguous()   # uniq order
+        C_W = comm.all_to_all(self.W.index_select(0, local_idx), recv_counts, send_counts).contiguous()
         if self._ws is None or self._ws_key != (B, F):
             self._ws, self._ws_key = ops.fm_workspace(B, F, self.dim, self.device), (B, F)
-        C_E, C_W = C_E.contiguous(), C_W.contiguous()
-        ops.fm_grad_step(C_E, C_W, self.bias3, compact, self.zero_offsets, label, global_batch, self.loss2, self._ws)
+        ops.fm_grad_step(C_E, C_W, self.bias3, p["compact"], self.zero_offsets, label, global_batch, self.loss2, self._ws)
+        if next_batch is not None:
+            self._next_plan = self.plan(next_batch, ids_ready=self.ids_ready)
         gE = comm.all_to_all(C_E, send_counts, recv_counts)
         gW = comm.all_to_all(C_W, send_counts, recv_counts)
         self._rows_ws = ops.sparse_rows_update(self.E, self.state.get("mE"), self.state.get("vE"), None, local_idx, gE,
@@ -556,6 +596,10 @@ class ShardedFM:
                                             self._w_ws, step=t)
         comm.all_reduce_sum(self.loss2)
         ops.scalar_step(self.bias3, self.loss2[1:], self.optim, step=t)
+        if self.device.type == "cuda":
+            done = torch.cuda.Event()
+            done.record()
+            self._plan_free[p["flip"]] = done
         return self.loss2[0]
 
     def gather_tables(self):
