@@ -60,8 +60,12 @@ static int32_t g_tc_kprime = 0;  // 0 = automatic, 16 or 32 = forced (rb2_fullso
 // powers of two), FP16 accumulators drained with .pack::16b, per-CTA MMAs; 2 = as 3 with CTA-pair MMAs
 // (cta_group::2)
 static int32_t g_tc_variant = 0;
+static float g_tc_fail_ema = 0.f;          // recent fraction of rows failing the FP16-accumulator certificate
+static int g_tc_calls = 0;
 extern "C" int rb2_fullsort_tc_set_variant(int32_t v) {
   if (v < 0 || v > 3) return RB2_EINVAL;
+  g_tc_fail_ema = 0.f;                     // (also forgets the first-pass statistics)
+  g_tc_calls = 0;
   g_tc_variant = v;
   return 0;
 }
@@ -1279,7 +1283,17 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
   size_t need = carve_tc(w, workspace, nq, n_local, D, k);
   RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_fullsort_topk(tc): workspace %zu < %zu", workspace_bytes, need);
   RB2_CUDA(cudaMemsetAsync(w.fail_count, 0, 4 * sizeof(int32_t), st));
-  int rc = tc_pass<D, KP, H16, H16, TWO_SM, TRACE>(w, query_p, query_ids, nullptr, nq, true, item_p, n_local, item_base,
+  // When most first-pass certificates fail (well-trained tables: E is relative to max ||v||, the score gaps are
+  // not) the FP16-accumulator pass is wasted work: the break-even is ~15 % failing rows.  Track the recent
+  // failure fraction and start with fp32 accumulators when it is above that, probing again every 16th call.
+  const bool fast_first = H16 && (g_tc_fail_ema < 0.15f || (g_tc_calls++ % 16) == 15);
+  int rc;
+  if (fast_first || !H16)
+    rc = tc_pass<D, KP, H16, H16, TWO_SM, TRACE>(w, query_p, query_ids, nullptr, nq, true, item_p, n_local, item_base,
+                                                 hist_indptr, hist_indices, k, out_ids, out_scores, w.fail_rows,
+                                                 w.fail_count, st);
+  else
+    rc = tc_pass<D, KP, true, false, false, false>(w, query_p, query_ids, nullptr, nq, true, item_p, n_local, item_base,
                                                    hist_indptr, hist_indices, k, out_ids, out_scores, w.fail_rows,
                                                    w.fail_count, st);
   if (rc) return rc;
@@ -1288,15 +1302,18 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
   RB2_CUDA(cudaStreamSynchronize(st));
   g_last_tc_pass2_rows = 0;
   const int32_t *final_rows = w.fail_rows;
-  if (H16 && n_fail > 0) {
-    g_last_tc_pass2_rows = n_fail;
-    rc = tc_pass<D, KP, true, false, false, false>(w, query_p, query_ids, w.fail_rows, n_fail, false, item_p, n_local,
-                                                   item_base, hist_indptr, hist_indices, k, out_ids, out_scores,
-                                                   w.fail_rows2, w.fail_count + 1, st);
-    if (rc) return rc;
-    RB2_CUDA(cudaMemcpyAsync(&n_fail, w.fail_count + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    RB2_CUDA(cudaStreamSynchronize(st));
-    final_rows = w.fail_rows2;
+  if (fast_first) {
+    if (nq >= 1024) g_tc_fail_ema = 0.5f * g_tc_fail_ema + 0.5f * (float)n_fail / (float)nq;
+    if (n_fail > 0) {
+      g_last_tc_pass2_rows = n_fail;
+      rc = tc_pass<D, KP, true, false, false, false>(w, query_p, query_ids, w.fail_rows, n_fail, false, item_p, n_local,
+                                                     item_base, hist_indptr, hist_indices, k, out_ids, out_scores,
+                                                     w.fail_rows2, w.fail_count + 1, st);
+      if (rc) return rc;
+      RB2_CUDA(cudaMemcpyAsync(&n_fail, w.fail_count + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      RB2_CUDA(cudaStreamSynchronize(st));
+      final_rows = w.fail_rows2;
+    }
   }
   g_last_tc_fallback_rows = n_fail;
   if (n_fail > 0) {   // redo exactly

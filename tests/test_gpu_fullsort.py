@@ -340,3 +340,32 @@ def test_fullsort_tc_variants_agree_with_fp32_kernel_at_size(tc_variant, variant
     assert lib.rb2_fullsort_tc_last_fallback_rows() == 0
     ids_f, sc_f = ops.fullsort_topk(Q, None, V, 10, hp, hi, mode="fp32")
     assert torch.equal(ids_t, ids_f) and torch.equal(sc_t, sc_f)
+
+
+def test_fullsort_tc_cascade_and_adaptive_first_pass(tc_variant):
+    """One item with a norm 300x the others inflates max ||v|| and with it every error bound: the
+    FP16-accumulator certificate fails for (nearly) all rows, they are re-scored by the fp32-accumulator pass
+    (and what still fails by the exact kernel), and from the second call on the scorer starts with fp32
+    accumulators.  Exact every time."""
+    from recbole_b200 import ops
+    from recbole_b200._lib import lib
+    from gpu_util import t
+    tc_variant(3)
+    nq, N, d, K = 2048, 3000, 128, 10
+    Q, V, hp, hi = _tc_case(d, nq, N, K, seed=3)
+    V[7] *= 300.0
+    o_ids, o_sc = ofs.full_sort_topk(Q, V, np.arange(nq), hp, hi, K)
+    pass2 = []
+    for _ in range(3):
+        ids, sc = ops.fullsort_topk(t(Q), None, t(V), K, t(hp), t(hi), mode="tc")
+        pass2.append(int(lib.rb2_fullsort_tc_last_pass2_rows()))
+        np.testing.assert_array_equal(ids.cpu().numpy(), o_ids)
+        np.testing.assert_array_equal(sc.cpu().numpy(), o_sc)
+    assert pass2[0] > nq // 4          # most rows needed the second pass ...
+    assert pass2[-1] == 0              # ... so later calls start with fp32 accumulators
+    # easy data brings the fast pass back (the failure estimate decays on the probing calls)
+    Q2, V2, hp2, hi2 = _tc_case(d, nq, N, K, seed=4)
+    o2, _ = ofs.full_sort_topk(Q2, V2, np.arange(nq), hp2, hi2, K)
+    for _ in range(40):
+        ids, _ = ops.fullsort_topk(t(Q2), None, t(V2), K, t(hp2), t(hi2), mode="tc")
+    np.testing.assert_array_equal(ids.cpu().numpy(), o2)
