@@ -20,9 +20,11 @@
 //                    passing score is appended to a small per-row buffer in shared memory and the buffers
 //                    are folded into the K' (16 or 32) candidate lists held in REGISTERS by all lanes
 //                    together; the two sets publish their list minima and filter with the larger one.
-//                    Pad / history are checked at the fold, history through a per-row Bloom filter in
-//                    shared memory so that the CSR binary search is almost never taken.  setmaxnreg moves
-//                    registers from the producer / MMA warp group to the epilogue warp groups.
+//                    Pad / history are checked at the append; history without a search: a set sees its
+//                    items in ascending order and the CSR row is sorted, so a cursor into the row only
+//                    moves forward.  setmaxnreg moves registers from the producer / MMA warp group to the
+//                    epilogue warp groups.  Rows whose certificate fails are re-scored by a second pass with
+//                    fp32 accumulators (same operands, ~10x tighter bound) before the exact kernel.
 //   k_refine         candidates are re-scored with the canonical fp32 chain s = fmaf(q[k], v[k], s)
 //                    and ordered (score desc, id asc).  Certificate per row:
 //                        exact_K  >  max_part(approx K'-th score) + E,
@@ -258,7 +260,7 @@ struct TcParams {
   int n_ut, n_split, tiles_per_split;   // work decomposition
   const int64_t *hist_indptr, *hist_indices;
   int *cand_ids;      // [n_split * 2][nq][KP]   (x2: one list per epilogue warp set)
-  float *cand_sc;     // approximate (bf16) scores, each list sorted descending
+  float *cand_sc;     // approximate scores; slot KP-1 of a list holds its minimum (the cut-off k_refine reads)
   long long *trace;   // diagnostics (rb2_fullsort_tc_set_trace), usually nullptr
   float *lse_m, *lse_s;   // LSE kernels: per (list, row) running max and sum of exp   [n_split * 2][nq]
   const int32_t *row_map; // second pass over the rows whose certificate failed: row of this pass -> caller's row
