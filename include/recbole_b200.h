@@ -130,6 +130,15 @@ int rb2_bpr_train_step_sharded(float *user_p, float *user_m, float *user_v, int3
                                every row written */, const void *item_plan /* nullable: the plan workspace
                                rb2_item_plan filled for this batch; its sorted occurrences are reused */,
                                void *workspace, size_t workspace_bytes, void *stream);
+/* Same; `rows_ready_event` (a cudaEvent_t, nullable) is waited for on `stream` after the id-only part of the
+ * step (keys, sorts) and before the first kernel that reads item_rows, so that the collective delivering
+ * item_rows on another stream overlaps with that part. */
+int rb2_bpr_train_step_sharded_ev(float *user_p, float *user_m, float *user_v, int32_t *user_last,
+                                  const float *item_rows, int64_t n_users, int64_t n_item_rows, int32_t dim,
+                                  const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t batch,
+                                  int64_t global_batch, const rb2_optim *h_opt, float *loss_out, double *loss_accum,
+                                  float *item_grad_out, int32_t *item_touched, const void *item_plan, void *workspace,
+                                  size_t workspace_bytes, void *stream, void *rows_ready_event);
 
 /* The id-only half of a sharded step (what the caller needs before any parameter is read): unique
  * item ids of the batch in ascending order (= grouped by owner shard), pos / neg rewritten as indices

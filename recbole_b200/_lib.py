@@ -47,6 +47,8 @@ SIGNATURES = {
                                           ctypes.POINTER(RB2Optim), _p, _p, _p, _sz, _p]),
     "rb2_bpr_train_step_sharded": (ctypes.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _i64, _i64,
                                                   ctypes.POINTER(RB2Optim), _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "rb2_bpr_train_step_sharded_ev": (ctypes.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _i64, _i64,
+                                                     ctypes.POINTER(RB2Optim), _p, _p, _p, _p, _p, _p, _sz, _p, _p]),
     "rb2_item_plan_workspace_bytes": (_sz, [_i64]),
     "rb2_item_plan": (ctypes.c_int, [_p, _p, _i64, _i64, _p, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "rb2_dense_rows_update": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, ctypes.POINTER(RB2Optim), _p]),

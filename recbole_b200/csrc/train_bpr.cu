@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(kThreads) k_bpr_loss(const float *__restrict__
 template <int D, bool LAZY>
 int launch_step(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, const OptScalars &o, float *loss_out,
                 double *loss_accum, cudaStream_t st, int64_t global_batch, const uint32_t *pre_ikey_s,
-                const uint32_t *pre_ival_s) {
+                const uint32_t *pre_ival_s, cudaEvent_t rows_ready) {
   constexpr int LANES = RowCfg<D>::LANES;
   const int Tu = pick_tile(B, LANES), Ti = pick_tile(2 * B, LANES);
   const int64_t ntu = (B + Tu - 1) / Tu, nti = (2 * B + Ti - 1) / Ti;
@@ -418,6 +418,9 @@ int launch_step(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, 
     RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ikey, w.ikey_s, w.ival, w.ival_s, (int)(2 * B), 0,
                                              bits_for(n_items), st));
   }
+  // sharded step: the keys and sorts above depend on the ids only and overlap with the collective that
+  // delivers the item rows on another stream; everything from here on reads them
+  if (rows_ready) RB2_CUDA(cudaStreamWaitEvent(st, rows_ready, 0));
   {
     ProfScope prof(RB2_ST_USER_SIDE, st);
     k_user_side<D, LAZY><<<blocks(ntu), kThreads, 0, st>>>(t, w, B, Tu, ntu, 1.f / (float)global_batch, o);
@@ -595,7 +598,7 @@ static int bpr_step_impl(float *user_p, float *user_m, float *user_v, int32_t *u
                          const rb2_optim *h_opt, float *loss_out, double *loss_accum, void *workspace,
                          size_t workspace_bytes, void *stream, float *item_grad_out, int64_t global_batch,
                          int32_t *item_touched, const uint32_t *pre_ikey_s = nullptr,
-                         const uint32_t *pre_ival_s = nullptr) {
+                         const uint32_t *pre_ival_s = nullptr, cudaEvent_t rows_ready = nullptr) {
   RB2_REQUIRE(user_p && item_p && user && pos && neg && h_opt && loss_out && workspace, RB2_EINVAL,
               "rb2_bpr_train_step: null argument");
   RB2_REQUIRE(batch > 0 && batch < ((int64_t)1 << 30), RB2_EINVAL, "rb2_bpr_train_step: batch %lld out of range",
@@ -629,9 +632,9 @@ static int bpr_step_impl(float *user_p, float *user_m, float *user_v, int32_t *u
               "rb2_bpr_train_step_sharded: adam_lazy is not available on the sharded path");
   RB2_DISPATCH_DIM(dim, {
     int rc = lazy ? launch_step<D_, true>(t, w, batch, n_users, n_items, o, loss_out, loss_accum, st, global_batch,
-                                          pre_ikey_s, pre_ival_s)
+                                          pre_ikey_s, pre_ival_s, rows_ready)
                   : launch_step<D_, false>(t, w, batch, n_users, n_items, o, loss_out, loss_accum, st, global_batch,
-                                           pre_ikey_s, pre_ival_s);
+                                           pre_ikey_s, pre_ival_s, rows_ready);
     if (rc) return rc;
   });
   return 0;
@@ -647,13 +650,13 @@ extern "C" int rb2_bpr_train_step(float *user_p, float *user_m, float *user_v, i
                        nullptr, 0, nullptr);
 }
 
-extern "C" int rb2_bpr_train_step_sharded(float *user_p, float *user_m, float *user_v, int32_t *user_last,
-                                          const float *item_rows, int64_t n_users, int64_t n_item_rows, int32_t dim,
-                                          const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t batch,
-                                          int64_t global_batch, const rb2_optim *h_opt, float *loss_out,
-                                          double *loss_accum, float *item_grad_out, int32_t *item_touched,
-                                          const void *item_plan, void *workspace, size_t workspace_bytes,
-                                          void *stream) {
+extern "C" int rb2_bpr_train_step_sharded_ev(float *user_p, float *user_m, float *user_v, int32_t *user_last,
+                                             const float *item_rows, int64_t n_users, int64_t n_item_rows, int32_t dim,
+                                             const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t batch,
+                                             int64_t global_batch, const rb2_optim *h_opt, float *loss_out,
+                                             double *loss_accum, float *item_grad_out, int32_t *item_touched,
+                                             const void *item_plan, void *workspace, size_t workspace_bytes,
+                                             void *stream, void *rows_ready_event) {
   RB2_REQUIRE(item_grad_out != nullptr, RB2_EINVAL, "rb2_bpr_train_step_sharded: item_grad_out is null");
   const uint32_t *pk = nullptr, *pv = nullptr;
   if (item_plan) {  // workspace filled by rb2_item_plan for THIS batch
@@ -664,7 +667,20 @@ extern "C" int rb2_bpr_train_step_sharded(float *user_p, float *user_m, float *u
   }
   return bpr_step_impl(user_p, user_m, user_v, user_last, const_cast<float *>(item_rows), nullptr, nullptr, nullptr,
                        n_users, n_item_rows, dim, user, pos, neg, batch, h_opt, loss_out, loss_accum, workspace,
-                       workspace_bytes, stream, item_grad_out, global_batch, item_touched, pk, pv);
+                       workspace_bytes, stream, item_grad_out, global_batch, item_touched, pk, pv,
+                       (cudaEvent_t)rows_ready_event);
+}
+
+extern "C" int rb2_bpr_train_step_sharded(float *user_p, float *user_m, float *user_v, int32_t *user_last,
+                                          const float *item_rows, int64_t n_users, int64_t n_item_rows, int32_t dim,
+                                          const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t batch,
+                                          int64_t global_batch, const rb2_optim *h_opt, float *loss_out,
+                                          double *loss_accum, float *item_grad_out, int32_t *item_touched,
+                                          const void *item_plan, void *workspace, size_t workspace_bytes,
+                                          void *stream) {
+  return rb2_bpr_train_step_sharded_ev(user_p, user_m, user_v, user_last, item_rows, n_users, n_item_rows, dim, user, pos,
+                                       neg, batch, global_batch, h_opt, loss_out, loss_accum, item_grad_out, item_touched,
+                                       item_plan, workspace, workspace_bytes, stream, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -344,7 +344,22 @@ class ShardedBPR:
     def _train_step_dense(self, user, pos, neg, global_batch, t):
         ops, comm = self.ops, self.comm
         B = int(user.numel())
-        V_all = comm.all_gather_equal(self.V)                       # [world * i_block, d]; global id == row
+        cuda = self.device.type == "cuda" and not comm.staged
+        rows_ready = None
+        if cuda:
+            # the all-gather of the item rows runs on its own stream; the id-only part of the step (keys, two radix
+            # sorts) and the clearing of the gradient buffers overlap with it
+            if not hasattr(self, "_comm_stream"):
+                self._comm_stream = torch.cuda.Stream(device=self.device)
+            cs = self._comm_stream
+            cs.wait_stream(torch.cuda.current_stream())               # the previous step's row update
+            with torch.cuda.stream(cs):
+                V_all = comm.all_gather_equal(self.V)                   # [world * i_block, d]; global id == row
+                rows_ready = torch.cuda.Event()
+                rows_ready.record(cs)
+            V_all.record_stream(torch.cuda.current_stream())
+        else:
+            V_all = comm.all_gather_equal(self.V)
         if not hasattr(self, "_G_all") or self._G_all.shape != V_all.shape:
             self._G_all = torch.empty_like(V_all)
             self._touched_all = torch.empty(V_all.shape[0], dtype=torch.int32, device=self.device)
@@ -353,7 +368,7 @@ class ShardedBPR:
         user_local = (user - self.u_lo).contiguous()
         ops.bpr_train_step_sharded(self.U, self.state, V_all, user_local, pos, neg, global_batch, self.optim,
                                    self.loss_out, None, self._G_all, self._workspace(B), step=t,
-                                   item_touched=self._touched_all)
+                                   item_touched=self._touched_all, rows_ready=rows_ready)
         G = comm.reduce_scatter_sum(self._G_all)
         touched = comm.reduce_scatter_sum(self._touched_all)
         ops.dense_rows_update(self.V, self.state.get("mV"), self.state.get("vV"), G, touched, self.optim, step=t)

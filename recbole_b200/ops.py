@@ -120,18 +120,20 @@ def bpr_train_step(U, V, state, user, pos, neg, optim, loss_out, loss_accum, ws)
 
 
 def bpr_train_step_sharded(U, state, item_rows, user, pos_c, neg_c, global_batch, optim, loss_out, loss_accum,
-                           item_grad_out, ws, step=None, item_touched=None, item_plan=None):
+                           item_grad_out, ws, step=None, item_touched=None, item_plan=None, rows_ready=None):
     """User side + per-compact-row item gradient sums (rb2_bpr_train_step_sharded).  optim.step is NOT
-    incremented here (the owner-side update of the same logical step shares it)."""
+    incremented here (the owner-side update of the same logical step shares it).  rows_ready: a
+    torch.cuda.Event recorded after the collective that fills item_rows on another stream; the id-only part
+    of the step (keys, sorts) runs before it is waited for."""
     o = optim.c_struct(U.device, step)
     f32, i64 = torch.float32, torch.int64
-    check(lib.rb2_bpr_train_step_sharded(
+    check(lib.rb2_bpr_train_step_sharded_ev(
         _ptr(U, f32), _ptr(state.get("mU"), f32, True), _ptr(state.get("vU"), f32, True),
         _ptr(state.get("lastU"), torch.int32, True), _ptr(item_rows, f32), U.shape[0], item_rows.shape[0],
         U.shape[1], _ptr(user, i64), _ptr(pos_c, i64), _ptr(neg_c, i64), user.numel(), int(global_batch),
         ctypes.byref(o), _ptr(loss_out, f32), _ptr(loss_accum, torch.float64, True), _ptr(item_grad_out, f32),
         _ptr(item_touched, torch.int32, True), item_plan.ptr() if item_plan is not None else None,
-        ws.ptr(), ws.nbytes, _stream()))
+        ws.ptr(), ws.nbytes, _stream(), ctypes.c_void_p(rows_ready.cuda_event) if rows_ready is not None else None))
 
 
 def item_plan(pos, neg, n_items, bounds_dev, world, plan_ws=None):
