@@ -72,6 +72,16 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        late = False
+        if not self.lines:
+            # the timed region was shorter than nvidia-smi's start-up: one query right after it
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+                self.lines = [ln.strip() for ln in out.splitlines() if ln.strip()]
+                late = True
+            except Exception:
+                pass
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
@@ -86,8 +96,11 @@ class ClockSampler:
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+        out = dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                   reasons=sorted(reasons), samples=len(sm))
+        if late:
+            out["note"] = "timed region shorter than the sampler's start-up: sampled right after it"
+        return out
 
 
 # -------------------------------------------------------------------------------------------------
