@@ -85,7 +85,10 @@ def test_two_ranks_equal_single_device_oracle(kind, mode, exchange):
 FM_DIMS = [7, 300, 3, 41, 1000, 2, 90, 513]
 
 
-def _fm_case(seed=5, B=2048, steps=3, d=16):
+def _fm_case(seed=5, B=2048, steps=3, d=16, dims=None):
+    global FM_DIMS
+    if dims is not None:
+        FM_DIMS = dims
     rng = np.random.default_rng(seed)
     rows = int(sum(FM_DIMS))
     E0 = (rng.standard_normal((rows, d)) * 0.1).astype(np.float32)
@@ -97,11 +100,11 @@ def _fm_case(seed=5, B=2048, steps=3, d=16):
     return E0, W0, batches
 
 
-def _fm_rank_fn(rank, world, kind):
+def _fm_rank_fn(rank, world, kind, B=2048, dims=None):
     from recbole_b200.dist import Comm, ShardedFM
     torch.cuda.set_device(0)
     dev = torch.device("cuda:0")
-    E0, W0, batches = _fm_case()
+    E0, W0, batches = _fm_case(B=B, dims=dims)
     comm = Comm(staged=True)
     m = ShardedFM(FM_DIMS, E0.shape[1], comm, dev, E_full=E0, W_full=W0, bias=0.05)
     m.build_optimizer(kind, lr=0.05 if kind == "sgd" else 2e-3)
@@ -115,14 +118,23 @@ def _fm_rank_fn(rank, world, kind):
     return dict(losses=losses, E=E.cpu().numpy(), W=W.cpu().numpy(), b=float(m.bias3[0].item()))
 
 
-@pytest.mark.parametrize("world,kind", [(2, "adam"), (3, "adam"), (2, "sgd")])
-def test_sharded_fm_equals_single_device_oracle(world, kind):
+@pytest.mark.parametrize("world,kind,B,dims", [(2, "adam", 2048, None), (3, "adam", 2048, None), (2, "sgd", 2048, None),
+                                               (2, "adam", 1001, [5, 300, 3, 41, 77, 2, 90])])   # odd B * F
+def test_sharded_fm_equals_single_device_oracle(world, kind, B, dims):
     """The table row-sharded over `world` ranks, the batch split by rows: losses, both tables and the bias match the
     oracle's single-device row-sparse step on the whole batch to 1e-5."""
     from oracle import fm as ofm
-    from oracle import optim as oopt
-    out = run_ranks(_fm_rank_fn, world, kind, timeout=300)
-    E0, W0, batches = _fm_case()
+    global FM_DIMS
+    saved = list(FM_DIMS)
+    try:
+        _check_sharded_fm(ofm, world, kind, B, dims)
+    finally:
+        FM_DIMS = saved
+
+
+def _check_sharded_fm(ofm, world, kind, B, dims):
+    out = run_ranks(_fm_rank_fn, world, kind, B, dims, timeout=300)
+    E0, W0, batches = _fm_case(B=B, dims=dims)
     st = ofm.new_state(E0, W0, 0.05)
     off = np.concatenate([[0], np.cumsum(FM_DIMS)[:-1]]).astype(np.int64)
     lr = 0.05 if kind == "sgd" else 2e-3
