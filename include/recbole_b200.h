@@ -15,7 +15,10 @@
  *     (reference: recbole/data/dataset/dataset.py:908-928,1699-1700).
  *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
  *     Calls are asynchronous on that stream unless stated otherwise and re-entrant per
- *     (device, stream); there is no global mutable state except the last-error string.
+ *     (device, stream); the only process-wide mutable state is the last-error string, the stage
+ *     profiler (rb2_profile_*), and the tuning knobs / diagnostics of the tensor-core scorer
+ *     (rb2_fullsort_tc_set_*, rb2_ce_head_set_scorer, rb2_fullsort_tc_last_*_rows and the failure
+ *     statistic that picks its first pass): they change speed, never results.
  *   - Return value: 0 on success, otherwise a cudaError_t or one of the RB2_E* codes;
  *     rb2_last_error() describes the failure.  There is no CPU fallback anywhere.
  *   - Workspace: query the size with the matching *_workspace_bytes() and pass a device buffer
