@@ -217,6 +217,59 @@ class ShardedBPR:
             z = torch.zeros_like
             self.state = dict(mU=z(self.U), vU=z(self.U), mV=z(self.V), vV=z(self.V))
 
+    # ---- checkpoint interop (trainer.py:191-232) ------------------------------------------
+    def state_dict(self):
+        """The reference's parameter names with the FULL tables (every rank gets the same dict; the user table is
+        all-gathered: 5 GB at cfg3 -- save from one rank)."""
+        U = self.comm.all_gather_equal(self.U)
+        V = self.comm.all_gather_equal(self.V)
+        # blocks are padded to equal size: rank r's rows sit at [r * block, r * block + its count)
+        return {"user_embedding.weight": self._unpad(U, self.user_bounds, self.u_block),
+                "item_embedding.weight": self._unpad(V, self.item_bounds, self.i_block)}
+
+    def load_state_dict(self, sd):
+        U, V = sd["user_embedding.weight"], sd["item_embedding.weight"]
+        if tuple(U.shape) != (self.n_users, self.dim) or tuple(V.shape) != (self.n_items, self.dim):
+            raise ValueError("state dict shapes %s / %s do not match the model (%d x %d, %d x %d)" % (
+                tuple(U.shape), tuple(V.shape), self.n_users, self.dim, self.n_items, self.dim))
+        self.U.zero_()
+        self.V.zero_()
+        self.U[: self.u_hi - self.u_lo] = U[self.u_lo:self.u_hi].to(self.device)
+        self.V[: self.i_hi - self.i_lo] = V[self.i_lo:self.i_hi].to(self.device)
+
+    def optimizer_state_dict(self):
+        """`torch.optim.Adam.state_dict()` layout for params [user_embedding.weight, item_embedding.weight]
+        (what `Trainer._save_checkpoint` stores, trainer.py:198-206)."""
+        o = self.optim
+        state = {}
+        if o.kind_name != "sgd":
+            step = torch.tensor(float(o.step))
+            g = lambda t, b, blk: self._unpad(self.comm.all_gather_equal(t), b, blk)   # noqa: E731
+            state = {0: dict(step=step, exp_avg=g(self.state["mU"], self.user_bounds, self.u_block),
+                             exp_avg_sq=g(self.state["vU"], self.user_bounds, self.u_block)),
+                     1: dict(step=step.clone(), exp_avg=g(self.state["mV"], self.item_bounds, self.i_block),
+                             exp_avg_sq=g(self.state["vV"], self.item_bounds, self.i_block))}
+        group = dict(lr=o.lr, betas=o.betas, eps=o.eps, weight_decay=o.weight_decay, params=[0, 1])
+        return dict(state=state, param_groups=[group], fused_kind=o.kind_name)
+
+    def load_optimizer_state_dict(self, sd):
+        o = self.optim
+        grp = sd["param_groups"][0]
+        o.lr, o.weight_decay = grp["lr"], grp["weight_decay"]
+        if sd["state"]:
+            o.step = int(sd["state"][0]["step"])
+            for k, idx, key, lo, hi in (("mU", 0, "exp_avg", self.u_lo, self.u_hi), ("vU", 0, "exp_avg_sq", self.u_lo, self.u_hi),
+                                        ("mV", 1, "exp_avg", self.i_lo, self.i_hi), ("vV", 1, "exp_avg_sq", self.i_lo, self.i_hi)):
+                self.state[k].zero_()
+                self.state[k][: hi - lo] = sd["state"][idx][key][lo:hi].to(self.device)
+
+    @staticmethod
+    def _unpad(full, bounds, block):
+        world = len(bounds) - 1
+        if world == 1:
+            return full[: int(bounds[1])]
+        return torch.cat([full[r * block: r * block + int(bounds[r + 1] - bounds[r])] for r in range(world)])
+
     def _workspace(self, batch):
         key = int(batch)
         if key not in self._ws:

@@ -79,3 +79,52 @@ def test_sharded_eval_index_split():
     all_hist = list(zip(np.repeat(np.arange(len(uid)), np.diff(hist[0])).tolist(), hist[1].tolist()))
     all_pos = list(zip(np.repeat(np.arange(len(uid)), np.diff(pos[0])).tolist(), pos[1].tolist()))
     assert sorted(seen_hist) == sorted(all_hist) and sorted(seen_pos) == sorted(all_pos)
+
+
+def _ckpt_rank(rank, world):
+    """Checkpoint interop of the sharded model on CPU tensors (no kernel runs here): the gathered state dicts use
+    the reference's parameter names and torch.optim.Adam's layout, and loading them back on a different world
+    layout reproduces every shard."""
+    from recbole_b200.dist import Comm, ShardedBPR
+    comm = Comm()
+    dev = torch.device("cpu")
+    rng = np.random.default_rng(3)
+    n_users, n_items, d = 103, 57, 8                     # not multiples of the world size: padded tail blocks
+    U0 = rng.standard_normal((n_users, d)).astype(np.float32)
+    V0 = rng.standard_normal((n_items, d)).astype(np.float32)
+    m = ShardedBPR(n_users, n_items, d, comm, dev, U_full=U0, V_full=V0)
+    m.build_optimizer("adam", lr=3e-3, weight_decay=1e-4)
+    m.optim.step = 7
+    for k in ("mU", "vU", "mV", "vV"):                   # recognisable moments: row index + a per-tensor offset
+        full = (U0 if k.endswith("U") else V0) * 0 + np.arange((n_users if k.endswith("U") else n_items))[:, None] + ord(k[0])
+        lo, hi = (m.u_lo, m.u_hi) if k.endswith("U") else (m.i_lo, m.i_hi)
+        m.state[k][: hi - lo] = torch.from_numpy(full[lo:hi].astype(np.float32))
+    sd, osd = m.state_dict(), m.optimizer_state_dict()
+    assert sorted(sd) == ["item_embedding.weight", "user_embedding.weight"]
+    assert np.array_equal(sd["user_embedding.weight"].numpy(), U0) and np.array_equal(sd["item_embedding.weight"].numpy(), V0)
+    assert float(osd["state"][0]["step"]) == 7 and osd["param_groups"][0]["lr"] == 3e-3
+    assert tuple(osd["state"][1]["exp_avg"].shape) == (n_items, d)
+    assert float(osd["state"][0]["exp_avg_sq"][50, 0]) == 50 + ord("v")
+    # a plain torch.optim.Adam accepts the optimizer dict (same layout as the reference's checkpoint)
+    pu, pv = torch.nn.Parameter(sd["user_embedding.weight"].clone()), torch.nn.Parameter(sd["item_embedding.weight"].clone())
+    ref = torch.optim.Adam([pu, pv], lr=1.0)
+    ref.load_state_dict({k: v for k, v in osd.items() if k != "fused_kind"})
+    assert ref.param_groups[0]["lr"] == 3e-3 and ref.param_groups[0]["weight_decay"] == 1e-4
+    assert torch.equal(ref.state[pv]["exp_avg"], osd["state"][1]["exp_avg"])
+    # round trip into a fresh model
+    m2 = ShardedBPR(n_users, n_items, d, comm, dev, U_full=U0 * 0, V_full=V0 * 0)
+    m2.build_optimizer("adam")
+    m2.load_state_dict(sd)
+    m2.load_optimizer_state_dict(osd)
+    assert torch.equal(m2.U, m.U) and torch.equal(m2.V, m.V) and m2.optim.step == 7 and m2.optim.lr == 3e-3
+    for k in ("mU", "vU", "mV", "vV"):
+        assert torch.equal(m2.state[k], m.state[k])
+    return True
+
+
+def test_sharded_checkpoint_interop_world2():
+    assert run_ranks(_ckpt_rank, 2) == [True, True]
+
+
+def test_sharded_checkpoint_interop_world3():
+    assert run_ranks(_ckpt_rank, 3) == [True, True, True]
