@@ -405,6 +405,11 @@ def main():
         import bench_extra
         bench_extra.run_cfg5_multi(args, rank, world, local_rank, load_peaks, ClockSampler)
         return
+    if args.workload in ("cfg4", "cfg5") and args.impl == "reference":
+        if rank == 0:
+            import bench_extra
+            bench_extra.run_reference(args)
+        return
     if args.workload in ("cfg4", "cfg5"):
         if rank == 0 and args.impl != "reference":
             import bench_extra

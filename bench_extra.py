@@ -301,3 +301,56 @@ def run_cfg5_multi(args, rank, world, local_rank, load_peaks, ClockSampler):
         print(json.dumps(line), flush=True)
     dist.barrier()
     dist.destroy_process_group()
+
+
+def run_reference(args):
+    """`bench.py --impl reference --workload cfg4|cfg5`: the reference's own CPU path (oracle/torch_port.py: the
+    torch calls the reference makes) on the host cores, a bounded sample of the workload, same metric and unit."""
+    import torch
+    from oracle import torch_port
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    if args.workload == "cfg5":
+        card, d = CRITEO_CARD, 16
+        B = args.batch or (1 << 18)
+        steps = max(min(args.steps, args.cpu_steps), 1)
+        m = torch_port.RefFM(card.tolist(), d)
+        o = torch.optim.Adam(m.parameters(), lr=1e-3)
+        cb = [(torch.from_numpy(i), torch.from_numpy(l)) for i, l in fm_batches(card, B, 2)]
+        torch_port.fm_train_steps(m, o, cb[:1])                     # warm-up
+        t0 = time.perf_counter()
+        torch_port.fm_train_steps(m, o, [cb[i % 2] for i in range(steps)])
+        dt = time.perf_counter() - t0
+        value, unit, metric = steps * B / dt, "samples/s", "fm_train_samples_per_s"
+        sample = "1 warm-up + %d timed steps of %d rows (FM forward, BCELoss, autograd, dense Adam over %d rows)" % (
+            steps, B, int(card.sum()))
+        config = {"workload": "cfg5", "fields": 26, "rows": int(card.sum()), "dim": d, "train_batch": B}
+        ms = dt / steps * 1e3
+    else:
+        nq, N, d, K = 4096, 1_000_001, 64, 10
+        rows_cpu = 256
+        rng = np.random.default_rng(2020)
+        X = rng.standard_normal((nq, d)).astype(np.float32)
+        X = ((X - X.mean(1, keepdims=True)) / X.std(1, keepdims=True)).astype(np.float32)
+        E = (rng.standard_normal((N, d)) * 0.02).astype(np.float32)
+        E[0] = 0
+        tgt = rng.integers(1, N, nq)
+        Ec = torch.from_numpy(E)
+        torch_port.ce_head(torch.from_numpy(X[:32]), Ec, torch.from_numpy(tgt[:32]), K)
+        steps = max(min(args.steps, 3), 1)
+        t0 = time.perf_counter()
+        for s in range(steps):
+            lo = (s * rows_cpu) % (nq - rows_cpu)
+            torch_port.ce_head(torch.from_numpy(X[lo:lo + rows_cpu]), Ec, torch.from_numpy(tgt[lo:lo + rows_cpu]), K)
+        dt = time.perf_counter() - t0
+        value, unit, metric = steps * rows_cpu / dt, "rows/s", "ce_head_rows_per_s"
+        sample = "%d x %d of the %d rows: torch.matmul + cross_entropy + masked topk (the full batch would materialise " \
+                 "16.4 GB of logits)" % (steps, rows_cpu, nq)
+        config = {"workload": "cfg4", "rows": nq, "n_items": N, "dim": d, "topk": K}
+        ms = dt / steps * 1e3
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": steps,
+            "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
