@@ -121,3 +121,22 @@ def test_model_mirror_api_surface():
     big = FusedBPR(Cfg(USER_ID_FIELD="u", ITEM_ID_FIELD="i", NEG_PREFIX="neg_", device="cpu", embedding_size=64),
                    type("D", (), {"num": lambda self, f: 4000})())
     assert abs(big.user_embedding.weight.std().item() - (2 / 4064) ** 0.5) < 2e-3
+
+
+def test_bench_reference_arm_cfg4_prints_one_json_line():
+    """`bench.py --impl reference` needs no GPU: one JSON line with the contract's keys (smallest workload arm)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "cfg4",
+                          "--steps", "1"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config",
+              "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
