@@ -55,7 +55,8 @@ enum {
   RB2_ST_KEYS = 0, RB2_ST_SORT_USER = 1, RB2_ST_SORT_ITEM = 2, RB2_ST_USER_SIDE = 3, RB2_ST_USER_FIXUP = 4,
   RB2_ST_ITEM_SIDE = 5, RB2_ST_ITEM_FIXUP = 6, RB2_ST_LOSS = 7, RB2_ST_FULLSORT = 8, RB2_ST_TOPK_MERGE = 9,
   RB2_ST_METRICS = 10, RB2_ST_SAMPLER = 11, RB2_ST_GATHER_DOT = 12, RB2_ST_TC_CONVERT = 13, RB2_ST_TC_SCORE = 14,
-  RB2_ST_TC_REFINE = 15, RB2_ST_FM_FWD = 16, RB2_ST_FM_UPDATE = 17, RB2_ST_MISC = 18, RB2_NUM_STAGES = 19
+  RB2_ST_TC_REFINE = 15, RB2_ST_FM_FWD = 16, RB2_ST_FM_UPDATE = 17, RB2_ST_MISC = 18, RB2_ST_PLAN = 19,
+  RB2_ST_BARRIER = 20, RB2_ST_OWNER = 21, RB2_NUM_STAGES = 22
 };
 int rb2_profile_enable(int on);
 int rb2_profile_read(float *h_ms /* [RB2_NUM_STAGES] */, int64_t *h_calls /* [RB2_NUM_STAGES] */,
@@ -172,6 +173,63 @@ int rb2_sparse_rows_update(float *p, float *m, float *v, int32_t *last, int64_t 
 int rb2_bpr_loss(const float *user_p, const float *item_p, int64_t n_users, int64_t n_items, int32_t dim,
                  const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t batch,
                  float *loss_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (1e) The same step over PEER MEMORY: the item table is row-sharded in equal contiguous blocks over
+ * the GPUs of one NVLink / NVSwitch domain, one process per GPU, and the kernels read the owners'
+ * rows and write the owners' gradient slots themselves (BASELINE north_star "row-sharded
+ * across the 8 GPUs ... exchanges rows and gradients ... over NVLink").  No NCCL call and no host
+ * synchronisation inside a step:
+ *   keys, two sorts (local) -> flag barrier A -> per occurrence source / destination (an item that
+ *   occurs ONCE in this rank's batch is read from its owner directly and its gradient is pushed
+ *   straight into the owner's slot by the user-side kernel; an item that occurs several times is
+ *   fetched once into item_cache and its summed gradient is pushed by the item-side walk) ->
+ *   flag barrier B (the ranks' loss sums travel with it) -> every owner sums, in rank order, the slots
+ *   stamped with this step and takes ONE optimizer step per touched local row.
+ * Result == rb2_bpr_train_step on the union of the ranks' batches (up to fp32 summation order).
+ *
+ * rb2_peers: pointers valid IN THIS PROCESS for every rank's buffers (own: plain device pointers;
+ * peers: mapped with rb2_ipc_open or any other peer mapping).  Per rank r:
+ *   item_p[r]      fp32 [item_block, dim]             its shard of the item table
+ *   grad_slots[r]  fp32 [world, item_block, dim]      slot s = the gradient rows rank s pushed
+ *   stamps[r]      int32 [world, item_block]          zero-initialised; == step where the slot row is valid
+ *   flags[r]       uint32 [2, RB2_MAX_PEERS]          zero-initialised barrier flags
+ *   loss_slots[r]  fp64 [2, RB2_MAX_PEERS]
+ * Every rank must call rb2_bpr_train_step_p2p the same number of times with h_opt->step = 1, 2, 3, ...
+ * (it is the barrier sequence number).  user holds global user ids, all inside THIS rank's block
+ * [user_base, user_base + n_users_local) of the user table; pos / neg are global item ids.  item_m / item_v: Adam moments of the local shard.
+ * item_cache: fp32 [world * item_block, dim] scratch.  A barrier that waits longer than 30 s gives up
+ * and sets the workspace's peer_timeout flag (second int32 of the workspace) instead of hanging.
+ * ---------------------------------------------------------------------------------------- */
+#define RB2_MAX_PEERS 8
+typedef struct rb2_peers {
+  int32_t world, me;
+  int64_t item_block;
+  const float *item_p[RB2_MAX_PEERS];
+  float *grad_slots[RB2_MAX_PEERS];
+  int32_t *stamps[RB2_MAX_PEERS];
+  uint32_t *flags[RB2_MAX_PEERS];
+  double *loss_slots[RB2_MAX_PEERS];
+} rb2_peers;
+
+size_t rb2_bpr_p2p_workspace_bytes(int64_t batch, int32_t dim);
+int rb2_bpr_train_step_p2p(float *user_p, float *user_m, float *user_v, float *item_m, float *item_v,
+                           int64_t n_users_local, int64_t n_items, int32_t dim, const int64_t *user,
+                           int64_t user_base, const int64_t *pos, const int64_t *neg, int64_t batch,
+                           int64_t global_batch,
+                           const rb2_optim *h_opt, const rb2_peers *h_peers, float *item_cache,
+                           float *loss_out, double *loss_accum, void *workspace, size_t workspace_bytes,
+                           void *stream);
+
+/* Peer mapping helpers (cudaIpc*; legacy IPC handles work between processes on one GPU and across
+ * NVLink peers).  rb2_ipc_export: 64-byte handle of the allocation that contains dev_ptr + the offset
+ * of dev_ptr inside it (PyTorch's caching allocator sub-allocates).  rb2_ipc_open maps a handle
+ * exported by ANOTHER process and returns base + offset; one mapping per (process, allocation) is
+ * kept and shared by later opens.  rb2_ipc_close_all unmaps everything this process opened. */
+#define RB2_IPC_HANDLE_BYTES 64
+int rb2_ipc_export(const void *dev_ptr, void *h_handle /* [64] */, int64_t *h_offset);
+int rb2_ipc_open(const void *h_handle /* [64] */, int64_t offset, void **h_mapped);
+int rb2_ipc_close_all(void);
 
 /* Flush for RB2_OPT_ADAM_LAZY: bring every row to step `h_opt->step` (replaying the zero-gradient
  * steps it missed) so the tables can be read by evaluation / checkpointing. */

@@ -20,7 +20,8 @@ METRIC_ORDER = ("recall", "mrr", "ndcg", "hit", "precision", "map")
 EINVAL, EWORKSPACE, ERANGE = 10001, 10002, 10003
 STAGES = ("keys", "sort_user", "sort_item", "user_side", "user_fixup", "item_side", "item_fixup", "loss", "fullsort",
           "topk_merge", "metrics", "sampler", "gather_dot", "tc_convert", "tc_score", "tc_refine", "fm_fwd",
-          "fm_update", "misc")
+          "fm_update", "misc", "plan", "barrier", "owner")
+MAX_PEERS = 8
 
 
 class RB2Optim(ctypes.Structure):
@@ -31,6 +32,15 @@ class RB2Optim(ctypes.Structure):
         ("one_minus_beta1", ctypes.c_float), ("one_minus_beta2", ctypes.c_float),
         ("eps", ctypes.c_float), ("step_size", ctypes.c_float), ("bc2_sqrt", ctypes.c_float),
         ("lazy_step_size", ctypes.c_void_p), ("lazy_bc2_sqrt", ctypes.c_void_p),
+    ]
+
+
+class RB2Peers(ctypes.Structure):
+    _fields_ = [
+        ("world", ctypes.c_int32), ("me", ctypes.c_int32), ("item_block", ctypes.c_int64),
+        ("item_p", ctypes.c_void_p * MAX_PEERS), ("grad_slots", ctypes.c_void_p * MAX_PEERS),
+        ("stamps", ctypes.c_void_p * MAX_PEERS), ("flags", ctypes.c_void_p * MAX_PEERS),
+        ("loss_slots", ctypes.c_void_p * MAX_PEERS),
     ]
 
 
@@ -49,6 +59,13 @@ SIGNATURES = {
                                                   ctypes.POINTER(RB2Optim), _p, _p, _p, _p, _p, _p, _sz, _p]),
     "rb2_bpr_train_step_sharded_ev": (ctypes.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _i64, _i64,
                                                      ctypes.POINTER(RB2Optim), _p, _p, _p, _p, _p, _p, _sz, _p, _p]),
+    "rb2_bpr_p2p_workspace_bytes": (_sz, [_i64, _i32]),
+    "rb2_bpr_train_step_p2p": (ctypes.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _i64, _p, _p, _i64, _i64,
+                                              ctypes.POINTER(RB2Optim), ctypes.POINTER(RB2Peers), _p, _p, _p, _p, _sz,
+                                              _p]),
+    "rb2_ipc_export": (ctypes.c_int, [_p, _p, ctypes.POINTER(_i64)]),
+    "rb2_ipc_open": (ctypes.c_int, [_p, _i64, ctypes.POINTER(_p)]),
+    "rb2_ipc_close_all": (ctypes.c_int, []),
     "rb2_item_plan_workspace_bytes": (_sz, [_i64]),
     "rb2_item_plan": (ctypes.c_int, [_p, _p, _i64, _i64, _p, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "rb2_dense_rows_update": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, ctypes.POINTER(RB2Optim), _p]),

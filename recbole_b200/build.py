@@ -64,7 +64,7 @@ def build(force=False, verbose=False):
     rebuilt = [n for n, r, _ in results if r]
     if rebuilt or not os.path.exists(LIB):
         objs = [os.path.join(OBJ, n[:-3] + ".o") for n in srcs]
-        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl"]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:
             raise RuntimeError("link failed:\n" + p.stdout + p.stderr)

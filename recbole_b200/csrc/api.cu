@@ -80,6 +80,81 @@ extern "C" int rb2_profile_read(float *h_ms, int64_t *h_calls, int64_t *h_launch
 }
 extern "C" int rb2_abi_version(void) { return RB2_ABI_VERSION; }
 
+// ---- peer mapping (cudaIpc) ------------------------------------------------------------------------------
+#include <dlfcn.h>
+#include <map>
+#include <string>
+namespace {
+std::mutex g_ipc_mu;
+std::map<std::string, void *> g_ipc_open;   // handle bytes -> mapped base (one mapping per allocation)
+
+// base address of the allocation containing p (driver API, resolved at run time: no link dependency)
+int alloc_base(const void *p, void **base) {
+  typedef int (*fn_t)(unsigned long long *, size_t *, unsigned long long);
+  static fn_t fn = nullptr;
+  if (!fn) {
+    void *h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (h) fn = (fn_t)dlsym(h, "cuMemGetAddressRange_v2");
+  }
+  RB2_REQUIRE(fn != nullptr, RB2_EINVAL, "rb2_ipc_export: cuMemGetAddressRange_v2 not found in libcuda.so.1");
+  unsigned long long b = 0;
+  size_t sz = 0;
+  int rc = fn(&b, &sz, (unsigned long long)(uintptr_t)p);
+  RB2_REQUIRE(rc == 0, RB2_EINVAL, "rb2_ipc_export: cuMemGetAddressRange failed (%d)", rc);
+  *base = (void *)(uintptr_t)b;
+  return 0;
+}
+}  // namespace
+
+extern "C" int rb2_ipc_export(const void *dev_ptr, void *h_handle, int64_t *h_offset) {
+  RB2_REQUIRE(dev_ptr && h_handle && h_offset, RB2_EINVAL, "rb2_ipc_export: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == RB2_IPC_HANDLE_BYTES, "handle size");
+  void *base = nullptr;
+  int rc = alloc_base(dev_ptr, &base);
+  if (rc) return rc;
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, base);
+  if (e != cudaSuccess) {
+    rb2_set_error("rb2_ipc_export: cudaIpcGetMemHandle failed: %s (memory from cudaMallocAsync / expandable segments "
+                  "cannot be exported; unset PYTORCH_CUDA_ALLOC_CONF=expandable_segments)", cudaGetErrorString(e));
+    cudaGetLastError();
+    return (int)e;
+  }
+  memcpy(h_handle, &h, sizeof(h));
+  *h_offset = (int64_t)((const char *)dev_ptr - (const char *)base);
+  return 0;
+}
+
+extern "C" int rb2_ipc_open(const void *h_handle, int64_t offset, void **h_mapped) {
+  RB2_REQUIRE(h_handle && h_mapped && offset >= 0, RB2_EINVAL, "rb2_ipc_open: bad argument");
+  std::lock_guard<std::mutex> lk(g_ipc_mu);
+  std::string key((const char *)h_handle, RB2_IPC_HANDLE_BYTES);
+  auto it = g_ipc_open.find(key);
+  void *base = nullptr;
+  if (it != g_ipc_open.end()) {
+    base = it->second;
+  } else {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, h_handle, sizeof(h));
+    cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      rb2_set_error("rb2_ipc_open: cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      return (int)e;
+    }
+    g_ipc_open[key] = base;
+  }
+  *h_mapped = (char *)base + offset;
+  return 0;
+}
+
+extern "C" int rb2_ipc_close_all(void) {
+  std::lock_guard<std::mutex> lk(g_ipc_mu);
+  for (auto &kv : g_ipc_open) cudaIpcCloseMemHandle(kv.second);
+  g_ipc_open.clear();
+  return 0;
+}
+
 namespace {
 // One lane-group per (user, item) pair: two coalesced row gathers and a shuffle reduction.
 template <int D>

@@ -58,7 +58,8 @@ struct Carver {
 // workspace header: sticky flags the host wrapper checks whenever it synchronises anyway
 struct WsHeader {
   int32_t range_error;  // an id was outside its table (clamped on device; reference raises IndexError)
-  int32_t pad[63];
+  int32_t peer_timeout; // a cross-GPU barrier of the peer-memory step gave up waiting (a rank died or fell out of step)
+  int32_t pad[62];
 };
 
 // tile length for the sorted-occurrence walks: long enough that few runs straddle tiles, short
@@ -194,6 +195,36 @@ __device__ __forceinline__ float row_dot_lane(const Row<D> &a, const Row<D> &b) 
   return s;
 }
 
+// ---- bulk-copy engine helpers (cp.async.bulk + mbarrier; UBLKCP / SYNCS in SASS) ----------------
+__device__ __forceinline__ uint32_t rb2_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rb2_mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rb2_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void rb2_mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void rb2_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rb2_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rb2_mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "RB2_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra RB2_WAIT_DONE;\n"
+      "bra RB2_WAIT_LOOP;\n"
+      "RB2_WAIT_DONE:\n"
+      "}\n" ::"r"(rb2_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16), completion counted in bytes on `bar`
+__device__ __forceinline__ void rb2_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   rb2_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(rb2_smem_u32(bar))
+               : "memory");
+}
+
 // ---- optimizer arithmetic (torch/optim/adam.py single-tensor path, see oracle/optim.py) -------
 struct OptScalars {
   int kind;
@@ -261,6 +292,28 @@ __device__ __forceinline__ void row_update(float *P, float *M, float *V, int64_t
     row_st<D>(P, row, lane, p);
     row_st<D>(M, row, lane, m);
     row_st<D>(V, row, lane, v);
+  }
+}
+
+// The same step on a row whose (p, m, v) are already in registers; the caller stores them.
+template <int D>
+__device__ __forceinline__ void row_step_regs(Row<D> &p, Row<D> &m, Row<D> &v, const Row<D> &g, const OptScalars &o) {
+  if (o.kind == RB2_OPT_SGD) {
+#pragma unroll
+    for (int i = 0; i < RowCfg<D>::VPL; ++i) {
+      sgd_elem(p.v[i].x, g.v[i].x, o);
+      sgd_elem(p.v[i].y, g.v[i].y, o);
+      sgd_elem(p.v[i].z, g.v[i].z, o);
+      sgd_elem(p.v[i].w, g.v[i].w, o);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < RowCfg<D>::VPL; ++i) {
+      adam_elem(p.v[i].x, m.v[i].x, v.v[i].x, g.v[i].x, o);
+      adam_elem(p.v[i].y, m.v[i].y, v.v[i].y, g.v[i].y, o);
+      adam_elem(p.v[i].z, m.v[i].z, v.v[i].z, g.v[i].z, o);
+      adam_elem(p.v[i].w, m.v[i].w, v.v[i].w, g.v[i].w, o);
+    }
   }
 }
 

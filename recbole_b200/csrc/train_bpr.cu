@@ -17,6 +17,8 @@
 //   k_fixup       ditto for items.
 //   k_loss        fixed-order reduction of the per-tile loss partials.
 // Every touched row is read (p, m, v) and written (p, m, v) exactly once per step.
+#include <algorithm>
+
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -37,9 +39,18 @@ struct BprWs {
   float *u_head, *u_tail, *i_head, *i_tail; // [tiles, D]
   uint8_t *u_fh, *u_ft, *i_fh, *i_ft;       // [tiles] flags
   double *loss_part;                        // [user tiles]
+  float *u_blk, *i_blk;                     // [tiles / kChainBlk + 1, D] sums of whole blocks of chain partials
+  uint8_t *u_blk_ok, *i_blk_ok;             // [tiles / kChainBlk + 1]
+  // peer-memory (multi-GPU) step only
+  unsigned long long *src, *dst;            // [2B] per item occurrence: where to read the row / push its gradient
+  uint32_t *fetch_list;                     // [2B] remote rows that occur more than once (fetched once)
+  uint32_t *fetch_count;                    // [1]
+  double *loss_sum;                         // [1] this rank's un-normalised loss sum
   void *cub_tmp;
   size_t cub_bytes;
 };
+constexpr int kChainBlk = 16;               // tiles per pre-reduced block of a long chain (k_chain_blocks)
+constexpr int kTileMax = 64;                // upper bound of pick_tile()
 
 // tile length: long enough that few runs straddle tiles, short enough to fill the machine
 inline int pick_tile(int64_t n_occ, int lanes) {
@@ -52,7 +63,7 @@ inline int pick_tile(int64_t n_occ, int lanes) {
 
 inline int64_t max_tiles(int64_t n_occ) { return (n_occ + 7) / 8; }
 
-size_t carve(BprWs &w, void *base, int64_t B, int dim) {
+size_t carve(BprWs &w, void *base, int64_t B, int dim, bool p2p = false) {
   Carver c(base);
   w.hdr = c.take<WsHeader>(1);
   w.ukey = c.take<uint32_t>(B);
@@ -75,6 +86,20 @@ size_t carve(BprWs &w, void *base, int64_t B, int dim) {
   w.i_fh = c.take<uint8_t>(ti);
   w.i_ft = c.take<uint8_t>(ti);
   w.loss_part = c.take<double>(tu > kLossParts ? tu : kLossParts);
+  w.u_blk = c.take<float>((tu / kChainBlk + 1) * dim);
+  w.i_blk = c.take<float>((ti / kChainBlk + 1) * dim);
+  w.u_blk_ok = c.take<uint8_t>(tu / kChainBlk + 1);
+  w.i_blk_ok = c.take<uint8_t>(ti / kChainBlk + 1);
+  w.src = w.dst = nullptr;
+  w.fetch_list = w.fetch_count = nullptr;
+  w.loss_sum = nullptr;
+  if (p2p) {
+    w.src = c.take<unsigned long long>(2 * B);
+    w.dst = c.take<unsigned long long>(2 * B);
+    w.fetch_list = c.take<uint32_t>(2 * B);
+    w.fetch_count = c.take<uint32_t>(64);
+    w.loss_sum = c.take<double>(32);
+  }
   size_t b1 = 0, b2 = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, b1, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
                                   (uint32_t *)nullptr, (int)B, 0, 32);
@@ -94,10 +119,10 @@ inline int bits_for(int64_t n) {
 // ---------------------------------------------------------------------------------------------
 __global__ void k_make_keys(const int64_t *__restrict__ user, const int64_t *__restrict__ pos,
                             const int64_t *__restrict__ neg, int64_t B, int64_t n_users, int64_t n_items,
-                            BprWs w) {
+                            BprWs w, int64_t user_base = 0) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= B) return;
-  int64_t u = user[s], p = pos[s], n = neg[s];
+  int64_t u = user[s] - user_base, p = pos[s], n = neg[s];
   bool bad = (u < 0) | (u >= n_users) | (p < 0) | (p >= n_items) | (n < 0) | (n >= n_items);
   if (bad) {
     w.hdr->range_error = 1;
@@ -343,6 +368,8 @@ __global__ void __launch_bounds__(kThreads) k_fixup(float *P, float *M, float *V
   }
 }
 
+#include "train_bpr_fused.cuh"
+
 __global__ void k_loss(const double *__restrict__ part, int64_t n, double inv_b, float *loss_out,
                        double *loss_accum) {
   // single block, fixed order: thread i sums part[i], part[i+blockDim], ... then a tree
@@ -392,11 +419,85 @@ __global__ void __launch_bounds__(kThreads) k_bpr_loss(const float *__restrict__
   if (lane == 0 && gid < ngroups) part[gid] = (double)local;
 }
 
+template <typename K>
+int allow_smem(K kernel, size_t bytes) {
+  RB2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+template <int D, bool ADAM, bool P2P>
+int launch_user_fused(const Tables &t, const BprWs &w, int64_t B, int Tu, int64_t ntu, float inv_b, const OptScalars &o,
+                      cudaStream_t st) {
+  using C = FusedCfg<D, ADAM, P2P>;
+  int rc = allow_smem(k_user_fused<D, ADAM, P2P>, C::kSmem);   // per device; a host-side attribute write
+  if (rc) return rc;
+  k_user_fused<D, ADAM, P2P><<<(unsigned)((ntu + C::GPB - 1) / C::GPB), kThreads, C::kSmem, st>>>(t, w, B, Tu, ntu,
+                                                                                                   inv_b, o);
+  return 0;
+}
+
+// the row-sparse Adam / SGD step, single GPU (train_bpr_fused.cuh)
+template <int D>
+int launch_step_fused(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, const OptScalars &o,
+                      float *loss_out, double *loss_accum, cudaStream_t st, int64_t global_batch) {
+  constexpr int LANES = RowCfg<D>::LANES;
+  const int Tu = std::min(pick_tile(B, LANES), FusedCfg<D, true, false>::TMAX), Ti = pick_tile(2 * B, LANES);
+  const int64_t ntu = (B + Tu - 1) / Tu, nti = (2 * B + Ti - 1) / Ti;
+  auto blocks = [](int64_t groups) { return (unsigned)((groups * LANES + kThreads - 1) / kThreads); };
+  const PeerTable none{};
+  size_t tmp = w.cub_bytes;
+  {
+    ProfScope prof(RB2_ST_SORT_USER, st, 2 + (bits_for(n_users) + 7) / 8);
+    RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ukey, w.ukey_s, w.uval, w.uval_s, (int)B, 0,
+                                             bits_for(n_users), st));
+  }
+  tmp = w.cub_bytes;
+  {
+    ProfScope prof(RB2_ST_SORT_ITEM, st, 2 + (bits_for(n_items) + 7) / 8);
+    RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ikey, w.ikey_s, w.ival, w.ival_s, (int)(2 * B), 0,
+                                             bits_for(n_items), st));
+  }
+  {
+    ProfScope prof(RB2_ST_PLAN, st);
+    k_mark_local<<<(unsigned)((2 * B + 255) / 256), 256, 0, st>>>(w, 2 * B);
+  }
+  {
+    ProfScope prof(RB2_ST_USER_SIDE, st);
+    int rc = (o.kind == RB2_OPT_SGD) ? launch_user_fused<D, false, false>(t, w, B, Tu, ntu, 1.f / (float)global_batch, o, st)
+                                     : launch_user_fused<D, true, false>(t, w, B, Tu, ntu, 1.f / (float)global_batch, o, st);
+    if (rc) return rc;
+  }
+  {
+    ProfScope prof(RB2_ST_USER_FIXUP, st, 2);
+    k_chain_blocks<D><<<blocks(ntu / kChainBlk + 1), kThreads, 0, st>>>(w.u_head, w.u_fh, w.u_blk, w.u_blk_ok, ntu);
+    k_fixup_fused<D, false><<<blocks(ntu), kThreads, 0, st>>>(t.up, t.um, t.uv, w.ukey_s, w.u_head, w.u_tail, w.u_fh,
+                                                               w.u_ft, w.u_blk, w.u_blk_ok, B, Tu, ntu, o, none);
+  }
+  {
+    ProfScope prof(RB2_ST_ITEM_SIDE, st);
+    k_item_fused<D, false><<<blocks(nti), kThreads, 0, st>>>(t, w, none, 2 * B, Ti, nti, o);
+  }
+  {
+    ProfScope prof(RB2_ST_ITEM_FIXUP, st, 2);
+    k_chain_blocks<D><<<blocks(nti / kChainBlk + 1), kThreads, 0, st>>>(w.i_head, w.i_fh, w.i_blk, w.i_blk_ok, nti);
+    k_fixup_fused<D, false><<<blocks(nti), kThreads, 0, st>>>(t.ip, t.im, t.iv, w.ikey_s, w.i_head, w.i_tail, w.i_fh,
+                                                               w.i_ft, w.i_blk, w.i_blk_ok, 2 * B, Ti, nti, o, none);
+  }
+  {
+    ProfScope prof(RB2_ST_LOSS, st);
+    k_loss<<<1, 256, 0, st>>>(w.loss_part, ntu, 1.0 / (double)global_batch, loss_out, loss_accum);
+  }
+  RB2_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int D, bool LAZY>
 int launch_step(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, const OptScalars &o, float *loss_out,
                 double *loss_accum, cudaStream_t st, int64_t global_batch, const uint32_t *pre_ikey_s,
                 const uint32_t *pre_ival_s, cudaEvent_t rows_ready) {
   constexpr int LANES = RowCfg<D>::LANES;
+  if (!LAZY && !t.ig && !pre_ikey_s && !rows_ready)
+    return launch_step_fused<D>(t, w, B, n_users, n_items, o, loss_out, loss_accum, st, global_batch);
   const int Tu = pick_tile(B, LANES), Ti = pick_tile(2 * B, LANES);
   const int64_t ntu = (B + Tu - 1) / Tu, nti = (2 * B + Ti - 1) / Ti;
   auto blocks = [](int64_t groups) { return (unsigned)((groups * LANES + kThreads - 1) / kThreads); };
@@ -603,8 +704,8 @@ static int bpr_step_impl(float *user_p, float *user_m, float *user_v, int32_t *u
               "rb2_bpr_train_step: null argument");
   RB2_REQUIRE(batch > 0 && batch < ((int64_t)1 << 30), RB2_EINVAL, "rb2_bpr_train_step: batch %lld out of range",
               (long long)batch);
-  RB2_REQUIRE(n_users > 0 && n_items > 0 && n_users < ((int64_t)1 << 32) - 1 && n_items < ((int64_t)1 << 32) - 1,
-              RB2_EINVAL, "rb2_bpr_train_step: table sizes must fit 32 bits");
+  RB2_REQUIRE(n_users > 0 && n_items > 0 && n_users < ((int64_t)1 << 32) - 1 && n_items < ((int64_t)1 << 31),
+              RB2_EINVAL, "rb2_bpr_train_step: table sizes must fit 32 / 31 bits");
   OptScalars o = rb2_opt_scalars(h_opt);
   RB2_REQUIRE(o.kind == RB2_OPT_SGD || o.kind == RB2_OPT_ADAM || o.kind == RB2_OPT_ADAM_LAZY, RB2_EINVAL,
               "rb2_bpr_train_step: unknown optimizer kind %d", o.kind);
@@ -858,6 +959,141 @@ extern "C" int rb2_adam_lazy_flush(float *p, float *m, float *v, int32_t *last, 
     constexpr int LANES = RowCfg<D_>::LANES;
     unsigned blocks = (unsigned)((rows * LANES + kThreads - 1) / kThreads);
     k_lazy_flush<D_><<<blocks, kThreads, 0, st>>>(p, m, v, last, rows, o);
+  });
+  RB2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Peer-memory step (include/recbole_b200.h (1d)): the item table is row-sharded over the GPUs of one NVLink
+// domain; rows are read from and gradients written to the owners' memory by the kernels themselves.
+extern "C" size_t rb2_bpr_p2p_workspace_bytes(int64_t batch, int32_t dim) {
+  BprWs w;
+  return carve(w, nullptr, batch, dim, true);
+}
+
+extern "C" int rb2_bpr_train_step_p2p(float *user_p, float *user_m, float *user_v, float *item_m, float *item_v,
+                                      int64_t n_users_local, int64_t n_items, int32_t dim, const int64_t *user,
+                                      int64_t user_base, const int64_t *pos, const int64_t *neg, int64_t batch,
+                                      int64_t global_batch,
+                                      const rb2_optim *h_opt, const rb2_peers *h_peers, float *item_cache,
+                                      float *loss_out, double *loss_accum, void *workspace, size_t workspace_bytes,
+                                      void *stream) {
+  RB2_REQUIRE(user_p && user && pos && neg && h_opt && h_peers && item_cache && loss_out && workspace, RB2_EINVAL,
+              "rb2_bpr_train_step_p2p: null argument");
+  RB2_REQUIRE(batch > 0 && batch < ((int64_t)1 << 30) && global_batch >= batch, RB2_EINVAL,
+              "rb2_bpr_train_step_p2p: bad batch sizes");
+  const rb2_peers &hp = *h_peers;
+  RB2_REQUIRE(hp.world >= 1 && hp.world <= RB2_MAX_PEERS && hp.me >= 0 && hp.me < hp.world && hp.item_block > 0 &&
+                  hp.item_block * hp.world >= n_items,
+              RB2_EINVAL, "rb2_bpr_train_step_p2p: bad peer table (world %d, me %d, block %lld)", hp.world, hp.me,
+              (long long)hp.item_block);
+  RB2_REQUIRE(n_users_local > 0 && n_items > 0 && n_users_local < ((int64_t)1 << 32) - 1 && n_items < ((int64_t)1 << 31),
+              RB2_EINVAL, "rb2_bpr_train_step_p2p: table sizes must fit 32 / 31 bits");
+  OptScalars o = rb2_opt_scalars(h_opt);
+  RB2_REQUIRE(o.kind == RB2_OPT_SGD || o.kind == RB2_OPT_ADAM, RB2_EINVAL,
+              "rb2_bpr_train_step_p2p: optimizer kind %d not supported (sgd, adam)", o.kind);
+  if (o.kind != RB2_OPT_SGD)
+    RB2_REQUIRE(user_m && user_v && item_m && item_v, RB2_EINVAL, "rb2_bpr_train_step_p2p: Adam needs m and v");
+  RB2_REQUIRE(o.step >= 1, RB2_EINVAL, "rb2_bpr_train_step_p2p: step must count from 1 (it is the barrier sequence)");
+  PeerTable pt{};
+  PeerSync ps{};
+  for (int r = 0; r < hp.world; ++r) {
+    RB2_REQUIRE(hp.item_p[r] && hp.grad_slots[r] && hp.stamps[r] && hp.flags[r] && hp.loss_slots[r], RB2_EINVAL,
+                "rb2_bpr_train_step_p2p: peer %d has a null buffer", r);
+    pt.V[r] = hp.item_p[r];
+    pt.G[r] = hp.grad_slots[r];
+    pt.stamp[r] = hp.stamps[r];
+    ps.flags[r] = hp.flags[r];
+    ps.loss[r] = hp.loss_slots[r];
+  }
+  pt.cache = item_cache;
+  pt.i_block = hp.item_block;
+  pt.me = ps.me = hp.me;
+  pt.world = ps.world = hp.world;
+  pt.step = o.step;
+  BprWs w;
+  size_t need = carve(w, workspace, batch, dim, true);
+  RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_bpr_train_step_p2p: workspace %zu < %zu", workspace_bytes,
+              need);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t B = batch;
+  float *item_local = const_cast<float *>(hp.item_p[hp.me]);
+  Tables t{user_p, user_m, user_v, nullptr, item_local, item_m, item_v, nullptr, nullptr, nullptr};
+  const unsigned long long timeout_ns = 30ull * 1000ull * 1000ull * 1000ull;
+  int64_t n_local = n_items - (int64_t)hp.me * hp.item_block;
+  if (n_local > hp.item_block) n_local = hp.item_block;
+  if (n_local < 0) n_local = 0;
+  {
+    ProfScope prof(RB2_ST_KEYS, st, 2);
+    RB2_CUDA(cudaMemsetAsync(w.fetch_count, 0, sizeof(uint32_t), st));
+    k_make_keys<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(user, pos, neg, B, n_users_local, n_items, w, user_base);
+  }
+  size_t tmp = w.cub_bytes;
+  {
+    ProfScope prof(RB2_ST_SORT_USER, st, 2 + (bits_for(n_users_local) + 7) / 8);
+    RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ukey, w.ukey_s, w.uval, w.uval_s, (int)B, 0,
+                                             bits_for(n_users_local), st));
+  }
+  tmp = w.cub_bytes;
+  {
+    ProfScope prof(RB2_ST_SORT_ITEM, st, 2 + (bits_for(n_items) + 7) / 8);
+    RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ikey, w.ikey_s, w.ival, w.ival_s, (int)(2 * B), 0,
+                                             bits_for(n_items), st));
+  }
+  {
+    // barrier A: every owner has finished the previous step's update; from here on peers' rows may be read and
+    // their slots / stamps written
+    ProfScope prof(RB2_ST_BARRIER, st);
+    k_peer_barrier<<<1, 32, 0, st>>>(ps, (uint32_t)o.step, 0, nullptr, 0.0, nullptr, nullptr, w.hdr, timeout_ns);
+  }
+  RB2_DISPATCH_DIM(dim, {
+    constexpr int LANES = RowCfg<D_>::LANES;
+    const int Tu = std::min(pick_tile(B, LANES), FusedCfg<D_, true, true>::TMAX), Ti = pick_tile(2 * B, LANES);
+    const int64_t ntu = (B + Tu - 1) / Tu, nti = (2 * B + Ti - 1) / Ti;
+    auto blocks = [](int64_t groups) { return (unsigned)((groups * LANES + kThreads - 1) / kThreads); };
+    {
+      ProfScope prof(RB2_ST_PLAN, st, 2);
+      k_plan_p2p<D_><<<(unsigned)((2 * B + 255) / 256), 256, 0, st>>>(w, pt, 2 * B);
+      k_fetch_rows<D_><<<(unsigned)rb2_num_sms() * 8, kThreads, 0, st>>>(w, pt);
+    }
+    {
+      ProfScope prof(RB2_ST_USER_SIDE, st);
+      const float inv_b = 1.f / (float)global_batch;
+      int rc = (o.kind == RB2_OPT_SGD) ? launch_user_fused<D_, false, true>(t, w, B, Tu, ntu, inv_b, o, st)
+                                       : launch_user_fused<D_, true, true>(t, w, B, Tu, ntu, inv_b, o, st);
+      if (rc) return rc;
+    }
+    {
+      ProfScope prof(RB2_ST_USER_FIXUP, st, 2);
+      k_chain_blocks<D_><<<blocks(ntu / kChainBlk + 1), kThreads, 0, st>>>(w.u_head, w.u_fh, w.u_blk, w.u_blk_ok, ntu);
+      k_fixup_fused<D_, false><<<blocks(ntu), kThreads, 0, st>>>(t.up, t.um, t.uv, w.ukey_s, w.u_head, w.u_tail, w.u_fh,
+                                                                  w.u_ft, w.u_blk, w.u_blk_ok, B, Tu, ntu, o, pt);
+    }
+    {
+      ProfScope prof(RB2_ST_ITEM_SIDE, st);
+      k_item_fused<D_, true><<<blocks(nti), kThreads, 0, st>>>(t, w, pt, 2 * B, Ti, nti, o);
+    }
+    {
+      ProfScope prof(RB2_ST_ITEM_FIXUP, st, 2);
+      k_chain_blocks<D_><<<blocks(nti / kChainBlk + 1), kThreads, 0, st>>>(w.i_head, w.i_fh, w.i_blk, w.i_blk_ok, nti);
+      k_fixup_fused<D_, true><<<blocks(nti), kThreads, 0, st>>>(nullptr, nullptr, nullptr, w.ikey_s, w.i_head, w.i_tail,
+                                                                 w.i_fh, w.i_ft, w.i_blk, w.i_blk_ok, 2 * B, Ti, nti, o, pt);
+    }
+    {
+      ProfScope prof(RB2_ST_LOSS, st);
+      k_loss_sum<<<1, 256, 0, st>>>(w.loss_part, ntu, w.loss_sum);
+    }
+    {
+      // barrier B: every rank's gradient rows have landed in the owners' slots; the loss sums travel with it
+      ProfScope prof(RB2_ST_BARRIER, st);
+      k_peer_barrier<<<1, 32, 0, st>>>(ps, (uint32_t)o.step, 1, w.loss_sum, 1.0 / (double)global_batch, loss_out,
+                                       loss_accum, w.hdr, timeout_ns);
+    }
+    if (n_local > 0) {
+      ProfScope prof(RB2_ST_OWNER, st);
+      k_owner_update<D_><<<blocks(n_local), kThreads, 0, st>>>(item_local, item_m, item_v, pt, n_local, o);
+    }
   });
   RB2_CUDA(cudaGetLastError());
   return 0;

@@ -130,6 +130,13 @@ class Comm:
         if self.world > 1:
             dist.barrier(group=self.group)
 
+    def all_gather_object(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
+
 
 # ---- exchange plumbing (pure index work; unit-tested on CPU with gloo) ------------------------------
 
@@ -183,7 +190,16 @@ class ShardedBPR:
         self.u_block = int(self.user_bounds[1] - self.user_bounds[0])
         self.i_block = int(self.item_bounds[1] - self.item_bounds[0])
         self.U = torch.zeros(self.u_block, dim, device=device)
-        self.V = torch.zeros(self.i_block, dim, device=device)
+        # "p2p": the kernels read the owners' rows and write the owners' gradient slots over NVLink themselves
+        #        (rb2_bpr_train_step_p2p); the item shard lives in an arena every rank maps with cudaIpc.
+        self.arena = None
+        if exchange == "p2p" or (exchange == "auto" and device.type == "cuda" and not comm.staged
+                                 and n_items * dim * 4 > (64 << 20) and comm.world <= 8):
+            exchange = "p2p"
+            self.arena = ops.PeerArena(comm, device, self.i_block, dim)
+            self.V = self.arena.item_p
+        else:
+            self.V = torch.zeros(self.i_block, dim, device=device)
         if U_full is not None:
             self.U[: self.u_hi - self.u_lo] = torch.as_tensor(U_full[self.u_lo:self.u_hi]).to(device)
             self.V[: self.i_hi - self.i_lo] = torch.as_tensor(V_full[self.i_lo:self.i_hi]).to(device)
@@ -198,7 +214,7 @@ class ShardedBPR:
         # "auto": dense (all-gather rows + reduce-scatter gradients, no plan, no host sync) for small tables and
         # whenever a rank's batch covers most of the item table anyway (B >= n_items: >= 86 % of the rows are
         # touched, measured at cfg3 on 8 GPUs: 7.9 ms dense vs 15.7 ms sparse at B = 2^22, 4.8 vs 4.1 at 2^20)
-        self.exchange_auto = exchange == "auto"
+        self.exchange_auto = exchange == "auto" and self.arena is None
         if exchange == "auto":
             exchange = "dense" if n_items * dim * 4 <= (64 << 20) else "sparse"
         self.exchange = exchange
@@ -208,6 +224,12 @@ class ShardedBPR:
         self.loss_accum = torch.zeros(1, dtype=torch.float64, device=device)
         self._ws = {}
         self._rows_ws = None
+        self._p2p_ws = None
+
+    def check_flags(self):
+        """Raise for sticky device-side errors (id out of range, peer barrier timeout); synchronises."""
+        for ws in list(self._ws.values()) + ([self._p2p_ws[1]] if self._p2p_ws else []):
+            ws.check_flags()
 
     def build_optimizer(self, kind="adam", lr=1e-3, weight_decay=0.0):
         if kind not in ("adam", "sgd"):
@@ -328,6 +350,13 @@ class ShardedBPR:
             global_batch = B * comm.world
         self.optim.step += 1
         t = self.optim.step
+        if self.exchange == "p2p":
+            self.last_exchange = "p2p"
+            if self._p2p_ws is None or self._p2p_ws[0] < B:
+                self._p2p_ws = (B, ops.bpr_p2p_workspace(B, self.dim, self.device))
+            ops.bpr_train_step_p2p(self.U, self.state, self.arena, user, self.u_lo, pos, neg, self.n_items,
+                                   global_batch, self.optim, self.loss_out, self.loss_accum, self._p2p_ws[1], step=t)
+            return self.loss_out
         if self.exchange == "dense" or (self.exchange_auto and B >= self.n_items):
             self.last_exchange = "dense"
             return self._train_step_dense(user, pos, neg, global_batch, t)

@@ -44,9 +44,13 @@ class Workspace:
         return ctypes.c_void_p(self.buf.data_ptr())
 
     def check_flags(self):
-        flag = int(self.buf[:4].view(torch.int32).item())
-        if flag:
-            self.buf[:4].zero_()
+        flags = self.buf[:8].view(torch.int32).tolist()
+        if flags[1]:
+            self.buf[:8].zero_()
+            raise RuntimeError("recbole_b200: a cross-GPU barrier of the peer-memory step timed out "
+                               "(a rank died or the ranks fell out of step)")
+        if flags[0]:
+            self.buf[:8].zero_()
             raise IndexError("recbole_b200: an id was outside its embedding table "
                              "(the reference raises IndexError in F.embedding)")
 
@@ -134,6 +138,68 @@ def bpr_train_step_sharded(U, state, item_rows, user, pos_c, neg_c, global_batch
         ctypes.byref(o), _ptr(loss_out, f32), _ptr(loss_accum, torch.float64, True), _ptr(item_grad_out, f32),
         _ptr(item_touched, torch.int32, True), item_plan.ptr() if item_plan is not None else None,
         ws.ptr(), ws.nbytes, _stream(), ctypes.c_void_p(rows_ready.cuda_event) if rows_ready is not None else None))
+
+
+class PeerArena:
+    """The per-rank buffers of the peer-memory step (include/recbole_b200.h (1e)), carved from ONE device
+    allocation so that a single cudaIpc handle per rank maps everything: the item shard, the gradient slots,
+    their stamps, the barrier flags and the loss slots.  `comm` needs all_gather_object() and barrier()."""
+
+    def __init__(self, comm, device, item_block, dim):
+        world, me = comm.world, comm.rank
+        if world > _lib.MAX_PEERS:
+            raise ValueError("the peer-memory step supports up to %d ranks" % _lib.MAX_PEERS)
+        self.world, self.me, self.item_block, self.dim = world, me, int(item_block), int(dim)
+        al = lambda x: (int(x) + 255) // 256 * 256       # noqa: E731
+        sizes = [("item_p", self.item_block * dim * 4), ("grad_slots", world * self.item_block * dim * 4),
+                 ("stamps", world * self.item_block * 4), ("flags", 2 * _lib.MAX_PEERS * 4),
+                 ("loss_slots", 2 * _lib.MAX_PEERS * 8)]
+        self.offsets, off = {}, 0
+        for name, nbytes in sizes:
+            self.offsets[name] = off
+            off += al(nbytes)
+        self.buf = torch.zeros(off, dtype=torch.uint8, device=device)
+        o = self.offsets
+        self.item_p = self.buf[o["item_p"]: o["item_p"] + self.item_block * dim * 4].view(torch.float32).view(
+            self.item_block, dim)
+        base = [self.buf.data_ptr()] * world
+        if world > 1:
+            handle = (ctypes.c_char * 64)()
+            offset = ctypes.c_int64(0)
+            check(lib.rb2_ipc_export(ctypes.c_void_p(self.buf.data_ptr()), handle, ctypes.byref(offset)))
+            torch.cuda.synchronize(device)               # the zero fill is complete before anybody maps the arena
+            everyone = comm.all_gather_object((bytes(handle.raw), int(offset.value)))
+            for r, (h, ofs) in enumerate(everyone):
+                if r == me:
+                    continue
+                mapped = ctypes.c_void_p()
+                check(lib.rb2_ipc_open(ctypes.c_char_p(h), ofs, ctypes.byref(mapped)))
+                base[r] = mapped.value
+            comm.barrier()
+        self.peers = _lib.RB2Peers()
+        self.peers.world, self.peers.me, self.peers.item_block = world, me, self.item_block
+        for r in range(world):
+            for name in ("item_p", "grad_slots", "stamps", "flags", "loss_slots"):
+                getattr(self.peers, name)[r] = base[r] + o[name]
+        self.cache = torch.empty((world * self.item_block, dim), dtype=torch.float32, device=device)
+
+
+def bpr_p2p_workspace(batch, dim, device):
+    return Workspace(lib.rb2_bpr_p2p_workspace_bytes(int(batch), int(dim)), device)
+
+
+def bpr_train_step_p2p(U, state, arena, user, user_base, pos, neg, n_items, global_batch, optim, loss_out, loss_accum,
+                       ws, step=None):
+    """rb2_bpr_train_step_p2p: the whole sharded step (both barriers, the owner update and the global mean
+    loss included).  optim.step is NOT incremented here; `step` must count 1, 2, 3, ... identically on every rank."""
+    o = optim.c_struct(U.device, step)
+    f32, i64 = torch.float32, torch.int64
+    check(lib.rb2_bpr_train_step_p2p(
+        _ptr(U, f32), _ptr(state.get("mU"), f32, True), _ptr(state.get("vU"), f32, True),
+        _ptr(state.get("mV"), f32, True), _ptr(state.get("vV"), f32, True), U.shape[0], int(n_items), U.shape[1],
+        _ptr(user, i64), int(user_base), _ptr(pos, i64), _ptr(neg, i64), user.numel(), int(global_batch),
+        ctypes.byref(o), ctypes.byref(arena.peers), _ptr(arena.cache, f32), _ptr(loss_out, f32),
+        _ptr(loss_accum, torch.float64, True), ws.ptr(), ws.nbytes, _stream()))
 
 
 def item_plan(pos, neg, n_items, bounds_dev, world, plan_ws=None):

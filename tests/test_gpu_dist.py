@@ -39,6 +39,9 @@ def _rank_fn(rank, world, kind, mode, exchange):
         t = lambda a: torch.from_numpy(a[mine]).to(dev)  # noqa: E731
         lo = m.train_step(t(u), t(p), t(n), global_batch=len(u))
         losses.append(float(lo.item()))
+    m.check_flags()
+    if exchange == "p2p":
+        comm.barrier()          # peers may still be reading this rank's shard through their mappings
 
     class Cfg(dict):
         def __getitem__(self, k):
@@ -56,7 +59,8 @@ def _rank_fn(rank, world, kind, mode, exchange):
 
 
 @pytest.mark.parametrize("kind,mode,exchange", [("adam", "tc", "sparse"), ("sgd", "fp32", "sparse"),
-                                                ("adam", "fp32", "dense"), ("sgd", "tc", "dense")])
+                                                ("adam", "fp32", "dense"), ("sgd", "tc", "dense"),
+                                                ("adam", "fp32", "p2p"), ("sgd", "tc", "p2p")])
 def test_two_ranks_equal_single_device_oracle(kind, mode, exchange):
     from oracle import bpr as obpr
     from oracle import fullsort as ofs

@@ -221,3 +221,33 @@ def test_full_size_cfg2_step_properties():
     assert abs(loss.item() - lo) <= TOL * abs(lo)
     assert rel_err(U.cpu().numpy(), st_o["U"]) < TOL
     assert rel_err(V.cpu().numpy(), st_o["V"]) < TOL
+
+
+@pytest.mark.parametrize("dim,B,n_users,n_items", [(64, 20000, 3000, 2000), (128, 4096, 100000, 50000),
+                                                   (16, 777, 50, 40), (256, 3000, 500, 400)])
+@pytest.mark.parametrize("kind", ["adam", "sgd"])
+def test_peer_memory_step_one_rank_vs_oracle(dim, B, n_users, n_items, kind):
+    """rb2_bpr_train_step_p2p with a world of one (every "peer" pointer is local): the plan, the cache fetch, the
+    pushes into the gradient slots, both barriers and the owner update against the oracle's row-sparse step."""
+    from recbole_b200.dist import Comm, ShardedBPR
+    from gpu_util import rel_err, t, dev
+    rng = np.random.default_rng(dim * 11 + B)
+    U0 = (rng.standard_normal((n_users, dim)) * 0.3).astype(np.float32)
+    V0 = (rng.standard_normal((n_items, dim)) * 0.3).astype(np.float32)
+    st_o = obpr.new_state(U0, V0)
+    m = ShardedBPR(n_users, n_items, dim, Comm(), dev(), U_full=U0, V_full=V0, exchange="p2p")
+    lr = 0.05 if kind == "sgd" else 2e-3
+    m.build_optimizer(kind, lr=lr)
+
+    def zipf(n, size):
+        return np.minimum((np.exp(rng.random(size) * np.log(n - 1))).astype(np.int64), n - 1).clip(1)
+
+    for s in range(3):
+        u, p, n = zipf(n_users, B), zipf(n_items, B), rng.integers(1, n_items, B)
+        loss = m.train_step(t(u), t(p), t(n))
+        lo = obpr.bpr_train_step(st_o, u, p, n, s + 1, optimizer=kind, lr=lr, dense=False)
+        assert abs(float(loss.item()) - lo) <= TOL * abs(lo)
+    m.check_flags()
+    assert m.last_exchange == "p2p"
+    assert rel_err(m.U.cpu().numpy(), st_o["U"]) < TOL
+    assert rel_err(m.V.cpu().numpy()[:n_items], st_o["V"]) < TOL
