@@ -3,14 +3,18 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
 
-Metric (BASELINE.json): BPR train samples/s (`value`) + full-sort eval users/s at top-10 (`eval`),
-on the synthetic ml-20m shape (configs[1]) by default.  One JSON line on stdout (rank 0).
+Metric (BASELINE.json): BPR train samples/s (`value`) + full-sort eval users/s at top-10 (`eval`).
+Default workload at every N: BASELINE.json configs[2] = cfg3 (10M users x 2M items x d=128, 2^20 triples per GPU
+and step), the configuration the metric's "at 1/2/4/8 B200" and north_star's 60 % / 50 % targets are quoted on; it
+fits one GPU (18.4 GB of tables + Adam state).  At N = 1 the line also carries `extra.cfg2` = the same measurement on
+configs[1] (the synthetic ml-20m shape; `--no-extra` skips it).  One JSON line on stdout (rank 0).
 
 A "step" is one fused training step over one batch of `train_batch` (user, pos, neg) triples.
   value      inputs resident in HBM, device-timed with CUDA events, every step a different batch
   e2e        the same through the public host API (FusedBPR.train_step) with the batch in pinned
              HOST memory: H2D of the ids and D2H of the loss inside the timed region, every step
-  roofline   dominant kernel (k_user_side) timed live by the library's per-stage CUDA events
+  roofline   dominant kernel (k_user_fused) timed live by the library's per-stage CUDA events
+  parity_check  a small problem through the same (multi-rank) path, checked against the oracle before timing
   cpu_baseline  oracle/torch_port (the reference's own torch calls) on the host cores, bounded sample
 `--impl reference` times that CPU path alone, with every host thread, on the same workload.
 """
@@ -107,31 +111,37 @@ class ClockSampler:
 # the reference's CPU path (oracle/torch_port.py) -- cpu_baseline leg and --impl reference arm
 # -------------------------------------------------------------------------------------------------
 
-def cpu_reference(w, train_steps, warmup_steps, eval_users, threads, budget_s=120.0):
+def cpu_reference(w, train_steps, warmup_steps, eval_users, threads, budget_s=240.0):
+    """The reference's own torch calls on the host cores.  Every step is a FULL batch (dense gradients and dense
+    Adam cost O(table) per step whatever the batch size, so truncating batches would understate the reference);
+    what is bounded is the NUMBER of steps: if `warmup_steps + train_steps` would exceed `budget_s`, fewer timed
+    steps are run (at least 3) and the line says so."""
     import torch
     from oracle import torch_port
     torch.set_num_threads(threads)
     torch.manual_seed(2020)
     model = torch_port.RefBPR(w.n_users, w.n_items, w.dim)
-    with torch.no_grad():
-        model.user_embedding.weight.copy_(torch.from_numpy(w.U0))
-        model.item_embedding.weight.copy_(torch.from_numpy(w.V0))
+    if getattr(w, "U0", None) is not None:
+        with torch.no_grad():
+            model.user_embedding.weight.copy_(torch.from_numpy(w.U0))
+            model.item_embedding.weight.copy_(torch.from_numpy(w.V0))
     opt = torch_port.build_optimizer(model, "adam", 1e-3, 0.0)
     batches = [tuple(torch.from_numpy(np.ascontiguousarray(x)) for x in b) for b in w.batches]
     nb = len(batches)
-    # bounded sample: if the whole run would exceed `budget_s`, every step processes only the first
-    # `per_step` triples of its batch (same arithmetic, same metric)
-    per_step = w.batch
     t0 = time.perf_counter()
-    torch_port.train_steps(model, opt, [batches[0]])
+    torch_port.train_steps(model, opt, [batches[0]])          # first step: allocates the dense grads / Adam state
+    t_first = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    torch_port.train_steps(model, opt, [batches[1 % nb]])
     t1 = time.perf_counter() - t0
-    total_steps = max(warmup_steps - 1, 0) + train_steps
-    if t1 * total_steps > budget_s:
-        per_step = max(1024, int(w.batch * budget_s / (t1 * total_steps)))
-    cut = lambda b: tuple(x[:per_step] for x in b)  # noqa: E731
-    torch_port.train_steps(model, opt, [cut(batches[i % nb]) for i in range(1, warmup_steps)])
+    warm_left = max(warmup_steps - 2, 0)
+    steps = train_steps
+    if t1 * (warm_left + steps) > budget_s:
+        warm_left = min(warm_left, 1)
+        steps = max(3, min(train_steps, int(budget_s / t1) - warm_left))
+    torch_port.train_steps(model, opt, [batches[(2 + i) % nb] for i in range(warm_left)])
     t0 = time.perf_counter()
-    loss = torch_port.train_steps(model, opt, [cut(batches[(warmup_steps + i) % nb]) for i in range(train_steps)])
+    loss = torch_port.train_steps(model, opt, [batches[(2 + warm_left + i) % nb] for i in range(steps)])
     t_train = time.perf_counter() - t0
     ne = min(eval_users, len(w.uid_list))
     hist = (w.hist[0][:ne + 1], w.hist[1])
@@ -139,41 +149,63 @@ def cpu_reference(w, train_steps, warmup_steps, eval_users, threads, budget_s=12
     t0 = time.perf_counter()
     res, _ = torch_port.full_sort_eval(model, w.uid_list[:ne], hist, pos, w.n_items, topk=(10,))
     t_eval = time.perf_counter() - t0
-    return dict(train_samples_per_s=train_steps * per_step / t_train, train_s=t_train, train_steps=train_steps,
-                per_step=per_step,
+    return dict(train_samples_per_s=steps * w.batch / t_train, train_s=t_train, train_steps=steps,
+                warmup_steps=2 + warm_left, per_step=w.batch, first_step_s=t_first,
                 eval_users_per_s=ne / t_eval, eval_s=t_eval, eval_users=ne, loss=loss, result=res)
+
+
+def _host_workload(args):
+    import bench_workloads as bw
+    if args.workload == "cfg3":
+        return bw.Cfg3Host(batch=args.batch or (1 << 20), n_batches=4, eval_users=args.ref_eval_users, scale=args.scale)
+    return bw.BprWorkload(args.workload, batch=args.batch, n_batches=args.n_batches)
+
+
+def _ref_sample_text(r, w):
+    return ("%d warm-up + %d timed steps of %d triples each (full batches; torch CPU: dense grads + dense Adam over "
+            "the %d x %d and %d x %d tables%s); eval of %d users (%.0f users/s)" % (
+                r["warmup_steps"], r["train_steps"], r["per_step"], w.n_users, w.dim, w.n_items, w.dim,
+                "; throughput extrapolated from this bounded number of steps" if w.name == "cfg3" else "",
+                r["eval_users"], r["eval_users_per_s"]))
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    import bench_workloads as bw
-    w = bw.BprWorkload(args.workload, batch=args.batch, n_batches=args.n_batches)
+    w = _host_workload(args)
     threads = os.cpu_count() or 1
     r = cpu_reference(w, args.steps, args.warmup, args.ref_eval_users, threads)
-    sample = "%d warm-up + %d timed steps of %d triples each (of the %d-triple batch; torch CPU, dense grads + dense Adam); eval of the first %d test users" % (
-        args.warmup, args.steps, r["per_step"], w.batch, r["eval_users"])
     line = {
         "impl": "reference", "metric": "bpr_train_samples_per_s", "value": r["train_samples_per_s"], "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * r["train_s"] / args.steps, "higher_is_better": True, "scaling": "weak",
+        "n_gpus": args.gpus, "steps": r["train_steps"], "warmup": r["warmup_steps"],
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": 1e3 * r["train_s"] / r["train_steps"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": w.describe(),
         "cpu_baseline": {"value": r["train_samples_per_s"], "unit": "samples/s", "cores": threads, "kind": "port",
-                         "sample": sample},
+                         "sample": _ref_sample_text(r, w)},
         "e2e": {"value": r["train_samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "eval": {"metric": "fullsort_eval_users_per_s", "value": r["eval_users_per_s"], "unit": "users/s",
                  "users": r["eval_users"], "result": r["result"]},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line, default=float), flush=True)
+
+
+def cpu_baseline_leg(args):
+    """cpu_baseline of the GPU arm's line (rank 0, N = 1): a bounded sample of the same workload."""
+    w = _host_workload(args)
+    threads = os.cpu_count() or 1
+    cb = cpu_reference(w, args.cpu_steps, 2, args.ref_eval_users, threads, budget_s=60.0)
+    return {"value": cb["train_samples_per_s"], "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": _ref_sample_text(cb, w), "eval_users_per_s": cb["eval_users_per_s"]}
 
 
 # -------------------------------------------------------------------------------------------------
 # our arm
 # -------------------------------------------------------------------------------------------------
 
-def run_ours(args, rank, world, local_rank):
+def run_ours(args, rank, world, local_rank, emit=True):
     import torch
     import torch.distributed as dist
 
@@ -183,7 +215,17 @@ def run_ours(args, rank, world, local_rank):
     from recbole_b200.evaluator import FusedTopKEvaluator
 
     if world > 1 or args.workload == "cfg3":
-        return run_ours_multi(args, rank, world, local_rank)
+        line = run_ours_multi(args, rank, world, local_rank)
+        if line is not None:
+            if world == 1 and args.workload == "cfg3" and not args.no_extra:
+                # configs[1] (the synthetic ml-20m shape) beside the headline, same process, same GPU
+                import copy
+                a2 = copy.copy(args)
+                a2.workload, a2.batch, a2.eval_reps = "cfg2", None, 3
+                torch.cuda.empty_cache()
+                line["extra"] = {"cfg2": run_ours(a2, rank, world, local_rank, emit=False)}
+            print(json.dumps(line, default=float), flush=True)
+        return line
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -315,10 +357,10 @@ def run_ours(args, rank, world, local_rank):
     alg_user = B * (32 * d + 24)                      # the share k_user_side must move
     step_kernels_ms = sum(v[0] for v in stages.values()) / args.steps
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(tp) and args.workload == "cfg2" and B == (1 << 20):
-        traffic = json.load(open(tp)).get("k_user_side@cfg2")     # bytes per launch, from the committed ncu capture
-    roofline = {"bound": "hbm", "kernel": "k_user_side", "achieved": alg_user / (us_ms * 1e-3) / 1e9 if us_ms else None,
+        traffic = json.load(open(tp)).get("k_user_fused@cfg2")    # bytes per launch, from the committed ncu capture
+    roofline = {"bound": "hbm", "kernel": "k_user_fused", "achieved": alg_user / (us_ms * 1e-3) / 1e9 if us_ms else None,
                 "peak": peaks["hbm"], "unit": "GB/s", "frac": None, "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg_user,
                 "peak_source": peaks["source"], "ms_per_launch": us_ms,
@@ -343,13 +385,11 @@ def run_ours(args, rank, world, local_rank):
     # ---- CPU baseline (bounded sample, rank 0) ------------------------------------------------------------
     threads = os.cpu_count() or 1
     if args.skip_cpu:
-        cb = dict(train_samples_per_s=None, eval_users=0, eval_users_per_s=0.0)
+        cpu_baseline = None
     else:
-        cb = cpu_reference(w, args.cpu_steps, 1, args.ref_eval_users, threads)
-    cpu_baseline = {"value": cb["train_samples_per_s"], "unit": "samples/s", "cores": threads, "kind": "port",
-                    "sample": "1 warm-up + %d timed steps of %d triples; eval of the first %d test users (%.0f users/s)"
-                              % (args.cpu_steps, B, cb["eval_users"], cb["eval_users_per_s"]),
-                    "eval_users_per_s": cb["eval_users_per_s"]}
+        cb = cpu_reference(w, args.cpu_steps, 2, args.ref_eval_users, threads, budget_s=60.0)
+        cpu_baseline = {"value": cb["train_samples_per_s"], "unit": "samples/s", "cores": threads, "kind": "port",
+                        "sample": _ref_sample_text(cb, w), "eval_users_per_s": cb["eval_users_per_s"]}
 
     line = {
         "metric": "bpr_train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": 1, "steps": args.steps,
@@ -372,12 +412,14 @@ def run_ours(args, rank, world, local_rank):
                  "tc_fallback_rows": int(_lib.rb2_fullsort_tc_last_fallback_rows()) if args.scorer == "tc" else None},
     }
     assert res2 == result
-    print(json.dumps(line), flush=True)
+    if emit:
+        print(json.dumps(line, default=float), flush=True)
+    return line
 
 
 def run_ours_multi(args, rank, world, local_rank):
-    from recbole_b200 import dist_bench
-    dist_bench.run(args, rank, world, local_rank, load_peaks, ClockSampler)
+    import bench_cfg3
+    return bench_cfg3.run(args, rank, world, local_rank, load_peaks, ClockSampler, cpu_reference=cpu_baseline_leg)
 
 
 def main():
@@ -386,20 +428,26 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--workload", default="cfg3")
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--n-batches", type=int, default=8, dest="n_batches")
     ap.add_argument("--scorer", default="tc", choices=["fp32", "tc"])
-    ap.add_argument("--eval-reps", type=int, default=3, dest="eval_reps")
-    ap.add_argument("--cpu-steps", type=int, default=4, dest="cpu_steps")
-    ap.add_argument("--ref-eval-users", type=int, default=4096, dest="ref_eval_users")
+    ap.add_argument("--eval-reps", type=int, default=None, dest="eval_reps")
+    ap.add_argument("--cpu-steps", type=int, default=3, dest="cpu_steps")
+    ap.add_argument("--ref-eval-users", type=int, default=None, dest="ref_eval_users")
     ap.add_argument("--eval-layout", default="auto", choices=["auto", "replicate", "sharded"], dest="eval_layout")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "dense", "sparse"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "dense", "sparse", "p2p"])
+    ap.add_argument("--no-extra", action="store_true", dest="no_extra", help="N=1: skip the cfg2 measurement")
+    ap.add_argument("--skip-parity", action="store_true", dest="skip_parity", help="profiling runs only")
     ap.add_argument("--scale", type=float, default=1.0, help="cfg3 only: shrink users/items by this factor")
     ap.add_argument("--skip-cpu", action="store_true", dest="skip_cpu", help="profiling runs only")
     ap.add_argument("--tc-kprime", type=int, default=0, dest="tc_kprime", choices=[0, 16, 32],
                     help="candidates per list of the tensor-core scorer (0 = automatic)")
     args = ap.parse_args()
+    if args.eval_reps is None:
+        args.eval_reps = 1 if args.workload == "cfg3" else 3     # one cfg3 pass is 5 PFLOP: seconds on one GPU
+    if args.ref_eval_users is None:
+        args.ref_eval_users = 512 if args.workload == "cfg3" else 4096
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.workload == "cfg5" and world > 1 and args.impl != "reference":
         import bench_extra

@@ -188,3 +188,35 @@ class Cfg3Device:
     def describe(self):
         return dict(workload="cfg3", desc=self.desc, n_users=self.n_users, n_items=self.n_items, dim=self.dim,
                     interactions=int((self.n_users - 1) * self.per_user), train_batch=self.batch, topk=10)
+
+
+class Cfg3Host:
+    """The cfg3 shape on the HOST for the reference's CPU arm (`cpu_baseline`, `--impl reference`): the same
+    distributions as Cfg3Device (users uniform, positives Zipf(1) with the popularity order decoupled from the id
+    by a multiplicative hash, uniform negatives), numpy with a fixed seed.  Evaluation data for a bounded sample of
+    users: `per_user` history items and `n_test` positives each."""
+
+    def __init__(self, n_users=10_000_001, n_items=2_000_001, dim=128, batch=1 << 20, n_batches=4, per_user=64,
+                 n_test=8, eval_users=1024, seed=2020, scale=1.0):
+        self.name = "cfg3"
+        self.n_users, self.n_items, self.dim, self.batch = int(n_users * scale) | 1, int(n_items * scale) | 1, dim, batch
+        rng = np.random.default_rng(seed)
+
+        def zipf_items(shape):
+            r = np.exp(rng.random(shape) * np.log(self.n_items - 1)).astype(np.int64).clip(1, self.n_items - 1)
+            return (r * 2654435761 % (self.n_items - 1)) + 1
+
+        self.batches = [(rng.integers(1, self.n_users, batch), zipf_items(batch), rng.integers(1, self.n_items, batch))
+                        for _ in range(n_batches)]
+        self.uid_list = np.sort(rng.choice(np.arange(1, self.n_users), eval_users, replace=False))
+        hist = np.sort(zipf_items((eval_users, per_user)), axis=1)
+        test = np.sort(zipf_items((eval_users, n_test)), axis=1)
+        # CSR rows must hold unique ids (a set in the reference)
+        self.hist = csr_from_pairs(eval_users, np.repeat(np.arange(eval_users), per_user), hist.reshape(-1), self.n_items)
+        self.pos = csr_from_pairs(eval_users, np.repeat(np.arange(eval_users), n_test), test.reshape(-1), self.n_items)
+        self.per_user, self.n_test = per_user, n_test
+
+    def describe(self):
+        return dict(workload="cfg3", desc="BPR-MF synthetic 10M users x 2M items x d=128 (device-generated, %d train "
+                    "items/user)" % self.per_user, n_users=self.n_users, n_items=self.n_items, dim=self.dim,
+                    interactions=int((self.n_users - 1) * self.per_user), train_batch=self.batch, topk=10)

@@ -436,6 +436,17 @@ int launch_user_fused(const Tables &t, const BprWs &w, int64_t B, int Tu, int64_
   return 0;
 }
 
+template <int D, bool ADAM, bool P2P>
+int launch_item_fused(const Tables &t, const BprWs &w, const PeerTable &pt, int64_t n_occ, int Ti, int64_t nti,
+                      const OptScalars &o, cudaStream_t st) {
+  using C = ItemCfg<D, ADAM, P2P>;
+  int rc = allow_smem(k_item_fused<D, ADAM, P2P>, C::kSmem);
+  if (rc) return rc;
+  k_item_fused<D, ADAM, P2P><<<(unsigned)((nti + C::GPB - 1) / C::GPB), kThreads, C::kSmem, st>>>(t, w, pt, n_occ, Ti,
+                                                                                                   nti, o);
+  return 0;
+}
+
 // the row-sparse Adam / SGD step, single GPU (train_bpr_fused.cuh)
 template <int D>
 int launch_step_fused(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, const OptScalars &o,
@@ -475,7 +486,9 @@ int launch_step_fused(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_i
   }
   {
     ProfScope prof(RB2_ST_ITEM_SIDE, st);
-    k_item_fused<D, false><<<blocks(nti), kThreads, 0, st>>>(t, w, none, 2 * B, Ti, nti, o);
+    int rc = (o.kind == RB2_OPT_SGD) ? launch_item_fused<D, false, false>(t, w, none, 2 * B, Ti, nti, o, st)
+                                     : launch_item_fused<D, true, false>(t, w, none, 2 * B, Ti, nti, o, st);
+    if (rc) return rc;
   }
   {
     ProfScope prof(RB2_ST_ITEM_FIXUP, st, 2);
@@ -1072,7 +1085,8 @@ extern "C" int rb2_bpr_train_step_p2p(float *user_p, float *user_m, float *user_
     }
     {
       ProfScope prof(RB2_ST_ITEM_SIDE, st);
-      k_item_fused<D_, true><<<blocks(nti), kThreads, 0, st>>>(t, w, pt, 2 * B, Ti, nti, o);
+      int rc = launch_item_fused<D_, false, true>(t, w, pt, 2 * B, Ti, nti, o, st);
+      if (rc) return rc;
     }
     {
       ProfScope prof(RB2_ST_ITEM_FIXUP, st, 2);

@@ -315,41 +315,107 @@ __global__ void __launch_bounds__(kThreads, 2) k_user_fused(Tables t, BprWs w, i
   }
 }
 
-// item side: the walk of k_item_side over the occurrences that are NOT single.  A finished run is stepped in
-// place (single GPU) or written into the owner's gradient slot (peer-memory step).
-template <int D, bool P2P>
-__global__ void __launch_bounds__(kThreads) k_item_fused(Tables t, BprWs w, PeerTable pt, int64_t n_occ, int T,
-                                                          int64_t n_tiles, OptScalars o) {
-  constexpr int LANES = RowCfg<D>::LANES;
-  constexpr int UNR = 4;
-  const int lane = threadIdx.x % LANES;
-  const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+// item side: the walk of k_item_side over the occurrences that are NOT single, with the same staging as the user
+// side: the gradient row gu[s] of every occurrence, and (single GPU) the row's (p, m, v) at the start of a run,
+// arrive through the bulk-copy engine; the loop body exists once (one optimizer-step site: small code).
+// A finished run is stepped in place (single GPU) or written into the owner's gradient slot (peer-memory step).
+template <int D, bool ADAM, bool P2P>
+struct ItemCfg {
+  static constexpr int LANES = RowCfg<D>::LANES;
+  static constexpr int GPB = kThreads / LANES;
+  static constexpr int ROWS = P2P ? 1 : (ADAM ? 4 : 2);        // gu | p | m v
+  static constexpr int S = 4;
+  static constexpr size_t kStageBytes = (size_t)GPB * S * ROWS * D * sizeof(float);
+  static constexpr size_t kIdBytes = (size_t)GPB * (kTileMax + 2) * sizeof(uint2);
+  static constexpr size_t kListBytes = (size_t)GPB * kTileMax;
+  static constexpr size_t kSmem = kStageBytes + kIdBytes + kListBytes + (size_t)GPB * S * sizeof(uint64_t);
+};
+enum { I_G = 0, I_P = 1, I_M = 2, I_V = 3 };
+
+template <int D, bool ADAM, bool P2P>
+__global__ void __launch_bounds__(kThreads, 2) k_item_fused(Tables t, BprWs w, PeerTable pt, int64_t n_occ, int T,
+                                                             int64_t n_tiles, OptScalars o) {
+  using C = ItemCfg<D, ADAM, P2P>;
+  constexpr int LANES = C::LANES, S = C::S, ROWS = C::ROWS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x % LANES, gib = threadIdx.x / LANES;
+  const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x % 32) / LANES * LANES));
+  const int64_t tile = (int64_t)blockIdx.x * C::GPB + gib;
   if (tile >= n_tiles) return;
+  float *stage = reinterpret_cast<float *>(smem_raw) + (size_t)gib * S * ROWS * D;
+  // (key, value) of the tile's occurrences, of the one before it [0] and of the one after it [n + 1]
+  uint2 *kv = reinterpret_cast<uint2 *>(smem_raw + C::kStageBytes) + (size_t)gib * (kTileMax + 2);
+  uint8_t *list = smem_raw + C::kStageBytes + C::kIdBytes + (size_t)gib * kTileMax;   // tile positions that are not single
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + C::kStageBytes + C::kIdBytes + C::kListBytes) + gib * S;
+
   const int64_t lo = tile * T, hi = min(lo + (int64_t)T, n_occ);
-  const uint32_t *__restrict__ keys = w.ikey_s;
-  const uint32_t *__restrict__ vals = w.ival_s;
+  const int n = (int)(hi - lo);
   const uint32_t kInvalid = 0xffffffffu;
-  const uint32_t prev_key = lo > 0 ? keys[lo - 1] : kInvalid;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) rb2_mbar_init(&bars[s], 1);
+    rb2_mbar_init_fence();
+  }
+  for (int j = lane; j < n + 2; j += LANES) {
+    const int64_t p = lo - 1 + j;
+    kv[j] = (p >= 0 && p < n_occ) ? make_uint2(w.ikey_s[p], w.ival_s[p]) : make_uint2(kInvalid, 0u);
+  }
+  __syncwarp(gmask);
+  // compact the non-single positions (order kept): every lane flags its positions, a ballot ranks them
+  int m = 0;
+  for (int j0 = 0; j0 < n; j0 += LANES) {
+    const int j = j0 + lane;
+    const bool keep = j < n && !(kv[j + 1].x != kv[j].x && kv[j + 1].x != kv[j + 2].x);
+    const unsigned bal = __ballot_sync(gmask, keep) & gmask;
+    if (keep) list[m + __popc(bal & ((1u << (threadIdx.x % 32)) - 1u))] = (uint8_t)j;
+    m += __popc(bal);
+  }
+  __syncwarp(gmask);
+  const uint32_t prev_key = kv[0].x, next_key = kv[n + 1].x;
+
+  auto issue = [&](int q) {
+    const int j = list[q];
+    const uint2 e = kv[j + 1];
+    float *sp = stage + (size_t)(q % S) * ROWS * D;
+    uint64_t *bar = &bars[q % S];
+    // the row itself is wanted where a run starts INSIDE this tile (a run that began earlier only adds a partial)
+    const bool need_p = !P2P && e.x != kv[j].x;
+    const int rows = 1 + (need_p ? ROWS - 1 : 0);
+    if (lane == 0) rb2_mbar_expect_tx(bar, (uint32_t)(rows * D * sizeof(float)));
+    for (int r = lane; r < ROWS; r += LANES) {
+      const float *src = nullptr;
+      switch (r) {
+        case I_G: src = w.gu + (int64_t)(e.y >> 1) * D; break;
+        case I_P: if (need_p) src = t.ip + (int64_t)e.x * D; break;
+        case I_M: if (need_p) src = t.im + (int64_t)e.x * D; break;
+        case I_V: if (need_p) src = t.iv + (int64_t)e.x * D; break;
+      }
+      if (src) rb2_bulk_g2s(sp + r * D, src, (uint32_t)(D * sizeof(float)), bar);
+    }
+  };
+  for (int q = 0; q < S && q < m; ++q) issue(q);
 
   uint32_t cur = kInvalid;
   bool started_before = false;
-  Row<D> acc = row_zero<D>();
+  Row<D> acc = row_zero<D>(), p = row_zero<D>(), mm = row_zero<D>(), vv = row_zero<D>();
   uint8_t fh = 0, ft = 0;
 
-  auto emit = [&](uint32_t key, const Row<D> &g) {
-    if (P2P) {
-      const int owner = (int)(key / pt.i_block);
-      const int64_t slot_row = (int64_t)pt.me * pt.i_block + ((int64_t)key - (int64_t)owner * pt.i_block);
-      row_st_ptr<D>(pt.G[owner] + slot_row * D, lane, g);
-      if (lane == 0) pt.stamp[owner][slot_row] = pt.step;
-    } else {
-      row_update_full<D, false>(t.ip, t.im, t.iv, nullptr, key, lane, g, o);
-    }
-  };
   auto finish_run = [&](bool continues) {
     if (cur == kInvalid) return;
     if (!started_before && !continues) {
-      emit(cur, acc);
+      if (P2P) {
+        const int owner = (int)(cur / pt.i_block);
+        const int64_t slot_row = (int64_t)pt.me * pt.i_block + ((int64_t)cur - (int64_t)owner * pt.i_block);
+        row_st_ptr<D>(pt.G[owner] + slot_row * D, lane, acc);
+        if (lane == 0) pt.stamp[owner][slot_row] = pt.step;
+      } else {
+        row_step_regs<D>(p, mm, vv, acc, o);
+        row_st<D>(t.ip, cur, lane, p);
+        if (ADAM) {
+          row_st<D>(t.im, cur, lane, mm);
+          row_st<D>(t.iv, cur, lane, vv);
+        }
+      }
     } else if (started_before) {
       row_st<D>(w.i_head, tile, lane, acc);
       fh = continues ? 2 : 1;
@@ -359,42 +425,31 @@ __global__ void __launch_bounds__(kThreads) k_item_fused(Tables t, BprWs w, Peer
     }
   };
 
-  uint32_t before = prev_key;                       // key of the occurrence just before `base`
-  for (int64_t base = lo; base < hi; base += UNR) {
-    uint32_t k[UNR + 1], s[UNR];                    // k[UNR] = look-ahead (possibly the next tile's first key)
-    Row<D> c[UNR];
-    bool single[UNR];
-#pragma unroll
-    for (int j = 0; j <= UNR; ++j) {
-      const int64_t p = base + j;
-      k[j] = (p < n_occ) ? keys[p] : kInvalid;
-      if (j < UNR) s[j] = (p < hi) ? vals[p] : 0u;
-    }
-#pragma unroll
-    for (int j = 0; j < UNR; ++j) {
-      const uint32_t kb = (j == 0) ? before : k[j - 1];
-      single[j] = (k[j] != kb) && (k[j] != k[j + 1]);
-      if (base + j < hi && !single[j]) c[j] = row_ld<D>(w.gu, s[j] >> 1, lane);
-    }
-#pragma unroll
-    for (int j = 0; j < UNR; ++j) {
-      if (base + j >= hi) break;
-      if (single[j]) {          // finished by the user side
-        finish_run(false);
-        cur = kInvalid;
-        continue;
+#pragma unroll 1
+  for (int q = 0; q < m; ++q) {
+    const float *sp = stage + (size_t)(q % S) * ROWS * D;
+    rb2_mbar_wait(&bars[q % S], (uint32_t)((q / S) & 1));
+    const int j = list[q];
+    const uint2 e = kv[j + 1];
+    if (e.x != cur) {
+      finish_run(false);
+      cur = e.x;
+      started_before = (cur == kv[j].x);          // only possible at j == 0: the run began in an earlier tile
+      if (!P2P && !started_before) {
+        p = row_lds<D>(sp + I_P * D, lane);
+        if (ADAM) {
+          mm = row_lds<D>(sp + I_M * D, lane);
+          vv = row_lds<D>(sp + I_V * D, lane);
+        }
       }
-      if (k[j] != cur) {
-        finish_run(false);
-        cur = k[j];
-        acc = row_zero<D>();
-        started_before = (base + j == lo) && (cur == prev_key);
-      }
-      row_fma<D>(acc, (s[j] & 1u) ? -1.f : 1.f, c[j]);
+      acc = row_zero<D>();
     }
-    before = k[UNR - 1];
+    const Row<D> g = row_lds<D>(sp + I_G * D, lane);
+    row_fma<D>(acc, (e.y & 1u) ? -1.f : 1.f, g);
+    __syncwarp(gmask);
+    if (q + S < m) issue(q + S);
   }
-  finish_run(hi < n_occ && keys[hi] == cur);
+  finish_run(next_key == cur);
   if (lane == 0) {
     w.i_fh[tile] = fh;
     w.i_ft[tile] = ft;

@@ -194,7 +194,7 @@ class ShardedBPR:
         #        (rb2_bpr_train_step_p2p); the item shard lives in an arena every rank maps with cudaIpc.
         self.arena = None
         if exchange == "p2p" or (exchange == "auto" and device.type == "cuda" and not comm.staged
-                                 and n_items * dim * 4 > (64 << 20) and comm.world <= 8):
+                                 and n_items * dim * 4 > (64 << 20) and 1 < comm.world <= 8):
             exchange = "p2p"
             self.arena = ops.PeerArena(comm, device, self.i_block, dim)
             self.V = self.arena.item_p
@@ -293,10 +293,7 @@ class ShardedBPR:
         return torch.cat([full[r * block: r * block + int(bounds[r + 1] - bounds[r])] for r in range(world)])
 
     def _workspace(self, batch):
-        key = int(batch)
-        if key not in self._ws:
-            self._ws = {key: self.ops.bpr_workspace(batch, self.dim, self.device)}
-        return self._ws[key]
+        return self.ops.grow_workspace(self._ws, batch, lambda b: self.ops.bpr_workspace(b, self.dim, self.device))
 
     def plan(self, user, pos, neg, ids_ready=False):
         """Everything of a sparse-exchange step that depends only on the batch IDS (not on the
@@ -350,6 +347,12 @@ class ShardedBPR:
             global_batch = B * comm.world
         self.optim.step += 1
         t = self.optim.step
+        if comm.world == 1 and self.exchange != "p2p":
+            # nothing to exchange: the single-GPU fused step on the whole tables
+            self.last_exchange = "local"
+            ops.bpr_train_step(self.U, self.V, self.state, user, pos, neg, self.optim, self.loss_out, self.loss_accum,
+                               self._workspace(B), step=t)
+            return self.loss_out
         if self.exchange == "p2p":
             self.last_exchange = "p2p"
             if self._p2p_ws is None or self._p2p_ws[0] < B:

@@ -67,7 +67,7 @@ class FusedBPR(nn.Module):
         self.item_embedding = nn.Embedding(self.n_items, self.embedding_size)
         xavier_normal_(self.user_embedding.weight.data)
         xavier_normal_(self.item_embedding.weight.data)
-        self._ws = {}
+        self._ws, self._ws_dev = {}, None
         self._pending = None
         self._optim = None      # ops.Optim
         self._opt_state = None  # dict of moment tensors
@@ -77,10 +77,9 @@ class FusedBPR(nn.Module):
     # ---- plumbing -----------------------------------------------------------------------------
     def _workspace(self, batch):
         dev = self.user_embedding.weight.device
-        key = (int(batch), str(dev))
-        if key not in self._ws:
-            self._ws = {key: ops.bpr_workspace(batch, self.embedding_size, dev)}
-        return self._ws[key]
+        if self._ws_dev != str(dev):
+            self._ws, self._ws_dev = {}, str(dev)
+        return ops.grow_workspace(self._ws, batch, lambda b: ops.bpr_workspace(b, self.embedding_size, dev))
 
     def build_optimizer(self, learner="adam", learning_rate=1e-3, weight_decay=0.0):
         """Trainer._build_optimizer (trainer.py:109-130) for the fused path.  ``learner``:

@@ -76,10 +76,10 @@ class FusedFM(nn.Module):
 
     def _workspace(self, batch):
         dev = self.token_embedding_table.embedding.weight.device
-        key = (int(batch), str(dev))
-        if key not in self._ws:
-            self._ws = {key: ops.fm_workspace(batch, self.num_feature_field, self.embedding_size, dev)}
-        return self._ws[key]
+        if getattr(self, "_ws_dev", None) != str(dev):
+            self._ws, self._ws_dev = {}, str(dev)
+        return ops.grow_workspace(self._ws, batch,
+                                  lambda b: ops.fm_workspace(b, self.num_feature_field, self.embedding_size, dev))
 
     def _ensure_device_state(self):
         dev = self.token_embedding_table.embedding.weight.device
@@ -175,10 +175,7 @@ class FusedMFSimple(nn.Module):
         self._bias3[0:1].copy_(self.bias.data)
 
     def _workspace(self, batch):
-        key = int(batch)
-        if key not in self._ws:
-            self._ws = {key: ops.fm_workspace(batch, 2, self.embedding_dim, self.table.device)}
-        return self._ws[key]
+        return ops.grow_workspace(self._ws, batch, lambda b: ops.fm_workspace(b, 2, self.embedding_dim, self.table.device))
 
     def build_optimizer(self, learner="adam", learning_rate=1e-3, weight_decay=0.0):
         self._optim = ops.Optim(learner.lower(), learning_rate, weight_decay)

@@ -55,6 +55,20 @@ class Workspace:
                              "(the reference raises IndexError in F.embedding)")
 
 
+def grow_workspace(cache, batch, make):
+    """`cache` is a one-entry dict {capacity: Workspace}.  Returns a workspace that holds at least `batch`
+    samples, keeping the largest one ever made (the C ABI only needs workspace_bytes >= need, so the short tail
+    batch of an epoch reuses the full-batch buffer and its sticky error flags survive until they are checked)."""
+    for cap, ws in cache.items():
+        if cap >= batch:
+            return ws
+    for ws in cache.values():
+        ws.check_flags()            # about to be dropped: do not lose a recorded error
+    cache.clear()
+    cache[int(batch)] = make(int(batch))
+    return cache[int(batch)]
+
+
 class Optim:
     """Optimizer hyper-parameters + step counter (replaces the torch.optim object of
     recbole/trainer/trainer.py:109-130).  Scalars are derived in Python doubles exactly as
@@ -108,11 +122,14 @@ def bpr_workspace(batch, dim, device):
     return Workspace(lib.rb2_bpr_workspace_bytes(int(batch), int(dim)), device)
 
 
-def bpr_train_step(U, V, state, user, pos, neg, optim, loss_out, loss_accum, ws):
+def bpr_train_step(U, V, state, user, pos, neg, optim, loss_out, loss_accum, ws, step=None):
     """One fused step (include/recbole_b200.h: rb2_bpr_train_step).  `state` holds mU, vU, mV, vV
-    (and lastU, lastV for adam_lazy).  optim.step is incremented here (t starts at 1)."""
-    optim.step += 1
-    o = optim.c_struct(U.device)
+    (and lastU, lastV for adam_lazy).  optim.step is incremented here (t starts at 1) unless the
+    caller passes the step it has already counted."""
+    if step is None:
+        optim.step += 1
+        step = optim.step
+    o = optim.c_struct(U.device, step)
     f32, i64 = torch.float32, torch.int64
     check(lib.rb2_bpr_train_step(
         _ptr(U, f32), _ptr(state.get("mU"), f32, True), _ptr(state.get("vU"), f32, True),
