@@ -117,7 +117,11 @@ def run(args, rank, world, local_rank, load_peaks, ClockSampler, cpu_reference=N
     comm = Comm()
     peaks = load_peaks()
     big = args.workload == "cfg3"
-    parity = None if args.skip_parity else parity_check(comm, dev, args.exchange)
+    # the parity problem goes through the exchange the TIMED model will use (a small table would pick "dense")
+    shape = (2000001, 128) if big else {"cfg2": (26745, 64)}.get(args.workload, (26745, 64))
+    n_it = int(shape[0] * (args.scale if big else 1.0))
+    timed_exchange = ShardedBPR.resolve_exchange(args.exchange, n_it, shape[1], comm, dev) if world > 1 else args.exchange
+    parity = None if args.skip_parity else parity_check(comm, dev, timed_exchange)
     if big:
         w = bw.Cfg3Device(rank, world, dev, batch=args.batch or (1 << 20), n_batches=args.n_batches,
                           scale=args.scale)
@@ -274,17 +278,24 @@ def run(args, rank, world, local_rank, load_peaks, ClockSampler, cpu_reference=N
     alg_step = GB * (72 * d + 24)
     # the user-side kernel's share of the algorithmic bytes: user row read + step (24 d), two item rows gathered
     # (8 d), ids (24), and the whole step (m, v read; p, m, v written: 20 d) of every single-occurrence item
-    alg_user = B * (32 * d + 24) + single_occ * 20 * d
+    exch = getattr(model, "last_exchange", model.exchange)
+    if exch == "local":
+        alg_user = B * (32 * d + 24) + single_occ * 20 * d
+    else:
+        # sharded step: the kernel steps the user row and gathers two item rows; the gradient rows it writes (into
+        # the owners' slots over NVLink or into gu) are traffic of the exchange and NOT counted as algorithmic
+        alg_user = B * (32 * d + 24)
     kernel = "k_user_fused"
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": alg_user / (us_ms * 1e-3) / 1e9 if us_ms else None,
-                "peak": peaks["hbm"], "unit": "GB/s", "frac": None, "traffic": _traffic(kernel, args.workload),
+                "peak": peaks["hbm"], "unit": "GB/s", "frac": None,
+                "traffic": _traffic(kernel, args.workload) if exch == "local" else None,
                 "algorithmic_bytes_per_launch": alg_user, "single_item_occurrences_per_batch": single_occ,
                 "peak_source": peaks["source"], "ms_per_launch": us_ms,
                 "share_of_step": us_ms / (sum(v[0] for v in stages.values()) / args.steps) if us_ms else None,
                 "step": {"achieved_all_gpus": alg_step / (train_ms * 1e-3) / 1e9,
                          "frac_of_n_gpu_peak": alg_step / (train_ms * 1e-3) / 1e9 / (peaks["hbm"] * world),
                          "bytes_per_sample": 72 * d + 24,
-                         "traffic_per_step": _traffic("step", args.workload)},
+                         "traffic_per_step": _traffic("step", args.workload) if exch == "local" else None},
                 "exchange_phases_ms_rank0": phases,
                 "stages_ms_per_step_rank0": {k: v[0] / args.steps for k, v in stages.items()}}
     if roofline["achieved"]:
@@ -298,7 +309,6 @@ def run(args, rank, world, local_rank, load_peaks, ClockSampler, cpu_reference=N
                  "whole_eval_frac_of_n_gpu_peak": 2.0 * nq * w.n_items * d / (eval_ms * 1e-3) / 1e12 / (peaks["tf"] * world),
                  "traffic": None, "ms_in_kernel_rank0": fs_ms,
                  "stages_ms_rank0": {k: v[0] / max(args.eval_reps, 1) for k, v in estages.items()}}
-    exch = getattr(model, "last_exchange", model.exchange)
     how = {"local": "single GPU: fused step on the whole tables",
            "p2p": "users range-partitioned, item table row-sharded x%d; rows read from / gradients pushed into the "
                   "owners' memory by the kernels over NVLink (cudaIpc peer mappings, flag barriers; no NCCL in the "

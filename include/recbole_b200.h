@@ -56,7 +56,7 @@ enum {
   RB2_ST_ITEM_SIDE = 5, RB2_ST_ITEM_FIXUP = 6, RB2_ST_LOSS = 7, RB2_ST_FULLSORT = 8, RB2_ST_TOPK_MERGE = 9,
   RB2_ST_METRICS = 10, RB2_ST_SAMPLER = 11, RB2_ST_GATHER_DOT = 12, RB2_ST_TC_CONVERT = 13, RB2_ST_TC_SCORE = 14,
   RB2_ST_TC_REFINE = 15, RB2_ST_FM_FWD = 16, RB2_ST_FM_UPDATE = 17, RB2_ST_MISC = 18, RB2_ST_PLAN = 19,
-  RB2_ST_BARRIER = 20, RB2_ST_OWNER = 21, RB2_NUM_STAGES = 22
+  RB2_ST_BARRIER = 20, RB2_ST_OWNER = 21, RB2_ST_FETCH = 22, RB2_ST_BARRIER_B = 23, RB2_NUM_STAGES = 24
 };
 int rb2_profile_enable(int on);
 int rb2_profile_read(float *h_ms /* [RB2_NUM_STAGES] */, int64_t *h_calls /* [RB2_NUM_STAGES] */,
@@ -180,7 +180,7 @@ int rb2_bpr_loss(const float *user_p, const float *item_p, int64_t n_users, int6
  * rows and write the owners' gradient slots themselves (BASELINE north_star "row-sharded
  * across the 8 GPUs ... exchanges rows and gradients ... over NVLink").  No NCCL call and no host
  * synchronisation inside a step:
- *   keys, two sorts (local) -> flag barrier A -> per occurrence source / destination (an item that
+ *   keys, two sorts (local) -> flag barrier A (wait half) -> per occurrence source / destination (an item that
  *   occurs ONCE in this rank's batch is read from its owner directly and its gradient is pushed
  *   straight into the owner's slot by the user-side kernel; an item that occurs several times is
  *   fetched once into item_cache and its summed gradient is pushed by the item-side walk) ->
@@ -195,8 +195,10 @@ int rb2_bpr_loss(const float *user_p, const float *item_p, int64_t n_users, int6
  *   stamps[r]      int32 [world, item_block]          zero-initialised; == step where the slot row is valid
  *   flags[r]       uint32 [2, RB2_MAX_PEERS]          zero-initialised barrier flags
  *   loss_slots[r]  fp64 [2, RB2_MAX_PEERS]
- * Every rank must call rb2_bpr_train_step_p2p the same number of times with h_opt->step = 1, 2, 3, ...
- * (it is the barrier sequence number).  user holds global user ids, all inside THIS rank's block
+ * Every rank must call rb2_bpr_train_step_p2p the same number of times with h_peers->seq = 1, 2, 3, ...
+ * (the barrier sequence number; independent of h_opt->step, which a resumed run restores from its checkpoint).
+ * The "owner update done" half of barrier A of call seq + 1 is signalled at the END of call seq, so a rank's keys
+ * and sorts never hold its peers up.  user holds global user ids, all inside THIS rank's block
  * [user_base, user_base + n_users_local) of the user table; pos / neg are global item ids.  item_m / item_v: Adam moments of the local shard.
  * item_cache: fp32 [world * item_block, dim] scratch.  A barrier that waits longer than 30 s gives up
  * and sets the workspace's peer_timeout flag (second int32 of the workspace) instead of hanging.
@@ -210,6 +212,8 @@ typedef struct rb2_peers {
   int32_t *stamps[RB2_MAX_PEERS];
   uint32_t *flags[RB2_MAX_PEERS];
   double *loss_slots[RB2_MAX_PEERS];
+  int64_t seq;   /* call number on THESE buffers: 1 for the first step after they were zero-initialised, then
+                    2, 3, ... (identical on every rank); it is the barrier sequence and the slot stamp */
 } rb2_peers;
 
 size_t rb2_bpr_p2p_workspace_bytes(int64_t batch, int32_t dim);
@@ -257,6 +261,11 @@ int rb2_fm_train_step(float *E, float *mE, float *vE, float *W, float *mW, float
 int rb2_fm_predict(const float *E, const float *W, const float *bias3, int64_t n_rows, int32_t dim,
                    const int64_t *ids, const int64_t *offsets, int32_t n_fields, int64_t batch, float *y_out,
                    void *workspace, size_t workspace_bytes, void *stream);
+/* forward + mean nn.BCELoss only (FM.calculate_loss fm.py:52-56 / MFSimple.calculate_loss mfsimple.py:48-57 as a
+ * VALUE: what an unmodified Trainer reads with loss.item(), trainer.py:168); nothing is kept for a backward. */
+int rb2_fm_loss(const float *E, const float *W, const float *bias3, int64_t n_rows, int32_t dim,
+                const int64_t *ids, const int64_t *offsets, int32_t n_fields, const float *label, int64_t batch,
+                float *loss_out, void *workspace, size_t workspace_bytes, void *stream);
 
 /* Row-sharded FM (one 33M-row table sharded over the GPUs, batch split by rows; no reference
  * counterpart).  rb2_fm_grad_step is the local part of a step: rows_e [n_rows, dim] / rows_w [n_rows] are the
@@ -301,6 +310,13 @@ int rb2_gather_dot(const float *user_p, const float *item_p, int64_t n_users, in
 enum { RB2_SCORER_FP32 = 0, RB2_SCORER_TC = 1 };
 
 size_t rb2_fullsort_workspace_bytes(int64_t nq, int64_t n_items_local, int32_t dim, int32_t k, int32_t mode);
+
+/* Compatibility path: the score matrix itself, out_scores fp32 [nq, n_items] = BPR.full_sort_predict (bpr.py:91-96)
+ * for an UNMODIFIED reference Trainer._full_sort_batch_eval (trainer.py:328-352), which masks and top-k's it with
+ * ATen, 1-2 users per call (general_dataloader.py:330-334).  Every score is the canonical fp32 chain of the top-K
+ * kernels.  query_ids may be NULL (row r of query_p); ids outside [0, n_query_rows) are clamped. */
+int rb2_fullsort_scores(const float *query_p, const int64_t *query_ids, int64_t nq, int64_t n_query_rows,
+                        const float *item_p, int64_t n_items, int32_t dim, float *out_scores, void *stream);
 
 int rb2_fullsort_topk(const float *query_p, const int64_t *query_ids, int64_t nq,
                       const float *item_p, int64_t n_items_local, int64_t item_base, int32_t dim,

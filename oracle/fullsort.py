@@ -84,12 +84,6 @@ def reference_batch_eval(scores, hist_rows, hist_cols, swap_row, swap_after, swa
     return s
 
 
-def reference_collect(masked_swapped, k):
-    """evaluators.py:68-75 with the tie rule made explicit: flip, then top-k by
-    (score desc, ORIGINAL item id asc).  Returns int64[users, k+1] (last column = N)."""
-    raise NotImplementedError("use reference_topk_idx() on item ids instead")
-
-
 def reference_topk_idx(topk_ids, pos_indptr, pos_indices, n_items):
     """Map top-K ITEM IDS to the reference's ``topk_idx`` coordinates (SURVEY.md 8a end).
 

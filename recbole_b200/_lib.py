@@ -20,7 +20,7 @@ METRIC_ORDER = ("recall", "mrr", "ndcg", "hit", "precision", "map")
 EINVAL, EWORKSPACE, ERANGE = 10001, 10002, 10003
 STAGES = ("keys", "sort_user", "sort_item", "user_side", "user_fixup", "item_side", "item_fixup", "loss", "fullsort",
           "topk_merge", "metrics", "sampler", "gather_dot", "tc_convert", "tc_score", "tc_refine", "fm_fwd",
-          "fm_update", "misc", "plan", "barrier", "owner")
+          "fm_update", "misc", "plan", "barrier", "owner", "fetch", "barrier_b")
 MAX_PEERS = 8
 
 
@@ -40,7 +40,7 @@ class RB2Peers(ctypes.Structure):
         ("world", ctypes.c_int32), ("me", ctypes.c_int32), ("item_block", ctypes.c_int64),
         ("item_p", ctypes.c_void_p * MAX_PEERS), ("grad_slots", ctypes.c_void_p * MAX_PEERS),
         ("stamps", ctypes.c_void_p * MAX_PEERS), ("flags", ctypes.c_void_p * MAX_PEERS),
-        ("loss_slots", ctypes.c_void_p * MAX_PEERS),
+        ("loss_slots", ctypes.c_void_p * MAX_PEERS), ("seq", ctypes.c_int64),
     ]
 
 
@@ -78,6 +78,7 @@ SIGNATURES = {
     "rb2_fm_train_step": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _i32, _p, _i64,
                                          ctypes.POINTER(RB2Optim), _p, _p, _p, _sz, _p]),
     "rb2_fm_predict": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _i32, _i64, _p, _p, _sz, _p]),
+    "rb2_fm_loss": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _i32, _p, _i64, _p, _p, _sz, _p]),
     "rb2_fm_grad_step": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _i32, _p, _i64, _i64, _p, _p, _sz, _p]),
     "rb2_scalar_rows_update_workspace_bytes": (_sz, [_i64]),
     "rb2_scalar_rows_update": (ctypes.c_int, [_p, _p, _p, _i64, _p, _p, _i64, ctypes.POINTER(RB2Optim), _p, _sz, _p]),
@@ -86,6 +87,7 @@ SIGNATURES = {
     "rb2_fullsort_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32, _i32]),
     "rb2_fullsort_topk": (ctypes.c_int, [_p, _p, _i64, _p, _i64, _i64, _i32, _p, _p, _i32, _i32, _p, _p, _p, _sz,
                                          _p]),
+    "rb2_fullsort_scores": (ctypes.c_int, [_p, _p, _i64, _i64, _p, _i64, _i32, _p, _p]),
     "rb2_ce_head_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "rb2_ce_head": (ctypes.c_int, [_p, _i64, _p, _i64, _i32, _p, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "rb2_ce_head_set_scorer": (ctypes.c_int, [_i32]),

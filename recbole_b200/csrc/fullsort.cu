@@ -12,6 +12,7 @@
 // so the shared-memory reads are broadcasts.  Scores are the canonical chain
 // s = fmaf(q[k], v[k], s), k ascending (see oracle/csrc/oracle.c).  History / pad masking costs
 // nothing per element: it is only checked for the rare element that beats the running threshold.
+#include <algorithm>
 #include "common.cuh"
 
 namespace {
@@ -639,6 +640,83 @@ extern "C" int rb2_ce_head(const float *x, int64_t nq, const float *item_p, int6
     case 128: k_ce_finish<128><<<blocks, 128, 0, st>>>(x, item_p, nq, n_items, target, lse_m, lse_s, parts, lse_out, row_loss); break;
   }
   if (loss_out) k_mean<<<1, 256, 0, st>>>(row_loss, nq, loss_out);
+  RB2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Compatibility path: the score matrix itself (BPR.full_sort_predict, bpr.py:91-96) for callers that insist on
+// it -- an UNMODIFIED reference Trainer._full_sort_batch_eval (trainer.py:328-352) masks and top-k's the matrix
+// with ATen.  The reference asks for 1-2 users per call (general_dataloader.py:330-334), so this is a stream over
+// the item table: one thread per item, kScoreQ query rows per pass held in shared memory, every score the
+// canonical fp32 chain s = fmaf(q[k], v[k], s), k ascending (bit-identical to the top-K kernels).
+namespace {
+constexpr int kScoreQ = 8;
+constexpr int kScoreThreads = 256;
+
+__global__ void __launch_bounds__(kScoreThreads) k_fullsort_scores(const float *__restrict__ query_p,
+                                                                   const int64_t *__restrict__ query_ids, int64_t nq,
+                                                                   int64_t n_query_rows,
+                                                                   const float *__restrict__ item_p, int64_t n_items,
+                                                                   int dim, float *__restrict__ out,
+                                                                   int32_t *range_error) {
+  extern __shared__ float qs[];                       // [kScoreQ, dim]
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int d4 = dim / 4;
+  for (int64_t q0 = (int64_t)blockIdx.y * kScoreQ; q0 < nq; q0 += (int64_t)gridDim.y * kScoreQ) {
+    const int nqq = (int)min((int64_t)kScoreQ, nq - q0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nqq * dim; i += blockDim.x) {
+      int64_t row = query_ids ? query_ids[q0 + i / dim] : q0 + i / dim;
+      if (row < 0 || row >= n_query_rows) {
+        if (range_error) *range_error = 1;
+        row = min(max(row, (int64_t)0), n_query_rows - 1);
+      }
+      qs[i] = query_p[row * dim + i % dim];
+    }
+    __syncthreads();
+    if (item < n_items) {
+      float s[kScoreQ];
+#pragma unroll
+      for (int q = 0; q < kScoreQ; ++q) s[q] = 0.f;
+      const float4 *vp = reinterpret_cast<const float4 *>(item_p + item * dim);
+      for (int k = 0; k < d4; ++k) {
+        const float4 v = __ldg(vp + k);
+#pragma unroll
+        for (int q = 0; q < kScoreQ; ++q) {
+          if (q < nqq) {
+            const float4 u = reinterpret_cast<const float4 *>(qs + q * dim)[k];    // broadcast
+            s[q] = fmaf(u.x, v.x, s[q]);
+            s[q] = fmaf(u.y, v.y, s[q]);
+            s[q] = fmaf(u.z, v.z, s[q]);
+            s[q] = fmaf(u.w, v.w, s[q]);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kScoreQ; ++q)
+        if (q < nqq) out[(q0 + q) * n_items + item] = s[q];
+    }
+  }
+}
+}  // namespace
+
+extern "C" int rb2_fullsort_scores(const float *query_p, const int64_t *query_ids, int64_t nq, int64_t n_query_rows,
+                                   const float *item_p, int64_t n_items, int32_t dim, float *out_scores,
+                                   void *stream) {
+  RB2_REQUIRE(query_p && item_p && out_scores, RB2_EINVAL, "rb2_fullsort_scores: null argument");
+  RB2_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 1024, RB2_EINVAL, "rb2_fullsort_scores: dim %d (multiple of 4, <= 1024)",
+              (int)dim);
+  RB2_REQUIRE(n_items > 0 && n_query_rows > 0 && nq >= 0, RB2_EINVAL, "rb2_fullsort_scores: sizes");
+  if (nq == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned bx = (unsigned)((n_items + kScoreThreads - 1) / kScoreThreads);
+  const int64_t passes = (nq + kScoreQ - 1) / kScoreQ;
+  // enough blocks to fill the machine; one y-slice walks several query passes when there are many
+  unsigned by = (unsigned)std::min<int64_t>(passes, std::max<int64_t>(1, (int64_t)rb2_num_sms() * 8 / bx));
+  ProfScope prof(RB2_ST_FULLSORT, st, 1);
+  k_fullsort_scores<<<dim3(bx, by), kScoreThreads, (size_t)kScoreQ * dim * sizeof(float), st>>>(
+      query_p, query_ids, nq, n_query_rows, item_p, n_items, dim, out_scores, nullptr);
   RB2_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1008,7 +1008,9 @@ extern "C" int rb2_bpr_train_step_p2p(float *user_p, float *user_m, float *user_
               "rb2_bpr_train_step_p2p: optimizer kind %d not supported (sgd, adam)", o.kind);
   if (o.kind != RB2_OPT_SGD)
     RB2_REQUIRE(user_m && user_v && item_m && item_v, RB2_EINVAL, "rb2_bpr_train_step_p2p: Adam needs m and v");
-  RB2_REQUIRE(o.step >= 1, RB2_EINVAL, "rb2_bpr_train_step_p2p: step must count from 1 (it is the barrier sequence)");
+  RB2_REQUIRE(hp.seq >= 1 && hp.seq < ((int64_t)1 << 31), RB2_EINVAL,
+              "rb2_bpr_train_step_p2p: h_peers->seq must count 1, 2, 3, ... (it is the barrier sequence)");
+  const uint32_t seq = (uint32_t)hp.seq;
   PeerTable pt{};
   PeerSync ps{};
   for (int r = 0; r < hp.world; ++r) {
@@ -1024,7 +1026,7 @@ extern "C" int rb2_bpr_train_step_p2p(float *user_p, float *user_m, float *user_
   pt.i_block = hp.item_block;
   pt.me = ps.me = hp.me;
   pt.world = ps.world = hp.world;
-  pt.step = o.step;
+  pt.step = (int32_t)seq;
   BprWs w;
   size_t need = carve(w, workspace, batch, dim, true);
   RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_bpr_train_step_p2p: workspace %zu < %zu", workspace_bytes,
@@ -1057,8 +1059,11 @@ extern "C" int rb2_bpr_train_step_p2p(float *user_p, float *user_m, float *user_
   {
     // barrier A: every owner has finished the previous step's update; from here on peers' rows may be read and
     // their slots / stamps written
+    // (the signal half was issued at the end of the previous step, right after the owner update: a rank does not
+    // hold the others up with its own keys / sorts; step 1 has no predecessor and does both halves here)
     ProfScope prof(RB2_ST_BARRIER, st);
-    k_peer_barrier<<<1, 32, 0, st>>>(ps, (uint32_t)o.step, 0, nullptr, 0.0, nullptr, nullptr, w.hdr, timeout_ns);
+    k_peer_barrier<<<1, 32, 0, st>>>(ps, seq, 0, seq == 1 ? (kBarSignal | kBarWait) : kBarWait, nullptr,
+                                     0.0, nullptr, nullptr, w.hdr, timeout_ns);
   }
   RB2_DISPATCH_DIM(dim, {
     constexpr int LANES = RowCfg<D_>::LANES;
@@ -1066,8 +1071,11 @@ extern "C" int rb2_bpr_train_step_p2p(float *user_p, float *user_m, float *user_
     const int64_t ntu = (B + Tu - 1) / Tu, nti = (2 * B + Ti - 1) / Ti;
     auto blocks = [](int64_t groups) { return (unsigned)((groups * LANES + kThreads - 1) / kThreads); };
     {
-      ProfScope prof(RB2_ST_PLAN, st, 2);
+      ProfScope prof(RB2_ST_PLAN, st, 1);
       k_plan_p2p<D_><<<(unsigned)((2 * B + 255) / 256), 256, 0, st>>>(w, pt, 2 * B);
+    }
+    {
+      ProfScope prof(RB2_ST_FETCH, st, 1);
       k_fetch_rows<D_><<<(unsigned)rb2_num_sms() * 8, kThreads, 0, st>>>(w, pt);
     }
     {
@@ -1100,13 +1108,17 @@ extern "C" int rb2_bpr_train_step_p2p(float *user_p, float *user_m, float *user_
     }
     {
       // barrier B: every rank's gradient rows have landed in the owners' slots; the loss sums travel with it
-      ProfScope prof(RB2_ST_BARRIER, st);
-      k_peer_barrier<<<1, 32, 0, st>>>(ps, (uint32_t)o.step, 1, w.loss_sum, 1.0 / (double)global_batch, loss_out,
-                                       loss_accum, w.hdr, timeout_ns);
+      ProfScope prof(RB2_ST_BARRIER_B, st);
+      k_peer_barrier<<<1, 32, 0, st>>>(ps, seq, 1, kBarSignal | kBarWait, w.loss_sum,
+                                       1.0 / (double)global_batch, loss_out, loss_accum, w.hdr, timeout_ns);
     }
-    if (n_local > 0) {
-      ProfScope prof(RB2_ST_OWNER, st);
-      k_owner_update<D_><<<blocks(n_local), kThreads, 0, st>>>(item_local, item_m, item_v, pt, n_local, o);
+    {
+      ProfScope prof(RB2_ST_OWNER, st, 2);
+      if (n_local > 0)
+        k_owner_update<D_><<<blocks(n_local), kThreads, 0, st>>>(item_local, item_m, item_v, pt, n_local, o);
+      // signal half of the NEXT step's barrier A: my rows are up to date, peers may read them and reuse my slots
+      k_peer_barrier<<<1, 32, 0, st>>>(ps, seq + 1u, 0, kBarSignal, nullptr, 0.0, nullptr, nullptr, w.hdr,
+                                       timeout_ns);
     }
   });
   RB2_CUDA(cudaGetLastError());

@@ -564,30 +564,37 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-// Flag barrier over the peers' memory: rank `me` writes `seq` into flag [which][me] of every rank, then waits until
-// every rank has written `seq` (or more) into its own.  Everything the calling stream wrote to peer memory before
-// this kernel is visible to the peers after they pass it.  With my_loss != NULL the ranks also exchange their loss
-// sums and every rank forms the same global mean (fixed rank order).
-__global__ void k_peer_barrier(PeerSync ps, uint32_t seq, int which, const double *my_loss, double inv_b,
+// Flag barrier over the peers' memory: rank `me` writes `seq` into flag [which][me] of every rank (mode & 1), then
+// waits until every rank has written `seq` (or more) into its own (mode & 2).  Everything the calling stream wrote
+// to peer memory before the signalling launch is visible to the peers after their wait.  The two halves may be
+// separate launches: a rank signals "my owner update is done" at the END of a step and waits for the others only
+// after the id-only work of the next one.  With my_loss != NULL the ranks also exchange their loss sums and every
+// rank forms the same global mean (fixed rank order).
+enum { kBarSignal = 1, kBarWait = 2 };
+__global__ void k_peer_barrier(PeerSync ps, uint32_t seq, int which, int mode, const double *my_loss, double inv_b,
                                float *loss_out, double *loss_accum, WsHeader *hdr, unsigned long long timeout_ns) {
   const int r = threadIdx.x;
   const int parity = (int)(seq & 1u);
   if (r < ps.world) {
-    if (my_loss) ps.loss[r][parity * RB2_MAX_PEERS + ps.me] = *my_loss;
-    __threadfence_system();
-    st_release_sys(ps.flags[r] + which * RB2_MAX_PEERS + ps.me, seq);
-    const uint32_t *mine = ps.flags[ps.me] + which * RB2_MAX_PEERS + r;
-    const unsigned long long t0 = globaltimer_ns();
-    while ((int32_t)(ld_acquire_sys(mine) - seq) < 0) {
-      __nanosleep(64);
-      if (globaltimer_ns() - t0 > timeout_ns) {
-        hdr->peer_timeout = 1;
-        break;
+    if (mode & kBarSignal) {
+      if (my_loss) ps.loss[r][parity * RB2_MAX_PEERS + ps.me] = *my_loss;
+      __threadfence_system();
+      st_release_sys(ps.flags[r] + which * RB2_MAX_PEERS + ps.me, seq);
+    }
+    if (mode & kBarWait) {
+      const uint32_t *mine = ps.flags[ps.me] + which * RB2_MAX_PEERS + r;
+      const unsigned long long t0 = globaltimer_ns();
+      while ((int32_t)(ld_acquire_sys(mine) - seq) < 0) {
+        __nanosleep(64);
+        if (globaltimer_ns() - t0 > timeout_ns) {
+          hdr->peer_timeout = 1;
+          break;
+        }
       }
     }
   }
   __syncwarp();
-  if (r == 0 && my_loss) {
+  if (r == 0 && my_loss && (mode & kBarWait)) {
     __threadfence_system();
     double s = 0.0;
     for (int q = 0; q < ps.world; ++q) s += ps.loss[ps.me][parity * RB2_MAX_PEERS + q];

@@ -79,6 +79,7 @@ size_t carve(FmWs &w, void *base, int64_t B, int F, int dim) {
 // internal optimizer kind of rb2_fm_grad_step: the row's summed gradient REPLACES the row (the tables are the
 // fetched copies of a sharded step; every row is processed exactly once, after the forward has read it)
 constexpr int kOptGradOut = 99;
+constexpr int kOptLossOnly = 98;   // rb2_fm_loss: the reduction writes the mean loss and nothing else
 
 struct FmTables {
   float *E, *mE, *vE;   // [rows, D]
@@ -88,7 +89,8 @@ struct FmTables {
 
 // ---------------------------------------------------------------------------------------------
 // forward (+ intermediates for the backward when TRAIN)
-template <int D, bool TRAIN>
+// STORE = false with TRAIN = true: loss only (rb2_fm_loss) -- nothing is kept for a backward
+template <int D, bool TRAIN, bool STORE = TRAIN>
 __global__ void __launch_bounds__(kThreads) k_fm_forward(FmTables t, const int64_t *__restrict__ ids,
                                                           const int64_t *__restrict__ offsets,
                                                           const float *__restrict__ label, int64_t B, int F,
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(kThreads) k_fm_forward(FmTables t, const int64
       }
       v = __ldg(reinterpret_cast<const float4 *>(t.E + row * D) + gl);
       if (gl == 0) first += __ldg(t.W + row);
-      if (TRAIN && gl == 0) {
+      if (STORE && gl == 0) {
         int64_t o = s * F + f;
         w.key[o] = (uint32_t)row;
         w.val[o] = (uint32_t)o;
@@ -175,9 +177,10 @@ __global__ void __launch_bounds__(kThreads) k_fm_forward(FmTables t, const int64
       if (lane == 0) {
         loss_local += -(lab * ly + (1.f - lab) * l1y);
         gz_local += gz;
-        w.gz[s] = gz;
+        if (STORE) w.gz[s] = gz;
       }
-      if (g == 0) reinterpret_cast<float4 *>(w.gs + s * D)[gl] = make_float4(gz * S.x, gz * S.y, gz * S.z, gz * S.w);
+      if (STORE && g == 0)
+        reinterpret_cast<float4 *>(w.gs + s * D)[gl] = make_float4(gz * S.x, gz * S.y, gz * S.z, gz * S.w);
     }
   }
   if (TRAIN && lane == 0 && warp_global < w.n_parts) {
@@ -396,6 +399,7 @@ __global__ void k_fm_bias_loss(FmTables t, FmWs w, int64_t n_parts, double inv_b
     float loss = (float)(sl[0] * inv_b);
     loss_out[0] = loss;
     if (loss_accum) loss_accum[0] += (double)loss;
+    if (o.kind == kOptLossOnly) return;
     float b = t.bias[0], gb = (float)sg[0];
     if (o.kind == kOptGradOut) {
       loss_out[1] = gb;          // this rank's share of d loss / d bias
@@ -597,6 +601,35 @@ extern "C" int rb2_scalar_step(float *p3, const float *grad, const rb2_optim *h_
   OptScalars o = rb2_opt_scalars(h_opt);
   RB2_REQUIRE(o.kind == RB2_OPT_SGD || o.kind == RB2_OPT_ADAM, RB2_EINVAL, "rb2_scalar_step: sgd or adam");
   k_scalar_step<<<1, 1, 0, (cudaStream_t)stream>>>(p3, grad, o);
+  RB2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+/* forward + mean BCE only (FM.calculate_loss, fm.py:52-56, without a backward): loss_out[0] = the batch's loss */
+extern "C" int rb2_fm_loss(const float *E, const float *W, const float *bias3, int64_t n_rows, int32_t dim,
+                           const int64_t *ids, const int64_t *offsets, int32_t n_fields, const float *label,
+                           int64_t batch, float *loss_out, void *workspace, size_t workspace_bytes, void *stream) {
+  RB2_REQUIRE(E && W && bias3 && ids && offsets && label && loss_out && workspace, RB2_EINVAL,
+              "rb2_fm_loss: null argument");
+  RB2_REQUIRE(batch > 0 && n_fields > 0, RB2_EINVAL, "rb2_fm_loss: empty batch");
+  FmWs w;
+  size_t need = carve(w, workspace, batch, n_fields, dim);
+  RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_fm_loss: workspace %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  FmTables t{const_cast<float *>(E), nullptr, nullptr, const_cast<float *>(W), nullptr, nullptr,
+             const_cast<float *>(bias3)};
+  OptScalars o = {};
+  o.kind = kOptLossOnly;
+  k_zero_parts<<<(unsigned)((w.n_parts + 255) / 256), 256, 0, st>>>(w);
+  RB2_FM_DIM(dim, {
+    int64_t warps = std::min<int64_t>(std::min<int64_t>(batch, w.n_parts), (int64_t)rb2_num_sms() * 64);
+    unsigned fblocks = (unsigned)((warps * 32 + kThreads - 1) / kThreads);
+    if ((int64_t)fblocks * (kThreads / 32) > w.n_parts) fblocks = (unsigned)std::max<int64_t>(1, w.n_parts / (kThreads / 32));
+    ProfScope prof(RB2_ST_FM_FWD, st, 2);
+    k_fm_forward<D_, true, false><<<fblocks, kThreads, 0, st>>>(t, ids, offsets, label, batch, n_fields, n_rows,
+                                                                (float)(1.0 / (double)batch), w, nullptr);
+    k_fm_bias_loss<<<1, 256, 0, st>>>(t, w, w.n_parts, 1.0 / (double)batch, o, loss_out, nullptr);
+  });
   RB2_CUDA(cudaGetLastError());
   return 0;
 }

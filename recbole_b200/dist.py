@@ -193,8 +193,7 @@ class ShardedBPR:
         # "p2p": the kernels read the owners' rows and write the owners' gradient slots over NVLink themselves
         #        (rb2_bpr_train_step_p2p); the item shard lives in an arena every rank maps with cudaIpc.
         self.arena = None
-        if exchange == "p2p" or (exchange == "auto" and device.type == "cuda" and not comm.staged
-                                 and n_items * dim * 4 > (64 << 20) and 1 < comm.world <= 8):
+        if self.resolve_exchange(exchange, n_items, dim, comm, device) == "p2p":
             exchange = "p2p"
             self.arena = ops.PeerArena(comm, device, self.i_block, dim)
             self.V = self.arena.item_p
@@ -225,6 +224,18 @@ class ShardedBPR:
         self._ws = {}
         self._rows_ws = None
         self._p2p_ws = None
+
+    @staticmethod
+    def resolve_exchange(exchange, n_items, dim, comm, device):
+        """The exchange a model of this shape runs when asked for `exchange` ("auto": peer memory for big tables on
+        2-8 CUDA ranks, else dense for small tables / sparse for big ones; the dense-vs-sparse choice can still flip
+        per batch, see train_step)."""
+        if exchange == "p2p" or (exchange == "auto" and device.type == "cuda" and not comm.staged
+                                 and n_items * dim * 4 > (64 << 20) and 1 < comm.world <= 8):
+            return "p2p"
+        if exchange == "auto":
+            return "dense" if n_items * dim * 4 <= (64 << 20) else "sparse"
+        return exchange
 
     def check_flags(self):
         """Raise for sticky device-side errors (id out of range, peer barrier timeout); synchronises."""

@@ -84,6 +84,19 @@ class Optim:
         self.step = 0
         self._lazy = None  # (step_size_tab, bc2_sqrt_tab) device tensors
 
+    def set_hyper(self, lr=None, weight_decay=None, betas=None, eps=None):
+        """Change hyper-parameters (checkpoint resume, trainer.py:230); the adam_lazy bias-correction tables are
+        functions of (lr, betas) and are rebuilt on the next step."""
+        if lr is not None:
+            self.lr = float(lr)
+        if weight_decay is not None:
+            self.weight_decay = float(weight_decay)
+        if betas is not None:
+            self.betas = tuple(float(b) for b in betas)
+        if eps is not None:
+            self.eps = float(eps)
+        self._lazy = None
+
     def _lazy_tables(self, device, upto):
         cap = 0 if self._lazy is None else self._lazy[0].numel()
         if upto + 1 > cap:
@@ -199,6 +212,7 @@ class PeerArena:
             for name in ("item_p", "grad_slots", "stamps", "flags", "loss_slots"):
                 getattr(self.peers, name)[r] = base[r] + o[name]
         self.cache = torch.empty((world * self.item_block, dim), dtype=torch.float32, device=device)
+        self.seq = 0            # calls of rb2_bpr_train_step_p2p on these buffers (the barrier sequence)
 
 
 def bpr_p2p_workspace(batch, dim, device):
@@ -211,6 +225,8 @@ def bpr_train_step_p2p(U, state, arena, user, user_base, pos, neg, n_items, glob
     loss included).  optim.step is NOT incremented here; `step` must count 1, 2, 3, ... identically on every rank."""
     o = optim.c_struct(U.device, step)
     f32, i64 = torch.float32, torch.int64
+    arena.seq += 1
+    arena.peers.seq = arena.seq
     check(lib.rb2_bpr_train_step_p2p(
         _ptr(U, f32), _ptr(state.get("mU"), f32, True), _ptr(state.get("vU"), f32, True),
         _ptr(state.get("mV"), f32, True), _ptr(state.get("vV"), f32, True), U.shape[0], int(n_items), U.shape[1],
@@ -330,6 +346,14 @@ def fm_predict(E, W, bias3, ids, offsets, ws=None):
     return y
 
 
+def fm_loss(E, W, bias3, ids, offsets, label, loss_out, ws):
+    """Forward + mean BCE only (rb2_fm_loss); loss_out[0] = the batch's loss."""
+    f32 = torch.float32
+    check(lib.rb2_fm_loss(_ptr(E, f32), _ptr(W, f32), _ptr(bias3, f32), E.shape[0], E.shape[1], _ptr(ids, torch.int64),
+                          _ptr(offsets, torch.int64), ids.shape[1], _ptr(label, f32), ids.shape[0], _ptr(loss_out, f32),
+                          ws.ptr(), ws.nbytes, _stream()))
+
+
 def gather_dot(U, V, user, item):
     out = torch.empty(user.numel(), dtype=torch.float32, device=U.device)
     check(lib.rb2_gather_dot(_ptr(U, torch.float32), _ptr(V, torch.float32), U.shape[0], V.shape[0], U.shape[1],
@@ -357,6 +381,15 @@ def fullsort_topk(Q, query_ids, V, k, hist_indptr=None, hist_indices=None, item_
         int(item_base), V.shape[1], _ptr(hist_indptr, torch.int64, True), _ptr(hist_indices, torch.int64, True),
         int(k), m, _ptr(ids), _ptr(sc), ws.ptr(), ws.nbytes, _stream()))
     return ids, sc
+
+
+def fullsort_scores(Q, query_ids, V):
+    """The [nq, n_items] score matrix (rb2_fullsort_scores): compatibility path for an unmodified reference Trainer."""
+    nq = int(query_ids.numel()) if query_ids is not None else Q.shape[0]
+    out = torch.empty((nq, V.shape[0]), dtype=torch.float32, device=Q.device)
+    check(lib.rb2_fullsort_scores(_ptr(Q, torch.float32), _ptr(query_ids, torch.int64, True), nq, Q.shape[0],
+                                  _ptr(V, torch.float32), V.shape[0], V.shape[1], _ptr(out), _stream()))
+    return out
 
 
 def ce_head(X, E, target, k=10, scorer="auto"):

@@ -50,7 +50,7 @@ class _Batches:
 def test_cfg1_trajectory_and_result_dict(golden):
     from recbole_b200 import EvalIndex, FusedTrainer
     g = golden("cfg1_train.npz")
-    cfg, model = _model(g, "adam_lazy")
+    cfg, model = _model(g, "adam")        # the config's 'adam' = dense Adam -> fused kind adam_lazy
     trainer = FusedTrainer(cfg, model)
     nb = len(g["batch_sizes"]) // 2
     for ep in range(2):
@@ -74,10 +74,10 @@ def test_cfg1_trajectory_and_result_dict(golden):
 
 
 def test_cfg1_row_sparse_adam_is_close_but_not_the_reference(golden):
-    """Documents the difference: plain row-sparse 'adam' skips the zero-gradient moves of dense Adam, so
+    """Documents the difference: the row-sparse kernel (learner 'sparse_adam') skips the zero-gradient moves of dense Adam, so
     after 80 steps the tables drift from the reference's (while 'adam_lazy' above does not)."""
     g = golden("cfg1_train.npz")
-    cfg, model = _model(g, "adam")
+    cfg, model = _model(g, "sparse_adam")
     from recbole_b200 import FusedTrainer
     trainer = FusedTrainer(cfg, model)
     nb = len(g["batch_sizes"]) // 2

@@ -47,7 +47,7 @@ def test_device_pipeline_fit_and_evaluate():
     trainer = FusedTrainer(cfg, model)
     index = EvalIndex.from_phase_pairs(n_users, n_items, phases, 2, dev)
     before = trainer.evaluate(index)
-    trainer.fit(loader, valid_data=None, verbose=False)
+    trainer.fit(loader, valid_data=None, verbose=False, saved=False)
     losses = [trainer.train_loss_dict[e] for e in range(6)]
     assert losses[-1] < losses[0]
     after = trainer.evaluate(index)

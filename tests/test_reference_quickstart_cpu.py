@@ -1,0 +1,147 @@
+"""CPU: INTEGRATION.md's quick-start against the REAL reference (/root/reference, import shims of SURVEY.md 8c):
+``Config(model=FusedBPR) -> create_dataset -> data_preparation -> FusedBPR(config, train_data) -> trainers``.
+
+Checks the things that broke in round 1: ``model_class.type`` / ``input_type`` must compare equal to (and hash
+like) the reference's ``ModelType`` / ``InputType`` members in ``configurator.py:237-258,275-276`` and
+``data/utils.py:40-52,262-286``, whichever of the two packages is imported first.  Runs in a subprocess (the
+reference's Config parses sys.argv and its import needs the shims on sys.path).  Skipped where the reference
+does not exist (the GPU box); no GPU needed -- nothing is computed, only wired.
+"""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+SHIMS = os.path.join(ROOT, "tests", "golden", "_shims")
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "recbole")),
+                                reason="the reference checkout is not present on this machine")
+
+PRELUDE = """
+import os, sys
+ROOT, REF, SHIMS, ORDER = {root!r}, {ref!r}, {shims!r}, {order!r}
+sys.argv = sys.argv[:1]
+sys.path.insert(0, ROOT)
+if ORDER == "fused_first":
+    import recbole_b200                      # the reference is NOT importable yet: stand-in enums
+    assert not recbole_b200.enums.FROM_REFERENCE
+sys.path.insert(0, REF)
+sys.path.insert(0, SHIMS)
+import numpy as np
+np.float = float
+import torch
+torch.set_num_threads(2)
+import logging
+from recbole.config import Config
+from recbole.data import create_dataset, data_preparation
+from recbole.utils import InputType, ModelType
+import recbole_b200
+if ORDER == "reference_first":
+    assert recbole_b200.enums.FROM_REFERENCE
+os.makedirs("/tmp/rb2_quickstart_scratch", exist_ok=True)
+os.chdir("/tmp/rb2_quickstart_scratch")      # the reference's Trainer makes ./saved, its logger ./log
+"""
+
+BPR_BODY = """
+from recbole_b200 import EvalIndex, FusedBPR, FusedTrainer
+config = Config(model=FusedBPR, dataset="ml-100k",
+                config_dict={{"data_path": os.path.join(REF, "dataset"), "load_col": {{"inter": ["user_id", "item_id"]}},
+                             "use_gpu": False, "topk": [10], "metrics": ["Recall", "NDCG"], "valid_metric": "Recall@10"}})
+logging.disable(logging.CRITICAL)
+assert config["MODEL_TYPE"] == ModelType.GENERAL and config["MODEL_TYPE"] in {{ModelType.GENERAL}}
+assert config["MODEL_INPUT_TYPE"] == InputType.PAIRWISE
+assert {{ModelType.GENERAL: "General"}}[config["MODEL_TYPE"]] == "General"          # data/utils.py:262-268
+assert config["model"] == "FusedBPR"
+dataset = create_dataset(config)
+train_data, valid_data, test_data = data_preparation(config, dataset)
+assert type(train_data).__name__ == "GeneralNegSampleDataLoader", type(train_data)
+assert type(test_data).__name__ == "GeneralFullDataLoader", type(test_data)
+model = FusedBPR(config, train_data).to(config["device"])
+assert (model.n_users, model.n_items, model.embedding_size) == (944, 1683, 64)
+assert sorted(model.state_dict()) == ["item_embedding.weight", "user_embedding.weight"]
+batch = next(iter(train_data))                      # pair-wise format: the three id fields the fused step reads
+for f in (model.USER_ID, model.ITEM_ID, model.NEG_ITEM_ID):
+    assert batch[f].dtype == torch.int64 and batch[f].shape == batch[model.USER_ID].shape
+trainer = FusedTrainer(config, model)               # maps learner 'adam' (dense torch Adam) to the adam_lazy kind
+assert model._optim.kind_name == "adam_lazy" and abs(model._optim.lr - config["learning_rate"]) < 1e-12
+# the evaluation index from the reference dataloader's own per-user arrays == its batches
+index = EvalIndex.from_reference_dataloader(test_data, "cpu")
+uid = index.uid_list.numpy()
+assert np.array_equal(uid, np.asarray(test_data.uid_list))
+hp, hi = index.hist_indptr.numpy(), index.hist_indices.numpy()
+for r in (0, 1, len(uid) // 2, len(uid) - 1):
+    want = np.sort(np.asarray(test_data.uid2history_item[uid[r]], dtype=np.int64))
+    assert np.array_equal(hi[hp[r]:hp[r + 1]], want)
+assert np.array_equal(index.pos_len().numpy(), np.asarray(test_data.uid2items_num)[uid])
+# a completely unmodified reference Trainer accepts the model too (torch optimizer over model.parameters())
+from recbole.trainer import Trainer
+ref_trainer = Trainer(config, model)
+assert len(ref_trainer.optimizer.param_groups[0]["params"]) == 2
+print("QUICKSTART-OK")
+"""
+
+FM_BODY = """
+from recbole_b200 import FusedFM, FusedMFSimple
+config = Config(model=FusedFM, dataset="ml-100k",
+                config_dict={{"data_path": os.path.join(REF, "dataset"), "use_gpu": False, "embedding_size": 16,
+                             "load_col": {{"inter": ["user_id", "item_id", "rating"], "user": ["user_id", "age", "gender", "occupation"],
+                                          "item": ["item_id", "release_year"]}}}})
+logging.disable(logging.CRITICAL)
+assert config["MODEL_TYPE"] == ModelType.CONTEXT and config["MODEL_TYPE"] in {{ModelType.CONTEXT, ModelType.DECISIONTREE}}
+assert config["MODEL_INPUT_TYPE"] == InputType.POINTWISE
+dataset = create_dataset(config)
+train_data, valid_data, test_data = data_preparation(config, dataset)
+assert type(train_data).__name__.startswith("Context"), type(train_data)
+model = FusedFM(config, train_data)
+assert model.num_feature_field == len(model.token_field_names) >= 5
+assert sorted(model.state_dict()) == ["first_order_linear.bias", "first_order_linear.token_embedding_table.embedding.weight",
+                                      "token_embedding_table.embedding.weight"]
+batch = next(iter(train_data))
+ids = model._ids(batch)
+assert ids.shape == (len(batch), model.num_feature_field) and batch[model.LABEL].dtype == torch.float32
+config2 = Config(model=FusedMFSimple, dataset="ml-100k",
+                 config_dict={{"data_path": os.path.join(REF, "dataset"), "use_gpu": False,
+                              "load_col": {{"inter": ["user_id", "item_id"]}}}})
+assert config2["MODEL_TYPE"] == ModelType.GENERAL and config2["MODEL_INPUT_TYPE"] == InputType.POINTWISE
+print("QUICKSTART-OK")
+"""
+
+
+def _run(body, order):
+    code = textwrap.dedent(PRELUDE.format(root=ROOT, ref=REF, shims=SHIMS, order=order)) + textwrap.dedent(body.format())
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "QUICKSTART-OK" in p.stdout, (p.stdout[-2000:], p.stderr[-4000:])
+
+
+@pytest.mark.parametrize("order", ["reference_first", "fused_first"])
+def test_quickstart_bpr_against_the_reference(order):
+    _run(BPR_BODY, order)
+
+
+def test_quickstart_fm_and_mfsimple_against_the_reference():
+    _run(FM_BODY, "reference_first")
+
+
+def test_standin_enums_equal_and_hash_like_the_reference_members():
+    from enum import Enum
+
+    from recbole_b200.enums import _InputType, _ModelType
+
+    class ModelType(Enum):          # what recbole/utils/enum_type.py:13-35 defines
+        GENERAL = 1
+        SEQUENTIAL = 2
+        CONTEXT = 3
+
+    class InputType(Enum):
+        POINTWISE = 1
+        PAIRWISE = 2
+
+    assert _ModelType.GENERAL == ModelType.GENERAL and ModelType.GENERAL == _ModelType.GENERAL
+    assert _ModelType.GENERAL != ModelType.CONTEXT and not (_ModelType.GENERAL == InputType.POINTWISE)
+    assert {ModelType.GENERAL: "General", ModelType.CONTEXT: "Context"}[_ModelType.CONTEXT] == "Context"
+    assert _ModelType.CONTEXT in {ModelType.CONTEXT, ModelType.SEQUENTIAL}
+    assert _InputType.PAIRWISE == InputType.PAIRWISE and _InputType.PAIRWISE != InputType.POINTWISE
