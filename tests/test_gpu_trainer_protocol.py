@@ -70,8 +70,7 @@ def test_reference_trainer_loop_protocol(golden, dim, opt_name, learner, lr, wd)
 
 
 def test_predict_and_full_sort_protocol(golden):
-    """predict() serves the Trainer's fallback when full_sort_predict raises NotImplementedError
-    (trainer.py:333-340): scores of explicit (user, item) pairs == the reference's predict()."""
+    """predict(): scores of explicit (user, item) pairs == the reference's predict() (bpr.py:85-89)."""
     from recbole_b200 import Interaction
     from gpu_util import rel_err
     g = golden("bpr_steps.npz")
@@ -81,8 +80,6 @@ def test_predict_and_full_sort_protocol(golden):
                            "item_embedding.weight": torch.from_numpy(g[key + "V3"])})
     inter = Interaction({"user_id": torch.from_numpy(g["d64_user_id0"]), "item_id": torch.from_numpy(g["d64_item_id0"])}).to("cuda")
     assert rel_err(model.predict(inter).cpu().numpy(), g[key + "pred"]) < 1e-5
-    with pytest.raises(NotImplementedError):
-        model.full_sort_predict(inter)
     ids, sc = model.full_sort_topk(inter["user_id"][:5].contiguous(), 3)
     assert ids.shape == (5, 3) and (sc[:, 0] >= sc[:, 1]).all()
 
