@@ -235,6 +235,16 @@ int rb2_ipc_export(const void *dev_ptr, void *h_handle /* [64] */, int64_t *h_of
 int rb2_ipc_open(const void *h_handle /* [64] */, int64_t offset, void **h_mapped);
 int rb2_ipc_close_all(void);
 
+/* ------------------------------------------------------------------------------------------
+ * The grouping primitive of the training steps: stable sort of (key, position) pairs for keys < 2^key_bits
+ * (row ids of a table).  keys_sorted ascending, positions[i] = index in `keys` of the i-th smallest key, equal keys
+ * in ascending position.  One persistent cooperative launch: LSD radix sort with 12-bit digits, warp-private
+ * shared-memory histograms, hand-written grid barrier (csrc/bucket_sort.cuh); no library code.
+ * ---------------------------------------------------------------------------------------- */
+size_t rb2_sort_positions_workspace_bytes(int64_t count);
+int rb2_sort_positions(const uint32_t *keys, int64_t count, int32_t key_bits, uint32_t *keys_sorted,
+                       uint32_t *positions, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Flush for RB2_OPT_ADAM_LAZY: bring every row to step `h_opt->step` (replaying the zero-gradient
  * steps it missed) so the tables can be read by evaluation / checkpointing. */
 int rb2_adam_lazy_flush(float *p, float *m, float *v, int32_t *last, int64_t rows, int32_t dim,
@@ -250,14 +260,19 @@ int rb2_adam_lazy_flush(float *p, float *m, float *v, int32_t *last, int64_t row
  *   W [n_rows]       = first_order_linear.token_embedding_table.embedding.weight  (output_dim 1)
  *   bias3 [3]        = first_order_linear.bias and its Adam moments (b, m, v)
  *   ids [batch, n_fields] raw per-field ids; row = ids[s, f] + offsets[f]   (layers.py:142)
- * dim in {16, 32, 64, 128}; optimizer RB2_OPT_SGD or RB2_OPT_ADAM (row-sparse; the bias is dense).
+ * dim in {16, 32, 64, 128}; optimizer RB2_OPT_SGD, RB2_OPT_ADAM (row-sparse) or RB2_OPT_ADAM_LAZY; the bias is dense.
  * rb2_fm_predict: y[s] = sigmoid(first_order + fm)  (FM.predict, fm.py:58-59).
  * ---------------------------------------------------------------------------------------- */
 size_t rb2_fm_workspace_bytes(int64_t batch, int32_t n_fields, int32_t dim);
 int rb2_fm_train_step(float *E, float *mE, float *vE, float *W, float *mW, float *vW, float *bias3,
-                      int64_t n_rows, int32_t dim, const int64_t *ids, const int64_t *offsets, int32_t n_fields,
-                      const float *label, int64_t batch, const rb2_optim *h_opt, float *loss_out,
+                      int32_t *row_last, int64_t n_rows, int32_t dim, const int64_t *ids, const int64_t *offsets,
+                      int32_t n_fields, const float *label, int64_t batch, const rb2_optim *h_opt, float *loss_out,
                       double *loss_accum, void *workspace, size_t workspace_bytes, void *stream);
+/* RB2_OPT_ADAM_LAZY (row_last: int32 [n_rows], zero-initialised, shared by E and W): the trajectory of the
+ * reference's DENSE torch.optim.Adam, weight decay included (MFSimple.yaml:2 sets 1e-8: every row moves at every
+ * step).  rb2_fm_lazy_flush brings all rows to step h_opt->step before predict / loss / a checkpoint read them. */
+int rb2_fm_lazy_flush(float *E, float *mE, float *vE, float *W, float *mW, float *vW, int32_t *row_last,
+                      int64_t n_rows, int32_t dim, const rb2_optim *h_opt, void *stream);
 int rb2_fm_predict(const float *E, const float *W, const float *bias3, int64_t n_rows, int32_t dim,
                    const int64_t *ids, const int64_t *offsets, int32_t n_fields, int64_t batch, float *y_out,
                    void *workspace, size_t workspace_bytes, void *stream);

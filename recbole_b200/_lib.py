@@ -73,10 +73,13 @@ SIGNATURES = {
     "rb2_sparse_rows_update": (ctypes.c_int, [_p, _p, _p, _p, _i64, _i32, _p, _p, _i64, ctypes.POINTER(RB2Optim),
                                               _p, _sz, _p]),
     "rb2_bpr_loss": (ctypes.c_int, [_p, _p, _i64, _i64, _i32, _p, _p, _p, _i64, _p, _p, _sz, _p]),
+    "rb2_sort_positions_workspace_bytes": (_sz, [_i64]),
+    "rb2_sort_positions": (ctypes.c_int, [_p, _i64, _i32, _p, _p, _p, _sz, _p]),
     "rb2_adam_lazy_flush": (ctypes.c_int, [_p, _p, _p, _p, _i64, _i32, ctypes.POINTER(RB2Optim), _p]),
     "rb2_fm_workspace_bytes": (_sz, [_i64, _i32, _i32]),
-    "rb2_fm_train_step": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _i32, _p, _i64,
+    "rb2_fm_train_step": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _i32, _p, _i64,
                                          ctypes.POINTER(RB2Optim), _p, _p, _p, _sz, _p]),
+    "rb2_fm_lazy_flush": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i32, ctypes.POINTER(RB2Optim), _p]),
     "rb2_fm_predict": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _i32, _i64, _p, _p, _sz, _p]),
     "rb2_fm_loss": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _i32, _p, _i64, _p, _p, _sz, _p]),
     "rb2_fm_grad_step": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _i32, _p, _i64, _i64, _p, _p, _sz, _p]),

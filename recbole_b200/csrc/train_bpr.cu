@@ -19,9 +19,9 @@
 // Every touched row is read (p, m, v) and written (p, m, v) exactly once per step.
 #include <algorithm>
 
-#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include "bucket_sort.cuh"
 #include "common.cuh"
 
 namespace {
@@ -101,10 +101,8 @@ size_t carve(BprWs &w, void *base, int64_t B, int dim, bool p2p = false) {
     w.loss_sum = c.take<double>(32);
   }
   size_t b1 = 0, b2 = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, b1, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
-                                  (uint32_t *)nullptr, (int)B, 0, 32);
-  cub::DeviceRadixSort::SortPairs(nullptr, b2, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
-                                  (uint32_t *)nullptr, (int)(2 * B), 0, 32);
+  b1 = rb2sort::tmp_bytes(B);
+  b2 = rb2sort::tmp_bytes(2 * B);
   w.cub_bytes = b1 > b2 ? b1 : b2;
   w.cub_tmp = c.take<char>(w.cub_bytes);
   return c.off;
@@ -459,14 +457,12 @@ int launch_step_fused(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_i
   size_t tmp = w.cub_bytes;
   {
     ProfScope prof(RB2_ST_SORT_USER, st, 2 + (bits_for(n_users) + 7) / 8);
-    RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ukey, w.ukey_s, w.uval, w.uval_s, (int)B, 0,
-                                             bits_for(n_users), st));
+    { int rc_ = rb2sort::sort_positions(w.ukey, w.ukey_s, w.uval_s, B, bits_for(n_users), w.cub_tmp, w.cub_bytes, st); if (rc_) return rc_; }
   }
   tmp = w.cub_bytes;
   {
     ProfScope prof(RB2_ST_SORT_ITEM, st, 2 + (bits_for(n_items) + 7) / 8);
-    RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ikey, w.ikey_s, w.ival, w.ival_s, (int)(2 * B), 0,
-                                             bits_for(n_items), st));
+    { int rc_ = rb2sort::sort_positions(w.ikey, w.ikey_s, w.ival_s, 2 * B, bits_for(n_items), w.cub_tmp, w.cub_bytes, st); if (rc_) return rc_; }
   }
   {
     ProfScope prof(RB2_ST_PLAN, st);
@@ -519,8 +515,7 @@ int launch_step(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, 
   {
     // cub one-sweep radix sort: histogram + scan + one kernel per 8-bit digit pass
     ProfScope prof(RB2_ST_SORT_USER, st, 2 + (bits_for(n_users) + 7) / 8);
-    RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ukey, w.ukey_s, w.uval, w.uval_s, (int)B, 0,
-                                             bits_for(n_users), st));
+    { int rc_ = rb2sort::sort_positions(w.ukey, w.ukey_s, w.uval_s, B, bits_for(n_users), w.cub_tmp, w.cub_bytes, st); if (rc_) return rc_; }
   }
   tmp = w.cub_bytes;
   if (pre_ikey_s) {
@@ -529,8 +524,7 @@ int launch_step(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, 
     w.ival_s = const_cast<uint32_t *>(pre_ival_s);
   } else {
     ProfScope prof(RB2_ST_SORT_ITEM, st, 2 + (bits_for(n_items) + 7) / 8);
-    RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ikey, w.ikey_s, w.ival, w.ival_s, (int)(2 * B), 0,
-                                             bits_for(n_items), st));
+    { int rc_ = rb2sort::sort_positions(w.ikey, w.ikey_s, w.ival_s, 2 * B, bits_for(n_items), w.cub_tmp, w.cub_bytes, st); if (rc_) return rc_; }
   }
   // sharded step: the keys and sorts above depend on the ids only and overlap with the collective that
   // delivers the item rows on another stream; everything from here on reads them
@@ -624,8 +618,7 @@ size_t carve_plan(PlanWs &w, void *base, int64_t B, int want_cub) {
   w.rank = c.take<uint32_t>(M);
   size_t b1 = 0, b2 = 0;
   if (want_cub) {
-    cub::DeviceRadixSort::SortPairs(nullptr, b1, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
-                                    (uint32_t *)nullptr, (int)M, 0, 32);
+    b1 = rb2sort::tmp_bytes(M);
     cub::DeviceScan::InclusiveSum(nullptr, b2, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)M);
   }
   w.cub_bytes = b1 > b2 ? b1 : b2;
@@ -694,8 +687,7 @@ extern "C" int rb2_item_plan(const int64_t *pos, const int64_t *neg, int64_t bat
   ProfScope prof(RB2_ST_MISC, st, 6 + (bits_for(n_items) + 7) / 8);
   k_plan_keys<<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(pos, neg, batch, n_items, w);
   size_t tmp = w.cub_bytes;
-  RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.key, w.key_s, w.val, w.val_s, (int)M, 0,
-                                           bits_for(n_items), st));
+  { int rc_ = rb2sort::sort_positions(w.key, w.key_s, w.val_s, M, bits_for(n_items), w.cub_tmp, w.cub_bytes, st); if (rc_) return rc_; }
   k_plan_flags<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(w, M);
   tmp = w.cub_bytes;
   RB2_CUDA(cub::DeviceScan::InclusiveSum(w.cub_tmp, tmp, w.flag, w.rank, (int)M, st));
@@ -822,8 +814,7 @@ size_t carve_rows(RowsWs &w, void *base, int64_t M, int dim) {
   w.fh = c.take<uint8_t>(tiles);
   w.ft = c.take<uint8_t>(tiles);
   size_t b = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, b, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
-                                  (uint32_t *)nullptr, (int)M, 0, 32);
+  b = rb2sort::tmp_bytes(M);
   w.cub_bytes = b;
   w.cub_tmp = c.take<char>(b);
   return c.off;
@@ -906,8 +897,7 @@ extern "C" int rb2_sparse_rows_update(float *p, float *m, float *v, int32_t *las
   size_t tmp = rw.cub_bytes;
   {
     ProfScope prof(RB2_ST_SORT_ITEM, st, 2 + (bits_for(n_rows) + 7) / 8);
-    RB2_CUDA(cub::DeviceRadixSort::SortPairs(rw.cub_tmp, tmp, rw.key, rw.key_s, rw.val, rw.val_s, (int)count, 0,
-                                             bits_for(n_rows), st));
+    { int rc_ = rb2sort::sort_positions(rw.key, rw.key_s, rw.val_s, count, bits_for(n_rows), rw.cub_tmp, rw.cub_bytes, st, 1); if (rc_) return rc_; }
   }
   BprWs w{};
   w.hdr = rw.hdr;
@@ -1047,14 +1037,12 @@ extern "C" int rb2_bpr_train_step_p2p(float *user_p, float *user_m, float *user_
   size_t tmp = w.cub_bytes;
   {
     ProfScope prof(RB2_ST_SORT_USER, st, 2 + (bits_for(n_users_local) + 7) / 8);
-    RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ukey, w.ukey_s, w.uval, w.uval_s, (int)B, 0,
-                                             bits_for(n_users_local), st));
+    { int rc_ = rb2sort::sort_positions(w.ukey, w.ukey_s, w.uval_s, B, bits_for(n_users_local), w.cub_tmp, w.cub_bytes, st); if (rc_) return rc_; }
   }
   tmp = w.cub_bytes;
   {
     ProfScope prof(RB2_ST_SORT_ITEM, st, 2 + (bits_for(n_items) + 7) / 8);
-    RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.ikey, w.ikey_s, w.ival, w.ival_s, (int)(2 * B), 0,
-                                             bits_for(n_items), st));
+    { int rc_ = rb2sort::sort_positions(w.ikey, w.ikey_s, w.ival_s, 2 * B, bits_for(n_items), w.cub_tmp, w.cub_bytes, st); if (rc_) return rc_; }
   }
   {
     // barrier A: every owner has finished the previous step's update; from here on peers' rows may be read and
@@ -1123,4 +1111,17 @@ extern "C" int rb2_bpr_train_step_p2p(float *user_p, float *user_m, float *user_
   });
   RB2_CUDA(cudaGetLastError());
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The grouping primitive of every step above, exported for tests and callers that build their own walks.
+extern "C" size_t rb2_sort_positions_workspace_bytes(int64_t count) { return rb2sort::tmp_bytes(count) + 256; }
+
+extern "C" int rb2_sort_positions(const uint32_t *keys, int64_t count, int32_t key_bits, uint32_t *keys_sorted,
+                                  uint32_t *positions, void *workspace, size_t workspace_bytes, void *stream) {
+  RB2_REQUIRE(keys && keys_sorted && positions && workspace, RB2_EINVAL, "rb2_sort_positions: null argument");
+  RB2_REQUIRE(count >= 0 && count < ((int64_t)1 << 32) && key_bits >= 1 && key_bits <= 32, RB2_EINVAL,
+              "rb2_sort_positions: count / key_bits out of range");
+  return rb2sort::sort_positions(keys, keys_sorted, positions, count, key_bits, workspace, workspace_bytes,
+                                 (cudaStream_t)stream);
 }

@@ -20,8 +20,8 @@
 //                 straddling runs go through the fixed-order fix-up (no float atomics).
 //   k_fm_bias     db = sum_s gz[s], dense Adam on the scalar bias; loss reduction.
 // Algorithmic bytes per sample: F*(24*d + 24) + 8*F + 4.
-#include <cub/device/device_radix_sort.cuh>
 
+#include "bucket_sort.cuh"
 #include "common.cuh"
 
 namespace {
@@ -69,8 +69,7 @@ size_t carve(FmWs &w, void *base, int64_t B, int F, int dim) {
   w.loss_part = c.take<double>(w.n_parts);
   w.gz_part = c.take<double>(w.n_parts);
   size_t b = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, b, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
-                                  (uint32_t *)nullptr, (int)M, 0, 32);
+  b = rb2sort::tmp_bytes(M);
   w.cub_bytes = b;
   w.cub_tmp = c.take<char>(b);
   return c.off;
@@ -85,6 +84,7 @@ struct FmTables {
   float *E, *mE, *vE;   // [rows, D]
   float *W, *mW, *vW;   // [rows]
   float *bias;          // [3]: b, m, v
+  int32_t *last;        // [rows] RB2_OPT_ADAM_LAZY: the step at which row r (of E and of W) was last brought up to date
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kThreads) k_fm_forward(FmTables t, const int64
                                                           const int64_t *__restrict__ offsets,
                                                           const float *__restrict__ label, int64_t B, int F,
                                                           int64_t n_rows, float inv_b, FmWs w,
-                                                          float *__restrict__ y_out) {
+                                                          float *__restrict__ y_out, OptScalars o) {
   constexpr int LANES = RowCfg<D>::LANES;
   constexpr int GROUPS = RowCfg<D>::GROUPS;
   static_assert(RowCfg<D>::VPL == 1, "FM path supports d <= 128");
@@ -104,6 +104,9 @@ __global__ void __launch_bounds__(kThreads) k_fm_forward(FmTables t, const int64
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
   const int64_t n_warps = (int64_t)gridDim.x * blockDim.x / 32;
   const float bias = t.bias[0];
+  // dense-Adam parity mode: a row is read as the reference's dense optimizer holds it after step - 1 (rows the
+  // previous batches did not touch kept moving on their momentum / weight decay; common.cuh row_replay)
+  const bool lazy = o.kind == RB2_OPT_ADAM_LAZY;
   float loss_local = 0.f, gz_local = 0.f;
   for (int64_t s = warp_global; s < B; s += n_warps) {
     float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -114,8 +117,21 @@ __global__ void __launch_bounds__(kThreads) k_fm_forward(FmTables t, const int64
         w.hdr->range_error = 1;
         row = min(max(row, (int64_t)0), n_rows - 1);
       }
-      v = __ldg(reinterpret_cast<const float4 *>(t.E + row * D) + gl);
-      if (gl == 0) first += __ldg(t.W + row);
+      if (lazy) {
+        v = row_ld_effective<D, true>(t.E, t.mE, t.vE, t.last, row, gl, o).v[0];
+        if (gl == 0) {
+          float pw = t.W[row];
+          const int last = t.last[row];
+          if (last < o.step - 1 && (last > 0 || o.wd != 0.f)) {
+            float mw = t.mW[row], vw = t.vW[row];
+            adam_replay_elem(pw, mw, vw, last + 1, o.step - 1, o);
+          }
+          first += pw;
+        }
+      } else {
+        v = __ldg(reinterpret_cast<const float4 *>(t.E + row * D) + gl);
+        if (gl == 0) first += __ldg(t.W + row);
+      }
       if (STORE && gl == 0) {
         int64_t o = s * F + f;
         w.key[o] = (uint32_t)row;
@@ -195,6 +211,33 @@ template <int D>
 __device__ __forceinline__ void fm_row_step(const FmTables &t, int64_t row, int lane, const Row<D> &gsum, float zsum,
                                             const OptScalars &o) {
   // dE = sum gs - zsum * v ;  dW = zsum
+  if (o.kind == RB2_OPT_ADAM_LAZY) {
+    Row<D> p = row_ld<D>(t.E, row, lane), m = row_ld<D>(t.mE, row, lane), v = row_ld<D>(t.vE, row, lane);
+    const int last = t.last[row];
+    row_replay<D>(p, m, v, last, o.step - 1, o);       // the value the forward read
+    Row<D> g = gsum;
+    row_fma<D>(g, -zsum, p);
+#pragma unroll
+    for (int i = 0; i < RowCfg<D>::VPL; ++i) {
+      adam_elem(p.v[i].x, m.v[i].x, v.v[i].x, g.v[i].x, o);
+      adam_elem(p.v[i].y, m.v[i].y, v.v[i].y, g.v[i].y, o);
+      adam_elem(p.v[i].z, m.v[i].z, v.v[i].z, g.v[i].z, o);
+      adam_elem(p.v[i].w, m.v[i].w, v.v[i].w, g.v[i].w, o);
+    }
+    row_st<D>(t.E, row, lane, p);
+    row_st<D>(t.mE, row, lane, m);
+    row_st<D>(t.vE, row, lane, v);
+    if (lane == 0) {
+      float pw = t.W[row], mw = t.mW[row], vw = t.vW[row];
+      if (last < o.step - 1 && (last > 0 || o.wd != 0.f)) adam_replay_elem(pw, mw, vw, last + 1, o.step - 1, o);
+      adam_elem(pw, mw, vw, zsum, o);
+      t.W[row] = pw;
+      t.mW[row] = mw;
+      t.vW[row] = vw;
+      t.last[row] = o.step;
+    }
+    return;
+  }
   Row<D> p = row_ld<D>(t.E, row, lane);
   Row<D> g = gsum;
   row_fma<D>(g, -zsum, p);
@@ -407,7 +450,7 @@ __global__ void k_fm_bias_loss(FmTables t, FmWs w, int64_t n_parts, double inv_b
     }
     if (o.kind == RB2_OPT_SGD) {
       sgd_elem(b, gb, o);
-    } else {
+    } else {                     // Adam (the bias is dense: stepped at every step, so lazy == plain)
       float m = t.bias[1], v = t.bias[2];
       adam_elem(b, m, v, gb, o);
       t.bias[1] = m;
@@ -460,13 +503,12 @@ static int fm_step(FmTables t, int64_t n_rows, int32_t dim, const int64_t *ids, 
     {
       ProfScope prof(RB2_ST_FM_FWD, st, 2);
       k_fm_forward<D_, true><<<fblocks, kThreads, 0, st>>>(t, ids, offsets, label, batch, n_fields, n_rows,
-                                                           (float)(1.0 / norm_batch), w, nullptr);
+                                                           (float)(1.0 / norm_batch), w, nullptr, o);
     }
     size_t tmp = w.cub_bytes;
     {
       ProfScope prof(RB2_ST_SORT_ITEM, st, 2 + (rb2_bits_for(n_rows) + 7) / 8);
-      RB2_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.key, w.key_s, w.val, w.val_s, (int)M, 0,
-                                               rb2_bits_for(n_rows), st));
+      { int rc_ = rb2sort::sort_positions(w.key, w.key_s, w.val_s, M, rb2_bits_for(n_rows), w.cub_tmp, w.cub_bytes, st); if (rc_) return rc_; }
     }
     const int T = rb2_pick_tile(M, LANES);
     const int64_t nt = (M + T - 1) / T;
@@ -485,17 +527,20 @@ static int fm_step(FmTables t, int64_t n_rows, int32_t dim, const int64_t *ids, 
 }
 
 extern "C" int rb2_fm_train_step(float *E, float *mE, float *vE, float *W, float *mW, float *vW, float *bias3,
-                                 int64_t n_rows, int32_t dim, const int64_t *ids, const int64_t *offsets,
-                                 int32_t n_fields, const float *label, int64_t batch, const rb2_optim *h_opt,
-                                 float *loss_out, double *loss_accum, void *workspace, size_t workspace_bytes,
-                                 void *stream) {
+                                 int32_t *row_last, int64_t n_rows, int32_t dim, const int64_t *ids,
+                                 const int64_t *offsets, int32_t n_fields, const float *label, int64_t batch,
+                                 const rb2_optim *h_opt, float *loss_out, double *loss_accum, void *workspace,
+                                 size_t workspace_bytes, void *stream) {
   RB2_REQUIRE(E && W && bias3 && ids && offsets && label && h_opt && loss_out && workspace, RB2_EINVAL,
               "rb2_fm_train_step: null argument");
   OptScalars o = rb2_opt_scalars(h_opt);
-  RB2_REQUIRE(o.kind == RB2_OPT_SGD || o.kind == RB2_OPT_ADAM, RB2_EINVAL,
-              "rb2_fm_train_step: optimizer kind %d not supported (sgd, adam)", o.kind);
+  RB2_REQUIRE(o.kind == RB2_OPT_SGD || o.kind == RB2_OPT_ADAM || o.kind == RB2_OPT_ADAM_LAZY, RB2_EINVAL,
+              "rb2_fm_train_step: optimizer kind %d not supported (sgd, adam, adam_lazy)", o.kind);
   if (o.kind != RB2_OPT_SGD) RB2_REQUIRE(mE && vE && mW && vW, RB2_EINVAL, "rb2_fm_train_step: Adam needs m and v");
-  FmTables t{E, mE, vE, W, mW, vW, bias3};
+  if (o.kind == RB2_OPT_ADAM_LAZY)
+    RB2_REQUIRE(row_last && o.lazy_step_size && o.lazy_bc2_sqrt, RB2_EINVAL,
+                "rb2_fm_train_step: adam_lazy needs row_last and the bias-correction tables");
+  FmTables t{E, mE, vE, W, mW, vW, bias3, row_last};
   return fm_step(t, n_rows, dim, ids, offsets, n_fields, label, batch, (double)batch, o, loss_out, loss_accum, workspace,
                  workspace_bytes, (cudaStream_t)stream, "rb2_fm_train_step");
 }
@@ -513,7 +558,7 @@ extern "C" int rb2_fm_grad_step(float *rows_e, float *rows_w, const float *bias3
   RB2_REQUIRE(global_batch >= batch, RB2_EINVAL, "rb2_fm_grad_step: global_batch < batch");
   OptScalars o = {};
   o.kind = kOptGradOut;
-  FmTables t{rows_e, nullptr, nullptr, rows_w, nullptr, nullptr, const_cast<float *>(bias3)};
+  FmTables t{rows_e, nullptr, nullptr, rows_w, nullptr, nullptr, const_cast<float *>(bias3), nullptr};
   return fm_step(t, n_rows, dim, ids, offsets, n_fields, label, batch, (double)global_batch, o, loss2, nullptr, workspace,
                  workspace_bytes, (cudaStream_t)stream, "rb2_fm_grad_step");
 }
@@ -565,8 +610,7 @@ extern "C" size_t rb2_scalar_rows_update_workspace_bytes(int64_t m) {
   Carver c(nullptr);
   c.take<uint32_t>(m); c.take<uint32_t>(m); c.take<uint32_t>(m); c.take<uint32_t>(m);
   size_t b = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, b, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
-                                  (uint32_t *)nullptr, (int)m, 0, 32);
+  b = rb2sort::tmp_bytes(m);
   c.take<char>(b);
   return c.off + 256;
 }
@@ -585,12 +629,11 @@ extern "C" int rb2_scalar_rows_update(float *p, float *m, float *v, int64_t n_ro
   cudaStream_t st = (cudaStream_t)stream;
   Carver c(workspace);
   uint32_t *key = c.take<uint32_t>(M), *key_s = c.take<uint32_t>(M), *val = c.take<uint32_t>(M), *val_s = c.take<uint32_t>(M);
-  size_t b = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, b, key, key_s, val, val_s, (int)M, 0, 32);
+  const size_t b = rb2sort::tmp_bytes(M);
   char *tmp = c.take<char>(b);
   unsigned blocks = (unsigned)((M + 255) / 256);
   k_scalar_keys<<<blocks, 256, 0, st>>>(ids, M, n_rows, key, val);
-  RB2_CUDA(cub::DeviceRadixSort::SortPairs(tmp, b, key, key_s, val, val_s, (int)M, 0, rb2_bits_for(n_rows), st));
+  { int rc_ = rb2sort::sort_positions(key, key_s, val_s, M, rb2_bits_for(n_rows), tmp, b, st); if (rc_) return rc_; }
   k_scalar_rows<<<blocks, 256, 0, st>>>(p, m, v, key_s, val_s, grads, M, o);
   RB2_CUDA(cudaGetLastError());
   return 0;
@@ -601,6 +644,52 @@ extern "C" int rb2_scalar_step(float *p3, const float *grad, const rb2_optim *h_
   OptScalars o = rb2_opt_scalars(h_opt);
   RB2_REQUIRE(o.kind == RB2_OPT_SGD || o.kind == RB2_OPT_ADAM, RB2_EINVAL, "rb2_scalar_step: sgd or adam");
   k_scalar_step<<<1, 1, 0, (cudaStream_t)stream>>>(p3, grad, o);
+  RB2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+/* RB2_OPT_ADAM_LAZY: bring every row of E and of W to step h_opt->step (the zero-gradient / weight-decay steps it
+ * missed) before the tables are read by predict / loss / a checkpoint. */
+namespace {
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_fm_lazy_flush(FmTables t, int64_t n_rows, OptScalars o) {
+  constexpr int LANES = RowCfg<D>::LANES;
+  const int lane = threadIdx.x % LANES;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  if (row >= n_rows) return;
+  const int last = t.last[row];
+  if (last >= o.step) return;
+  if (last > 0 || o.wd != 0.f) {
+    Row<D> p = row_ld<D>(t.E, row, lane), m = row_ld<D>(t.mE, row, lane), v = row_ld<D>(t.vE, row, lane);
+    row_replay<D>(p, m, v, last, o.step, o);
+    row_st<D>(t.E, row, lane, p);
+    row_st<D>(t.mE, row, lane, m);
+    row_st<D>(t.vE, row, lane, v);
+    if (lane == 0) {
+      float pw = t.W[row], mw = t.mW[row], vw = t.vW[row];
+      adam_replay_elem(pw, mw, vw, last + 1, o.step, o);
+      t.W[row] = pw;
+      t.mW[row] = mw;
+      t.vW[row] = vw;
+    }
+  }
+  if (lane == 0) t.last[row] = o.step;
+}
+}  // namespace
+
+extern "C" int rb2_fm_lazy_flush(float *E, float *mE, float *vE, float *W, float *mW, float *vW, int32_t *row_last,
+                                 int64_t n_rows, int32_t dim, const rb2_optim *h_opt, void *stream) {
+  RB2_REQUIRE(E && mE && vE && W && mW && vW && row_last && h_opt, RB2_EINVAL, "rb2_fm_lazy_flush: null argument");
+  OptScalars o = rb2_opt_scalars(h_opt);
+  RB2_REQUIRE(o.kind == RB2_OPT_ADAM_LAZY && o.lazy_step_size && o.lazy_bc2_sqrt, RB2_EINVAL,
+              "rb2_fm_lazy_flush: needs an adam_lazy optimizer description");
+  if (n_rows <= 0 || o.step <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  FmTables t{E, mE, vE, W, mW, vW, nullptr, row_last};
+  RB2_FM_DIM(dim, {
+    constexpr int LANES = RowCfg<D_>::LANES;
+    k_fm_lazy_flush<D_><<<(unsigned)((n_rows * LANES + kThreads - 1) / kThreads), kThreads, 0, st>>>(t, n_rows, o);
+  });
   RB2_CUDA(cudaGetLastError());
   return 0;
 }
@@ -617,7 +706,7 @@ extern "C" int rb2_fm_loss(const float *E, const float *W, const float *bias3, i
   RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_fm_loss: workspace %zu < %zu", workspace_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
   FmTables t{const_cast<float *>(E), nullptr, nullptr, const_cast<float *>(W), nullptr, nullptr,
-             const_cast<float *>(bias3)};
+             const_cast<float *>(bias3), nullptr};
   OptScalars o = {};
   o.kind = kOptLossOnly;
   k_zero_parts<<<(unsigned)((w.n_parts + 255) / 256), 256, 0, st>>>(w);
@@ -627,7 +716,7 @@ extern "C" int rb2_fm_loss(const float *E, const float *W, const float *bias3, i
     if ((int64_t)fblocks * (kThreads / 32) > w.n_parts) fblocks = (unsigned)std::max<int64_t>(1, w.n_parts / (kThreads / 32));
     ProfScope prof(RB2_ST_FM_FWD, st, 2);
     k_fm_forward<D_, true, false><<<fblocks, kThreads, 0, st>>>(t, ids, offsets, label, batch, n_fields, n_rows,
-                                                                (float)(1.0 / (double)batch), w, nullptr);
+                                                                (float)(1.0 / (double)batch), w, nullptr, o);
     k_fm_bias_loss<<<1, 256, 0, st>>>(t, w, w.n_parts, 1.0 / (double)batch, o, loss_out, nullptr);
   });
   RB2_CUDA(cudaGetLastError());
@@ -644,13 +733,14 @@ extern "C" int rb2_fm_predict(const float *E, const float *W, const float *bias3
   RB2_REQUIRE(workspace_bytes >= need, RB2_EWORKSPACE, "rb2_fm_predict: workspace %zu < %zu", workspace_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
   FmTables t{const_cast<float *>(E), nullptr, nullptr, const_cast<float *>(W), nullptr, nullptr,
-             const_cast<float *>(bias3)};
+             const_cast<float *>(bias3), nullptr};
   RB2_FM_DIM(dim, {
     int64_t warps = std::min<int64_t>(batch, (int64_t)rb2_num_sms() * 64);
     unsigned fblocks = (unsigned)((warps * 32 + kThreads - 1) / kThreads);
     ProfScope prof(RB2_ST_FM_FWD, st);
+    OptScalars none = {};
     k_fm_forward<D_, false><<<fblocks, kThreads, 0, st>>>(t, ids, offsets, nullptr, batch, n_fields, n_rows, 1.f, w,
-                                                          y_out);
+                                                          y_out, none);
   });
   RB2_CUDA(cudaGetLastError());
   return 0;

@@ -51,19 +51,38 @@ class _PointwiseMixin:
         self._autostep = True
 
     def flush(self):
-        pass
+        """adam_lazy only: bring every row up to the current step before the tables are read."""
+        if self._optim is not None and self._optim.kind_name == "adam_lazy" and self._optim.step > 0:
+            E, W = self._tables()
+            ops.fm_lazy_flush(E, W, self._state, self._optim)
+
+    def state_dict(self, *args, **kwargs):
+        self.flush()
+        return self._state_dict_impl(*args, **kwargs)
+
+    def _new_state(self, kind, E, W):
+        st = {}
+        if kind != "sgd":
+            st = dict(mE=torch.zeros_like(E), vE=torch.zeros_like(E), mW=torch.zeros_like(W), vW=torch.zeros_like(W))
+        if kind == "adam_lazy":
+            st["last"] = torch.zeros(E.shape[0], dtype=torch.int32, device=E.device)
+        return st
+
+    def _after_state_load(self):
+        if "last" in self._state:
+            self._state["last"].fill_(self._optim.step)
 
     def _apply_pending(self):
         if self._optim is None:     # unmodified Trainer: hyper-parameters from the config it reads itself
             learner, lr, wd = self._hyper
-            kind = fused_learner(learner)
-            self._make_optimizer("adam" if kind == "adam_lazy" else kind, lr if lr is not None else 1e-3, wd or 0.0)
+            self._make_optimizer(fused_learner(learner), lr if lr is not None else 1e-3, wd or 0.0)
         inter = self._pending
         self._pending = None
         self._fused_step(inter, None)
 
     def build_optimizer(self, learner="adam", learning_rate=1e-3, weight_decay=0.0):
-        """Trainer._build_optimizer (trainer.py:109-130) for the fused path: 'adam' (row-sparse) or 'sgd'.  Returns a
+        """Trainer._build_optimizer (trainer.py:109-130) for the fused path: 'adam' (row-sparse), 'adam_lazy' (row-
+        sparse work, the trajectory of the reference's dense Adam incl. weight decay) or 'sgd'.  Returns a
         FusedOptimizer (zero_grad / step / state_dict / load_state_dict); train_step() needs nothing else."""
         self._make_optimizer(learner.lower(), learning_rate, weight_decay or 0.0)
         self._autostep = False
@@ -150,14 +169,10 @@ class FusedFM(_PointwiseMixin, nn.Module):
         self._bias3[0:1].copy_(self.first_order_linear.bias.data)
 
     def _make_optimizer(self, kind, learning_rate, weight_decay):
-        if kind not in ("adam", "sgd"):
-            raise ValueError("FusedFM implements the fused kinds {adam (row-sparse), sgd}")
+        if kind not in ("adam", "adam_lazy", "sgd"):
+            raise ValueError("FusedFM implements the fused kinds {adam (row-sparse), adam_lazy, sgd}")
         self._optim = ops.Optim(kind, learning_rate, weight_decay)
-        E, W = self._tables()
-        self._state = {}
-        if kind == "adam":
-            self._state = dict(mE=torch.zeros_like(E), vE=torch.zeros_like(E), mW=torch.zeros_like(W),
-                               vW=torch.zeros_like(W))
+        self._state = self._new_state(kind, *self._tables())
         self._ensure_device_state()
 
     def _opt_entries(self):
@@ -165,8 +180,8 @@ class FusedFM(_PointwiseMixin, nn.Module):
         st = self._state
         return [(st["mE"], st["vE"]), (self._bias3[1:2], self._bias3[2:3]), (st["mW"], st["vW"])]
 
-    def _after_state_load(self):
-        pass
+    def _state_dict_impl(self, *args, **kwargs):
+        return nn.Module.state_dict(self, *args, **kwargs)
 
     # ---- fused step ----------------------------------------------------------------------------------
     def _fused_step(self, interaction, loss_accum):
@@ -179,6 +194,7 @@ class FusedFM(_PointwiseMixin, nn.Module):
         return self._loss_out
 
     def _loss_value(self, interaction):
+        self.flush()
         self._ensure_device_state()
         ids = self._ids(interaction)
         E, W = self._tables()
@@ -189,6 +205,7 @@ class FusedFM(_PointwiseMixin, nn.Module):
 
     # ---- the reference's plugin API ---------------------------------------------------------------------
     def predict(self, interaction):  # fm.py:58-59
+        self.flush()
         self._ensure_device_state()
         ids = self._ids(interaction)
         E, W = self._tables()
@@ -218,8 +235,11 @@ class FusedMFSimple(_PointwiseMixin, nn.Module):
         self.bias = nn.Parameter(torch.zeros(1))
         self._init_fused(config)
 
+    def _tables(self):
+        return self.table.data, self.biases.data
+
     # reference-compatible state dict -------------------------------------------------------------------
-    def state_dict(self, *a, **k):
+    def _state_dict_impl(self, *a, **k):
         nu = self.n_users
         return {"user_embedding.weight": self.table.data[:nu], "item_embedding.weight": self.table.data[nu:],
                 "user_bias": self.biases.data[:nu], "item_bias": self.biases.data[nu:], "bias": self.bias.data}
@@ -246,14 +266,10 @@ class FusedMFSimple(_PointwiseMixin, nn.Module):
         return ops.grow_workspace(self._ws, batch, lambda b: ops.fm_workspace(b, 2, self.embedding_dim, self.table.device))
 
     def _make_optimizer(self, kind, learning_rate, weight_decay):
-        if kind not in ("adam", "sgd"):
-            raise ValueError("FusedMFSimple implements the fused kinds {adam (row-sparse), sgd}")
+        if kind not in ("adam", "adam_lazy", "sgd"):
+            raise ValueError("FusedMFSimple implements the fused kinds {adam (row-sparse), adam_lazy, sgd}")
         self._optim = ops.Optim(kind, learning_rate, weight_decay)
-        self._state = {}
-        if kind == "adam":
-            z = torch.zeros_like
-            self._state = dict(mE=z(self.table.data), vE=z(self.table.data), mW=z(self.biases.data),
-                               vW=z(self.biases.data))
+        self._state = self._new_state(kind, *self._tables())
         self._prep()
 
     def _opt_entries(self):
@@ -262,9 +278,6 @@ class FusedMFSimple(_PointwiseMixin, nn.Module):
         st, nu = self._state, self.n_users
         return [(st["mW"][:nu], st["vW"][:nu]), (st["mW"][nu:], st["vW"][nu:]), (self._bias3[1:2], self._bias3[2:3]),
                 (st["mE"][:nu], st["vE"][:nu]), (st["mE"][nu:], st["vE"][nu:])]
-
-    def _after_state_load(self):
-        pass
 
     def _ids(self, interaction):
         return torch.stack([interaction[self.USER_ID], interaction[self.ITEM_ID]], dim=1).contiguous()
@@ -279,6 +292,7 @@ class FusedMFSimple(_PointwiseMixin, nn.Module):
         return self._loss_out
 
     def _loss_value(self, interaction):
+        self.flush()
         self._prep()
         ids = self._ids(interaction)
         out = torch.empty(1, dtype=torch.float32, device=self.table.device)
@@ -287,6 +301,7 @@ class FusedMFSimple(_PointwiseMixin, nn.Module):
         return out[0]
 
     def predict(self, interaction):  # mfsimple.py:59-62
+        self.flush()
         self._prep()
         ids = self._ids(interaction)
         return ops.fm_predict(self.table.data, self.biases.data, self._bias3, ids, self._offsets,

@@ -282,6 +282,18 @@ def bpr_loss(U, V, user, pos, neg, loss_out, ws):
                            _stream()))
 
 
+def sort_positions(keys, key_bits, ws=None):
+    """Stable (key, position) sort of uint32-valued keys < 2^key_bits held in an int32 tensor (rb2_sort_positions).
+    Returns (keys_sorted, positions) as int32 tensors (bit patterns of uint32)."""
+    n = int(keys.numel())
+    if ws is None:
+        ws = Workspace(lib.rb2_sort_positions_workspace_bytes(n), keys.device)
+    ks, pos = torch.empty_like(keys), torch.empty_like(keys)
+    check(lib.rb2_sort_positions(_ptr(keys, torch.int32), n, int(key_bits), _ptr(ks), _ptr(pos), ws.ptr(), ws.nbytes,
+                                 _stream()))
+    return ks, pos
+
+
 def adam_lazy_flush(P, M, V, last, optim):
     o = optim.c_struct(P.device)
     check(lib.rb2_adam_lazy_flush(_ptr(P, torch.float32), _ptr(M, torch.float32), _ptr(V, torch.float32),
@@ -299,10 +311,20 @@ def fm_train_step(E, W, bias3, state, ids, offsets, label, optim, loss_out, loss
     f32 = torch.float32
     check(lib.rb2_fm_train_step(_ptr(E, f32), _ptr(state.get("mE"), f32, True), _ptr(state.get("vE"), f32, True),
                                 _ptr(W, f32), _ptr(state.get("mW"), f32, True), _ptr(state.get("vW"), f32, True),
-                                _ptr(bias3, f32), E.shape[0], E.shape[1], _ptr(ids, torch.int64),
+                                _ptr(bias3, f32), _ptr(state.get("last"), torch.int32, True), E.shape[0], E.shape[1],
+                                _ptr(ids, torch.int64),
                                 _ptr(offsets, torch.int64), ids.shape[1], _ptr(label, f32), ids.shape[0],
                                 ctypes.byref(o), _ptr(loss_out, f32), _ptr(loss_accum, torch.float64, True), ws.ptr(),
                                 ws.nbytes, _stream()))
+
+
+def fm_lazy_flush(E, W, state, optim):
+    """adam_lazy: bring every row of E and W to the optimizer's current step (rb2_fm_lazy_flush)."""
+    o = optim.c_struct(E.device)
+    f32 = torch.float32
+    check(lib.rb2_fm_lazy_flush(_ptr(E, f32), _ptr(state["mE"], f32), _ptr(state["vE"], f32), _ptr(W, f32),
+                                _ptr(state["mW"], f32), _ptr(state["vW"], f32), _ptr(state["last"], torch.int32),
+                                E.shape[0], E.shape[1], ctypes.byref(o), _stream()))
 
 
 def fm_grad_step(rows_e, rows_w, bias3, ids, offsets, label, global_batch, loss2, ws):

@@ -61,17 +61,7 @@ class FusedTrainer:
 
     def _build_optimizer(self, params):  # trainer.py:109-130
         kind = fused_learner(self.learner, self.config["fused_learner"])
-        try:
-            return self.model.build_optimizer(kind, self.learning_rate, self.weight_decay)
-        except ValueError:
-            if kind != "adam_lazy":
-                raise
-            # the point-wise models have no dense-trajectory kind yet: say so instead of silently changing algorithm
-            import warnings
-            warnings.warn("%s has no 'adam_lazy' kind; learner 'adam' runs the ROW-SPARSE Adam kernel, which differs "
-                          "from the reference's dense torch.optim.Adam on rows a batch does not touch"
-                          % type(self.model).__name__)
-            return self.model.build_optimizer("adam", self.learning_rate, self.weight_decay)
+        return self.model.build_optimizer(kind, self.learning_rate, self.weight_decay)
 
     # ---- checkpoints (trainer.py:191-232) ---------------------------------------------------------------------
     def _save_checkpoint(self, epoch):

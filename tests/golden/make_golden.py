@@ -17,6 +17,8 @@ modified or copied.  Every array saved here is an INPUT or an OUTPUT of referenc
                  BPR.full_sort_predict -> Trainer._full_sort_batch_eval -> TopKEvaluator
   sampler.npz    recbole.sampler.Sampler.sample_by_user_ids with its random_list / random_pr state
   fm_steps.npz   recbole FM (token fields) + BCELoss + Adam, 2 steps
+  dense_adam_pointwise.npz  FM (wd 0 / 1e-3) and MFSimple (its yaml: wd 1e-8, lr 2e-3) under dense torch.optim.Adam for
+                 4-5 steps on batches that leave most rows untouched (pins the fused 'adam_lazy' kind)
   ce_head.npz    the SASRec head expressions of sasrec.py:137-141,152-158
   cfg1_train.npz BASELINE config 1: the reference pipeline on ml-100k, 2 epochs of Trainer._train_epoch
                  (every batch recorded) + Trainer.evaluate
@@ -392,6 +394,77 @@ def g_fm(out):
     np.savez_compressed(out, **d)
 
 
+def g_dense_adam_pointwise(out):
+    """Dense torch.optim.Adam trajectories of the two point-wise models, on batches that leave most rows UNTOUCHED
+    (so row-sparse Adam and the reference's dense Adam differ from step 2 on): recbole FM, 4 steps, weight_decay 0
+    and 1e-3; the fork's MFSimple with ITS config (MFSimple.yaml: weight_decay 1e-08, learning_rate 0.002), 5 steps."""
+    from recbole.model.context_aware_recommender.fm import FM
+    from recbole.model.general_recommender.mfsimple import MFSimple
+    from recbole.utils import FeatureType
+    d = {}
+    field_dims = {"f0": 40, "f1": 300, "f2": 3, "f3": 90, "f4": 11, "f5": 700}
+    dim, B, steps = 16, 48, 4
+    f2t = {k: FeatureType.TOKEN for k in field_dims}
+    f2t["label"] = FeatureType.FLOAT
+    nums = dict(field_dims)
+    nums["label"] = 1
+    for tag, wd in (("fm_wd0", 0.0), ("fm_wd", 1e-3)):
+        torch.manual_seed(9)
+        model = FM(StubConfig(LABEL_FIELD="label", embedding_size=dim, device="cpu", double_tower=None),
+                   StubDataset(nums, f2t))
+        with torch.no_grad():
+            for p in model.parameters():
+                p.mul_(2.0)
+        rng = np.random.default_rng(13)
+        d[tag + "_field_dims"] = np.array(list(field_dims.values()))
+        d[tag + "_offsets"] = np.asarray(model.token_field_offsets)
+        for n, p in model.named_parameters():
+            d[tag + "_p0_" + n] = p.detach().numpy().copy()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-2, weight_decay=wd)
+        for s in range(steps):
+            inter = {k: torch.from_numpy(rng.integers(0, v, B)) for k, v in field_dims.items()}
+            inter["label"] = torch.from_numpy((rng.random(B) < 0.3).astype(np.float32))
+            d[tag + "_ids%d" % s] = np.stack([inter[k].numpy() for k in field_dims], axis=1)
+            d[tag + "_label%d" % s] = inter["label"].numpy()
+            opt.zero_grad()
+            loss = model.calculate_loss(inter)
+            loss.backward()
+            opt.step()
+            d[tag + "_loss%d" % s] = np.float32(loss.item())
+        for n, p in model.named_parameters():
+            d[tag + "_pN_" + n] = p.detach().numpy().copy()
+        with torch.no_grad():
+            d[tag + "_predN"] = model.predict(inter).numpy().copy()
+    # MFSimple, its own hyper-parameters (properties/model/MFSimple.yaml)
+    torch.manual_seed(21)
+    n_users, n_items, B, dim, steps = 200, 300, 64, 32, 5
+    cfg = StubConfig(USER_ID_FIELD="user_id", ITEM_ID_FIELD="item_id", NEG_PREFIX="neg_", device="cpu",
+                     embedding_dimension=dim, LABEL_FIELD="label")
+    model = MFSimple(cfg, StubDataset({"user_id": n_users, "item_id": n_items}))
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.ndim == 2:
+                p.mul_(30.0)
+    rng = np.random.default_rng(17)
+    for n, p in model.named_parameters():
+        d["mf_p0_" + n] = p.detach().numpy().copy()
+    opt = torch.optim.Adam(model.parameters(), lr=0.002, weight_decay=1e-08)
+    for s in range(steps):
+        inter = dict(user_id=torch.from_numpy(rng.integers(1, n_users, B)),
+                     item_id=torch.from_numpy(rng.integers(1, n_items, B)),
+                     label=torch.from_numpy((rng.random(B) < 0.3).astype(np.float32)))
+        for k, v in inter.items():
+            d["mf_%s%d" % (k, s)] = v.numpy()
+        opt.zero_grad()
+        loss = model.calculate_loss(inter)
+        loss.backward()
+        opt.step()
+        d["mf_loss%d" % s] = np.float32(loss.item())
+    for n, p in model.named_parameters():
+        d["mf_pN_" + n] = p.detach().numpy().copy()
+    np.savez_compressed(out, **d)
+
+
 def g_ce(out):
     torch.manual_seed(9)
     B, N, H, K = 48, 700, 64, 10
@@ -415,6 +488,7 @@ if __name__ == "__main__":
     g_bpr(o("bpr_steps.npz"))
     g_dot(o("dot_steps.npz"))
     g_fm(o("fm_steps.npz"))
+    g_dense_adam_pointwise(o("dense_adam_pointwise.npz"))
     g_ce(o("ce_head.npz"))
     g_fullsort_small(o("fullsort_small.npz"))
     g_fullsort_ml100k(o("fullsort_ml100k.npz"), o("sampler.npz"))

@@ -152,3 +152,93 @@ def test_mfsimple_dot_loss_vs_reference_golden(golden):
     # the gradient itself (not hidden behind the parameter magnitude)
     gU = (g["p_user_embedding.weight"] - sd["user_embedding.weight"].cpu().numpy()) / lr
     assert rel_err(gU, g["g_user_embedding.weight"]) < 1e-4
+
+
+def _fm_model(g, tag, names, dims, dim, learner, lr, wd):
+    from recbole_b200 import FusedFM
+
+    class Cfg(dict):
+        def __getitem__(self, k):
+            return self.get(k)
+
+    class DS:
+        field2type = dict({n: "token" for n in names}, label="float")
+
+        def fields(self):
+            return names + ["label"]
+
+        def num(self, f):
+            return int(dims[names.index(f)])
+
+    cfg = Cfg(LABEL_FIELD="label", embedding_size=dim, device="cuda", learner=learner, learning_rate=lr, weight_decay=wd)
+    m = FusedFM(cfg, DS()).to("cuda")
+    m.load_state_dict({k[len(tag) + 4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(tag + "_p0_")})
+    return m
+
+
+@pytest.mark.parametrize("tag,wd", [("fm_wd0", 0.0), ("fm_wd", 1e-3)])
+def test_fm_dense_adam_trajectory_with_untouched_rows(golden, tag, wd):
+    """The reference's FM under DENSE torch.optim.Adam for 4 steps on batches that touch a small part of the 1 144-row
+    table (weight decay 0 and 1e-3: with decay every row moves at every step).  The fused kind 'adam_lazy'
+    reproduces it: losses, every parameter and predictions to 1e-5; the row-sparse kind does not."""
+    from recbole_b200 import Interaction
+    from gpu_util import rel_err
+    g = golden("dense_adam_pointwise.npz")
+    dims = g[tag + "_field_dims"]
+    names = ["f%d" % i for i in range(len(dims))]
+    dim = g[tag + "_p0_token_embedding_table.embedding.weight"].shape[1]
+    for kind in ("adam_lazy", "adam"):
+        m = _fm_model(g, tag, names, dims, dim, "adam", 1e-2, wd)
+        m.build_optimizer(kind, 1e-2, wd)
+        for s in range(4):
+            inter = Interaction(dict({n: torch.from_numpy(g[tag + "_ids%d" % s][:, i].astype(np.int64))
+                                      for i, n in enumerate(names)},
+                                     label=torch.from_numpy(g[tag + "_label%d" % s]))).to("cuda")
+            loss = m.train_step(inter).item()
+            if kind == "adam_lazy":
+                ref = float(g[tag + "_loss%d" % s])
+                assert abs(loss - ref) <= TOL * abs(ref), (s, loss, ref)
+        pred = m.predict(inter).cpu().numpy()            # flushes the lazy rows
+        sd = m.state_dict()
+        errs = {n: rel_err(sd[n].cpu().numpy(), g[tag + "_pN_" + n]) for n in sd}
+        if kind == "adam_lazy":
+            assert max(errs.values()) < TOL, errs
+            assert rel_err(pred, g[tag + "_predN"]) < TOL
+        else:
+            assert errs["token_embedding_table.embedding.weight"] > 10 * TOL   # a different algorithm, by design
+
+
+def test_mfsimple_reference_hyperparameters_dense_adam(golden):
+    """The fork's MFSimple with its own config (MFSimple.yaml: Adam lr 0.002, weight_decay 1e-08 -- the decay makes
+    dense Adam move EVERY row at every step) for 5 steps; FusedMFSimple with the 'adam_lazy' kind, all five
+    parameter tensors to 1e-5."""
+    from recbole_b200 import FusedMFSimple, Interaction
+    from gpu_util import rel_err
+    g = golden("dense_adam_pointwise.npz")
+
+    class Cfg(dict):
+        def __getitem__(self, k):
+            return self.get(k)
+
+    n_users, n_items = g["mf_p0_user_embedding.weight"].shape[0], g["mf_p0_item_embedding.weight"].shape[0]
+
+    class DS:
+        def num(self, f):
+            return {"user_id": n_users, "item_id": n_items}[f]
+
+    cfg = Cfg(USER_ID_FIELD="user_id", ITEM_ID_FIELD="item_id", LABEL_FIELD="label", device="cuda",
+              embedding_dimension=g["mf_p0_user_embedding.weight"].shape[1], learner="adam", learning_rate=0.002,
+              weight_decay=1e-08)
+    m = FusedMFSimple(cfg, DS()).to("cuda")
+    m.load_state_dict({k[6:]: torch.from_numpy(g[k]).cuda() for k in g.files if k.startswith("mf_p0_")})
+    m.build_optimizer("adam_lazy", 0.002, 1e-08)
+    for s in range(5):
+        inter = Interaction({f: torch.from_numpy(g["mf_%s%d" % (f, s)]) for f in ("user_id", "item_id", "label")}).to("cuda")
+        loss = m.train_step(inter).item()
+        ref = float(g["mf_loss%d" % s])
+        assert abs(loss - ref) <= TOL * abs(ref), (s, loss, ref)
+    sd = m.state_dict()
+    for n in ("user_embedding.weight", "item_embedding.weight", "user_bias", "item_bias", "bias"):
+        # element-wise: |a - b| <= 1e-5 * |b| + 1e-7 (biases start at 0 and are O(1e-2))
+        a, b = sd[n].cpu().numpy(), g["mf_pN_" + n]
+        assert np.all(np.abs(a - b) <= TOL * np.abs(b) + 1e-7), (n, np.abs(a - b).max())
