@@ -359,6 +359,20 @@ int rb2_ce_head(const float *x, int64_t nq, const float *item_p, int64_t n_items
  * certified exact top-k as RB2_SCORER_TC.  mode 1 forces the CUDA-core fp32 kernel, 0 = automatic. */
 int rb2_ce_head_set_scorer(int32_t mode);
 
+/* Backward of the same head (autograd of sasrec.py:137-141: G = (softmax(logits) - onehot(target)) * grad_scale,
+ * dx = G @ E, de = G^T @ x) on the tensor cores, hidden size 64.  Neither the logits nor G ([nq, n_items] fp32 each in
+ * the reference) are materialised: the logits are recomputed tile by tile from `lse` (the row logsumexp rb2_ce_head
+ * returned), G tiles live in shared memory as split-bf16 MMA operands.  grad_scale = upstream gradient / nq for the
+ * mean loss.  dx_out [nq, dim] and/or de_out [n_items, dim] (either may be NULL); both are complete gradients --
+ * every class has one, so the item table's optimizer step is dense: rb2_dense_step (torch.optim.Adam / SGD on the
+ * whole tensor, as trainer.py:173 does).  Deterministic (no float atomics). */
+size_t rb2_ce_head_backward_workspace_bytes(int64_t nq, int64_t n_items, int32_t dim);
+int rb2_ce_head_backward(const float *x, int64_t nq, const float *item_p, int64_t n_items, int32_t dim,
+                         const int64_t *target, const float *lse, float grad_scale, float *dx_out, float *de_out,
+                         void *workspace, size_t workspace_bytes, void *stream);
+int rb2_dense_step(float *p, float *m, float *v, const float *grad, int64_t count, const rb2_optim *h_opt,
+                   void *stream);
+
 /* Diagnostic: how many rows of the last RB2_SCORER_TC call failed the certificate and were redone by
  * the fp32 kernel (or nq if the shape is not covered by the MMA tiling: dim not in {64,128}, k > 16). */
 int32_t rb2_fullsort_tc_last_fallback_rows(void);

@@ -30,3 +30,16 @@ def ce_loss(X, E, target):
 def full_sort_topk(X, E, k):
     nu = X.shape[0]
     return _clib.fullsort_topk(X, E, np.arange(nu), np.zeros(nu + 1, np.int64), np.zeros(0, np.int64), k)
+
+
+def ce_backward(X, E, target, grad_scale=None):
+    """Gradients of mean CE w.r.t. X and E (autograd of sasrec.py:137-141), float64 ground truth:
+    G = (softmax(X E^T) - onehot(target)) * grad_scale; dX = G E; dE = G^T X."""
+    X64, E64 = X.astype(np.float64), E.astype(np.float64)
+    L = X64 @ E64.T
+    L -= L.max(axis=1, keepdims=True)
+    P = np.exp(L)
+    P /= P.sum(axis=1, keepdims=True)
+    P[np.arange(len(target)), target] -= 1.0
+    P *= (1.0 / X.shape[0]) if grad_scale is None else grad_scale
+    return (P @ E64).astype(F32), (P.T @ X64).astype(F32)

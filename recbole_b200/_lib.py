@@ -94,6 +94,9 @@ SIGNATURES = {
     "rb2_ce_head_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "rb2_ce_head": (ctypes.c_int, [_p, _i64, _p, _i64, _i32, _p, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "rb2_ce_head_set_scorer": (ctypes.c_int, [_i32]),
+    "rb2_ce_head_backward_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "rb2_ce_head_backward": (ctypes.c_int, [_p, _i64, _p, _i64, _i32, _p, _p, ctypes.c_float, _p, _p, _p, _sz, _p]),
+    "rb2_dense_step": (ctypes.c_int, [_p, _p, _p, _p, _i64, ctypes.POINTER(RB2Optim), _p]),
     "rb2_fullsort_tc_last_fallback_rows": (_i32, []),
     "rb2_fullsort_tc_last_pass2_rows": (_i32, []),
     "rb2_fullsort_tc_set_kprime": (ctypes.c_int, [_i32]),

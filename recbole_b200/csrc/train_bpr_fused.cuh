@@ -81,7 +81,7 @@ __global__ void k_plan_p2p(BprWs w, PeerTable pt, int64_t M) {
 template <int D>
 __global__ void __launch_bounds__(kThreads) k_fetch_rows(BprWs w, PeerTable pt) {
   constexpr int LANES = RowCfg<D>::LANES;
-  constexpr int UNR = 4;
+  constexpr int UNR = 8;      // rows in flight per lane group: the loads cross NVLink (microseconds of latency)
   const int lane = threadIdx.x % LANES;
   const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
   const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / LANES;

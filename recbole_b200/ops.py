@@ -430,6 +430,58 @@ def ce_head(X, E, target, k=10, scorer="auto"):
     return dict(loss=loss[0], lse=lse, ids=ids, scores=sc)
 
 
+def ce_head_backward(X, E, target, lse, grad_scale=None, want_dx=True, want_de=True, ws=None):
+    """Backward of the full-sort CE head (rb2_ce_head_backward): returns (dX [nq, d] or None, dE [N, d] or None) for
+    loss = mean_b(logsumexp_b - logit[b, target_b]) * upstream; grad_scale defaults to 1 / nq."""
+    nq, dev = X.shape[0], X.device
+    if grad_scale is None:
+        grad_scale = 1.0 / nq
+    need = lib.rb2_ce_head_backward_workspace_bytes(nq, E.shape[0], E.shape[1])
+    if need == 0:
+        raise ValueError("ce_head_backward: hidden size %d is not served (64)" % E.shape[1])
+    if ws is None or ws.nbytes < need:
+        ws = Workspace(need, dev)
+    dx = torch.empty_like(X) if want_dx else None
+    de = torch.empty_like(E) if want_de else None
+    f32 = torch.float32
+    check(lib.rb2_ce_head_backward(_ptr(X, f32), nq, _ptr(E, f32), E.shape[0], E.shape[1], _ptr(target, torch.int64),
+                                   _ptr(lse, f32), float(grad_scale), _ptr(dx, f32, True), _ptr(de, f32, True),
+                                   ws.ptr(), ws.nbytes, _stream()))
+    return dx, de
+
+
+def dense_step(P, M, V, grad, optim, step=None):
+    """One dense optimizer step over a whole tensor (rb2_dense_step; optim.step is NOT incremented here)."""
+    o = optim.c_struct(P.device, step)
+    f32 = torch.float32
+    check(lib.rb2_dense_step(_ptr(P, f32), _ptr(M, f32, True), _ptr(V, f32, True), _ptr(grad, f32), P.numel(),
+                             ctypes.byref(o), _stream()))
+
+
+class CEHeadFunction(torch.autograd.Function):
+    """loss = CrossEntropy(seq_output @ item_emb.T, pos) (sasrec.py:137-141) as ONE autograd node: forward = rb2_ce_head
+    (tensor cores, logits never written), backward = rb2_ce_head_backward.  Gradients flow to seq_output (so the
+    transformer below it trains with ordinary autograd) and to the item table."""
+
+    @staticmethod
+    def forward(ctx, seq_output, item_weight, pos_items):
+        x, e = seq_output.detach().contiguous(), item_weight.detach().contiguous()
+        out = ce_head(x, e, pos_items.contiguous(), k=1)
+        ctx.save_for_backward(x, e, pos_items.contiguous(), out["lse"])
+        return out["loss"].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, e, pos, lse = ctx.saved_tensors
+        scale = float(grad_out.item()) / x.shape[0]        # the upstream of a scalar loss is a scalar (usually 1)
+        dx, de = ce_head_backward(x, e, pos, lse, scale, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return dx, de, None
+
+
+def ce_head_loss(seq_output, item_weight, pos_items):
+    return CEHeadFunction.apply(seq_output, item_weight, pos_items)
+
+
 def topk_merge(ids, scores):
     """[parts, nq, k] sorted lists -> global [nq, k]."""
     parts, nq, k = ids.shape

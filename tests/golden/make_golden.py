@@ -19,6 +19,7 @@ modified or copied.  Every array saved here is an INPUT or an OUTPUT of referenc
   fm_steps.npz   recbole FM (token fields) + BCELoss + Adam, 2 steps
   dense_adam_pointwise.npz  FM (wd 0 / 1e-3) and MFSimple (its yaml: wd 1e-8, lr 2e-3) under dense torch.optim.Adam for
                  4-5 steps on batches that leave most rows untouched (pins the fused 'adam_lazy' kind)
+  ce_backward.npz  torch autograd of that head w.r.t. seq_output and the item table + one dense Adam step
   ce_head.npz    the SASRec head expressions of sasrec.py:137-141,152-158
   cfg1_train.npz BASELINE config 1: the reference pipeline on ml-100k, 2 epochs of Trainer._train_epoch
                  (every batch recorded) + Trainer.evaluate
@@ -482,6 +483,28 @@ def g_ce(out):
                         lse=torch.logsumexp(logits, dim=1).numpy())
 
 
+def g_ce_backward(out):
+    """autograd of the CE branch (sasrec.py:137-141) w.r.t. seq_output and item_embedding.weight, and one dense
+    torch.optim.Adam step on the item table with that gradient (trainer.py:170-173)."""
+    torch.manual_seed(10)
+    B, N, H = 200, 1500, 64
+    X = torch.nn.functional.layer_norm(torch.randn(B, H), (H,)).requires_grad_(True)
+    E = (torch.randn(N, H) * 0.02 * 20)
+    with torch.no_grad():
+        E[0] = 0
+    E.requires_grad_(True)
+    pos = torch.randint(1, N, (B,))
+    opt = torch.optim.Adam([E], lr=1e-3)
+    logits = torch.matmul(X, E.transpose(0, 1))
+    loss = torch.nn.CrossEntropyLoss()(logits, pos)
+    loss.backward()
+    d = dict(X=X.detach().numpy().copy(), E=E.detach().numpy().copy(), pos=pos.numpy(), loss=np.float32(loss.item()),
+             dX=X.grad.numpy().copy(), dE=E.grad.numpy().copy())
+    opt.step()
+    d["E1"] = E.detach().numpy().copy()
+    np.savez_compressed(out, **d)
+
+
 if __name__ == "__main__":
     o = lambda n: os.path.join(HERE, n)  # noqa: E731
     g_metrics(o("metrics.npz"))
@@ -490,6 +513,7 @@ if __name__ == "__main__":
     g_fm(o("fm_steps.npz"))
     g_dense_adam_pointwise(o("dense_adam_pointwise.npz"))
     g_ce(o("ce_head.npz"))
+    g_ce_backward(o("ce_backward.npz"))
     g_fullsort_small(o("fullsort_small.npz"))
     g_fullsort_ml100k(o("fullsort_ml100k.npz"), o("sampler.npz"))
     g_cfg1_train(o("cfg1_train.npz"))

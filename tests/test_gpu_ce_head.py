@@ -76,3 +76,94 @@ def test_ce_head_tensor_core_vs_fp32_kernel_at_cfg4_size(scale):
     assert rel < 1e-5, rel
     assert abs(a["loss"].item() - b["loss"].item()) <= 1e-5 * abs(b["loss"].item())
     ops.ce_head(X[:8], E[:100], tgt[:8] % 100, 10, scorer="auto")   # leaves the knob at its default
+
+
+def _elementwise_ok(a, b, rtol=1e-5):
+    """|a - b| <= rtol * |b| + rtol * rms(b): element-wise relative with an absolute floor at the tensor's scale."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    floor = rtol * np.sqrt((b * b).mean())
+    bad = np.abs(a - b) > rtol * np.abs(b) + floor
+    return int(bad.sum()), float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def test_ce_backward_vs_torch_autograd_golden(golden):
+    """rb2_ce_head_backward vs torch autograd of the reference's CE branch (sasrec.py:137-141): dX, dE element-wise
+    to 1e-5; one dense Adam step on the item table == torch.optim.Adam's."""
+    from recbole_b200 import ops
+    from gpu_util import t
+    g = golden("ce_backward.npz")
+    X, E, pos = t(g["X"]), t(g["E"]), t(g["pos"])
+    out = ops.ce_head(X, E, pos, k=1)
+    assert abs(out["loss"].item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    dx, de = ops.ce_head_backward(X, E, pos, out["lse"])
+    nbad, rel = _elementwise_ok(dx.cpu().numpy(), g["dX"])
+    assert nbad == 0, (nbad, rel)
+    nbad, rel = _elementwise_ok(de.cpu().numpy(), g["dE"])
+    assert nbad == 0, (nbad, rel)
+    opt = ops.Optim("adam", lr=1e-3)
+    m, v = torch.zeros_like(E), torch.zeros_like(E)
+    ops.dense_step(E, m, v, de, opt, step=1)
+    # Adam's first step moves every element by ~lr * sign(g): elements whose gradient is ~eps are ill-conditioned
+    d = np.abs(E.cpu().numpy() - g["E1"])
+    assert (d > 1e-5 * np.abs(g["E1"]).max()).sum() <= 3 and d.max() <= 2e-3
+
+
+def test_ce_head_autograd_function(golden):
+    """ops.ce_head_loss is one autograd node: loss.backward() fills .grad of the sequence output and of the item table."""
+    from recbole_b200 import ops
+    from gpu_util import t
+    g = golden("ce_backward.npz")
+    X = t(g["X"]).requires_grad_(True)
+    W = torch.nn.Parameter(t(g["E"]))
+    pre = (X * 2.0)                                   # an ordinary autograd op below the head
+    loss = ops.ce_head_loss(pre * 0.5, W, t(g["pos"]))
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    loss.backward()
+    assert _elementwise_ok(X.grad.cpu().numpy(), g["dX"])[0] == 0
+    assert _elementwise_ok(W.grad.cpu().numpy(), g["dE"])[0] == 0
+
+
+@pytest.mark.parametrize("nq,N", [(1, 3), (130, 127), (700, 40000), (4096, 300001)])
+def test_ce_backward_random_vs_oracle(nq, N):
+    """Shapes that do not fill tiles, many item ranges, and (last) a BASELINE-config-4-sized batch against a table
+    large enough that the float64 oracle is only run on subsets: all of dX for 64 rows, dE for 512 item rows."""
+    from recbole_b200 import ops
+    from gpu_util import t
+    rng = np.random.default_rng(nq + N)
+    d = 64
+    X = rng.standard_normal((nq, d)).astype(np.float32)
+    X = (X - X.mean(1, keepdims=True)) / X.std(1, keepdims=True)
+    E = (rng.standard_normal((N, d)) * 0.02 * 20).astype(np.float32)
+    E[0] = 0
+    tgt = rng.integers(1, N, nq) if N > 1 else np.zeros(nq, np.int64)
+    Xd, Ed, td = t(X), t(E), t(tgt)
+    out = ops.ce_head(Xd, Ed, td, k=1)
+    dx, de = ops.ce_head_backward(Xd, Ed, td, out["lse"])
+    dx, de = dx.cpu().numpy(), de.cpu().numpy()
+    if nq * N <= 40_000_000:
+        o_dx, o_de = oce.ce_backward(X, E, tgt)
+        assert _elementwise_ok(dx, o_dx)[0] == 0, _elementwise_ok(dx, o_dx)
+        assert _elementwise_ok(de, o_de)[0] == 0, _elementwise_ok(de, o_de)
+    else:
+        # float64 softmax of every row is needed for dE anyway: do it in row blocks, keep only what is compared
+        rows = np.sort(rng.choice(nq, 64, replace=False))
+        items = np.unique(np.concatenate([rng.choice(N, 500, replace=False), tgt[:12]]))
+        E64 = E.astype(np.float64)
+        o_de = np.zeros((len(items), d))
+        o_dx = np.zeros((len(rows), d))
+        for lo in range(0, nq, 256):
+            L = X[lo:lo + 256].astype(np.float64) @ E64.T
+            L -= L.max(axis=1, keepdims=True)
+            P = np.exp(L)
+            P /= P.sum(axis=1, keepdims=True)
+            P[np.arange(P.shape[0]), tgt[lo:lo + 256]] -= 1.0
+            P /= nq
+            o_de += P[:, items].T @ X[lo:lo + 256].astype(np.float64)
+            sel = (rows >= lo) & (rows < lo + 256)
+            if sel.any():
+                o_dx[sel] = P[rows[sel] - lo] @ E64
+        assert _elementwise_ok(dx[rows], o_dx)[0] == 0, _elementwise_ok(dx[rows], o_dx)
+        assert _elementwise_ok(de[items], o_de)[0] == 0, _elementwise_ok(de[items], o_de)
+    # determinism: bit-identical reruns (no float atomics)
+    dx2, de2 = ops.ce_head_backward(Xd, Ed, td, out["lse"])
+    assert np.array_equal(dx2.cpu().numpy(), dx) and np.array_equal(de2.cpu().numpy(), de)
