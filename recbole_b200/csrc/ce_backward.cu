@@ -14,14 +14,26 @@
 // Recomputing S in both passes costs 1/3 more MMA work than a single pass but needs no [tiles x tiles] flush of
 // partial accumulators and no float atomics (results are bit-reproducible).
 //
-// Per (P tile, Q tile of 64 rows), all operands bf16 split in two (x = hi + lo, |lo| <= 2^-9 |x|):
-//   MMA 1   S[128 x 64]  = P_hi Q_hi^T + P_hi Q_lo^T + P_lo Q_hi^T          (fp32 in TMEM, error ~2^-17 |p||q|)
+// Per (P tile, Q tile of 64 rows), every operand is a two-way split x = hi + lo:
+//   MMA 1   S[128 x 64]  = P_hi Q_hi^T + P_hi Q_lo^T + P_lo Q_hi^T          (fp32 in TMEM)
 //   epilogue (2 sets of 4 warps, thread <-> TMEM lane <-> P row):  g = (exp2(s*log2e - lse*log2e) - [hit]) * scale,
-//            g = g_hi + g_lo written as the K-major, 128-byte-swizzled A operand of
+//            written as the K-major, 128-byte-swizzled A operand of
 //   MMA 2   Out[128 x 64] += G_hi QT_hi + G_hi QT_lo + G_lo QT_hi           (K = the 64 Q rows; QT = Q transposed)
+// The halves are FP16 (11 + 11 significant bits), not bf16 (8 + 8): a logit error d changes every softmax weight
+// by a factor 1 + d, and with peaked rows (|x||e| ~ 25 at BASELINE config 4's scales) nothing averages out -- a
+// two-way bf16 split leaves d ~ 1.4e-5 rms / 1e-4 max and gradients 2e-5 off; the fp16 split gives d ~ 2e-7 rms and
+// gradients at 1e-6 (measured against torch autograd).  FP16's range is met by exact power-of-two rescales: X and E
+// by 2^kx, 2^ke (from max |.|, measured on the device), g by 2^kg (|g| <= |scale|, chosen on the host), so that the
+// largest magnitudes sit at 2^13..2^14; the epilogue / drain multiply by 2^-(kp+kq) and 2^-(kg+kq).
+// The tensor core's fp32 accumulate truncates: a chain of thousands of accumulations into one TMEM accumulator drifts
+// (measured: 7.8e-6 of the gradient's scale after 1 500 MMAs, growing linearly).  Out is therefore drained every
+// FLUSH tiles (two ping-pong accumulators, so the MMAs never wait) and the chunks are summed in fp32 by CUDA cores.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 4-7 / 8-11 = the epilogue sets
 // (alternate Q tiles).  TMEM: two 64-column S stages + one 64-column Out accumulator.
 #include <algorithm>
+#include <cmath>
+
+#include <cuda_fp16.h>
 
 #include "tc_helpers.cuh"
 
@@ -33,22 +45,28 @@ constexpr int D = 64;                 // hidden size served by this path
 constexpr int PM = 128;               // P rows per tile = TMEM lanes
 constexpr int QN = 64;                // Q rows per tile
 constexpr int NS = 3;                 // Q ring stages
+constexpr int FLUSH = 16;             // Q tiles accumulated in TMEM before the Out accumulator is drained (even)
 constexpr int kThreadsCe = 384;
 constexpr int TILE_P = PM * D * 2;    // 16 KB: one bf16 [128 x 64] operand tile
 constexpr int TILE_Q = QN * D * 2;    // 8 KB
 constexpr int STAGE_BYTES = 4 * TILE_Q;          // Q_hi, Q_lo, QT_hi, QT_lo
 constexpr int G_BYTES = 2 * TILE_P;              // G_hi, G_lo of one epilogue set
-constexpr size_t kSmemCe = 1024 + 2 * TILE_P + (size_t)NS * STAGE_BYTES + 2 * G_BYTES + 2 * QN * 8 + 512;
+constexpr size_t kSmemCe = 1024 + 2 * TILE_P + (size_t)NS * STAGE_BYTES + 2 * G_BYTES + 2 * QN * 12 + 512;
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct CeBwdParams {
   int64_t nP, nQ;                 // valid rows of P and Q
   int64_t n_items;                // classes of the softmax (rows of E)
   int n_ptiles, n_split, qtiles_per_split, n_qtiles;
+  const float *omp;               // dE pass: [queries] 1 - softmax[b, target_b], from the dX pass (well-conditioned)
   const float *lse;               // [queries] row logsumexp of the forward pass
   const int64_t *target;          // [queries]
-  float scale;                    // upstream gradient / number of rows of the mean
+  float scale;                    // upstream gradient / number of rows of the mean, times 2^kg
+  float inv_gscale;               // 2^-kg
+  const float *q_inv_scale;       // device: 2^-kq of the Q-side table (written by k_ce_scale)
+  const float *p_inv_scale;       // device: 2^-kp of the P-side table
   float *out;                     // ROWS_Q: [n_split][n_ptiles * 128][64] partials; else [nP][64]
+  float *zpart;                   // ROWS_Q: [n_split * 2][n_ptiles * 128] partial sums of exp(logit - lse)
 };
 
 // ROWS_Q = true: P rows are queries (dX pass); false: P rows are items (dE pass)
@@ -64,9 +82,10 @@ k_ce_bwd(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__ CUten
   unsigned char *sG = sQ + (size_t)NS * STAGE_BYTES;          // [2 sets][G_hi, G_lo]
   float *col_nl = reinterpret_cast<float *>(sG + 2 * G_BYTES);          // [2][QN]  -lse * log2e of the tile's queries (dE pass)
   int *col_pos = reinterpret_cast<int *>(col_nl + 2 * QN);              // [2][QN]  their targets
-  uint64_t *bars = reinterpret_cast<uint64_t *>(col_pos + 2 * QN);
-  uint64_t *p_full = bars, *p_empty = bars + 1, *o_full = bars + 2, *o_empty = bars + 3;
-  uint64_t *q_full = bars + 4, *q_empty = q_full + NS;
+  float *col_omp = reinterpret_cast<float *>(col_pos + 2 * QN);         // [2][QN]  -(1 - p[target]) * scale
+  uint64_t *bars = reinterpret_cast<uint64_t *>(col_omp + 2 * QN);
+  uint64_t *p_full = bars, *p_empty = bars + 1, *o_full = bars + 2, *o_empty = bars + 4;     // o_*: [2]
+  uint64_t *q_full = bars + 6, *q_empty = q_full + NS;
   uint64_t *s_full = q_empty + NS, *s_empty = s_full + 2, *g_full = s_empty + 2, *g_empty = g_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(g_empty + 2);
 
@@ -74,7 +93,8 @@ k_ce_bwd(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__ CUten
   const int n_work = p.n_ptiles * p.n_split;
 
   if (threadIdx.x == 0) {
-    mbar_init(p_full, 1); mbar_init(p_empty, 1); mbar_init(o_full, 1); mbar_init(o_empty, 128);
+    mbar_init(p_full, 1); mbar_init(p_empty, 1);
+    for (int o = 0; o < 2; ++o) { mbar_init(&o_full[o], 1); mbar_init(&o_empty[o], 128); }
     for (int s = 0; s < NS; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
     for (int e = 0; e < 2; ++e) {
       mbar_init(&s_full[e], 1); mbar_init(&s_empty[e], 128);
@@ -93,7 +113,8 @@ k_ce_bwd(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__ CUten
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t kIdesc = idesc_bf16_f32(PM, QN);     // both MMAs are M = 128, N = 64, K = 16
+  // both MMAs: M = 128, N = 64, K = 16, FP16 A and B (format 0), fp32 accumulate
+  constexpr uint32_t kIdescH = (1u << 4) | ((uint32_t)(QN >> 3) << 17) | ((uint32_t)(PM >> 4) << 24);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -125,14 +146,20 @@ k_ce_bwd(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__ CUten
       int stage = 0;
       uint32_t phase = 0, wc = 0;
       uint32_t n1[2] = {0, 0}, n2[2] = {0, 0};      // MMA-1 / MMA-2 groups issued for each epilogue set
-      const uint32_t tmem_o = tmem_base + 2 * QN;
+      uint32_t oc = 0, ouse[2] = {0, 0};            // Out chunks started so far; uses of each Out accumulator
       const uint64_t dPh = make_smem_desc(smem_u32(sP)), dPl = make_smem_desc(smem_u32(sP + TILE_P));
 
-      auto mma2 = [&](int stg, int i, bool first) {
+      auto mma2 = [&](int stg, int i, int T) {
         const int e = i & 1;
+        const bool first = (i % FLUSH) == 0, last = (i % FLUSH) == FLUSH - 1 || i == T - 1;
+        const int oi = (int)(oc & 1u);
+        const uint32_t tmem_o = tmem_base + (uint32_t)(2 * QN + oi * QN);
         mbar_wait_wd(&g_full[e], n2[e] & 1);
         ++n2[e];
-        if (first) mbar_wait_wd(o_empty, (wc & 1) ^ 1);      // the previous work item's Out has been drained
+        if (first) {                                         // this accumulator's previous chunk has been drained
+          mbar_wait_wd(&o_empty[oi], (ouse[oi] & 1) ^ 1);
+          ++ouse[oi];
+        }
         tc_fence_after();
         const unsigned char *st = sQ + (size_t)stg * STAGE_BYTES;
         const uint64_t dGh = make_smem_desc(smem_u32(sG + (size_t)e * G_BYTES));
@@ -143,10 +170,14 @@ k_ce_bwd(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__ CUten
           const uint64_t a = term == 2 ? dGl : dGh, b = term == 1 ? dTl : dTh;
 #pragma unroll
           for (int k4 = 0; k4 < D / 16; ++k4)
-            tc_mma_bf16(tmem_o, a + (uint64_t)(2 * k4), b + (uint64_t)(2 * k4), kIdesc, (first && term == 0 && k4 == 0) ? 0u : 1u);
+            tc_mma_bf16(tmem_o, a + (uint64_t)(2 * k4), b + (uint64_t)(2 * k4), kIdescH, (first && term == 0 && k4 == 0) ? 0u : 1u);
         }
         tc_commit(&g_empty[e]);        // G of this set may be overwritten
         tc_commit(&q_empty[stg]);      // both MMAs that read this Q stage are complete
+        if (last) {
+          tc_commit(&o_full[oi]);      // the chunk is complete: the drainer may read it
+          ++oc;
+        }
       };
 
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++wc) {
@@ -170,15 +201,14 @@ k_ce_bwd(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__ CUten
             const uint64_t a = term == 2 ? dPl : dPh, b = term == 1 ? dQl : dQh;
 #pragma unroll
             for (int k4 = 0; k4 < D / 16; ++k4)
-              tc_mma_bf16(tmem_s, a + (uint64_t)(2 * k4), b + (uint64_t)(2 * k4), kIdesc, (term | k4) ? 1u : 0u);
+              tc_mma_bf16(tmem_s, a + (uint64_t)(2 * k4), b + (uint64_t)(2 * k4), kIdescH, (term | k4) ? 1u : 0u);
           }
           tc_commit(&s_full[e]);
-          if (i > 0) mma2(prev_stage, i - 1, i - 1 == 0);
+          if (i > 0) mma2(prev_stage, i - 1, T);
           prev_stage = stage;
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
-        mma2(prev_stage, T - 1, T == 1);
-        tc_commit(o_full);       // Out of this work item is complete
+        mma2(prev_stage, T - 1, T);
         tc_commit(p_empty);      // every MMA that read this P tile is complete
       }
     }
@@ -192,13 +222,54 @@ k_ce_bwd(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__ CUten
     unsigned char *gh = sG + (size_t)e * G_BYTES, *gl = gh + TILE_P;
     float *nl = col_nl + e * QN;
     int *cp = col_pos + e * QN;
+    float *co = col_omp + e * QN;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float s2 = __ldg(p.p_inv_scale) * __ldg(p.q_inv_scale) * kLog2e;    // TMEM holds 2^(kp+kq) * logit
+    const float om = p.inv_gscale * __ldg(p.q_inv_scale);                     // exact: both are powers of two
+    uint32_t odone = 0;                                                        // Out chunks drained so far (set 1)
+    float *out_row = nullptr;
+    // Set 1 drains every chunk of FLUSH tiles (chunks end on odd tiles, i.e. its own, except possibly the last one of
+    // a work item): Out -> registers -> added to the row's fp32 result in global memory (first chunk: stored).
+    auto drain = [&](int last_tile) {
+      const int oi = (int)(odone & 1u);
+      mbar_wait_wd(&o_full[oi], (odone >> 1) & 1);
+      ++odone;
+      tc_fence_after();
+      uint32_t va[32], vb[32];
+      const uint32_t taddr = lane_addr + (uint32_t)(2 * QN + oi * QN);
+      TC_LD32(taddr, va);
+      TC_LD32(taddr + 32, vb);
+      tmem_wait_ld();
+      TC_REGS_AFTER_WAIT(va);
+      TC_REGS_AFTER_WAIT(vb);
+      tc_fence_before();
+      mbar_arrive(&o_empty[oi]);
+      if (out_row) {
+        const bool first_chunk = last_tile < FLUSH;
+        float4 *o4 = reinterpret_cast<float4 *>(out_row);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 a = make_float4(__uint_as_float(va[4 * j]) * om, __uint_as_float(va[4 * j + 1]) * om,
+                                 __uint_as_float(va[4 * j + 2]) * om, __uint_as_float(va[4 * j + 3]) * om);
+          float4 b = make_float4(__uint_as_float(vb[4 * j]) * om, __uint_as_float(vb[4 * j + 1]) * om,
+                                 __uint_as_float(vb[4 * j + 2]) * om, __uint_as_float(vb[4 * j + 3]) * om);
+          if (!first_chunk) {
+            const float4 pa = o4[j], pb = o4[8 + j];
+            a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w;
+            b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
+          }
+          o4[j] = a;
+          o4[8 + j] = b;
+        }
+      }
+    };
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++wc) {
       const int pt = w % p.n_ptiles, sp = w / p.n_ptiles;
       const int64_t row = (int64_t)pt * PM + t;
       const int q0 = sp * p.qtiles_per_split, q1 = min(q0 + p.qtiles_per_split, p.n_qtiles);
       const int T = q1 - q0;
-      float row_nl = 0.f;
+      out_row = ROWS_Q ? p.out + ((size_t)sp * p.n_ptiles * PM + row) * D : (row < p.nP ? p.out + (size_t)row * D : nullptr);
+      float row_nl = 0.f, zsum = 0.f;
       int64_t row_pos = -1;
       if (ROWS_Q && row < p.nP) {
         row_nl = -p.lse[row] * kLog2e;
@@ -213,6 +284,7 @@ k_ce_bwd(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__ CUten
             const int64_t b = qbase + tin;
             nl[tin] = b < p.nQ ? -p.lse[b] * kLog2e : -INFINITY;
             cp[tin] = b < p.nQ ? (int)p.target[b] : -1;
+            co[tin] = b < p.nQ ? -p.omp[b] * p.scale : 0.f;
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
         }
@@ -242,20 +314,24 @@ k_ce_bwd(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__ CUten
               const float s = __uint_as_float(j < 32 ? va[j & 31] : vb[j & 31]);
               float g;
               if (ROWS_Q) {
+                // every class but the target: k_ce_reduce adds the target's own weight to the row's sum of exp (the
+                // softmax normaliser against the forward pass's lse) and applies -(1 - p[target]) * E[target] in fp32
+                // from that sum -- no p - 1 cancellation for confident rows
                 const int64_t item = qbase + j;
-                const float ex = ex2_approx(fmaf(s, kLog2e, row_nl));
-                g = (item < p.n_items) ? (ex - (item == row_pos ? 1.f : 0.f)) * p.scale : 0.f;
+                const float ex = (item < p.n_items && item != row_pos) ? ex2_approx(fmaf(s, s2, row_nl)) : 0.f;
+                zsum += ex;
+                g = ex * p.scale;
               } else {
-                const float ex = ex2_approx(fmaf(s, kLog2e, nl[j]));       // ex2(-inf) = 0 for padded queries
-                g = (ex - ((int64_t)cp[j] == row ? 1.f : 0.f)) * p.scale;
+                const float ex = ex2_approx(fmaf(s, s2, nl[j]));           // ex2(-inf) = 0 for padded queries
+                g = ((int64_t)cp[j] == row) ? co[j] : ex * p.scale;        // target: -(1 - p) * scale from the dX pass
               }
               g2[u] = g;
             }
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(g2[0]), h1 = __float2bfloat16_rn(g2[1]);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(g2[0] - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(g2[1] - __bfloat162float(h1));
-            hw[h] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lw[h] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            const __half h0 = __float2half_rn(g2[0]), h1 = __float2half_rn(g2[1]);
+            const __half l0 = __float2half_rn(g2[0] - __half2float(h0));
+            const __half l1 = __float2half_rn(g2[1] - __half2float(h1));
+            hw[h] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            lw[h] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
           }
           // K-major, 128-byte swizzle: row t, 16-byte chunk c sits at chunk position c ^ (t & 7)
           const uint32_t off = (uint32_t)t * 128u + (uint32_t)((c ^ (t & 7)) << 4);
@@ -264,33 +340,10 @@ k_ce_bwd(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__ CUten
         }
         fence_proxy_async_smem();           // generic-proxy writes -> visible to the tensor core's async proxy
         mbar_arrive(&g_full[e]);
+        if (e == 1 && ((i % FLUSH) == FLUSH - 1 || i == T - 1)) drain(i);
       }
-      if (e == 0) {
-        // drain the Out accumulator of this work item
-        mbar_wait_wd(o_full, wc & 1);
-        tc_fence_after();
-        uint32_t va[32], vb[32];
-        const uint32_t taddr = lane_addr + (uint32_t)(2 * QN);
-        TC_LD32(taddr, va);
-        TC_LD32(taddr + 32, vb);
-        tmem_wait_ld();
-        TC_REGS_AFTER_WAIT(va);
-        TC_REGS_AFTER_WAIT(vb);
-        tc_fence_before();
-        mbar_arrive(o_empty);
-        const bool store = ROWS_Q ? true : row < p.nP;
-        if (store) {
-          float *o = ROWS_Q ? p.out + ((size_t)sp * p.n_ptiles * PM + row) * D : p.out + (size_t)row * D;
-          float4 *o4 = reinterpret_cast<float4 *>(o);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            o4[j] = make_float4(__uint_as_float(va[4 * j]), __uint_as_float(va[4 * j + 1]), __uint_as_float(va[4 * j + 2]),
-                                __uint_as_float(va[4 * j + 3]));
-            o4[8 + j] = make_float4(__uint_as_float(vb[4 * j]), __uint_as_float(vb[4 * j + 1]), __uint_as_float(vb[4 * j + 2]),
-                                    __uint_as_float(vb[4 * j + 3]));
-          }
-        }
-      }
+      if (ROWS_Q) p.zpart[(size_t)(sp * 2 + e) * p.n_ptiles * PM + row] = zsum;
+      if (e == 1 && ((T - 1) & 1) == 0) drain(T - 1);       // the last chunk ends on a tile of the other set
     }
   }
 
@@ -302,13 +355,37 @@ k_ce_bwd(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__ CUten
   }
 }
 
-// fp32 [rows, 64] -> bf16 hi / lo, row-major [rows_pad, 64] and transposed [64, rows_pad]; rows >= `rows` are zero.
-// One block per 64-row slab.
+// max |x| of a tensor as the bit pattern of a non-negative float (compared as an int); then the power-of-two scale
+// that puts it in [2^13, 2^14): sc[0] = 2^kq, sc[1] = 2^-kq
+__global__ void __launch_bounds__(256) k_ce_absmax(const float *__restrict__ src, int64_t n4, int *__restrict__ out_bits) {
+  int m = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 x = __ldg(reinterpret_cast<const float4 *>(src) + i);
+    const float a = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));
+    if (a < INFINITY) m = max(m, __float_as_int(a));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out_bits, m);
+}
+__global__ void k_ce_scale(const int *__restrict__ max_bits, float *__restrict__ sc) {
+  const float m = __int_as_float(*max_bits);
+  int e = 0;
+  if (m > 0.f) frexpf(m, &e);            // m = f * 2^e, f in [0.5, 1)
+  const int k = m > 0.f ? 14 - e : 0;
+  sc[0] = ldexpf(1.f, k);
+  sc[1] = ldexpf(1.f, -k);
+}
+
+// fp32 [rows, 64] -> rescaled FP16 hi / lo, row-major [rows_pad, 64] (MMA 1) and transposed [64, rows_pad] (MMA 2);
+// rows >= `rows` are zero.  One block per 64-row slab.
 __global__ void __launch_bounds__(256) k_ce_split_t(const float *__restrict__ src, int64_t rows, int64_t rows_pad,
-                                                    uint16_t *__restrict__ hi, uint16_t *__restrict__ lo,
-                                                    uint16_t *__restrict__ hiT, uint16_t *__restrict__ loT) {
+                                                    const float *__restrict__ sc, uint16_t *__restrict__ hi,
+                                                    uint16_t *__restrict__ lo, uint16_t *__restrict__ hiT,
+                                                    uint16_t *__restrict__ loT) {
   __shared__ uint16_t th[64][66], tl[64][66];
   const int64_t r0 = (int64_t)blockIdx.x * 64;
+  const float qs = __ldg(sc);
   for (int i = threadIdx.x; i < 64 * 16; i += 256) {      // 64 rows x 16 float4
     const int r = i / 16, c4 = i % 16;
     const int64_t row = r0 + r;
@@ -318,10 +395,11 @@ __global__ void __launch_bounds__(256) k_ce_split_t(const float *__restrict__ sr
     uint16_t h[4], l[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const __nv_bfloat16 hb = __float2bfloat16_rn(f[k]);
-      const __nv_bfloat16 lb = __float2bfloat16_rn(f[k] - __bfloat162float(hb));
-      h[k] = __bfloat16_as_ushort(hb);
-      l[k] = __bfloat16_as_ushort(lb);
+      const float fs = f[k] * qs;                          // exact (power of two); |fs| < 2^14
+      const __half hh = __float2half_rn(fs);
+      const __half hl = __float2half_rn(fs - __half2float(hh));
+      h[k] = __half_as_ushort(hh);
+      l[k] = __half_as_ushort(hl);
       th[c4 * 4 + k][r] = h[k];
       tl[c4 * 4 + k][r] = l[k];
     }
@@ -341,23 +419,58 @@ __global__ void __launch_bounds__(256) k_ce_split_t(const float *__restrict__ sr
   }
 }
 
-// dX[row] = sum over the item ranges of the partials, in range order
-__global__ void __launch_bounds__(256) k_ce_reduce(const float *__restrict__ part, int n_split, int64_t rows_pad,
-                                                   int64_t rows, float *__restrict__ out) {
+// Per query row b (fixed summation order):
+//   Z' = sum over the item ranges of the partial sums of exp(logit_j - lse_fwd), j != target;
+//   Z  = Z' + exp(<x_b, e_target> - lse_fwd)   (= 1 up to the error of the forward pass's logsumexp, which used bf16
+//        halves);  lse_corr = lse_fwd + log Z  and  omp = Z' / Z = 1 - softmax[b, target]  for the dE pass;
+//   dX[b] = (sum of the partials) / Z - grad_scale * omp * E[target]          (partials = grad_scale * sum' exp_j E_j).
+__global__ void __launch_bounds__(256) k_ce_reduce(const float *__restrict__ part, const float *__restrict__ zpart,
+                                                   int n_split, int64_t rows_pad, int64_t rows,
+                                                   const float *__restrict__ x, const float *__restrict__ item_p,
+                                                   const int64_t *__restrict__ target, const float *__restrict__ lse,
+                                                   float grad_scale, float *__restrict__ dx_out,
+                                                   float *__restrict__ lse_corr, float *__restrict__ omp) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // float4 index
   if (i >= rows * (D / 4)) return;
+  const int64_t row = i / (D / 4);
+  const int c4 = (int)(i % (D / 4));
+  float zp = 0.f;
+  for (int s = 0; s < 2 * n_split; ++s) zp += __ldg(zpart + (size_t)s * rows_pad + row);
+  const float4 *xr = reinterpret_cast<const float4 *>(x + row * D);
+  const float4 *er = reinterpret_cast<const float4 *>(item_p + target[row] * D);
+  float sp = 0.f;
+#pragma unroll
+  for (int k = 0; k < D / 4; ++k) {
+    const float4 a = __ldg(xr + k), b = __ldg(er + k);
+    sp = fmaf(a.x, b.x, sp); sp = fmaf(a.y, b.y, sp); sp = fmaf(a.z, b.z, sp); sp = fmaf(a.w, b.w, sp);
+  }
+  const float z = zp + expf(sp - lse[row]);
+  const float om = zp / z;
+  if (c4 == 0) {
+    lse_corr[row] = lse[row] + logf(z);
+    omp[row] = om;
+  }
+  if (!dx_out) return;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int s = 0; s < n_split; ++s) {
     const float4 v = __ldg(reinterpret_cast<const float4 *>(part + (size_t)s * rows_pad * D) + i);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
-  reinterpret_cast<float4 *>(out)[i] = acc;
+  const float iz = 1.f / z, c = -grad_scale * om;
+  const float4 e = __ldg(er + c4);
+  reinterpret_cast<float4 *>(dx_out)[i] =
+      make_float4(fmaf(acc.x, iz, c * e.x), fmaf(acc.y, iz, c * e.y), fmaf(acc.z, iz, c * e.z), fmaf(acc.w, iz, c * e.w));
 }
 
 struct CeBwdWs {
   uint16_t *xh, *xl, *xth, *xtl;      // queries
   uint16_t *eh, *el, *eth, *etl;      // items
   float *part;                        // dX partials
+  float *zpart;                       // [n_split_x * 2][nq_pad]
+  float *lse_corr;                    // [nq] logsumexp consistent with THIS pass's logits
+  float *omp;                         // [nq] 1 - softmax[b, target_b]
+  int *max_bits;                      // [2]: max |x|, max |e| (bit patterns)
+  float *sc_x, *sc_e;                 // [2] each: 2^kq, 2^-kq
   int n_split_x;
 };
 
@@ -388,6 +501,12 @@ size_t carve_ce_bwd(CeBwdWs &w, void *base, int64_t nq, int64_t n_items) {
   w.eth = c.take<uint16_t>(ni_pad * D); w.etl = c.take<uint16_t>(ni_pad * D);
   w.n_split_x = pick_split((int)(nq_pad / PM), (int)(ni_pad / QN), rb2_num_sms());
   w.part = c.take<float>((size_t)w.n_split_x * nq_pad * D);
+  w.zpart = c.take<float>((size_t)w.n_split_x * 2 * nq_pad);
+  w.lse_corr = c.take<float>(nq_pad);
+  w.omp = c.take<float>(nq_pad);
+  w.max_bits = c.take<int>(2);
+  w.sc_x = c.take<float>(2);
+  w.sc_e = c.take<float>(2);
   return c.off;
 }
 
@@ -400,7 +519,8 @@ int launch_pass(const CeBwdParams &p, uint16_t *ph, uint16_t *pl, int64_t p_rows
   if ((rc = make_map_bf16(&mPl, pl, p_rows_pad, D, PM))) return rc;
   if ((rc = make_map_bf16(&mQh, qh, q_rows_pad, D, QN))) return rc;
   if ((rc = make_map_bf16(&mQl, ql, q_rows_pad, D, QN))) return rc;
-  if ((rc = make_map_bf16(&mQTh, qth, D, q_rows_pad, D))) return rc;     // [64 dims][rows]: box = 64 rows (K) x 64 dims
+  // [64 dims][rows] FP16 (16-bit elements move the same way): box = 64 rows (K) x 64 dims
+  if ((rc = make_map_bf16(&mQTh, qth, D, q_rows_pad, D))) return rc;
   if ((rc = make_map_bf16(&mQTl, qtl, D, q_rows_pad, D))) return rc;
   auto kern = k_ce_bwd<ROWS_Q>;
   RB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCe));
@@ -452,27 +572,47 @@ extern "C" int rb2_ce_head_backward(const float *x, int64_t nq, const float *ite
   const int64_t nq_pad = (nq + PM - 1) / PM * PM, ni_pad = (n_items + PM - 1) / PM * PM;
   {
     ProfScope prof(RB2_ST_TC_CONVERT, st, 2);
-    k_ce_split_t<<<(unsigned)(nq_pad / 64), 256, 0, st>>>(x, nq, nq_pad, w.xh, w.xl, w.xth, w.xtl);
-    k_ce_split_t<<<(unsigned)(ni_pad / 64), 256, 0, st>>>(item_p, n_items, ni_pad, w.eh, w.el, w.eth, w.etl);
+    RB2_CUDA(cudaMemsetAsync(w.max_bits, 0, 2 * sizeof(int), st));
+    const int mb = rb2_num_sms() * 8;
+    k_ce_absmax<<<(unsigned)std::min<int64_t>(mb, (nq * (D / 4) + 255) / 256), 256, 0, st>>>(x, nq * (D / 4), w.max_bits);
+    k_ce_absmax<<<(unsigned)std::min<int64_t>(mb, (n_items * (D / 4) + 255) / 256), 256, 0, st>>>(item_p, n_items * (D / 4),
+                                                                                              w.max_bits + 1);
+    k_ce_scale<<<1, 1, 0, st>>>(w.max_bits, w.sc_x);
+    k_ce_scale<<<1, 1, 0, st>>>(w.max_bits + 1, w.sc_e);
+    k_ce_split_t<<<(unsigned)(nq_pad / 64), 256, 0, st>>>(x, nq, nq_pad, w.sc_x, w.xh, w.xl, w.xth, w.xtl);
+    k_ce_split_t<<<(unsigned)(ni_pad / 64), 256, 0, st>>>(item_p, n_items, ni_pad, w.sc_e, w.eh, w.el, w.eth, w.etl);
     RB2_CUDA(cudaGetLastError());
   }
   CeBwdParams p{};
   p.n_items = n_items;
   p.lse = lse;
   p.target = target;
-  p.scale = grad_scale;
-  if (dx_out) {
-    // pass dX: P = queries, Q = items in n_split ranges
+  // |g| <= |grad_scale|: 2^kg puts it at 2^13..2^14
+  int ge = 0;
+  if (grad_scale != 0.f && std::isfinite(grad_scale)) std::frexp(std::fabs(grad_scale), &ge);
+  const int kg = (grad_scale != 0.f && std::isfinite(grad_scale)) ? 14 - ge : 0;
+  p.scale = std::ldexp(grad_scale, kg);
+  p.inv_gscale = std::ldexp(1.f, -kg);
+  {
+    // pass dX: P = queries, Q = items in n_split ranges.  Always run: it also measures every row's softmax
+    // normaliser against the forward pass's lse (the dE pass needs a logsumexp consistent to ~1e-6).
     ProfScope prof(RB2_ST_TC_SCORE, st, 2);
     p.nP = nq; p.nQ = n_items;
     p.n_ptiles = (int)(nq_pad / PM);
     p.n_qtiles = (int)(ni_pad / QN);
     p.n_split = w.n_split_x;
     p.qtiles_per_split = (p.n_qtiles + p.n_split - 1) / p.n_split;
+    p.n_split = (p.n_qtiles + p.qtiles_per_split - 1) / p.qtiles_per_split;
     p.out = w.part;
+    p.zpart = w.zpart;
+    p.q_inv_scale = w.sc_e + 1;
+    p.p_inv_scale = w.sc_x + 1;
     int rc = launch_pass<true>(p, w.xh, w.xl, nq_pad, w.eh, w.el, w.eth, w.etl, ni_pad, st);
     if (rc) return rc;
-    k_ce_reduce<<<(unsigned)((nq * (D / 4) + 255) / 256), 256, 0, st>>>(w.part, p.n_split, nq_pad, nq, dx_out);
+    // the partials hold scale' * sum_j exp_j E_j with scale' = grad_scale (the 2^kg is undone in the drain)
+    k_ce_reduce<<<(unsigned)((nq * (D / 4) + 255) / 256), 256, 0, st>>>(w.part, w.zpart, p.n_split, nq_pad, nq, x, item_p,
+                                                                         target, lse, grad_scale, dx_out, w.lse_corr,
+                                                                         w.omp);
     RB2_CUDA(cudaGetLastError());
   }
   if (de_out) {
@@ -484,6 +624,11 @@ extern "C" int rb2_ce_head_backward(const float *x, int64_t nq, const float *ite
     p.n_split = 1;
     p.qtiles_per_split = p.n_qtiles;
     p.out = de_out;
+    p.zpart = nullptr;
+    p.lse = w.lse_corr;
+    p.omp = w.omp;
+    p.q_inv_scale = w.sc_x + 1;
+    p.p_inv_scale = w.sc_e + 1;
     int rc = launch_pass<false>(p, w.eh, w.el, ni_pad, w.xh, w.xl, w.xth, w.xtl, nq_pad, st);
     if (rc) return rc;
   }

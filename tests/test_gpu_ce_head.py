@@ -79,11 +79,15 @@ def test_ce_head_tensor_core_vs_fp32_kernel_at_cfg4_size(scale):
 
 
 def _elementwise_ok(a, b, rtol=1e-5):
-    """|a - b| <= rtol * |b| + rtol * rms(b): element-wise relative with an absolute floor at the tensor's scale."""
+    """Two criteria.  (1) north_star's: max |a - b| <= 1e-5 * max |b|.  (2) element-wise: |a - b| <= rtol * |b| +
+    rtol * rms(row of b) -- relative, with an absolute floor at the scale of the element's own gradient ROW (the rows of
+    target items are orders of magnitude larger than the others, a tensor-wide floor would say nothing about them).
+    Returns (number of elements failing (2), or -1 when (1) fails; max error / max |b|)."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
-    floor = rtol * np.sqrt((b * b).mean())
+    glob = float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+    floor = rtol * np.sqrt((b * b).mean(axis=-1, keepdims=True))
     bad = np.abs(a - b) > rtol * np.abs(b) + floor
-    return int(bad.sum()), float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+    return (int(bad.sum()) if glob <= 1e-5 else -1), glob
 
 
 def test_ce_backward_vs_torch_autograd_golden(golden):
