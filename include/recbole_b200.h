@@ -324,6 +324,25 @@ int rb2_gather_dot(const float *user_p, const float *item_p, int64_t n_users, in
  * ---------------------------------------------------------------------------------------- */
 enum { RB2_SCORER_FP32 = 0, RB2_SCORER_TC = 1 };
 
+/* Scorer state, owned by the CALLER (host memory; zero-initialise): the knobs, the adaptive statistics that choose the
+ * tensor-core scorer's first pass, and what the last call did.  The *_s entry points below read and update the state
+ * they are given and nothing else, so a process can run one state per (device, stream, model) from as many threads
+ * as it likes.  The entry points without a state argument use a default state private to the CALLING THREAD; the
+ * rb2_fullsort_tc_set_* / rb2_ce_head_set_scorer / rb2_fullsort_tc_last_* calls address that thread-default state.
+ * (The tensor-core scorer synchronises the stream once or twice per call to read how many rows failed their
+ * certificate: it is not capturable in a CUDA graph.) */
+typedef struct rb2_scorer_state {
+  int32_t variant;             /* 0 = default; 1 = bf16 / fp32 accumulators; 2 = CTA-pair MMAs; 3 = fp16 / FP16 accumulators */
+  int32_t kprime;              /* candidates per list: 0 = automatic, 16, 32 */
+  int32_t ce_scorer;           /* rb2_ce_head: 0 = tensor cores where covered, 1 = CUDA-core kernel */
+  float fail_ema;              /* recent fraction of rows failing the first certificate */
+  int32_t calls;
+  int32_t last_fallback_rows;  /* rows the last call redid with the exact CUDA-core kernel */
+  int32_t last_pass2_rows;     /* rows the last call sent through the second (fp32-accumulator) tensor pass */
+  int32_t reserved;
+  void *trace;                 /* diagnostics: device buffer (tools/tc_trace.py) or NULL */
+} rb2_scorer_state;
+
 size_t rb2_fullsort_workspace_bytes(int64_t nq, int64_t n_items_local, int32_t dim, int32_t k, int32_t mode);
 
 /* Compatibility path: the score matrix itself, out_scores fp32 [nq, n_items] = BPR.full_sort_predict (bpr.py:91-96)
@@ -338,6 +357,12 @@ int rb2_fullsort_topk(const float *query_p, const int64_t *query_ids, int64_t nq
                       const int64_t *hist_indptr, const int64_t *hist_indices, int32_t k, int32_t mode,
                       int64_t *out_ids, float *out_scores,
                       void *workspace, size_t workspace_bytes, void *stream);
+int rb2_fullsort_topk_s(const float *query_p, const int64_t *query_ids, int64_t nq,
+                      const float *item_p, int64_t n_items_local, int64_t item_base, int32_t dim,
+                      const int64_t *hist_indptr, const int64_t *hist_indices, int32_t k, int32_t mode,
+                      int64_t *out_ids, float *out_scores,
+                      void *workspace, size_t workspace_bytes, void *stream,
+                        rb2_scorer_state *h_state);
 
 /* ------------------------------------------------------------------------------------------
  * (2c) Full-sort cross-entropy head (SASRec-style, loss_type='CE').  Replaces
@@ -353,6 +378,10 @@ size_t rb2_ce_head_workspace_bytes(int64_t nq, int64_t n_items, int32_t dim, int
 int rb2_ce_head(const float *x, int64_t nq, const float *item_p, int64_t n_items, int32_t dim,
                 const int64_t *target, int32_t k, float *loss_out, float *lse_out, int64_t *topk_ids,
                 float *topk_scores, void *workspace, size_t workspace_bytes, void *stream);
+int rb2_ce_head_s(const float *x, int64_t nq, const float *item_p, int64_t n_items, int32_t dim,
+                const int64_t *target, int32_t k, float *loss_out, float *lse_out, int64_t *topk_ids,
+                float *topk_scores, void *workspace, size_t workspace_bytes, void *stream,
+                  rb2_scorer_state *h_state);
 
 /* rb2_ce_head runs on the tensor cores where covered (dim == 64, k <= 16): bf16 hi/lo split operands, one
  * K = 192 GEMM with fp32 accumulators (logits good to ~2^-16 ||x|| ||e||), online logsumexp in the epilogue,

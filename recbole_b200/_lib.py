@@ -35,6 +35,13 @@ class RB2Optim(ctypes.Structure):
     ]
 
 
+class RB2ScorerState(ctypes.Structure):
+    """include/recbole_b200.h: rb2_scorer_state (caller-owned knobs + adaptive statistics + last-call counters)."""
+    _fields_ = [("variant", ctypes.c_int32), ("kprime", ctypes.c_int32), ("ce_scorer", ctypes.c_int32),
+                ("fail_ema", ctypes.c_float), ("calls", ctypes.c_int32), ("last_fallback_rows", ctypes.c_int32),
+                ("last_pass2_rows", ctypes.c_int32), ("reserved", ctypes.c_int32), ("trace", ctypes.c_void_p)]
+
+
 class RB2Peers(ctypes.Structure):
     _fields_ = [
         ("world", ctypes.c_int32), ("me", ctypes.c_int32), ("item_block", ctypes.c_int64),
@@ -91,6 +98,10 @@ SIGNATURES = {
     "rb2_fullsort_topk": (ctypes.c_int, [_p, _p, _i64, _p, _i64, _i64, _i32, _p, _p, _i32, _i32, _p, _p, _p, _sz,
                                          _p]),
     "rb2_fullsort_scores": (ctypes.c_int, [_p, _p, _i64, _i64, _p, _i64, _i32, _p, _p]),
+    "rb2_fullsort_topk_s": (ctypes.c_int, [_p, _p, _i64, _p, _i64, _i64, _i32, _p, _p, _i32, _i32, _p, _p, _p, _sz,
+                                           _p, ctypes.POINTER(RB2ScorerState)]),
+    "rb2_ce_head_s": (ctypes.c_int, [_p, _i64, _p, _i64, _i32, _p, _i32, _p, _p, _p, _p, _p, _sz, _p,
+                                     ctypes.POINTER(RB2ScorerState)]),
     "rb2_ce_head_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "rb2_ce_head": (ctypes.c_int, [_p, _i64, _p, _i64, _i32, _p, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "rb2_ce_head_set_scorer": (ctypes.c_int, [_i32]),

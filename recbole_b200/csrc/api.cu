@@ -204,3 +204,13 @@ extern "C" int rb2_gather_dot(const float *user_p, const float *item_p, int64_t 
   RB2_CUDA(cudaGetLastError());
   return 0;
 }
+
+
+// ---- scorer state plumbing -------------------------------------------------------------------------------------
+namespace {
+thread_local rb2_scorer_state t_default_scorer = {};
+thread_local rb2_scorer_state *t_cur_scorer = nullptr;
+}  // namespace
+rb2_scorer_state &rb2_cur_scorer() { return t_cur_scorer ? *t_cur_scorer : t_default_scorer; }
+ScorerScope::ScorerScope(rb2_scorer_state *s) : prev(t_cur_scorer) { if (s) t_cur_scorer = s; }
+ScorerScope::~ScorerScope() { t_cur_scorer = prev; }

@@ -327,11 +327,15 @@ k_ce_bwd(const __grid_constant__ CUtensorMap tmPh, const __grid_constant__ CUten
               }
               g2[u] = g;
             }
-            const __half h0 = __float2half_rn(g2[0]), h1 = __float2half_rn(g2[1]);
-            const __half l0 = __float2half_rn(g2[0] - __half2float(h0));
-            const __half l1 = __float2half_rn(g2[1] - __half2float(h1));
-            hw[h] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-            lw[h] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            // hi = g with the mantissa cut to FP16's 10 bits (exact in FP16 for normal values: no conversion back is
+            // needed to form lo = g - hi); both halves leave through the packed converter (one instruction per pair;
+            // the scalar F2F conversions ran on the same quarter-rate pipe as the exponentials)
+            const float h0f = __uint_as_float(__float_as_uint(g2[0]) & 0xFFFFE000u);
+            const float h1f = __uint_as_float(__float_as_uint(g2[1]) & 0xFFFFE000u);
+            const __half2 hp = __floats2half2_rn(h0f, h1f);
+            const __half2 lp = __floats2half2_rn(g2[0] - h0f, g2[1] - h1f);
+            hw[h] = *reinterpret_cast<const uint32_t *>(&hp);
+            lw[h] = *reinterpret_cast<const uint32_t *>(&lp);
           }
           // K-major, 128-byte swizzle: row t, 16-byte chunk c sits at chunk position c ^ (t & 7)
           const uint32_t off = (uint32_t)t * 128u + (uint32_t)((c ^ (t & 7)) << 4);

@@ -31,6 +31,15 @@ void rb2_set_error(const char *fmt, ...);
 void rb2_prof_begin(int stage, cudaStream_t st);
 void rb2_prof_end(int stage, cudaStream_t st, int launches);
 
+// scorer state (include/recbole_b200.h rb2_scorer_state): the state of the call in flight on this thread -- the caller's
+// (entry points *_s) or the thread's default (api.cu)
+rb2_scorer_state &rb2_cur_scorer();
+struct ScorerScope {
+  rb2_scorer_state *prev;
+  explicit ScorerScope(rb2_scorer_state *s);
+  ~ScorerScope();
+};
+
 struct ProfScope {
   int stage, launches;
   cudaStream_t st;

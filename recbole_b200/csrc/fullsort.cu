@@ -471,9 +471,24 @@ int rb2_fullsort_fp32_lse(const float *query_p, const int64_t *query_ids, int64_
                           void *workspace, size_t workspace_bytes, cudaStream_t st, const int32_t *row_map,
                           float *lse_m, float *lse_s, int *parts_out) {
   FsPlan p = plan_any(dim, nq, n_items_local, k);
-  if (parts_out) *parts_out = p.n_split;
   RB2_REQUIRE(p.n_split > 0, RB2_EINVAL, "rb2_fullsort_topk: embedding dim %d not supported by the fp32 scorer (16, 32, 64, 128)",
               (int)dim);
+  {
+    // The workspace may have been sized for a different row count (the tensor-core scorer's fallback re-scores
+    // n_fail < nq rows with the buffer of the full call, and fewer rows want MORE item splits): never split further
+    // than the per-split lists fit -- fewer splits only cost parallelism.
+    const size_t per_list = (size_t)nq * k * (sizeof(int64_t) + sizeof(float)) + 512;
+    int64_t fit = (int64_t)(workspace_bytes / per_list);
+    if (fit < 1) fit = 1;
+    if (p.n_split > fit && !lse_m) {
+      const int ti = dim == 16 ? FsCfg<16>::TI : dim == 32 ? FsCfg<32>::TI : dim == 64 ? FsCfg<64>::TI : FsCfg<128>::TI;
+      int64_t per = (n_items_local + fit - 1) / fit;
+      per = (per + ti - 1) / ti * ti;
+      p.items_per_split = per;
+      p.n_split = (int)((n_items_local + per - 1) / per);
+    }
+  }
+  if (parts_out) *parts_out = p.n_split;
   RB2_REQUIRE(p.smem <= 200 * 1024, RB2_EINVAL, "rb2_fullsort_topk: k=%d too large", (int)k);
   Carver c(workspace);
   int64_t *part_ids = c.take<int64_t>((size_t)p.n_split * nq * k);
@@ -583,15 +598,24 @@ extern "C" int rb2_topk_metrics(const int64_t *topk_ids, int64_t nq, int32_t k, 
   return 0;
 }
 
+extern "C" int rb2_fullsort_topk_s(const float *query_p, const int64_t *query_ids, int64_t nq, const float *item_p,
+                                   int64_t n_items_local, int64_t item_base, int32_t dim, const int64_t *hist_indptr,
+                                   const int64_t *hist_indices, int32_t k, int32_t mode, int64_t *out_ids,
+                                   float *out_scores, void *workspace, size_t workspace_bytes, void *stream,
+                                   rb2_scorer_state *h_state) {
+  ScorerScope scope(h_state);
+  return rb2_fullsort_topk(query_p, query_ids, nq, item_p, n_items_local, item_base, dim, hist_indptr, hist_indices, k,
+                           mode, out_ids, out_scores, workspace, workspace_bytes, stream);
+}
+
 // tensor-core form (fullsort_tc.cu), dim == 64 and k <= 16
 size_t rb2_fullsort_tc_lse_workspace_bytes(int64_t nq, int64_t n_items, int32_t dim, int32_t k);
 int rb2_fullsort_tc_lse(const float *x, int64_t nq, const float *item_p, int64_t n_items, int32_t dim, int32_t k,
                         int64_t *out_ids, float *out_scores, void *workspace, size_t workspace_bytes, cudaStream_t st,
                         float *lse_m, float *lse_s, int *parts_out);
-static int32_t g_ce_scorer = 0;   // 0 = tensor cores where covered, 1 = CUDA-core fp32 kernel
-extern "C" int rb2_ce_head_set_scorer(int32_t mode) {
+extern "C" int rb2_ce_head_set_scorer(int32_t mode) {   // 0 = tensor cores where covered, 1 = CUDA-core fp32 kernel
   if (mode != 0 && mode != 1) return RB2_EINVAL;
-  g_ce_scorer = mode;
+  rb2_cur_scorer().ce_scorer = mode;
   return 0;
 }
 
@@ -621,7 +645,7 @@ extern "C" int rb2_ce_head(const float *x, int64_t nq, const float *item_p, int6
   float *row_loss = c.take<float>(nq);
   size_t fs_bytes = rb2_fullsort_fp32_workspace(nq, n_items, dim, k);
   size_t tc_bytes = rb2_fullsort_tc_lse_workspace_bytes(nq, n_items, dim, k);
-  const bool use_tc = g_ce_scorer == 0 && tc_bytes > 0;
+  const bool use_tc = rb2_cur_scorer().ce_scorer == 0 && tc_bytes > 0;
   if (use_tc && tc_bytes > fs_bytes) fs_bytes = tc_bytes;
   void *fs_ws = c.take<char>(fs_bytes);
   RB2_REQUIRE(c.off <= workspace_bytes, RB2_EWORKSPACE, "rb2_ce_head: workspace %zu < %zu", workspace_bytes, c.off);
@@ -719,4 +743,13 @@ extern "C" int rb2_fullsort_scores(const float *query_p, const int64_t *query_id
       query_p, query_ids, nq, n_query_rows, item_p, n_items, dim, out_scores, nullptr);
   RB2_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int rb2_ce_head_s(const float *x, int64_t nq, const float *item_p, int64_t n_items, int32_t dim,
+                             const int64_t *target, int32_t k, float *loss_out, float *lse_out, int64_t *topk_ids,
+                             float *topk_scores, void *workspace, size_t workspace_bytes, void *stream,
+                             rb2_scorer_state *h_state) {
+  ScorerScope scope(h_state);
+  return rb2_ce_head(x, nq, item_p, n_items, dim, target, k, loss_out, lse_out, topk_ids, topk_scores, workspace,
+                     workspace_bytes, stream);
 }

@@ -54,35 +54,29 @@ int rb2_fullsort_fp32(const float *query_p, const int64_t *query_ids, int64_t nq
                       size_t workspace_bytes, cudaStream_t st, const int32_t *row_map);
 size_t rb2_fullsort_fp32_workspace(int64_t nq, int64_t n_items_local, int32_t dim, int32_t k);
 
-// number of rows the last RB2_SCORER_TC call had to redo in fp32 (diagnostic for bench / tests)
-static int32_t g_last_tc_fallback_rows = 0;
-static int32_t g_last_tc_pass2_rows = 0;   // rows the last call sent through the second (fp32-accumulator) tensor pass
-static int32_t g_tc_kprime = 0;  // 0 = automatic, 16 or 32 = forced (rb2_fullsort_tc_set_kprime)
-// 0 = default (= 3); 1 = bf16 operands, fp32 accumulators, per-CTA MMAs; 3 = fp16 operands (rows rescaled by
-// powers of two), FP16 accumulators drained with .pack::16b, per-CTA MMAs; 2 = as 3 with CTA-pair MMAs
-// (cta_group::2)
-static int32_t g_tc_variant = 0;
-static float g_tc_fail_ema = 0.f;          // recent fraction of rows failing the FP16-accumulator certificate
-static int g_tc_calls = 0;
+// Knobs, adaptive statistics and last-call counters live in an rb2_scorer_state (caller-owned, or the calling thread's
+// default): rb2_cur_scorer().  variant: 0 = default (= 3); 1 = bf16 operands, fp32 accumulators, per-CTA MMAs;
+// 3 = fp16 operands (rows rescaled by powers of two), FP16 accumulators drained with .pack::16b, per-CTA MMAs;
+// 2 = as 3 with CTA-pair MMAs (cta_group::2).
 extern "C" int rb2_fullsort_tc_set_variant(int32_t v) {
   if (v < 0 || v > 3) return RB2_EINVAL;
-  g_tc_fail_ema = 0.f;                     // (also forgets the first-pass statistics)
-  g_tc_calls = 0;
-  g_tc_variant = v;
+  rb2_scorer_state &S = rb2_cur_scorer();
+  S.fail_ema = 0.f;                     // (also forgets the first-pass statistics)
+  S.calls = 0;
+  S.variant = v;
   return 0;
 }
 extern "C" int rb2_fullsort_tc_set_kprime(int32_t kp) {
   if (kp != 0 && kp != 16 && kp != 32) return RB2_EINVAL;
-  g_tc_kprime = kp;
+  rb2_cur_scorer().kprime = kp;
   return 0;
 }
-extern "C" int32_t rb2_fullsort_tc_last_fallback_rows(void) { return g_last_tc_fallback_rows; }
-extern "C" int32_t rb2_fullsort_tc_last_pass2_rows(void) { return g_last_tc_pass2_rows; }
+extern "C" int32_t rb2_fullsort_tc_last_fallback_rows(void) { return rb2_cur_scorer().last_fallback_rows; }
+extern "C" int32_t rb2_fullsort_tc_last_pass2_rows(void) { return rb2_cur_scorer().last_pass2_rows; }
 // diagnostics: device buffer of 16 int64 per CTA that k_fullsort_tc fills with the cycles its producer / MMA /
 // epilogue roles spent waiting on each barrier (nullptr = off)
-static long long *g_tc_trace = nullptr;
 extern "C" int rb2_fullsort_tc_set_trace(void *device_buffer) {
-  g_tc_trace = static_cast<long long *>(device_buffer);
+  rb2_cur_scorer().trace = device_buffer;
   return 0;
 }
 
@@ -1232,7 +1226,7 @@ int tc_pass(const TcWs &w, const float *query_p, const int64_t *query_ids, const
   p.n_ut = pl.n_ut; p.n_split = pl.n_split; p.tiles_per_split = pl.tiles_per_split;
   p.hist_indptr = hist_indptr; p.hist_indices = hist_indices;
   p.cand_ids = w.cand_ids; p.cand_sc = w.cand_sc;
-  p.trace = g_tc_trace;
+  p.trace = static_cast<long long *>(rb2_cur_scorer().trace);
   p.lse_m = nullptr; p.lse_s = nullptr;
   p.row_map = row_map;
   const size_t smem = TcSmem<KB, NSTAGE, TWO_SM>::TOTAL;
@@ -1288,7 +1282,8 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
   // When most first-pass certificates fail (well-trained tables: E is relative to max ||v||, the score gaps are
   // not) the FP16-accumulator pass is wasted work: the break-even is ~15 % failing rows.  Track the recent
   // failure fraction and start with fp32 accumulators when it is above that, probing again every 16th call.
-  const bool fast_first = H16 && (g_tc_fail_ema < 0.15f || (g_tc_calls++ % 16) == 15);
+  rb2_scorer_state &S = rb2_cur_scorer();
+  const bool fast_first = H16 && (S.fail_ema < 0.15f || (S.calls++ % 16) == 15);
   int rc;
   if (fast_first || !H16)
     rc = tc_pass<D, KP, H16, H16, TWO_SM, TRACE>(w, query_p, query_ids, nullptr, nq, true, item_p, n_local, item_base,
@@ -1302,12 +1297,12 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
   int32_t n_fail = 0;
   RB2_CUDA(cudaMemcpyAsync(&n_fail, w.fail_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   RB2_CUDA(cudaStreamSynchronize(st));
-  g_last_tc_pass2_rows = 0;
+  S.last_pass2_rows = 0;
   const int32_t *final_rows = w.fail_rows;
   if (fast_first) {
-    if (nq >= 1024) g_tc_fail_ema = 0.5f * g_tc_fail_ema + 0.5f * (float)n_fail / (float)nq;
+    if (nq >= 1024) S.fail_ema = 0.5f * S.fail_ema + 0.5f * (float)n_fail / (float)nq;
     if (n_fail > 0) {
-      g_last_tc_pass2_rows = n_fail;
+      S.last_pass2_rows = n_fail;
       rc = tc_pass<D, KP, true, false, false, false>(w, query_p, query_ids, w.fail_rows, n_fail, false, item_p, n_local,
                                                      item_base, hist_indptr, hist_indices, k, out_ids, out_scores,
                                                      w.fail_rows2, w.fail_count + 1, st);
@@ -1317,7 +1312,7 @@ int run_tc(const float *query_p, const int64_t *query_ids, int64_t nq, const flo
       final_rows = w.fail_rows2;
     }
   }
-  g_last_tc_fallback_rows = n_fail;
+  S.last_fallback_rows = n_fail;
   if (n_fail > 0) {   // redo exactly
     rc = rb2_fullsort_fp32(query_p, query_ids, n_fail, item_p, n_local, item_base, D, hist_indptr, hist_indices, k,
                            out_ids, out_scores, w.fp32_ws, w.fp32_bytes, st, final_rows);
@@ -1428,7 +1423,7 @@ int run_tc_lse(const float *x, int64_t nq, const float *item_p, int64_t n_items,
   int32_t n_fail = 0;
   RB2_CUDA(cudaMemcpyAsync(&n_fail, w.fail_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   RB2_CUDA(cudaStreamSynchronize(st));
-  g_last_tc_fallback_rows = n_fail;
+  rb2_cur_scorer().last_fallback_rows = n_fail;
   if (n_fail > 0) {
     rc = rb2_fullsort_fp32(x, nullptr, n_fail, item_p, n_items, 0, D, nullptr, nullptr, k, out_ids, out_scores, w.fp32_ws,
                            w.fp32_bytes, st, w.fail_rows);
@@ -1452,28 +1447,29 @@ int rb2_fullsort_tc(const float *query_p, const int64_t *query_ids, int64_t nq, 
   if ((dim != 64 && dim != 128) || k > 16) {
     // the MMA tiling covers d = 64 / 128 and K <= 16 (K' = 32 candidates); other shapes take the
     // exact CUDA-core kernel
-    g_last_tc_fallback_rows = (int32_t)(nq > INT32_MAX ? INT32_MAX : nq);
+    rb2_cur_scorer().last_fallback_rows = (int32_t)(nq > INT32_MAX ? INT32_MAX : nq);
     return rb2_fullsort_fp32(query_p, query_ids, nq, item_p, n_items_local, item_base, dim, hist_indptr,
                              hist_indices, k, out_ids, out_scores, workspace, workspace_bytes, st, nullptr);
   }
   // K' = 16 candidates per list for small K, and for short item ranges (list upkeep dominates there and a
   // row whose certificate fails is cheap to redo); 32 otherwise
-  const bool small_list = (g_tc_kprime == 16) || (g_tc_kprime == 0 && (k <= 8 || (k <= 12 && n_items_local <= 262144)));
+  const int32_t tc_kprime = rb2_cur_scorer().kprime, tc_variant = rb2_cur_scorer().variant;
+  const bool small_list = (tc_kprime == 16) || (tc_kprime == 0 && (k <= 8 || (k <= 12 && n_items_local <= 262144)));
 #define RB2_TC_ARGS                                                                                           \
   (query_p, query_ids, nq, item_p, n_items_local, item_base, hist_indptr, hist_indices, k, out_ids, out_scores, \
    workspace, workspace_bytes, st)
 #define RB2_TC(D_, KP_)                                                        \
-  return (g_tc_variant == 1)   ? run_tc<D_, KP_, false, false> RB2_TC_ARGS     \
-         : (g_tc_variant == 2) ? run_tc<D_, KP_, true, true> RB2_TC_ARGS       \
+  return (tc_variant == 1)   ? run_tc<D_, KP_, false, false> RB2_TC_ARGS     \
+         : (tc_variant == 2) ? run_tc<D_, KP_, true, true> RB2_TC_ARGS       \
                                : run_tc<D_, KP_, true, false> RB2_TC_ARGS
   if (dim == 64) {
     if (small_list) RB2_TC(64, 16);
     RB2_TC(64, 32);
   }
   if (small_list) RB2_TC(128, 16);
-  if (g_tc_trace) {   // the instrumented build exists for d = 128, K' = 32 only (tools/tc_trace.py)
-    if (g_tc_variant == 2) return run_tc<128, 32, true, true, true> RB2_TC_ARGS;
-    if (g_tc_variant != 1) return run_tc<128, 32, true, false, true> RB2_TC_ARGS;
+  if (rb2_cur_scorer().trace) {   // the instrumented build exists for d = 128, K' = 32 only (tools/tc_trace.py)
+    if (tc_variant == 2) return run_tc<128, 32, true, true, true> RB2_TC_ARGS;
+    if (tc_variant != 1) return run_tc<128, 32, true, false, true> RB2_TC_ARGS;
   }
   RB2_TC(128, 32);
 #undef RB2_TC

@@ -507,12 +507,14 @@ class ShardedBPR:
             for lo in range(0, n, user_tile):
                 hi = min(lo + user_tile, n)
                 ptr = index.own_hist_indptr[lo:hi + 1].contiguous()
+                if not hasattr(self, "_scorer_state"):
+                    self._scorer_state = ops.ScorerState()      # this model's own knobs + adaptive statistics
                 i, _ = ops.fullsort_topk(self.U, local_users[lo:hi].contiguous(), V_all, K, ptr,
-                                         index.own_hist_indices, mode=mode)
+                                         index.own_hist_indices, mode=mode, state=self._scorer_state)
                 ids[lo:hi] = i
                 if mode == "tc":
-                    self.last_eval_fallback_rows += int(ops.lib.rb2_fullsort_tc_last_fallback_rows())
-                    self.last_eval_pass2_rows += int(ops.lib.rb2_fullsort_tc_last_pass2_rows())
+                    self.last_eval_fallback_rows += self._scorer_state.last_fallback_rows
+                    self.last_eval_pass2_rows += self._scorer_state.last_pass2_rows
             if n > 0:
                 sums = ops.topk_metrics(ids, index.pos_indptr, index.pos_indices, self.n_items)["sums"]
             else:

@@ -383,8 +383,26 @@ def gather_dot(U, V, user, item):
     return out
 
 
+class ScorerState:
+    """Caller-owned scorer state (include/recbole_b200.h rb2_scorer_state): knobs, the adaptive statistics that pick
+    the tensor-core scorer's first pass, and what the last call did.  One per model / device / stream; calls that
+    pass none share the calling thread's default state inside the library."""
+
+    def __init__(self, variant=0, kprime=0, ce_scorer=0):
+        self.c = _lib.RB2ScorerState()
+        self.c.variant, self.c.kprime, self.c.ce_scorer = int(variant), int(kprime), int(ce_scorer)
+
+    @property
+    def last_fallback_rows(self):
+        return int(self.c.last_fallback_rows)
+
+    @property
+    def last_pass2_rows(self):
+        return int(self.c.last_pass2_rows)
+
+
 def fullsort_topk(Q, query_ids, V, k, hist_indptr=None, hist_indices=None, item_base=0, mode="fp32", ws=None,
-                  out=None):
+                  out=None, state=None):
     """Top-k item ids / scores per query row (rb2_fullsort_topk).  Returns (ids int64[nq,k],
     scores fp32[nq,k])."""
     nq = int(query_ids.numel()) if query_ids is not None else int(Q.shape[0])
@@ -398,10 +416,13 @@ def fullsort_topk(Q, query_ids, V, k, hist_indptr=None, hist_indices=None, item_
         sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
     else:
         ids, sc = out
-    check(lib.rb2_fullsort_topk(
-        _ptr(Q, torch.float32), _ptr(query_ids, torch.int64, True), nq, _ptr(V, torch.float32), V.shape[0],
-        int(item_base), V.shape[1], _ptr(hist_indptr, torch.int64, True), _ptr(hist_indices, torch.int64, True),
-        int(k), m, _ptr(ids), _ptr(sc), ws.ptr(), ws.nbytes, _stream()))
+    args = (_ptr(Q, torch.float32), _ptr(query_ids, torch.int64, True), nq, _ptr(V, torch.float32), V.shape[0],
+            int(item_base), V.shape[1], _ptr(hist_indptr, torch.int64, True), _ptr(hist_indices, torch.int64, True),
+            int(k), m, _ptr(ids), _ptr(sc), ws.ptr(), ws.nbytes, _stream())
+    if state is None:
+        check(lib.rb2_fullsort_topk(*args))
+    else:
+        check(lib.rb2_fullsort_topk_s(*args, ctypes.byref(state.c)))
     return ids, sc
 
 
@@ -418,15 +439,15 @@ def ce_head(X, E, target, k=10, scorer="auto"):
     """Fused full-sort CE head (rb2_ce_head): returns dict(loss 0-dim, lse [nq], ids [nq,k], scores [nq,k]).
     scorer: "auto" = tensor cores where covered (dim 64, k <= 16), "fp32" = the CUDA-core kernel."""
     nq, dev = X.shape[0], X.device
-    check(lib.rb2_ce_head_set_scorer({"auto": 0, "tc": 0, "fp32": 1}[scorer]))
+    state = ScorerState(ce_scorer={"auto": 0, "tc": 0, "fp32": 1}[scorer])
     ws = Workspace(lib.rb2_ce_head_workspace_bytes(nq, E.shape[0], E.shape[1], int(k)), dev)
     loss = torch.zeros(1, dtype=torch.float32, device=dev)
     lse = torch.empty(nq, dtype=torch.float32, device=dev)
     ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
     sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    check(lib.rb2_ce_head(_ptr(X, torch.float32), nq, _ptr(E, torch.float32), E.shape[0], E.shape[1],
-                          _ptr(target, torch.int64, True), int(k), _ptr(loss), _ptr(lse), _ptr(ids), _ptr(sc),
-                          ws.ptr(), ws.nbytes, _stream()))
+    check(lib.rb2_ce_head_s(_ptr(X, torch.float32), nq, _ptr(E, torch.float32), E.shape[0], E.shape[1],
+                            _ptr(target, torch.int64, True), int(k), _ptr(loss), _ptr(lse), _ptr(ids), _ptr(sc),
+                            ws.ptr(), ws.nbytes, _stream(), ctypes.byref(state.c)))
     return dict(loss=loss[0], lse=lse, ids=ids, scores=sc)
 
 

@@ -115,7 +115,7 @@ def test_model_mirror_api_surface():
     assert (m.n_users, m.n_items, m.NEG_ITEM_ID) == (11, 7, "neg_item_id")
     for name in ("calculate_loss", "predict", "full_sort_predict"):
         assert callable(getattr(m, name))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match="no CPU path"):        # the product path fails loudly off the GPU
         m.full_sort_predict({"user_id": torch.tensor([1])})
     # xavier-normal std (init.py:27): sqrt(2 / (rows + d))
     big = FusedBPR(Cfg(USER_ID_FIELD="u", ITEM_ID_FIELD="i", NEG_PREFIX="neg_", device="cpu", embedding_size=64),

@@ -369,3 +369,21 @@ def test_fullsort_tc_cascade_and_adaptive_first_pass(tc_variant):
     for _ in range(40):
         ids, _ = ops.fullsort_topk(t(Q2), None, t(V2), K, t(hp2), t(hi2), mode="tc")
     np.testing.assert_array_equal(ids.cpu().numpy(), o2)
+
+
+@pytest.mark.parametrize("nq", [4097, 40000])
+def test_tc_every_certificate_fails_fallback_fits_its_workspace(nq):
+    """All item rows equal: every score ties, every tensor-core certificate fails and ALL rows are re-scored by the exact
+    kernel with the workspace of the full call (fewer rows want more item splits than that buffer was sized for).  The
+    result is the oracle's: the k lowest ids."""
+    from recbole_b200 import ops
+    from gpu_util import t
+    rng = np.random.default_rng(nq)
+    d, N, k = 64, 3001, 10
+    U = rng.standard_normal((nq, d)).astype(np.float32)
+    V = np.tile(rng.standard_normal((1, d)).astype(np.float32), (N, 1))
+    st = ops.ScorerState()
+    ids, sc = ops.fullsort_topk(t(U), None, t(V), k, mode="tc", state=st)
+    assert st.last_fallback_rows + st.last_pass2_rows > 0
+    want = np.tile(np.arange(1, k + 1, dtype=np.int64), (nq, 1))          # id 0 is [PAD]
+    np.testing.assert_array_equal(ids.cpu().numpy(), want)
