@@ -200,6 +200,9 @@ int rb2_bpr_loss(const float *user_p, const float *item_p, int64_t n_users, int6
  * The "owner update done" half of barrier A of call seq + 1 is signalled at the END of call seq, so a rank's keys
  * and sorts never hold its peers up.  user holds global user ids, all inside THIS rank's block
  * [user_base, user_base + n_users_local) of the user table; pos / neg are global item ids.  item_m / item_v: Adam moments of the local shard.
+ * next_user / next_pos / next_neg (all NULL, or the ids of the batch the NEXT call will train on, same batch size): their
+ * keys and sorts are computed into the workspace's other batch slot while this call waits for its peers in barrier B;
+ * the next call then passes prepared = 1 (same workspace, same ids) and skips that work.
  * item_cache: fp32 [world * item_block, dim] scratch.  A barrier that waits longer than 30 s gives up
  * and sets the workspace's peer_timeout flag (second int32 of the workspace) instead of hanging.
  * ---------------------------------------------------------------------------------------- */
@@ -223,7 +226,8 @@ int rb2_bpr_train_step_p2p(float *user_p, float *user_m, float *user_v, float *i
                            int64_t global_batch,
                            const rb2_optim *h_opt, const rb2_peers *h_peers, float *item_cache,
                            float *loss_out, double *loss_accum, void *workspace, size_t workspace_bytes,
-                           void *stream);
+                           void *stream, int32_t prepared, const int64_t *next_user, const int64_t *next_pos,
+                           const int64_t *next_neg);
 
 /* Peer mapping helpers (cudaIpc*; legacy IPC handles work between processes on one GPU and across
  * NVLink peers).  rb2_ipc_export: 64-byte handle of the allocation that contains dev_ptr + the offset

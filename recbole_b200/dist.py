@@ -368,8 +368,11 @@ class ShardedBPR:
             self.last_exchange = "p2p"
             if self._p2p_ws is None or self._p2p_ws[0] < B:
                 self._p2p_ws = (B, ops.bpr_p2p_workspace(B, self.dim, self.device))
+            # next_batch: its keys and sorts are computed inside this call, while it waits for the slower peers;
+            # only sound when those id tensors are complete already (resident batches: ids_ready)
             ops.bpr_train_step_p2p(self.U, self.state, self.arena, user, self.u_lo, pos, neg, self.n_items,
-                                   global_batch, self.optim, self.loss_out, self.loss_accum, self._p2p_ws[1], step=t)
+                                   global_batch, self.optim, self.loss_out, self.loss_accum, self._p2p_ws[1], step=t,
+                                   next_batch=next_batch if self.ids_ready else None)
             return self.loss_out
         if self.exchange == "dense" or (self.exchange_auto and B >= self.n_items):
             self.last_exchange = "dense"

@@ -220,19 +220,28 @@ def bpr_p2p_workspace(batch, dim, device):
 
 
 def bpr_train_step_p2p(U, state, arena, user, user_base, pos, neg, n_items, global_batch, optim, loss_out, loss_accum,
-                       ws, step=None):
+                       ws, step=None, next_batch=None):
     """rb2_bpr_train_step_p2p: the whole sharded step (both barriers, the owner update and the global mean
     loss included).  optim.step is NOT incremented here; `step` must count 1, 2, 3, ... identically on every rank."""
     o = optim.c_struct(U.device, step)
     f32, i64 = torch.float32, torch.int64
     arena.seq += 1
     arena.peers.seq = arena.seq
+    # the previous call sorted THIS batch's keys while it waited for its peers (same workspace, same id tensors)?
+    key_now = (ws.buf.data_ptr(), user.data_ptr(), pos.data_ptr(), neg.data_ptr(), int(user.numel()))
+    prepared = 1 if getattr(arena, "prepared_for", None) == key_now else 0
+    nxt, key_next = (None, None, None), None
+    if next_batch is not None and int(next_batch[0].numel()) == int(user.numel()):
+        nu, np_, nn = next_batch
+        nxt = (_ptr(nu, i64), _ptr(np_, i64), _ptr(nn, i64))
+        key_next = (ws.buf.data_ptr(), nu.data_ptr(), np_.data_ptr(), nn.data_ptr(), int(nu.numel()))
     check(lib.rb2_bpr_train_step_p2p(
         _ptr(U, f32), _ptr(state.get("mU"), f32, True), _ptr(state.get("vU"), f32, True),
         _ptr(state.get("mV"), f32, True), _ptr(state.get("vV"), f32, True), U.shape[0], int(n_items), U.shape[1],
         _ptr(user, i64), int(user_base), _ptr(pos, i64), _ptr(neg, i64), user.numel(), int(global_batch),
         ctypes.byref(o), ctypes.byref(arena.peers), _ptr(arena.cache, f32), _ptr(loss_out, f32),
-        _ptr(loss_accum, torch.float64, True), ws.ptr(), ws.nbytes, _stream()))
+        _ptr(loss_accum, torch.float64, True), ws.ptr(), ws.nbytes, _stream(), prepared, *nxt))
+    arena.prepared_for = key_next
 
 
 def item_plan(pos, neg, n_items, bounds_dev, world, plan_ws=None):
