@@ -167,6 +167,33 @@ def run_cfg4(args, load_peaks, ClockSampler):
     torch.cuda.synchronize()
     ms_fp32 = e0.elapsed_time(e1) / 3
     ops.profile_read()
+    # backward of the head (rb2_ce_head_backward: dX and dE, logits and softmax - onehot never materialised) and one dense
+    # Adam step on the item table with its gradient = the training step of the head (sasrec.py:137-141, trainer.py:170-173)
+    bws = ops.Workspace(ops.lib.rb2_ce_head_backward_workspace_bytes(nq, N, d), dev)
+    mE, vE, opt = torch.zeros_like(Ed), torch.zeros_like(Ed), ops.Optim("adam", 1e-3)
+    Etrain = Ed.clone()
+    for _ in range(2):
+        ops.ce_head_backward(Xd, Etrain, td, out["lse"], ws=bws)
+    torch.cuda.synchronize()
+    ops.profile_read()
+    e0.record()
+    for i in range(steps):
+        o_tr = ops.ce_head(Xd, Etrain, td, 1)
+        dx, de = ops.ce_head_backward(Xd, Etrain, td, o_tr["lse"], ws=bws)
+        opt.step += 1
+        ops.dense_step(Etrain, mE, vE, de, opt)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_train = e0.elapsed_time(e1) / steps
+    st_bw = ops.profile_read()
+    e0.record()
+    for i in range(steps):
+        ops.ce_head_backward(Xd, Etrain, td, o_tr["lse"], ws=bws)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_bwd = e0.elapsed_time(e1) / steps
+    ops.profile_read()
+    del Etrain, mE, vE, dx, de
     ops.ce_head(Xd[:8], Ed[:64], td[:8] % 64, K, scorer="auto")
     ops.profile_enable(False)
     t0 = time.perf_counter()
@@ -208,6 +235,14 @@ def run_cfg4(args, load_peaks, ClockSampler):
                      "note": "achieved counts the algorithmic 2*rows*items*d flops; the kernel executes 3x (split precision) "
                              "and one exp per logit (4.1e9 MUFU.EX2 per call)"},
         "fp32_cuda_core_kernel_ms": ms_fp32,
+        "backward": {"metric": "ce_head_backward_rows_per_s", "value": nq / (ms_bwd * 1e-3), "unit": "rows/s",
+                     "ms_per_call": ms_bwd, "kernel": "k_ce_bwd<dX> + k_ce_bwd<dE> (tcgen05, FP16 two-way splits, logits "
+                     "recomputed in both passes)", "achieved": 3 * flops / (ms_bwd * 1e-3) / 1e12, "unit_roofline": "TFLOP/s",
+                     "frac": 3 * flops / (ms_bwd * 1e-3) / 1e12 / peaks["tf"],
+                     "note": "algorithmic flops = 3 x 2*rows*items*d (logits, dX, dE); the two passes execute 12 such "
+                             "units of MMA work (3 split terms x (2 x logits + dX + dE))",
+                     "train_step_ms": ms_train, "train_step": "forward (loss, lse) + backward + dense Adam on the item table",
+                     "stages_ms": {k: v[0] / max(v[1], 1) for k, v in st_bw.items() if v[1]}},
         "cpu_baseline": cpu,
         "e2e": {"value": nq / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": nq * (4 * d + 8),
                 "d2h_bytes_per_step": nq * K * 8 + 4},

@@ -251,3 +251,33 @@ def test_peer_memory_step_one_rank_vs_oracle(dim, B, n_users, n_items, kind):
     assert m.last_exchange == "p2p"
     assert rel_err(m.U.cpu().numpy(), st_o["U"]) < TOL
     assert rel_err(m.V.cpu().numpy()[:n_items], st_o["V"]) < TOL
+
+
+def test_peer_memory_step_prepares_the_next_batch(golden):
+    """next_batch: the following batch's keys and sorts are computed inside the current call (between the two halves
+    of barrier B) into the workspace's other slot, and the next call skips them.  Five chained steps == the same five
+    steps without the hand-over, bit for bit; a batch that was NOT announced is still sorted by its own call."""
+    from recbole_b200.dist import Comm, ShardedBPR
+    from gpu_util import t, dev
+    rng = np.random.default_rng(5)
+    n_users, n_items, dim, B = 5000, 3000, 128, 8192
+    U0 = (rng.standard_normal((n_users, dim)) * 0.3).astype(np.float32)
+    V0 = (rng.standard_normal((n_items, dim)) * 0.3).astype(np.float32)
+    batches = [tuple(t(rng.integers(1, hi, B)) for hi in (n_users, n_items, n_items)) for _ in range(5)]
+
+    def run(chain):
+        m = ShardedBPR(n_users, n_items, dim, Comm(), dev(), U_full=U0, V_full=V0, exchange="p2p")
+        m.build_optimizer("adam", lr=2e-3)
+        m.ids_ready = True
+        losses = []
+        for s, b in enumerate(batches):
+            nxt = batches[s + 1] if (chain and s + 1 < len(batches) and s != 2) else None     # step 2 announces nothing
+            losses.append(float(m.train_step(*b, next_batch=nxt).item()))
+        m.check_flags()
+        return losses, m.U.clone(), m.V.clone(), m
+
+    l0, U_a, V_a, _ = run(False)
+    l1, U_b, V_b, m = run(True)
+    assert l0 == l1
+    assert torch.equal(U_a, U_b) and torch.equal(V_a, V_b)
+    assert m.arena.prepared_for is None            # the last call announced nothing
