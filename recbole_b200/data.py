@@ -9,6 +9,29 @@ import numpy as np
 import torch
 
 
+def _bits(n):
+    b = 1
+    while b < 32 and (1 << b) < n:
+        b += 1
+    return b
+
+
+def _sorted_pairs(rows, cols, n_rows, n_cols):
+    """(row, col) pairs in (row, col) order.  On the GPU the two sorts are the library's own bounded-key sort
+    (rb2_sort_positions: least-significant key first, stable), the gathers are plumbing; on the CPU (host-side tests)
+    a torch sort of the combined key."""
+    if rows.is_cuda and rows.numel() < (1 << 31) and n_rows < (1 << 31) and n_cols < (1 << 31):
+        from . import ops
+        _, o1 = ops.sort_positions(cols.to(torch.int32).contiguous(), _bits(int(n_cols)))
+        o1 = o1.to(torch.int64)
+        _, o2 = ops.sort_positions(rows[o1].to(torch.int32).contiguous(), _bits(int(n_rows)))
+        order = o1[o2.to(torch.int64)]
+        return rows[order], cols[order]
+    key = torch.sort(rows * int(n_cols) + cols).values
+    r = torch.div(key, int(n_cols), rounding_mode="floor")
+    return r, key - r * int(n_cols)
+
+
 def build_csr(n_rows, rows, cols, n_cols, device):
     """Sorted, de-duplicated CSR of (row, col) pairs: (indptr int64[n_rows+1], indices int64)."""
     rows = torch.as_tensor(rows, dtype=torch.int64, device=device)
@@ -16,9 +39,10 @@ def build_csr(n_rows, rows, cols, n_cols, device):
     if rows.numel() == 0:
         return torch.zeros(n_rows + 1, dtype=torch.int64, device=device), torch.zeros(0, dtype=torch.int64,
                                                                                       device=device)
-    key = torch.unique(rows * int(n_cols) + cols)  # sorted
-    r = torch.div(key, int(n_cols), rounding_mode="floor")
-    c = key - r * int(n_cols)
+    r, c = _sorted_pairs(rows, cols, n_rows, n_cols)
+    keep = torch.ones(r.numel(), dtype=torch.bool, device=device)
+    keep[1:] = (r[1:] != r[:-1]) | (c[1:] != c[:-1])
+    r, c = r[keep], c[keep]
     counts = torch.bincount(r, minlength=n_rows)
     indptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=device)
     indptr[1:] = torch.cumsum(counts, 0)
@@ -72,8 +96,23 @@ class EvalIndex:
 
     @classmethod
     def from_reference_dataloader(cls, eval_data, device):
-        """From an unmodified reference GeneralFullDataLoader: its public per-user arrays
-        uid_list / uid2history_item (general_dataloader.py:294-313) and the phase's interactions."""
+        """From an unmodified reference GeneralFullDataLoader, WITHOUT its per-user Python structures: the loader's
+        sampler keeps the datasets of all phases (sampler.py:171-184); used ids of the loader's phase = interactions of
+        the phases up to it (sampler.py:206-218), positives = the loader's own dataset, history = used - positives
+        (general_dataloader.py:319-321) -- three id-pair lists, sorted and de-duplicated on the device.  (The loops the
+        reference runs to build uid2history_item / uid2swap_idx are what SURVEY.md 8f-2 replaces.)"""
+        ds, smp = eval_data.dataset, eval_data.sampler
+        if not (hasattr(smp, "datasets") and hasattr(smp, "phases") and getattr(smp, "phase", None) in smp.phases):
+            return cls._from_reference_dataloader_loops(eval_data, device)
+        upto = smp.phases.index(smp.phase)
+        pairs = [(d.inter_feat[d.uid_field], d.inter_feat[d.iid_field]) for d in smp.datasets[:upto + 1]]
+        pairs.append((ds.inter_feat[ds.uid_field], ds.inter_feat[ds.iid_field]))
+        return cls.from_phase_pairs(ds.user_num, ds.item_num, pairs, len(pairs) - 1, device)
+
+    @classmethod
+    def _from_reference_dataloader_loops(cls, eval_data, device):
+        """The same index from the loader's public per-user arrays uid_list / uid2history_item
+        (general_dataloader.py:294-313); kept as the cross-check of from_reference_dataloader."""
         ds = eval_data.dataset
         n_items = ds.item_num
         uid_list = torch.as_tensor(np.asarray(eval_data.uid_list), dtype=torch.int64, device=device)

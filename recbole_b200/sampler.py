@@ -38,17 +38,28 @@ class DeviceSampler:
     def from_reference_sampler(cls, sampler, device, mode="ref"):
         """Build from an unmodified reference Sampler (after set_phase): same used ids, same
         random_list, same pointer."""
-        from .data import build_csr
-        rows, cols = [], []
-        for u, s in enumerate(sampler.used_ids):
-            if len(s):
-                rows.append(np.full(len(s), u, dtype=np.int64))
-                cols.append(np.fromiter(s, dtype=np.int64, count=len(s)))
-        rows = np.concatenate(rows) if rows else np.zeros(0, np.int64)
-        cols = np.concatenate(cols) if cols else np.zeros(0, np.int64)
-        indptr, indices = build_csr(sampler.n_users, rows, cols, sampler.n_items, device)
+        indptr, indices = cls._used_csr(sampler, device)
         return cls(sampler.n_items, indptr, indices, mode=mode, random_list=np.asarray(sampler.random_list),
                    random_pr=sampler.random_pr)
+
+    @staticmethod
+    def _used_csr(sampler, device):
+        from .data import build_csr
+        if hasattr(sampler, "datasets") and getattr(sampler, "phase", None) in getattr(sampler, "phases", []):
+            # used ids of the phase = the interactions of the phases up to it (sampler.py:206-218): id pairs straight
+            # from the datasets the sampler keeps, no per-user sets
+            upto = sampler.phases.index(sampler.phase)
+            rows = torch.cat([d.inter_feat[sampler.uid_field] for d in sampler.datasets[:upto + 1]])
+            cols = torch.cat([d.inter_feat[sampler.iid_field] for d in sampler.datasets[:upto + 1]])
+        else:
+            rows, cols = [], []
+            for u, s in enumerate(sampler.used_ids):
+                if len(s):
+                    rows.append(np.full(len(s), u, dtype=np.int64))
+                    cols.append(np.fromiter(s, dtype=np.int64, count=len(s)))
+            rows = np.concatenate(rows) if rows else np.zeros(0, np.int64)
+            cols = np.concatenate(cols) if cols else np.zeros(0, np.int64)
+        return build_csr(sampler.n_users, rows, cols, sampler.n_items, device)
 
     def sample_by_user_ids(self, user_ids, num):
         user_ids = torch.as_tensor(user_ids, dtype=torch.int64, device=self.device).contiguous()

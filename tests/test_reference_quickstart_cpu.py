@@ -77,6 +77,18 @@ for r in (0, 1, len(uid) // 2, len(uid) - 1):
     want = np.sort(np.asarray(test_data.uid2history_item[uid[r]], dtype=np.int64))
     assert np.array_equal(hi[hp[r]:hp[r + 1]], want)
 assert np.array_equal(index.pos_len().numpy(), np.asarray(test_data.uid2items_num)[uid])
+# ... and equals, array for array, the index built by looping over the loader's per-user structures
+loops = EvalIndex._from_reference_dataloader_loops(test_data, "cpu")
+for name in ("uid_list", "hist_indptr", "hist_indices", "pos_indptr", "pos_indices"):
+    assert torch.equal(getattr(index, name), getattr(loops, name)), name
+# the sampler's used-id CSR from the datasets it keeps == its per-user sets (sampler.py:206-227)
+from recbole_b200.sampler import DeviceSampler
+smp = train_data.sampler
+assert smp.phase == "train"
+used_ptr, used_idx = DeviceSampler._used_csr(smp, "cpu")
+for u in (1, 2, 500, 943):
+    assert set(used_idx[used_ptr[u]:used_ptr[u + 1]].tolist()) == set(int(i) for i in smp.used_ids[u])
+assert int(used_ptr[-1]) == sum(len(s_) for s_ in smp.used_ids)
 # a completely unmodified reference Trainer accepts the model too (torch optimizer over model.parameters())
 from recbole.trainer import Trainer
 ref_trainer = Trainer(config, model)
