@@ -313,6 +313,35 @@ def run_ours(args, rank, world, local_rank, emit=True):
     e2e_value = B * args.steps / e2e_s
     clk = clocks.stop()
 
+    # ---- device-resident batch pipeline: one EPOCH through DeviceTrainLoader -- the train
+    # interactions live in HBM, the epoch is a device-side permutation, negatives come from the sampler kernel
+    # (rejecting the user's train positives from a device CSR), every batch feeds the fused step; no host round trip
+    from recbole_b200 import DeviceSampler, DeviceTrainLoader
+    from recbole_b200.data import build_csr
+    tu, ti = (torch.from_numpy(x).to(dev) for x in w.phases[0])
+    used = build_csr(w.n_users, tu, ti, w.n_items, dev)
+    loader = DeviceTrainLoader(tu, ti, DeviceSampler(w.n_items, used[0], used[1], mode="hash", seed=2020), B)
+    n_train = int(tu.numel())
+    it = iter(loader)
+    for _ in range(2):
+        model.train_step(next(it))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record()
+    n_seen = 0
+    for inter in loader:                                       # one full pass over the train interactions
+        model.train_step(inter)
+        n_seen += len(inter)
+    e1.record()
+    torch.cuda.synchronize()
+    pipe_ms, pipe_wall = e0.elapsed_time(e1), time.perf_counter() - t0
+    pipeline = {"metric": "bpr_epoch_samples_per_s", "value": n_seen / (pipe_ms * 1e-3), "unit": "samples/s",
+                "interactions": n_train, "batches": len(loader), "epoch_ms": pipe_ms, "wall_s": pipe_wall,
+                "what": "DeviceTrainLoader (device permutation + gather) + rb2_neg_sample_hash + fused step, per batch; "
+                        "replaces GeneralNegSampleDataLoader._next_batch_data + Interaction.to + Sampler.sample_by_user_ids "
+                        "(general_dataloader.py:212-241, trainer.py:158-159, sampler.py:103-154)"}
+    del loader, tu, ti, used
+
     # ---- evaluation: all test users, top-10, metrics on device ------------------------------------------
     index = EvalIndex(torch.from_numpy(w.uid_list).to(dev), (torch.from_numpy(w.hist[0]).to(dev),
                                                              torch.from_numpy(w.hist[1]).to(dev)),
@@ -359,8 +388,10 @@ def run_ours(args, rank, world, local_rank, emit=True):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(tp) and args.workload == "cfg2" and B == (1 << 20):
-        traffic = json.load(open(tp)).get("k_user_fused@cfg2")    # bytes per launch, from the committed ncu capture
-    roofline = {"bound": "hbm", "kernel": "k_user_fused", "achieved": alg_user / (us_ms * 1e-3) / 1e9 if us_ms else None,
+        traffic = json.load(open(tp)).get("%s@cfg2" % ("k_user_side" if B >= w.n_users else "k_user_fused"))
+    dense_batch = B >= w.n_users and 2 * B >= 4 * w.n_items        # train_bpr.cu launch_step: register-path kernels
+    kname = "k_user_side" if dense_batch else "k_user_fused"
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": alg_user / (us_ms * 1e-3) / 1e9 if us_ms else None,
                 "peak": peaks["hbm"], "unit": "GB/s", "frac": None, "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg_user,
                 "peak_source": peaks["source"], "ms_per_launch": us_ms,
@@ -403,6 +434,7 @@ def run_ours(args, rank, world, local_rank, emit=True):
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": 24 * B, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
         "loss": final_loss,
+        "pipeline": pipeline,
         "eval": {"metric": "fullsort_eval_users_per_s", "value": nq / (eval_ms * 1e-3), "unit": "users/s",
                  "users": nq, "ms": eval_ms, "topk": 10, "roofline": eval_roof,
                  "e2e": {"value": nq / eval_e2e_s, "unit": "users/s", "h2d_bytes_per_step": 8 * nq,

@@ -264,14 +264,29 @@ int rb2_adam_lazy_flush(float *p, float *m, float *v, int32_t *last, int64_t row
  *   W [n_rows]       = first_order_linear.token_embedding_table.embedding.weight  (output_dim 1)
  *   bias3 [3]        = first_order_linear.bias and its Adam moments (b, m, v)
  *   ids [batch, n_fields] raw per-field ids; row = ids[s, f] + offsets[f]   (layers.py:142)
+ * TOKEN fields through E / W, FLOAT fields through rb2_fm_float (below); TOKEN_SEQ fields are not served.
  * dim in {16, 32, 64, 128}; optimizer RB2_OPT_SGD, RB2_OPT_ADAM (row-sparse) or RB2_OPT_ADAM_LAZY; the bias is dense.
  * rb2_fm_predict: y[s] = sigmoid(first_order + fm)  (FM.predict, fm.py:58-59).
  * ---------------------------------------------------------------------------------------- */
+/* FLOAT fields (ContextRecommender.embed_float_fields abstract_recommender.py:236-258, FMFirstOrderLinear
+ * layers.py:947-966): field f owns one row Ef[f] of float_embedding_table.weight [n_float, dim] and one scalar Wf[f]
+ * of first_order_linear.float_embedding_table.weight; sample s contributes values[s, f] * Ef[f] as that field's
+ * vector.  Every sample touches every float row, so their gradients are dense reductions over the batch and their
+ * optimizer step is the reference's dense one at every step.  NULL = no float fields. */
+#define RB2_FM_MAX_FLOAT 64
+typedef struct rb2_fm_float {
+  const float *values;        /* [batch, n_float] */
+  int32_t n_float;
+  float *Ef, *mEf, *vEf;      /* [n_float, dim] (m, v: Adam moments, NULL for SGD / predict / loss) */
+  float *Wf, *mWf, *vWf;      /* [n_float] */
+} rb2_fm_float;
+
 size_t rb2_fm_workspace_bytes(int64_t batch, int32_t n_fields, int32_t dim);
 int rb2_fm_train_step(float *E, float *mE, float *vE, float *W, float *mW, float *vW, float *bias3,
                       int32_t *row_last, int64_t n_rows, int32_t dim, const int64_t *ids, const int64_t *offsets,
                       int32_t n_fields, const float *label, int64_t batch, const rb2_optim *h_opt, float *loss_out,
-                      double *loss_accum, void *workspace, size_t workspace_bytes, void *stream);
+                      double *loss_accum, void *workspace, size_t workspace_bytes, void *stream,
+                      const rb2_fm_float *h_float);
 /* RB2_OPT_ADAM_LAZY (row_last: int32 [n_rows], zero-initialised, shared by E and W): the trajectory of the
  * reference's DENSE torch.optim.Adam, weight decay included (MFSimple.yaml:2 sets 1e-8: every row moves at every
  * step).  rb2_fm_lazy_flush brings all rows to step h_opt->step before predict / loss / a checkpoint read them. */
@@ -279,12 +294,12 @@ int rb2_fm_lazy_flush(float *E, float *mE, float *vE, float *W, float *mW, float
                       int64_t n_rows, int32_t dim, const rb2_optim *h_opt, void *stream);
 int rb2_fm_predict(const float *E, const float *W, const float *bias3, int64_t n_rows, int32_t dim,
                    const int64_t *ids, const int64_t *offsets, int32_t n_fields, int64_t batch, float *y_out,
-                   void *workspace, size_t workspace_bytes, void *stream);
+                   void *workspace, size_t workspace_bytes, void *stream, const rb2_fm_float *h_float);
 /* forward + mean nn.BCELoss only (FM.calculate_loss fm.py:52-56 / MFSimple.calculate_loss mfsimple.py:48-57 as a
  * VALUE: what an unmodified Trainer reads with loss.item(), trainer.py:168); nothing is kept for a backward. */
 int rb2_fm_loss(const float *E, const float *W, const float *bias3, int64_t n_rows, int32_t dim,
                 const int64_t *ids, const int64_t *offsets, int32_t n_fields, const float *label, int64_t batch,
-                float *loss_out, void *workspace, size_t workspace_bytes, void *stream);
+                float *loss_out, void *workspace, size_t workspace_bytes, void *stream, const rb2_fm_float *h_float);
 
 /* Row-sharded FM (one 33M-row table sharded over the GPUs, batch split by rows; no reference
  * counterpart).  rb2_fm_grad_step is the local part of a step: rows_e [n_rows, dim] / rows_w [n_rows] are the

@@ -42,6 +42,13 @@ class RB2ScorerState(ctypes.Structure):
                 ("last_pass2_rows", ctypes.c_int32), ("reserved", ctypes.c_int32), ("trace", ctypes.c_void_p)]
 
 
+class RB2FmFloat(ctypes.Structure):
+    """include/recbole_b200.h: rb2_fm_float (the FLOAT fields of a context-aware model)."""
+    _fields_ = [("values", ctypes.c_void_p), ("n_float", ctypes.c_int32), ("Ef", ctypes.c_void_p),
+                ("mEf", ctypes.c_void_p), ("vEf", ctypes.c_void_p), ("Wf", ctypes.c_void_p), ("mWf", ctypes.c_void_p),
+                ("vWf", ctypes.c_void_p)]
+
+
 class RB2Peers(ctypes.Structure):
     _fields_ = [
         ("world", ctypes.c_int32), ("me", ctypes.c_int32), ("item_block", ctypes.c_int64),
@@ -85,10 +92,12 @@ SIGNATURES = {
     "rb2_adam_lazy_flush": (ctypes.c_int, [_p, _p, _p, _p, _i64, _i32, ctypes.POINTER(RB2Optim), _p]),
     "rb2_fm_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "rb2_fm_train_step": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _i32, _p, _i64,
-                                         ctypes.POINTER(RB2Optim), _p, _p, _p, _sz, _p]),
+                                         ctypes.POINTER(RB2Optim), _p, _p, _p, _sz, _p, ctypes.POINTER(RB2FmFloat)]),
     "rb2_fm_lazy_flush": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i32, ctypes.POINTER(RB2Optim), _p]),
-    "rb2_fm_predict": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _i32, _i64, _p, _p, _sz, _p]),
-    "rb2_fm_loss": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _i32, _p, _i64, _p, _p, _sz, _p]),
+    "rb2_fm_predict": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _i32, _i64, _p, _p, _sz, _p,
+                                      ctypes.POINTER(RB2FmFloat)]),
+    "rb2_fm_loss": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _i32, _p, _i64, _p, _p, _sz, _p,
+                                   ctypes.POINTER(RB2FmFloat)]),
     "rb2_fm_grad_step": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _i32, _p, _i64, _i64, _p, _p, _sz, _p]),
     "rb2_scalar_rows_update_workspace_bytes": (_sz, [_i64]),
     "rb2_scalar_rows_update": (ctypes.c_int, [_p, _p, _p, _i64, _p, _p, _i64, ctypes.POINTER(RB2Optim), _p, _sz, _p]),

@@ -39,6 +39,7 @@ struct FmWs {
   float *blk_head, *blk_z;               // [tiles / 64, D], [tiles / 64]: sums of 64 interior head partials
   uint8_t *blk_ok;                       // [tiles / 64]
   double *loss_part, *gz_part;           // [warps blocks]
+  float *float_part;                     // [kMaxFloat][chunks][D + 2] partial sums of the FLOAT fields' gradients
   void *cub_tmp;
   size_t cub_bytes;
   int64_t n_parts;
@@ -68,6 +69,7 @@ size_t carve(FmWs &w, void *base, int64_t B, int F, int dim) {
   w.n_parts = (B + 7) / 8 + 64;
   w.loss_part = c.take<double>(w.n_parts);
   w.gz_part = c.take<double>(w.n_parts);
+  w.float_part = c.take<float>((size_t)RB2_FM_MAX_FLOAT * ((B + 4095) / 4096) * (dim + 2));
   size_t b = 0;
   b = rb2sort::tmp_bytes(M);
   w.cub_bytes = b;
@@ -85,6 +87,12 @@ struct FmTables {
   float *W, *mW, *vW;   // [rows]
   float *bias;          // [3]: b, m, v
   int32_t *last;        // [rows] RB2_OPT_ADAM_LAZY: the step at which row r (of E and of W) was last brought up to date
+  // FLOAT fields (abstract_recommender.py:236-258, layers.py:947-966): field f owns ONE row Ef[f] (and one scalar
+  // Wf[f]) that every sample scales by its value x[s, f]
+  const float *fx;      // [B, n_float] values, or nullptr
+  int n_float;
+  float *Ef, *mEf, *vEf;   // [n_float, D]
+  float *Wf, *mWf, *vWf;   // [n_float]
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -138,7 +146,7 @@ __global__ void __launch_bounds__(kThreads) k_fm_forward(FmTables t, const int64
         w.val[o] = (uint32_t)o;
       }
     };
-    if (F == 2) {
+    if (F == 2 && t.n_float == 0) {
       // two fields = the point-wise "dot" model (fork's MFSimple, mfsimple.py:39-46:
       // sigmoid(<u,v> + b_u + b_i + b)): take the product directly instead of the
       // 0.5*[(u+v)^2 - u^2 - v^2] identity, which cancels badly in fp32
@@ -157,6 +165,17 @@ __global__ void __launch_bounds__(kThreads) k_fm_forward(FmTables t, const int64
         sq = fmaf(v.x, v.x, sq); sq = fmaf(v.y, v.y, sq); sq = fmaf(v.z, v.z, sq); sq = fmaf(v.w, v.w, sq);
       }
     }
+    if (t.n_float > 0) {
+      // FLOAT fields: e_f = x * Ef[f] joins the sum and the sum of squares like any other field's vector
+      for (int f = g; f < t.n_float; f += GROUPS) {
+        const float x = __ldg(t.fx + s * t.n_float + f);
+        float4 v = __ldg(reinterpret_cast<const float4 *>(t.Ef + (size_t)f * D) + gl);
+        v.x *= x; v.y *= x; v.z *= x; v.w *= x;
+        S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
+        sq = fmaf(v.x, v.x, sq); sq = fmaf(v.y, v.y, sq); sq = fmaf(v.z, v.z, sq); sq = fmaf(v.w, v.w, sq);
+        if (gl == 0) first = fmaf(x, __ldg(t.Wf + f), first);
+      }
+    }
     // across the lane groups of the warp: S (per lane-in-group), sq / cross / first (everything)
 #pragma unroll
     for (int o = LANES; o < 32; o <<= 1) {
@@ -172,7 +191,7 @@ __global__ void __launch_bounds__(kThreads) k_fm_forward(FmTables t, const int64
       first += __shfl_xor_sync(0xffffffffu, first, o);
     }
     float second;
-    if (F == 2) {
+    if (F == 2 && t.n_float == 0) {
       second = cross;
     } else {
       // sum_k S_k^2 over the d elements: every group holds the full S after the reduction above
@@ -460,6 +479,76 @@ __global__ void k_fm_bias_loss(FmTables t, FmWs w, int64_t n_parts, double inv_b
   }
 }
 
+// ---- FLOAT fields: every sample touches every float row, so their gradients are dense reductions over the batch:
+//   dEf[f] = sum_s x_sf * gs[s] - (sum_s x_sf^2 gz[s]) * Ef[f]        (e_f = x Ef[f]; d z / d e_f = S - e_f)
+//   dWf[f] = sum_s x_sf * gz[s]
+// k_fm_float_reduce: one block per (chunk of kFloatChunk samples, field), fixed-order sums; k_fm_float_update: one
+// block per field sums the chunk partials in chunk order and takes the optimizer step (dense: stepped every step).
+constexpr int kFloatChunk = 4096;
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_fm_float_reduce(FmTables t, FmWs w, int64_t B, float *__restrict__ part) {
+  constexpr int LANES = RowCfg<D>::LANES, GR = kThreads / LANES;
+  __shared__ float sm[GR][D + 2];
+  const int lane = threadIdx.x % LANES, grp = threadIdx.x / LANES;
+  const int f = blockIdx.y;
+  const int64_t lo = (int64_t)blockIdx.x * kFloatChunk, hi = min(lo + (int64_t)kFloatChunk, B);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float z2 = 0.f, z1 = 0.f;
+  for (int64_t s = lo + grp; s < hi; s += GR) {
+    const float x = __ldg(t.fx + s * t.n_float + f);
+    const float4 gv = __ldg(reinterpret_cast<const float4 *>(w.gs + s * D) + lane);
+    acc.x = fmaf(x, gv.x, acc.x); acc.y = fmaf(x, gv.y, acc.y); acc.z = fmaf(x, gv.z, acc.z); acc.w = fmaf(x, gv.w, acc.w);
+    if (lane == 0) {
+      const float gz = __ldg(w.gz + s);
+      z2 = fmaf(x * x, gz, z2);
+      z1 = fmaf(x, gz, z1);
+    }
+  }
+  sm[grp][4 * lane] = acc.x; sm[grp][4 * lane + 1] = acc.y; sm[grp][4 * lane + 2] = acc.z; sm[grp][4 * lane + 3] = acc.w;
+  if (lane == 0) { sm[grp][D] = z2; sm[grp][D + 1] = z1; }
+  __syncthreads();
+  if (threadIdx.x < D + 2) {
+    float a = 0.f;
+    for (int gI = 0; gI < GR; ++gI) a += sm[gI][threadIdx.x];
+    part[((size_t)f * gridDim.x + blockIdx.x) * (D + 2) + threadIdx.x] = a;
+  }
+}
+template <int D>
+__global__ void __launch_bounds__(256) k_fm_float_update(FmTables t, const float *__restrict__ part, int n_chunks,
+                                                         OptScalars o) {
+  const int f = blockIdx.x, k = threadIdx.x;
+  if (k >= D + 2) return;
+  __shared__ float zz[2];
+  float a = 0.f;
+  for (int c = 0; c < n_chunks; ++c) a += part[((size_t)f * n_chunks + c) * (D + 2) + k];
+  if (k >= D) zz[k - D] = a;
+  __syncthreads();
+  if (k < D) {
+    float p = t.Ef[(size_t)f * D + k];
+    const float g = fmaf(-zz[0], p, a);
+    if (o.kind == RB2_OPT_SGD) {
+      sgd_elem(p, g, o);
+    } else {
+      float m = t.mEf[(size_t)f * D + k], v = t.vEf[(size_t)f * D + k];
+      adam_elem(p, m, v, g, o);
+      t.mEf[(size_t)f * D + k] = m;
+      t.vEf[(size_t)f * D + k] = v;
+    }
+    t.Ef[(size_t)f * D + k] = p;
+  } else if (k == D + 1) {
+    float p = t.Wf[f];
+    if (o.kind == RB2_OPT_SGD) {
+      sgd_elem(p, a, o);
+    } else {
+      float m = t.mWf[f], v = t.vWf[f];
+      adam_elem(p, m, v, a, o);
+      t.mWf[f] = m;
+      t.vWf[f] = v;
+    }
+    t.Wf[f] = p;
+  }
+}
+
 __global__ void k_zero_parts(FmWs w) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < w.n_parts) { w.loss_part[i] = 0.0; w.gz_part[i] = 0.0; }
@@ -477,6 +566,19 @@ __global__ void k_zero_parts(FmWs w) {
       rb2_set_error("FM embedding dim %d not supported (16, 32, 64, 128)", (int)(dim));       \
       return RB2_EINVAL;                                                                      \
   }
+
+static int fm_set_float(FmTables &t, const rb2_fm_float *f, bool train, const char *who) {
+  if (!f || f->n_float <= 0) return 0;
+  RB2_REQUIRE(f->n_float <= RB2_FM_MAX_FLOAT, RB2_EINVAL, "%s: %d float fields (max %d)", who, (int)f->n_float,
+              (int)RB2_FM_MAX_FLOAT);
+  RB2_REQUIRE(f->values && f->Ef && f->Wf, RB2_EINVAL, "%s: float fields need values, Ef and Wf", who);
+  t.fx = f->values;
+  t.n_float = f->n_float;
+  t.Ef = f->Ef; t.mEf = f->mEf; t.vEf = f->vEf;
+  t.Wf = f->Wf; t.mWf = f->mWf; t.vWf = f->vWf;
+  (void)train;
+  return 0;
+}
 
 extern "C" size_t rb2_fm_workspace_bytes(int64_t batch, int32_t n_fields, int32_t dim) {
   FmWs w;
@@ -505,6 +607,12 @@ static int fm_step(FmTables t, int64_t n_rows, int32_t dim, const int64_t *ids, 
       k_fm_forward<D_, true><<<fblocks, kThreads, 0, st>>>(t, ids, offsets, label, batch, n_fields, n_rows,
                                                            (float)(1.0 / norm_batch), w, nullptr, o);
     }
+    if (t.n_float > 0 && o.kind != kOptGradOut) {
+      ProfScope prof(RB2_ST_FM_UPDATE, st, 2);
+      const int n_chunks = (int)((batch + kFloatChunk - 1) / kFloatChunk);
+      k_fm_float_reduce<D_><<<dim3((unsigned)n_chunks, (unsigned)t.n_float), kThreads, 0, st>>>(t, w, batch, w.float_part);
+      k_fm_float_update<D_><<<(unsigned)t.n_float, 256, 0, st>>>(t, w.float_part, n_chunks, o);
+    }
     size_t tmp = w.cub_bytes;
     {
       ProfScope prof(RB2_ST_SORT_ITEM, st, 2 + (rb2_bits_for(n_rows) + 7) / 8);
@@ -530,7 +638,7 @@ extern "C" int rb2_fm_train_step(float *E, float *mE, float *vE, float *W, float
                                  int32_t *row_last, int64_t n_rows, int32_t dim, const int64_t *ids,
                                  const int64_t *offsets, int32_t n_fields, const float *label, int64_t batch,
                                  const rb2_optim *h_opt, float *loss_out, double *loss_accum, void *workspace,
-                                 size_t workspace_bytes, void *stream) {
+                                 size_t workspace_bytes, void *stream, const rb2_fm_float *h_float) {
   RB2_REQUIRE(E && W && bias3 && ids && offsets && label && h_opt && loss_out && workspace, RB2_EINVAL,
               "rb2_fm_train_step: null argument");
   OptScalars o = rb2_opt_scalars(h_opt);
@@ -541,6 +649,9 @@ extern "C" int rb2_fm_train_step(float *E, float *mE, float *vE, float *W, float
     RB2_REQUIRE(row_last && o.lazy_step_size && o.lazy_bc2_sqrt, RB2_EINVAL,
                 "rb2_fm_train_step: adam_lazy needs row_last and the bias-correction tables");
   FmTables t{E, mE, vE, W, mW, vW, bias3, row_last};
+  if (int rc = fm_set_float(t, h_float, true, "rb2_fm_train_step")) return rc;
+  if (t.n_float > 0 && o.kind != RB2_OPT_SGD)
+    RB2_REQUIRE(t.mEf && t.vEf && t.mWf && t.vWf, RB2_EINVAL, "rb2_fm_train_step: Adam needs the float fields' m and v");
   return fm_step(t, n_rows, dim, ids, offsets, n_fields, label, batch, (double)batch, o, loss_out, loss_accum, workspace,
                  workspace_bytes, (cudaStream_t)stream, "rb2_fm_train_step");
 }
@@ -697,7 +808,8 @@ extern "C" int rb2_fm_lazy_flush(float *E, float *mE, float *vE, float *W, float
 /* forward + mean BCE only (FM.calculate_loss, fm.py:52-56, without a backward): loss_out[0] = the batch's loss */
 extern "C" int rb2_fm_loss(const float *E, const float *W, const float *bias3, int64_t n_rows, int32_t dim,
                            const int64_t *ids, const int64_t *offsets, int32_t n_fields, const float *label,
-                           int64_t batch, float *loss_out, void *workspace, size_t workspace_bytes, void *stream) {
+                           int64_t batch, float *loss_out, void *workspace, size_t workspace_bytes, void *stream,
+                           const rb2_fm_float *h_float) {
   RB2_REQUIRE(E && W && bias3 && ids && offsets && label && loss_out && workspace, RB2_EINVAL,
               "rb2_fm_loss: null argument");
   RB2_REQUIRE(batch > 0 && n_fields > 0, RB2_EINVAL, "rb2_fm_loss: empty batch");
@@ -707,6 +819,7 @@ extern "C" int rb2_fm_loss(const float *E, const float *W, const float *bias3, i
   cudaStream_t st = (cudaStream_t)stream;
   FmTables t{const_cast<float *>(E), nullptr, nullptr, const_cast<float *>(W), nullptr, nullptr,
              const_cast<float *>(bias3), nullptr};
+  if (int rc = fm_set_float(t, h_float, false, "rb2_fm_loss")) return rc;
   OptScalars o = {};
   o.kind = kOptLossOnly;
   k_zero_parts<<<(unsigned)((w.n_parts + 255) / 256), 256, 0, st>>>(w);
@@ -725,7 +838,8 @@ extern "C" int rb2_fm_loss(const float *E, const float *W, const float *bias3, i
 
 extern "C" int rb2_fm_predict(const float *E, const float *W, const float *bias3, int64_t n_rows, int32_t dim,
                               const int64_t *ids, const int64_t *offsets, int32_t n_fields, int64_t batch,
-                              float *y_out, void *workspace, size_t workspace_bytes, void *stream) {
+                              float *y_out, void *workspace, size_t workspace_bytes, void *stream,
+                              const rb2_fm_float *h_float) {
   RB2_REQUIRE(E && W && bias3 && ids && offsets && y_out && workspace, RB2_EINVAL, "rb2_fm_predict: null argument");
   if (batch <= 0) return 0;
   FmWs w;
@@ -734,6 +848,7 @@ extern "C" int rb2_fm_predict(const float *E, const float *W, const float *bias3
   cudaStream_t st = (cudaStream_t)stream;
   FmTables t{const_cast<float *>(E), nullptr, nullptr, const_cast<float *>(W), nullptr, nullptr,
              const_cast<float *>(bias3), nullptr};
+  if (int rc = fm_set_float(t, h_float, false, "rb2_fm_predict")) return rc;
   RB2_FM_DIM(dim, {
     int64_t warps = std::min<int64_t>(batch, (int64_t)rb2_num_sms() * 64);
     unsigned fblocks = (unsigned)((warps * 32 + kThreads - 1) / kThreads);

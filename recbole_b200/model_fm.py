@@ -107,46 +107,100 @@ class _Table(nn.Module):
 
 
 class _FirstOrder(nn.Module):
-    def __init__(self, rows):
+    def __init__(self, rows, n_float=0):
         super().__init__()
         self.token_embedding_table = _Table(rows, 1)
+        if n_float:
+            self.float_embedding_table = nn.Embedding(n_float, 1)       # layers.py:939-940
         self.bias = nn.Parameter(torch.zeros((1,)), requires_grad=True)  # layers.py:945
 
 
+FEATURE_FLOAT = "float"
+_KERNEL_DIMS = (16, 32, 64, 128)
+
+
 class FusedFM(_PointwiseMixin, nn.Module):
+    """TOKEN and FLOAT fields (abstract_recommender.py:205-258); TOKEN_SEQ fields raise.  Any embedding_size up to 128
+    (FM.yaml's default is 10): the kernels work on rows of 16 / 32 / 64 / 128 floats, other sizes live in zero-padded
+    rows whose padding never moves (its gradient is exactly zero) and the parameters are views of the first
+    embedding_size columns."""
     input_type = InputType.POINTWISE   # abstract_recommender.py:157
     type = ModelType.CONTEXT           # abstract_recommender.py:156
 
     def __init__(self, config, dataset):
         super().__init__()
         self.LABEL = config["LABEL_FIELD"]
-        self.embedding_size = config["embedding_size"]
+        self.embedding_size = int(config["embedding_size"] or 10)          # properties/model/FM.yaml:1
+        if self.embedding_size > _KERNEL_DIMS[-1]:
+            raise ValueError("FusedFM: embedding_size %d > %d" % (self.embedding_size, _KERNEL_DIMS[-1]))
+        self._dpad = next(k for k in _KERNEL_DIMS if k >= self.embedding_size)
         self.device = config["device"]
-        self.token_field_names, self.token_field_dims = [], []
+        self.token_field_names, self.token_field_dims, self.float_field_names = [], [], []
         for name in dataset.fields():                       # abstract_recommender.py:205-219
             if name == self.LABEL:
                 continue
-            if not _is_token(dataset.field2type[name]):
-                raise NotImplementedError("FusedFM handles TOKEN fields only; field %r is %r"
-                                          % (name, dataset.field2type[name]))
-            self.token_field_names.append(name)
-            self.token_field_dims.append(int(dataset.num(name)))
-        self.num_feature_field = len(self.token_field_names)
+            ftype = getattr(dataset.field2type[name], "value", dataset.field2type[name])
+            if ftype == FEATURE_TOKEN:
+                self.token_field_names.append(name)
+                self.token_field_dims.append(int(dataset.num(name)))
+            elif ftype == FEATURE_FLOAT:
+                if int(dataset.num(name)) != 1:
+                    raise NotImplementedError("FusedFM: float field %r has %d columns (1 supported)" % (name, dataset.num(name)))
+                self.float_field_names.append(name)
+            else:
+                raise NotImplementedError("FusedFM handles TOKEN and FLOAT fields; field %r is %r" % (name, ftype))
+        if not self.token_field_names:
+            raise NotImplementedError("FusedFM needs at least one TOKEN field")
+        self.n_float = len(self.float_field_names)
+        self.num_feature_field = len(self.token_field_names)      # token fields (the kernels' F)
         # abstract_recommender.py:220-224: one table, per-field offsets
         self.token_field_offsets = np.array((0, *np.cumsum(self.token_field_dims)[:-1]), dtype=np.int64)
         rows = int(sum(self.token_field_dims))
+        # registration order = ContextRecommender.__init__'s (the optimizer state is indexed by parameter position)
         self.token_embedding_table = _Table(rows, self.embedding_size)
-        self.first_order_linear = _FirstOrder(rows)
+        if self.n_float:
+            self.float_embedding_table = nn.Embedding(self.n_float, self.embedding_size)     # :225-228
+        self.first_order_linear = _FirstOrder(rows, self.n_float)
         # fm.py:41-45: xavier_normal_ on every nn.Embedding
-        xavier_normal_(self.token_embedding_table.embedding.weight.data)
-        xavier_normal_(self.first_order_linear.token_embedding_table.embedding.weight.data)
+        for m in self.modules():
+            if isinstance(m, nn.Embedding):
+                xavier_normal_(m.weight.data)
+        self._pads = {}          # parameter name -> zero-padded [rows, dpad] storage the parameter is a view of
         self._init_fused(config)
 
     # ---- plumbing -----------------------------------------------------------------------------------
+    def _padded(self, key, param):
+        """The [rows, dpad] tensor the kernels work on.  embedding_size == dpad: the parameter itself.  Otherwise the
+        parameter's data is (re)made a view of the first embedding_size columns of a zero-padded buffer -- after
+        construction and after every Module.to(), which replaces the data by a compact copy."""
+        d, dp = self.embedding_size, self._dpad
+        if d == dp:
+            return param.data
+        pad = self._pads.get(key)
+        w = param.data
+        if pad is None or pad.device != w.device or w.data_ptr() != pad.data_ptr() or w.stride(0) != dp:
+            pad = torch.zeros((w.shape[0], dp), dtype=torch.float32, device=w.device)
+            pad[:, :d] = w
+            param.data = pad[:, :d]
+            self._pads[key] = pad
+        return pad
+
     def _tables(self):
-        E = self.token_embedding_table.embedding.weight.data
+        E = self._padded("E", self.token_embedding_table.embedding.weight)
         W = self.first_order_linear.token_embedding_table.embedding.weight.data.view(-1)
         return E, W
+
+    def _float_tables(self):
+        Ef = self._padded("Ef", self.float_embedding_table.weight)
+        Wf = self.first_order_linear.float_embedding_table.weight.data.view(-1)
+        return Ef, Wf
+
+    def _floats(self, interaction):
+        """(values [B, Ff], Ef, Wf) for the kernels, or None (abstract_recommender.py:361-372)."""
+        if not self.n_float:
+            return None
+        vals = torch.stack([interaction[n].reshape(-1).to(torch.float32) for n in self.float_field_names], dim=1)
+        return (vals.contiguous(),) + self._float_tables()
 
     def _ids(self, interaction):
         # abstract_recommender.py:381-388: stack the per-field id columns -> [B, F]
@@ -157,7 +211,7 @@ class FusedFM(_PointwiseMixin, nn.Module):
         if getattr(self, "_ws_dev", None) != str(dev):
             self._ws, self._ws_dev = {}, str(dev)
         return ops.grow_workspace(self._ws, batch,
-                                  lambda b: ops.fm_workspace(b, self.num_feature_field, self.embedding_size, dev))
+                                  lambda b: ops.fm_workspace(b, self.num_feature_field, self._dpad, dev))
 
     def _ensure_device_state(self):
         dev = self.token_embedding_table.embedding.weight.device
@@ -173,15 +227,32 @@ class FusedFM(_PointwiseMixin, nn.Module):
             raise ValueError("FusedFM implements the fused kinds {adam (row-sparse), adam_lazy, sgd}")
         self._optim = ops.Optim(kind, learning_rate, weight_decay)
         self._state = self._new_state(kind, *self._tables())
+        if self.n_float and kind != "sgd":
+            Ef, Wf = self._float_tables()
+            z = torch.zeros_like
+            self._state.update(mEf=z(Ef), vEf=z(Ef), mWf=z(Wf), vWf=z(Wf))
         self._ensure_device_state()
 
     def _opt_entries(self):
-        # model.parameters() order: E, first_order_linear.bias, first_order_linear...weight (same as the reference's FM)
-        st = self._state
-        return [(st["mE"], st["vE"]), (self._bias3[1:2], self._bias3[2:3]), (st["mW"], st["vW"])]
+        # model.parameters() order of the reference's FM: token table, float table, first_order_linear.bias,
+        # first-order token table, first-order float table (a module's own parameters precede its children's)
+        st, d = self._state, self.embedding_size
+        out = [(st["mE"][:, :d], st["vE"][:, :d])]
+        if self.n_float:
+            out.append((st["mEf"][:, :d], st["vEf"][:, :d]))
+        out.append((self._bias3[1:2], self._bias3[2:3]))
+        out.append((st["mW"], st["vW"]))
+        if self.n_float:
+            out.append((st["mWf"], st["vWf"]))
+        return out
 
     def _state_dict_impl(self, *args, **kwargs):
-        return nn.Module.state_dict(self, *args, **kwargs)
+        sd = nn.Module.state_dict(self, *args, **kwargs)
+        if self.embedding_size != self._dpad:          # compact copies: a checkpoint should not drag the padding along
+            for k, v in list(sd.items()):
+                if v.dim() == 2 and v.stride(0) == self._dpad and v.shape[1] == self.embedding_size:
+                    sd[k] = v.contiguous()
+        return sd
 
     # ---- fused step ----------------------------------------------------------------------------------
     def _fused_step(self, interaction, loss_accum):
@@ -189,7 +260,8 @@ class FusedFM(_PointwiseMixin, nn.Module):
         ids = self._ids(interaction)
         E, W = self._tables()
         ops.fm_train_step(E, W, self._bias3, self._state, ids, self._offsets, interaction[self.LABEL].contiguous(),
-                          self._optim, self._loss_out, loss_accum, self._workspace(ids.shape[0]))
+                          self._optim, self._loss_out, loss_accum, self._workspace(ids.shape[0]),
+                          floats=self._floats(interaction))
         self.first_order_linear.bias.data.copy_(self._bias3[0:1])
         return self._loss_out
 
@@ -200,7 +272,7 @@ class FusedFM(_PointwiseMixin, nn.Module):
         E, W = self._tables()
         out = torch.empty(1, dtype=torch.float32, device=E.device)
         ops.fm_loss(E, W, self._bias3, ids, self._offsets, interaction[self.LABEL].contiguous(), out,
-                    self._workspace(ids.shape[0]))
+                    self._workspace(ids.shape[0]), floats=self._floats(interaction))
         return out[0]
 
     # ---- the reference's plugin API ---------------------------------------------------------------------
@@ -209,7 +281,8 @@ class FusedFM(_PointwiseMixin, nn.Module):
         self._ensure_device_state()
         ids = self._ids(interaction)
         E, W = self._tables()
-        return ops.fm_predict(E, W, self._bias3, ids, self._offsets, self._workspace(ids.shape[0]))
+        return ops.fm_predict(E, W, self._bias3, ids, self._offsets, self._workspace(ids.shape[0]),
+                              floats=self._floats(interaction))
 
 
 class FusedMFSimple(_PointwiseMixin, nn.Module):

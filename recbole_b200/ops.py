@@ -313,8 +313,24 @@ def fm_workspace(batch, n_fields, dim, device):
     return Workspace(lib.rb2_fm_workspace_bytes(int(batch), int(n_fields), int(dim)), device)
 
 
-def fm_train_step(E, W, bias3, state, ids, offsets, label, optim, loss_out, loss_accum, ws):
-    """One fused FM step (rb2_fm_train_step).  state: mE, vE, mW, vW for Adam."""
+def _fm_float(fl, state=None):
+    """fl = (values [B, Ff], Ef [Ff, d], Wf [Ff]) or None -> ctypes pointer to an rb2_fm_float (or None)."""
+    if fl is None:
+        return None
+    values, Ef, Wf = fl
+    f32 = torch.float32
+    c = _lib.RB2FmFloat()
+    c.values, c.n_float = _ptr(values, f32).value, int(values.shape[1])
+    c.Ef, c.Wf = _ptr(Ef, f32).value, _ptr(Wf, f32).value
+    if state is not None and "mEf" in state:
+        c.mEf, c.vEf = _ptr(state["mEf"], f32).value, _ptr(state["vEf"], f32).value
+        c.mWf, c.vWf = _ptr(state["mWf"], f32).value, _ptr(state["vWf"], f32).value
+    return ctypes.byref(c)
+
+
+def fm_train_step(E, W, bias3, state, ids, offsets, label, optim, loss_out, loss_accum, ws, floats=None):
+    """One fused FM step (rb2_fm_train_step).  state: mE, vE, mW, vW for Adam (+ mEf, vEf, mWf, vWf with float fields:
+    floats = (values [B, Ff], Ef [Ff, d], Wf [Ff]))."""
     optim.step += 1
     o = optim.c_struct(E.device)
     f32 = torch.float32
@@ -324,7 +340,7 @@ def fm_train_step(E, W, bias3, state, ids, offsets, label, optim, loss_out, loss
                                 _ptr(ids, torch.int64),
                                 _ptr(offsets, torch.int64), ids.shape[1], _ptr(label, f32), ids.shape[0],
                                 ctypes.byref(o), _ptr(loss_out, f32), _ptr(loss_accum, torch.float64, True), ws.ptr(),
-                                ws.nbytes, _stream()))
+                                ws.nbytes, _stream(), _fm_float(floats, state)))
 
 
 def fm_lazy_flush(E, W, state, optim):
@@ -365,7 +381,7 @@ def scalar_step(p3, grad, optim, step=None):
     check(lib.rb2_scalar_step(_ptr(p3, torch.float32), _ptr(grad, torch.float32), ctypes.byref(o), _stream()))
 
 
-def fm_predict(E, W, bias3, ids, offsets, ws=None):
+def fm_predict(E, W, bias3, ids, offsets, ws=None, floats=None):
     B, F = ids.shape
     if ws is None:
         ws = fm_workspace(B, F, E.shape[1], E.device)
@@ -373,16 +389,16 @@ def fm_predict(E, W, bias3, ids, offsets, ws=None):
     f32 = torch.float32
     check(lib.rb2_fm_predict(_ptr(E, f32), _ptr(W, f32), _ptr(bias3, f32), E.shape[0], E.shape[1],
                              _ptr(ids, torch.int64), _ptr(offsets, torch.int64), F, B, _ptr(y), ws.ptr(), ws.nbytes,
-                             _stream()))
+                             _stream(), _fm_float(floats)))
     return y
 
 
-def fm_loss(E, W, bias3, ids, offsets, label, loss_out, ws):
+def fm_loss(E, W, bias3, ids, offsets, label, loss_out, ws, floats=None):
     """Forward + mean BCE only (rb2_fm_loss); loss_out[0] = the batch's loss."""
     f32 = torch.float32
     check(lib.rb2_fm_loss(_ptr(E, f32), _ptr(W, f32), _ptr(bias3, f32), E.shape[0], E.shape[1], _ptr(ids, torch.int64),
                           _ptr(offsets, torch.int64), ids.shape[1], _ptr(label, f32), ids.shape[0], _ptr(loss_out, f32),
-                          ws.ptr(), ws.nbytes, _stream()))
+                          ws.ptr(), ws.nbytes, _stream(), _fm_float(floats)))
 
 
 def gather_dot(U, V, user, item):

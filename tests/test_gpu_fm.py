@@ -250,3 +250,61 @@ def test_mfsimple_reference_hyperparameters_dense_adam(golden):
         # element-wise: |a - b| <= 1e-5 * |b| + 1e-7 (biases start at 0 and are O(1e-2))
         a, b = sd[n].cpu().numpy(), g["mf_pN_" + n]
         assert np.all(np.abs(a - b) <= TOL * np.abs(b) + 1e-7), (n, np.abs(a - b).max())
+
+
+def test_fm_float_fields_default_embedding_size_vs_reference_golden(golden):
+    """The reference's FM with TOKEN + FLOAT fields at FM.yaml's default embedding_size = 10 under dense
+    torch.optim.Adam for 4 steps.  FusedFM: rows padded to 16 floats (parameters = views of the first 10 columns), float
+    fields as value-scaled rows with dense reductions for their gradients, 'adam_lazy' for the token rows: losses,
+    every parameter tensor (in the reference's parameter order) and predictions."""
+    from recbole_b200 import FusedFM, Interaction
+    from gpu_util import rel_err
+    g = golden("fm_float.npz")
+    tdims = g["token_dims"]
+    tnames = ["t%d" % i for i in range(len(tdims))]
+    fnames = ["x%d" % i for i in range(int(g["n_float"]))]
+
+    class Cfg(dict):
+        def __getitem__(self, k):
+            return self.get(k)
+
+    class DS:
+        field2type = dict({n: "token" for n in tnames}, **{n: "float" for n in fnames}, label="float")
+
+        def fields(self):
+            return tnames + fnames + ["label"]
+
+        def num(self, f):
+            return int(tdims[tnames.index(f)]) if f in tnames else 1
+
+    m = FusedFM(Cfg(LABEL_FIELD="label", embedding_size=None, device="cuda", learner="adam", learning_rate=1e-2), DS())
+    assert m.embedding_size == 10 and [n for n, _ in m.named_parameters()] == [str(x) for x in g["param_order"]]
+    m = m.to("cuda")
+    m.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("p0_")})
+    opt = m.build_optimizer("adam_lazy", 1e-2)
+    for s in range(4):
+        cols = {n: torch.from_numpy(g["ids%d" % s][:, i].astype(np.int64)) for i, n in enumerate(tnames)}
+        cols.update({n: torch.from_numpy(g["fx%d" % s][:, i]) for i, n in enumerate(fnames)})
+        inter = Interaction(dict(cols, label=torch.from_numpy(g["label%d" % s]))).to("cuda")
+        if s % 2 == 0:
+            loss = m.train_step(inter).item()
+        else:                                       # the reference Trainer's protocol: loss -> backward -> step
+            opt.zero_grad()
+            lt = m.calculate_loss(inter)
+            loss = lt.item()
+            lt.backward()
+            opt.step()
+        ref = float(g["loss%d" % s])
+        assert abs(loss - ref) <= TOL * abs(ref), (s, loss, ref)
+    assert rel_err(m.predict(inter).cpu().numpy(), g["predN"]) < 10 * TOL
+    sd = m.state_dict()
+    for n in sd:
+        a, b = sd[n].cpu().numpy().astype(np.float64), g["pN_" + n].astype(np.float64)
+        assert a.shape == b.shape
+        d = np.abs(a - b)
+        bad = d > TOL * np.abs(b).max()
+        assert bad.sum() <= 2 and d.max() <= 2e-4, (n, int(bad.sum()), float(d.max()))     # eps-conditioned elements
+    # the padding never moved, the optimizer state has the reference's layout
+    assert float(m._pads["E"][:, 10:].abs().max()) == 0.0 and float(m._pads["Ef"][:, 10:].abs().max()) == 0.0
+    osd = opt.state_dict()
+    assert sorted(osd["state"]) == [0, 1, 2, 3, 4] and tuple(osd["state"][1]["exp_avg"].shape) == (2, 10)
