@@ -264,7 +264,7 @@ int rb2_adam_lazy_flush(float *p, float *m, float *v, int32_t *last, int64_t row
  *   W [n_rows]       = first_order_linear.token_embedding_table.embedding.weight  (output_dim 1)
  *   bias3 [3]        = first_order_linear.bias and its Adam moments (b, m, v)
  *   ids [batch, n_fields] raw per-field ids; row = ids[s, f] + offsets[f]   (layers.py:142)
- * TOKEN fields through E / W, FLOAT fields through rb2_fm_float (below); TOKEN_SEQ fields are not served.
+ * TOKEN fields through E / W, FLOAT fields through rb2_fm_float, TOKEN_SEQ fields (mean pooling) through rb2_fm_seq.
  * dim in {16, 32, 64, 128}; optimizer RB2_OPT_SGD, RB2_OPT_ADAM (row-sparse) or RB2_OPT_ADAM_LAZY; the bias is dense.
  * rb2_fm_predict: y[s] = sigmoid(first_order + fm)  (FM.predict, fm.py:58-59).
  * ---------------------------------------------------------------------------------------- */
@@ -281,12 +281,28 @@ typedef struct rb2_fm_float {
   float *Wf, *mWf, *vWf;      /* [n_float] */
 } rb2_fm_float;
 
+/* TOKEN_SEQ fields (ContextRecommender.embed_token_seq_fields abstract_recommender.py:277-314, mode 'mean'; first order
+ * layers.py:989-1019): the id matrix gets extra columns -- after the n_token_cols TOKEN columns, the padded sequence
+ * of every TOKEN_SEQ field (field j: columns [seq_start[j], seq_start[j + 1]), id 0 = padding = masked) -- and
+ * offsets[col] places a sequence column's ids in that field's own table, stored as rows >= seq_row_base of E / W.
+ * Field j contributes e_j = sum over its unmasked ids of the row / (count + 1e-8).  n_fields counts ALL columns.
+ * pooled [batch, n_seq, dim] and coef [batch, n_seq] keep e_j and 1 / (count + 1e-8) for the backward (training only).
+ * NULL = no such fields. */
+#define RB2_FM_MAX_SEQ 16
+typedef struct rb2_fm_seq {
+  int32_t n_seq, n_token_cols;
+  const int32_t *seq_start;   /* device [n_seq + 1] */
+  const int32_t *col_seq;     /* device [n_fields]: the TOKEN_SEQ field of a column, -1 for TOKEN columns */
+  int64_t seq_row_base;
+  float *pooled, *coef;
+} rb2_fm_seq;
+
 size_t rb2_fm_workspace_bytes(int64_t batch, int32_t n_fields, int32_t dim);
 int rb2_fm_train_step(float *E, float *mE, float *vE, float *W, float *mW, float *vW, float *bias3,
                       int32_t *row_last, int64_t n_rows, int32_t dim, const int64_t *ids, const int64_t *offsets,
                       int32_t n_fields, const float *label, int64_t batch, const rb2_optim *h_opt, float *loss_out,
                       double *loss_accum, void *workspace, size_t workspace_bytes, void *stream,
-                      const rb2_fm_float *h_float);
+                      const rb2_fm_float *h_float, const rb2_fm_seq *h_seq);
 /* RB2_OPT_ADAM_LAZY (row_last: int32 [n_rows], zero-initialised, shared by E and W): the trajectory of the
  * reference's DENSE torch.optim.Adam, weight decay included (MFSimple.yaml:2 sets 1e-8: every row moves at every
  * step).  rb2_fm_lazy_flush brings all rows to step h_opt->step before predict / loss / a checkpoint read them. */
@@ -294,12 +310,14 @@ int rb2_fm_lazy_flush(float *E, float *mE, float *vE, float *W, float *mW, float
                       int64_t n_rows, int32_t dim, const rb2_optim *h_opt, void *stream);
 int rb2_fm_predict(const float *E, const float *W, const float *bias3, int64_t n_rows, int32_t dim,
                    const int64_t *ids, const int64_t *offsets, int32_t n_fields, int64_t batch, float *y_out,
-                   void *workspace, size_t workspace_bytes, void *stream, const rb2_fm_float *h_float);
+                   void *workspace, size_t workspace_bytes, void *stream, const rb2_fm_float *h_float,
+                   const rb2_fm_seq *h_seq);
 /* forward + mean nn.BCELoss only (FM.calculate_loss fm.py:52-56 / MFSimple.calculate_loss mfsimple.py:48-57 as a
  * VALUE: what an unmodified Trainer reads with loss.item(), trainer.py:168); nothing is kept for a backward. */
 int rb2_fm_loss(const float *E, const float *W, const float *bias3, int64_t n_rows, int32_t dim,
                 const int64_t *ids, const int64_t *offsets, int32_t n_fields, const float *label, int64_t batch,
-                float *loss_out, void *workspace, size_t workspace_bytes, void *stream, const rb2_fm_float *h_float);
+                float *loss_out, void *workspace, size_t workspace_bytes, void *stream, const rb2_fm_float *h_float,
+                const rb2_fm_seq *h_seq);
 
 /* Row-sharded FM (one 33M-row table sharded over the GPUs, batch split by rows; no reference
  * counterpart).  rb2_fm_grad_step is the local part of a step: rows_e [n_rows, dim] / rows_w [n_rows] are the

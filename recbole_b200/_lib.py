@@ -49,6 +49,13 @@ class RB2FmFloat(ctypes.Structure):
                 ("vWf", ctypes.c_void_p)]
 
 
+class RB2FmSeq(ctypes.Structure):
+    """include/recbole_b200.h: rb2_fm_seq (the TOKEN_SEQ fields of a context-aware model)."""
+    _fields_ = [("n_seq", ctypes.c_int32), ("n_token_cols", ctypes.c_int32), ("seq_start", ctypes.c_void_p),
+                ("col_seq", ctypes.c_void_p), ("seq_row_base", ctypes.c_int64), ("pooled", ctypes.c_void_p),
+                ("coef", ctypes.c_void_p)]
+
+
 class RB2Peers(ctypes.Structure):
     _fields_ = [
         ("world", ctypes.c_int32), ("me", ctypes.c_int32), ("item_block", ctypes.c_int64),
@@ -92,12 +99,13 @@ SIGNATURES = {
     "rb2_adam_lazy_flush": (ctypes.c_int, [_p, _p, _p, _p, _i64, _i32, ctypes.POINTER(RB2Optim), _p]),
     "rb2_fm_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "rb2_fm_train_step": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _i32, _p, _i64,
-                                         ctypes.POINTER(RB2Optim), _p, _p, _p, _sz, _p, ctypes.POINTER(RB2FmFloat)]),
+                                         ctypes.POINTER(RB2Optim), _p, _p, _p, _sz, _p, ctypes.POINTER(RB2FmFloat),
+                                         ctypes.POINTER(RB2FmSeq)]),
     "rb2_fm_lazy_flush": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i32, ctypes.POINTER(RB2Optim), _p]),
     "rb2_fm_predict": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _i32, _i64, _p, _p, _sz, _p,
-                                      ctypes.POINTER(RB2FmFloat)]),
+                                      ctypes.POINTER(RB2FmFloat), ctypes.POINTER(RB2FmSeq)]),
     "rb2_fm_loss": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _i32, _p, _i64, _p, _p, _sz, _p,
-                                   ctypes.POINTER(RB2FmFloat)]),
+                                   ctypes.POINTER(RB2FmFloat), ctypes.POINTER(RB2FmSeq)]),
     "rb2_fm_grad_step": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _p, _p, _i32, _p, _i64, _i64, _p, _p, _sz, _p]),
     "rb2_scalar_rows_update_workspace_bytes": (_sz, [_i64]),
     "rb2_scalar_rows_update": (ctypes.c_int, [_p, _p, _p, _i64, _p, _p, _i64, ctypes.POINTER(RB2Optim), _p, _sz, _p]),

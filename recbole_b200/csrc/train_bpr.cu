@@ -454,6 +454,34 @@ int launch_item_fused(const Tables &t, const BprWs &w, const PeerTable &pt, int6
   return 0;
 }
 
+// RB2_OPT_ADAM_LAZY on the fused path: before anything reads them, the rows this batch touches are brought to the value
+// the reference's dense Adam holds after step - 1 (common.cuh row_replay), ONCE per distinct row: one lane group per
+// sorted occurrence, the first occurrence of a run does the work.  After that the row-sparse kernels compute exactly
+// the dense step for these rows (same m, v, bias corrections), so the row is marked as being at `step`.
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_lazy_catchup(float *P, float *M, float *V, int32_t *L,
+                                                            const uint32_t *__restrict__ keys_s, int64_t n_occ,
+                                                            int64_t n_rows, OptScalars o, float sqrt_beta2) {
+  constexpr int LANES = RowCfg<D>::LANES;
+  const int lane = threadIdx.x % LANES;
+  const int64_t pos = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+  if (pos >= n_occ) return;
+  const uint32_t key = keys_s[pos];
+  if ((pos > 0 && keys_s[pos - 1] == key) || key >= n_rows) return;
+  const int last = L[key];
+  if (last < o.step - 1 && (last > 0 || o.wd != 0.f)) {
+    Row<D> p = row_ld<D>(P, key, lane), m = row_ld<D>(M, key, lane), v = row_ld<D>(V, key, lane);
+    if (o.wd == 0.f)
+      row_replay_fast<D>(p, m, v, last, o.step - 1, o, sqrt_beta2);
+    else
+      row_replay<D>(p, m, v, last, o.step - 1, o);
+    row_st<D>(P, key, lane, p);
+    row_st<D>(M, key, lane, m);
+    row_st<D>(V, key, lane, v);
+  }
+  if (lane == 0) L[key] = o.step;
+}
+
 // the row-sparse Adam / SGD step, single GPU (train_bpr_fused.cuh)
 template <int D>
 int launch_step_fused(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, const OptScalars &o,
@@ -474,8 +502,13 @@ int launch_step_fused(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_i
     { int rc_ = rb2sort::sort_positions(w.ikey, w.ikey_s, w.ival_s, 2 * B, bits_for(n_items), w.cub_tmp, w.cub_bytes, st); if (rc_) return rc_; }
   }
   {
-    ProfScope prof(RB2_ST_PLAN, st);
+    ProfScope prof(RB2_ST_PLAN, st, o.kind == RB2_OPT_ADAM_LAZY ? 3 : 1);
     k_mark_local<<<(unsigned)((2 * B + 255) / 256), 256, 0, st>>>(w, 2 * B);
+    if (o.kind == RB2_OPT_ADAM_LAZY) {
+      const float sb2 = sqrtf(o.beta2);
+      k_lazy_catchup<D><<<blocks(B), kThreads, 0, st>>>(t.up, t.um, t.uv, t.ul, w.ukey_s, B, n_users, o, sb2);
+      k_lazy_catchup<D><<<blocks(2 * B), kThreads, 0, st>>>(t.ip, t.im, t.iv, t.il, w.ikey_s, 2 * B, n_items, o, sb2);
+    }
   }
   {
     ProfScope prof(RB2_ST_USER_SIDE, st);
@@ -518,7 +551,8 @@ int launch_step(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, 
   // + state resident in L2) are bound by issue slots, not by memory latency: the register-path kernels below do that
   // shape in 0.61 ms against 0.98 ms for the staged ones (measured), which win wherever rows are mostly distinct.
   const bool dense_batch = B >= n_users && 2 * B >= 4 * n_items;
-  if (!LAZY && !t.ig && !pre_ikey_s && !rows_ready && !dense_batch)
+  // (adam_lazy takes the same kernels behind k_lazy_catchup)
+  if (!t.ig && !pre_ikey_s && !rows_ready && !dense_batch)
     return launch_step_fused<D>(t, w, B, n_users, n_items, o, loss_out, loss_accum, st, global_batch);
   const int Tu = pick_tile(B, LANES), Ti = pick_tile(2 * B, LANES);
   const int64_t ntu = (B + Tu - 1) / Tu, nti = (2 * B + Ti - 1) / Ti;
@@ -542,23 +576,29 @@ int launch_step(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, 
   // sharded step: the keys and sorts above depend on the ids only and overlap with the collective that
   // delivers the item rows on another stream; everything from here on reads them
   if (rows_ready) RB2_CUDA(cudaStreamWaitEvent(st, rows_ready, 0));
+  if (LAZY) {   // single-GPU only (the sharded entry points refuse adam_lazy): catch the touched rows up, once per row
+    ProfScope prof(RB2_ST_PLAN, st, 2);
+    const float sb2 = sqrtf(o.beta2);
+    k_lazy_catchup<D><<<blocks(B), kThreads, 0, st>>>(t.up, t.um, t.uv, t.ul, w.ukey_s, B, n_users, o, sb2);
+    k_lazy_catchup<D><<<blocks(2 * B), kThreads, 0, st>>>(t.ip, t.im, t.iv, t.il, w.ikey_s, 2 * B, n_items, o, sb2);
+  }
   {
     ProfScope prof(RB2_ST_USER_SIDE, st);
-    k_user_side<D, LAZY><<<blocks(ntu), kThreads, 0, st>>>(t, w, B, Tu, ntu, 1.f / (float)global_batch, o);
+    k_user_side<D, false><<<blocks(ntu), kThreads, 0, st>>>(t, w, B, Tu, ntu, 1.f / (float)global_batch, o);
   }
   {
     ProfScope prof(RB2_ST_USER_FIXUP, st);
-    k_fixup<D, LAZY><<<blocks(ntu), kThreads, 0, st>>>(t.up, t.um, t.uv, t.ul, w.ukey_s, w.u_head, w.u_tail, w.u_fh,
-                                                       w.u_ft, B, Tu, ntu, o, nullptr, nullptr);
+    k_fixup<D, false><<<blocks(ntu), kThreads, 0, st>>>(t.up, t.um, t.uv, t.ul, w.ukey_s, w.u_head, w.u_tail, w.u_fh,
+                                                        w.u_ft, B, Tu, ntu, o, nullptr, nullptr);
   }
   {
     ProfScope prof(RB2_ST_ITEM_SIDE, st);
-    k_item_side<D, LAZY><<<blocks(nti), kThreads, 0, st>>>(t, w, 2 * B, Ti, nti, o);
+    k_item_side<D, false><<<blocks(nti), kThreads, 0, st>>>(t, w, 2 * B, Ti, nti, o);
   }
   {
     ProfScope prof(RB2_ST_ITEM_FIXUP, st);
-    k_fixup<D, LAZY><<<blocks(nti), kThreads, 0, st>>>(t.ip, t.im, t.iv, t.il, w.ikey_s, w.i_head, w.i_tail, w.i_fh,
-                                                       w.i_ft, 2 * B, Ti, nti, o, t.ig, t.itouched);
+    k_fixup<D, false><<<blocks(nti), kThreads, 0, st>>>(t.ip, t.im, t.iv, t.il, w.ikey_s, w.i_head, w.i_tail, w.i_fh,
+                                                        w.i_ft, 2 * B, Ti, nti, o, t.ig, t.itouched);
   }
   {
     ProfScope prof(RB2_ST_LOSS, st);

@@ -93,6 +93,16 @@ struct FmTables {
   int n_float;
   float *Ef, *mEf, *vEf;   // [n_float, D]
   float *Wf, *mWf, *vWf;   // [n_float]
+  // TOKEN_SEQ fields (abstract_recommender.py:277-314, mean pooling): the id columns [n_tok, n_cols) of a sample are the
+  // padded sequences of n_seq fields (field j: columns [seq_start[j], seq_start[j + 1])); id 0 = padding = masked.
+  // Field j's vector is e_j = c_j * sum over its unmasked ids of the row, c_j = 1 / (count + 1e-8).  Its tables are
+  // rows >= seq_row_base of E / W (ids + offsets like any token column).
+  int n_tok, n_seq;
+  const int32_t *seq_start;   // [n_seq + 1] column ranges (device)
+  const int32_t *col_seq;     // [n_cols] seq field of a column, -1 for token columns (device)
+  int64_t seq_row_base, n_rows;
+  float *ef;                  // [B, n_seq, D] the pooled vectors (kept for the backward)
+  float *coef;                // [B, n_seq]    c_j
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -146,7 +156,7 @@ __global__ void __launch_bounds__(kThreads) k_fm_forward(FmTables t, const int64
         w.val[o] = (uint32_t)o;
       }
     };
-    if (F == 2 && t.n_float == 0) {
+    if (F == 2 && t.n_float == 0 && t.n_seq == 0) {
       // two fields = the point-wise "dot" model (fork's MFSimple, mfsimple.py:39-46:
       // sigmoid(<u,v> + b_u + b_i + b)): take the product directly instead of the
       // 0.5*[(u+v)^2 - u^2 - v^2] identity, which cancels badly in fp32
@@ -158,11 +168,40 @@ __global__ void __launch_bounds__(kThreads) k_fm_forward(FmTables t, const int64
         cross = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
       }
     } else {
-      for (int f = g; f < F; f += GROUPS) {
+      const int n_tok = t.n_seq > 0 ? t.n_tok : F;
+      for (int f = g; f < n_tok; f += GROUPS) {
         float4 v;
         fetch(f, v);
         S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
         sq = fmaf(v.x, v.x, sq); sq = fmaf(v.y, v.y, sq); sq = fmaf(v.z, v.z, sq); sq = fmaf(v.w, v.w, sq);
+      }
+      // TOKEN_SEQ fields: one lane group pools a whole field (masked mean, abstract_recommender.py:293-309); the pooled
+      // vector is the field's.  First order: the plain masked SUM of the scalars (layers.py:1000-1012), which fetch()
+      // already adds to `first`.
+      for (int j = g; j < t.n_seq; j += GROUPS) {
+        const int c0 = t.seq_start[j], c1 = t.seq_start[j + 1];
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        int cnt = 0;
+        for (int col = c0; col < c1; ++col) {
+          if (ids[s * F + col] != 0) {
+            float4 v;
+            fetch(col, v);                         // also records (row, occurrence)
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            ++cnt;
+          } else if (STORE && gl == 0) {           // masked: an occurrence of no row (sorted behind every real one)
+            const int64_t oo = s * F + col;
+            w.key[oo] = (uint32_t)n_rows;
+            w.val[oo] = (uint32_t)oo;
+          }
+        }
+        const float c = 1.f / ((float)cnt + 1e-8f);
+        a.x *= c; a.y *= c; a.z *= c; a.w *= c;
+        S.x += a.x; S.y += a.y; S.z += a.z; S.w += a.w;
+        sq = fmaf(a.x, a.x, sq); sq = fmaf(a.y, a.y, sq); sq = fmaf(a.z, a.z, sq); sq = fmaf(a.w, a.w, sq);
+        if (STORE) {
+          reinterpret_cast<float4 *>(t.ef + ((size_t)s * t.n_seq + j) * D)[gl] = a;
+          if (gl == 0) t.coef[(size_t)s * t.n_seq + j] = c;
+        }
       }
     }
     if (t.n_float > 0) {
@@ -191,7 +230,7 @@ __global__ void __launch_bounds__(kThreads) k_fm_forward(FmTables t, const int64
       first += __shfl_xor_sync(0xffffffffu, first, o);
     }
     float second;
-    if (F == 2 && t.n_float == 0) {
+    if (F == 2 && t.n_float == 0 && t.n_seq == 0) {
       second = cross;
     } else {
       // sum_k S_k^2 over the d elements: every group holds the full S after the reduction above
@@ -229,13 +268,15 @@ __global__ void __launch_bounds__(kThreads) k_fm_forward(FmTables t, const int64
 template <int D>
 __device__ __forceinline__ void fm_row_step(const FmTables &t, int64_t row, int lane, const Row<D> &gsum, float zsum,
                                             const OptScalars &o) {
-  // dE = sum gs - zsum * v ;  dW = zsum
+  // dE = sum gs - zsum * v ;  dW = zsum      (rows of TOKEN_SEQ tables: gsum is complete, no -zsum * v term)
+  if (t.n_seq > 0 && row >= t.n_rows) return;          // the masked sequence entries' pseudo row
+  const float zv = (t.n_seq > 0 && row >= t.seq_row_base) ? 0.f : zsum;
   if (o.kind == RB2_OPT_ADAM_LAZY) {
     Row<D> p = row_ld<D>(t.E, row, lane), m = row_ld<D>(t.mE, row, lane), v = row_ld<D>(t.vE, row, lane);
     const int last = t.last[row];
     row_replay<D>(p, m, v, last, o.step - 1, o);       // the value the forward read
     Row<D> g = gsum;
-    row_fma<D>(g, -zsum, p);
+    row_fma<D>(g, -zv, p);
 #pragma unroll
     for (int i = 0; i < RowCfg<D>::VPL; ++i) {
       adam_elem(p.v[i].x, m.v[i].x, v.v[i].x, g.v[i].x, o);
@@ -259,7 +300,7 @@ __device__ __forceinline__ void fm_row_step(const FmTables &t, int64_t row, int 
   }
   Row<D> p = row_ld<D>(t.E, row, lane);
   Row<D> g = gsum;
-  row_fma<D>(g, -zsum, p);
+  row_fma<D>(g, -zv, p);
   if (o.kind == kOptGradOut) {
     row_st<D>(t.E, row, lane, g);
     if (lane == 0) t.W[row] = zsum;
@@ -323,6 +364,7 @@ __global__ void __launch_bounds__(kThreads) k_fm_rows(FmTables t, FmWs w, int64_
       int64_t p = base + j;
       bool ok = p < hi;
       k[j] = ok ? keys[p] : kInvalid;
+      if (t.n_seq > 0 && k[j] >= (uint32_t)t.n_rows) k[j] = kInvalid;      // masked sequence entries (sorted last)
       s[j] = ok ? vals[p] / (uint32_t)F : 0u;
     }
 #pragma unroll
@@ -330,6 +372,17 @@ __global__ void __launch_bounds__(kThreads) k_fm_rows(FmTables t, FmWs w, int64_
       if (k[j] != kInvalid) {
         c[j] = row_ld<D>(w.gs, s[j], lane);
         z[j] = w.gz[s[j]];
+        if (t.n_seq > 0) {
+          const int col = (int)(vals[base + j] % (uint32_t)F);
+          const int sj = col >= t.n_tok ? t.col_seq[col] : -1;
+          if (sj >= 0) {          // an entry of a pooled field: c_j * (gz * S - gz * e_j) for the row, gz for W (a sum)
+            const size_t q = (size_t)s[j] * t.n_seq + sj;
+            const float cf = t.coef[q];
+            const Row<D> e = row_ld<D>(t.ef, (int64_t)q, lane);
+            row_fma<D>(c[j], -z[j], e);
+            c[j] = row_scale<D>(cf, c[j]);
+          }
+        }
       }
 #pragma unroll
     for (int j = 0; j < UNR; ++j) {
@@ -580,6 +633,25 @@ static int fm_set_float(FmTables &t, const rb2_fm_float *f, bool train, const ch
   return 0;
 }
 
+static int fm_set_seq(FmTables &t, const rb2_fm_seq *q, int64_t n_rows, int32_t n_fields, bool train, const char *who) {
+  t.n_rows = n_rows;
+  if (!q || q->n_seq <= 0) return 0;
+  RB2_REQUIRE(q->n_seq <= RB2_FM_MAX_SEQ && q->n_token_cols >= 0 && q->n_token_cols < n_fields, RB2_EINVAL,
+              "%s: bad TOKEN_SEQ description (n_seq %d, token columns %d of %d)", who, (int)q->n_seq,
+              (int)q->n_token_cols, (int)n_fields);
+  RB2_REQUIRE(q->seq_start && q->col_seq && q->seq_row_base >= 0 && q->seq_row_base <= n_rows, RB2_EINVAL,
+              "%s: TOKEN_SEQ fields need seq_start, col_seq and seq_row_base", who);
+  if (train) RB2_REQUIRE(q->pooled && q->coef, RB2_EINVAL, "%s: TOKEN_SEQ training needs the pooled / coef buffers", who);
+  t.n_tok = q->n_token_cols;
+  t.n_seq = q->n_seq;
+  t.seq_start = q->seq_start;
+  t.col_seq = q->col_seq;
+  t.seq_row_base = q->seq_row_base;
+  t.ef = q->pooled;
+  t.coef = q->coef;
+  return 0;
+}
+
 extern "C" size_t rb2_fm_workspace_bytes(int64_t batch, int32_t n_fields, int32_t dim) {
   FmWs w;
   return carve(w, nullptr, batch, n_fields, dim);
@@ -616,7 +688,7 @@ static int fm_step(FmTables t, int64_t n_rows, int32_t dim, const int64_t *ids, 
     size_t tmp = w.cub_bytes;
     {
       ProfScope prof(RB2_ST_SORT_ITEM, st, 2 + (rb2_bits_for(n_rows) + 7) / 8);
-      { int rc_ = rb2sort::sort_positions(w.key, w.key_s, w.val_s, M, rb2_bits_for(n_rows), w.cub_tmp, w.cub_bytes, st); if (rc_) return rc_; }
+      { int rc_ = rb2sort::sort_positions(w.key, w.key_s, w.val_s, M, rb2_bits_for(n_rows + (t.n_seq > 0 ? 1 : 0)), w.cub_tmp, w.cub_bytes, st); if (rc_) return rc_; }
     }
     const int T = rb2_pick_tile(M, LANES);
     const int64_t nt = (M + T - 1) / T;
@@ -638,7 +710,8 @@ extern "C" int rb2_fm_train_step(float *E, float *mE, float *vE, float *W, float
                                  int32_t *row_last, int64_t n_rows, int32_t dim, const int64_t *ids,
                                  const int64_t *offsets, int32_t n_fields, const float *label, int64_t batch,
                                  const rb2_optim *h_opt, float *loss_out, double *loss_accum, void *workspace,
-                                 size_t workspace_bytes, void *stream, const rb2_fm_float *h_float) {
+                                 size_t workspace_bytes, void *stream, const rb2_fm_float *h_float,
+                                 const rb2_fm_seq *h_seq) {
   RB2_REQUIRE(E && W && bias3 && ids && offsets && label && h_opt && loss_out && workspace, RB2_EINVAL,
               "rb2_fm_train_step: null argument");
   OptScalars o = rb2_opt_scalars(h_opt);
@@ -650,6 +723,7 @@ extern "C" int rb2_fm_train_step(float *E, float *mE, float *vE, float *W, float
                 "rb2_fm_train_step: adam_lazy needs row_last and the bias-correction tables");
   FmTables t{E, mE, vE, W, mW, vW, bias3, row_last};
   if (int rc = fm_set_float(t, h_float, true, "rb2_fm_train_step")) return rc;
+  if (int rc = fm_set_seq(t, h_seq, n_rows, n_fields, true, "rb2_fm_train_step")) return rc;
   if (t.n_float > 0 && o.kind != RB2_OPT_SGD)
     RB2_REQUIRE(t.mEf && t.vEf && t.mWf && t.vWf, RB2_EINVAL, "rb2_fm_train_step: Adam needs the float fields' m and v");
   return fm_step(t, n_rows, dim, ids, offsets, n_fields, label, batch, (double)batch, o, loss_out, loss_accum, workspace,
@@ -809,7 +883,7 @@ extern "C" int rb2_fm_lazy_flush(float *E, float *mE, float *vE, float *W, float
 extern "C" int rb2_fm_loss(const float *E, const float *W, const float *bias3, int64_t n_rows, int32_t dim,
                            const int64_t *ids, const int64_t *offsets, int32_t n_fields, const float *label,
                            int64_t batch, float *loss_out, void *workspace, size_t workspace_bytes, void *stream,
-                           const rb2_fm_float *h_float) {
+                           const rb2_fm_float *h_float, const rb2_fm_seq *h_seq) {
   RB2_REQUIRE(E && W && bias3 && ids && offsets && label && loss_out && workspace, RB2_EINVAL,
               "rb2_fm_loss: null argument");
   RB2_REQUIRE(batch > 0 && n_fields > 0, RB2_EINVAL, "rb2_fm_loss: empty batch");
@@ -820,6 +894,7 @@ extern "C" int rb2_fm_loss(const float *E, const float *W, const float *bias3, i
   FmTables t{const_cast<float *>(E), nullptr, nullptr, const_cast<float *>(W), nullptr, nullptr,
              const_cast<float *>(bias3), nullptr};
   if (int rc = fm_set_float(t, h_float, false, "rb2_fm_loss")) return rc;
+  if (int rc = fm_set_seq(t, h_seq, n_rows, n_fields, false, "rb2_fm_loss")) return rc;
   OptScalars o = {};
   o.kind = kOptLossOnly;
   k_zero_parts<<<(unsigned)((w.n_parts + 255) / 256), 256, 0, st>>>(w);
@@ -839,7 +914,7 @@ extern "C" int rb2_fm_loss(const float *E, const float *W, const float *bias3, i
 extern "C" int rb2_fm_predict(const float *E, const float *W, const float *bias3, int64_t n_rows, int32_t dim,
                               const int64_t *ids, const int64_t *offsets, int32_t n_fields, int64_t batch,
                               float *y_out, void *workspace, size_t workspace_bytes, void *stream,
-                              const rb2_fm_float *h_float) {
+                              const rb2_fm_float *h_float, const rb2_fm_seq *h_seq) {
   RB2_REQUIRE(E && W && bias3 && ids && offsets && y_out && workspace, RB2_EINVAL, "rb2_fm_predict: null argument");
   if (batch <= 0) return 0;
   FmWs w;
@@ -849,6 +924,7 @@ extern "C" int rb2_fm_predict(const float *E, const float *W, const float *bias3
   FmTables t{const_cast<float *>(E), nullptr, nullptr, const_cast<float *>(W), nullptr, nullptr,
              const_cast<float *>(bias3), nullptr};
   if (int rc = fm_set_float(t, h_float, false, "rb2_fm_predict")) return rc;
+  if (int rc = fm_set_seq(t, h_seq, n_rows, n_fields, false, "rb2_fm_predict")) return rc;
   RB2_FM_DIM(dim, {
     int64_t warps = std::min<int64_t>(batch, (int64_t)rb2_num_sms() * 64);
     unsigned fblocks = (unsigned)((warps * 32 + kThreads - 1) / kThreads);

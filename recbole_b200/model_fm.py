@@ -4,8 +4,8 @@
 (fm.py:26-59) on top of ``ContextRecommender`` (recbole/model/abstract_recommender.py:151-412):
 constructor ``(config, dataset)``, ``calculate_loss / predict``, and parameters under the reference's
 names (``token_embedding_table.embedding.weight``, ``first_order_linear.token_embedding_table.embedding.weight``,
-``first_order_linear.bias``) so state dicts interchange.  TOKEN fields only (BASELINE config 5 names
-categorical fields; float / token_seq fields stay on the reference path and raise here).
+``first_order_linear.bias``, ``float_embedding_table.weight``, ``token_seq_embedding_table.<i>.weight`` ...) so state
+dicts interchange.  TOKEN, FLOAT and TOKEN_SEQ (mean-pooled) fields.
 """
 import numpy as np
 import torch
@@ -107,23 +107,27 @@ class _Table(nn.Module):
 
 
 class _FirstOrder(nn.Module):
-    def __init__(self, rows, n_float=0):
+    def __init__(self, rows, n_float=0, seq_dims=()):
         super().__init__()
         self.token_embedding_table = _Table(rows, 1)
         if n_float:
             self.float_embedding_table = nn.Embedding(n_float, 1)       # layers.py:939-940
+        if seq_dims:
+            self.token_seq_embedding_table = nn.ModuleList(nn.Embedding(n, 1) for n in seq_dims)   # layers.py:941-944
         self.bias = nn.Parameter(torch.zeros((1,)), requires_grad=True)  # layers.py:945
 
 
 FEATURE_FLOAT = "float"
+FEATURE_TOKEN_SEQ = "token_seq"
 _KERNEL_DIMS = (16, 32, 64, 128)
 
 
 class FusedFM(_PointwiseMixin, nn.Module):
-    """TOKEN and FLOAT fields (abstract_recommender.py:205-258); TOKEN_SEQ fields raise.  Any embedding_size up to 128
-    (FM.yaml's default is 10): the kernels work on rows of 16 / 32 / 64 / 128 floats, other sizes live in zero-padded
-    rows whose padding never moves (its gradient is exactly zero) and the parameters are views of the first
-    embedding_size columns."""
+    """TOKEN, FLOAT and TOKEN_SEQ fields (abstract_recommender.py:205-314; sequences are mean-pooled over their non-zero
+    ids, the reference's default mode).  Any embedding_size up to 128 (FM.yaml's default is 10): the kernels work on
+    rows of 16 / 32 / 64 / 128 floats, other sizes live in zero-padded rows whose padding never moves (its gradient is
+    exactly zero) and the parameters are views of the first embedding_size columns.  With TOKEN_SEQ fields the token
+    table and every sequence table are views of ONE row range (token rows first), which is what the kernels index."""
     input_type = InputType.POINTWISE   # abstract_recommender.py:157
     type = ModelType.CONTEXT           # abstract_recommender.py:156
 
@@ -136,6 +140,7 @@ class FusedFM(_PointwiseMixin, nn.Module):
         self._dpad = next(k for k in _KERNEL_DIMS if k >= self.embedding_size)
         self.device = config["device"]
         self.token_field_names, self.token_field_dims, self.float_field_names = [], [], []
+        self.token_seq_field_names, self.token_seq_field_dims = [], []
         for name in dataset.fields():                       # abstract_recommender.py:205-219
             if name == self.LABEL:
                 continue
@@ -147,25 +152,38 @@ class FusedFM(_PointwiseMixin, nn.Module):
                 if int(dataset.num(name)) != 1:
                     raise NotImplementedError("FusedFM: float field %r has %d columns (1 supported)" % (name, dataset.num(name)))
                 self.float_field_names.append(name)
+            elif ftype == FEATURE_TOKEN_SEQ:
+                self.token_seq_field_names.append(name)
+                self.token_seq_field_dims.append(int(dataset.num(name)))
             else:
-                raise NotImplementedError("FusedFM handles TOKEN and FLOAT fields; field %r is %r" % (name, ftype))
+                raise NotImplementedError("FusedFM handles TOKEN, FLOAT and TOKEN_SEQ fields; field %r is %r" % (name, ftype))
+        if len(self.token_seq_field_names) > ops.FM_MAX_SEQ:
+            raise NotImplementedError("FusedFM: at most %d TOKEN_SEQ fields" % ops.FM_MAX_SEQ)
         if not self.token_field_names:
             raise NotImplementedError("FusedFM needs at least one TOKEN field")
         self.n_float = len(self.float_field_names)
-        self.num_feature_field = len(self.token_field_names)      # token fields (the kernels' F)
+        self.n_seq = len(self.token_seq_field_names)
+        self.num_feature_field = len(self.token_field_names)      # token fields (the kernels' F without sequences)
         # abstract_recommender.py:220-224: one table, per-field offsets
         self.token_field_offsets = np.array((0, *np.cumsum(self.token_field_dims)[:-1]), dtype=np.int64)
         rows = int(sum(self.token_field_dims))
+        self._tok_rows = rows
+        self._seq_bases = [rows + int(x) for x in np.cumsum([0] + self.token_seq_field_dims[:-1])] if self.n_seq else []
+        self._all_rows = rows + int(sum(self.token_seq_field_dims))
         # registration order = ContextRecommender.__init__'s (the optimizer state is indexed by parameter position)
         self.token_embedding_table = _Table(rows, self.embedding_size)
         if self.n_float:
             self.float_embedding_table = nn.Embedding(self.n_float, self.embedding_size)     # :225-228
-        self.first_order_linear = _FirstOrder(rows, self.n_float)
+        if self.n_seq:                                                                       # :229-232
+            self.token_seq_embedding_table = nn.ModuleList(nn.Embedding(n, self.embedding_size)
+                                                           for n in self.token_seq_field_dims)
+        self.first_order_linear = _FirstOrder(rows, self.n_float, self.token_seq_field_dims)
         # fm.py:41-45: xavier_normal_ on every nn.Embedding
         for m in self.modules():
             if isinstance(m, nn.Embedding):
                 xavier_normal_(m.weight.data)
         self._pads = {}          # parameter name -> zero-padded [rows, dpad] storage the parameter is a view of
+        self._seq_meta = {}      # (device, total id columns) -> offsets / column maps of a batch layout
         self._init_fused(config)
 
     # ---- plumbing -----------------------------------------------------------------------------------
@@ -185,7 +203,35 @@ class FusedFM(_PointwiseMixin, nn.Module):
             self._pads[key] = pad
         return pad
 
+    def _joined(self, key, params, width):
+        """One [all rows, width] tensor holding the token table followed by every TOKEN_SEQ table; the parameters are
+        (re)made views of their row ranges (first embedding_size columns), like _padded does for a single table."""
+        dev = params[0].device
+        buf = self._pads.get(key)
+        d = params[0].shape[1]
+        bases = [0] + self._seq_bases
+        ok = buf is not None and buf.device == dev
+        if ok:
+            for p, b in zip(params, bases):
+                w = p.data
+                if w.data_ptr() != buf.data_ptr() + 4 * b * width or w.stride(0) != width or w.device != dev:
+                    ok = False
+        if not ok:
+            buf = torch.zeros((self._all_rows, width), dtype=torch.float32, device=dev)
+            for p, b in zip(params, bases):
+                buf[b:b + p.shape[0], :d] = p.data
+                p.data = buf[b:b + p.shape[0], :d]
+            self._pads[key] = buf
+        return buf
+
     def _tables(self):
+        if self.n_seq:
+            fo = self.first_order_linear
+            E = self._joined("E", [self.token_embedding_table.embedding.weight] +
+                             [t.weight for t in self.token_seq_embedding_table], self._dpad)
+            W = self._joined("W", [fo.token_embedding_table.embedding.weight] +
+                             [t.weight for t in fo.token_seq_embedding_table], 1)
+            return E, W.view(-1)
         E = self._padded("E", self.token_embedding_table.embedding.weight)
         W = self.first_order_linear.token_embedding_table.embedding.weight.data.view(-1)
         return E, W
@@ -203,15 +249,49 @@ class FusedFM(_PointwiseMixin, nn.Module):
         return (vals.contiguous(),) + self._float_tables()
 
     def _ids(self, interaction):
-        # abstract_recommender.py:381-388: stack the per-field id columns -> [B, F]
-        return torch.stack([interaction[n] for n in self.token_field_names], dim=1).contiguous()
+        # abstract_recommender.py:381-395: the per-field id columns -> [B, F] (+ the padded sequences' columns)
+        cols = [interaction[n].reshape(-1, 1) for n in self.token_field_names]
+        cols += [interaction[n].reshape(cols[0].shape[0], -1) for n in self.token_seq_field_names]
+        return torch.cat(cols, dim=1).contiguous()
 
-    def _workspace(self, batch):
+    def _make_layout(self, dev, lens):
+        n_tok = len(self.token_field_names)
+        starts = np.concatenate([[n_tok], n_tok + np.cumsum(lens)]).astype(np.int32)
+        offs = list(self.token_field_offsets) + [b for b, n in zip(self._seq_bases, lens) for _ in range(n)]
+        col_seq = [-1] * n_tok + [j for j, n in enumerate(lens) for _ in range(n)]
+        return dict(n_token_cols=n_tok, seq_row_base=self._tok_rows,
+                    offsets=torch.tensor(offs, dtype=torch.int64, device=dev),
+                    seq_start=torch.from_numpy(starts).to(dev),
+                    col_seq=torch.tensor(col_seq, dtype=torch.int32, device=dev))
+
+    def _batch(self, interaction, train):
+        """ids, offsets and the TOKEN_SEQ description of one batch (pooled / coef buffers when training)."""
+        ids = self._ids(interaction)
+        if not self.n_seq:
+            self._ensure_device_state()
+            return ids, self._offsets, None
+        lens = [int(interaction[n].shape[1]) if interaction[n].dim() > 1 else 1 for n in self.token_seq_field_names]
+        key = (str(ids.device),) + tuple(lens)
+        meta = self._seq_meta.get(key)
+        if meta is None:
+            meta = self._seq_meta[key] = self._make_layout(ids.device, lens)
+        seq = dict(meta)
+        if train:
+            B = ids.shape[0]
+            buf = self._seq_meta.get("pooled")
+            if buf is None or buf[0].shape[0] < B or buf[0].device != ids.device:
+                buf = (torch.empty((B, self.n_seq, self._dpad), dtype=torch.float32, device=ids.device),
+                       torch.empty((B, self.n_seq), dtype=torch.float32, device=ids.device))
+                self._seq_meta["pooled"] = buf
+            seq["pooled"], seq["coef"] = buf
+        return ids, meta["offsets"], seq
+
+    def _workspace(self, batch, n_cols=None):
         dev = self.token_embedding_table.embedding.weight.device
-        if getattr(self, "_ws_dev", None) != str(dev):
-            self._ws, self._ws_dev = {}, str(dev)
-        return ops.grow_workspace(self._ws, batch,
-                                  lambda b: ops.fm_workspace(b, self.num_feature_field, self._dpad, dev))
+        F = int(n_cols or self.num_feature_field)
+        if getattr(self, "_ws_dev", None) != (str(dev), F):
+            self._ws, self._ws_dev = {}, (str(dev), F)
+        return ops.grow_workspace(self._ws, batch, lambda b: ops.fm_workspace(b, F, self._dpad, dev))
 
     def _ensure_device_state(self):
         dev = self.token_embedding_table.embedding.weight.device
@@ -237,13 +317,18 @@ class FusedFM(_PointwiseMixin, nn.Module):
         # model.parameters() order of the reference's FM: token table, float table, first_order_linear.bias,
         # first-order token table, first-order float table (a module's own parameters precede its children's)
         st, d = self._state, self.embedding_size
-        out = [(st["mE"][:, :d], st["vE"][:, :d])]
+        # (with TOKEN_SEQ fields: ... float table, sequence tables, bias, first-order token / float / sequence tables)
+        tr = self._tok_rows
+        seq = [(b, b + n) for b, n in zip(self._seq_bases, self.token_seq_field_dims)]
+        out = [(st["mE"][:tr, :d], st["vE"][:tr, :d])]
         if self.n_float:
             out.append((st["mEf"][:, :d], st["vEf"][:, :d]))
+        out += [(st["mE"][a:b, :d], st["vE"][a:b, :d]) for a, b in seq]
         out.append((self._bias3[1:2], self._bias3[2:3]))
-        out.append((st["mW"], st["vW"]))
+        out.append((st["mW"][:tr], st["vW"][:tr]))
         if self.n_float:
             out.append((st["mWf"], st["vWf"]))
+        out += [(st["mW"][a:b], st["vW"][a:b]) for a, b in seq]
         return out
 
     def _state_dict_impl(self, *args, **kwargs):
@@ -256,33 +341,30 @@ class FusedFM(_PointwiseMixin, nn.Module):
 
     # ---- fused step ----------------------------------------------------------------------------------
     def _fused_step(self, interaction, loss_accum):
-        self._ensure_device_state()
-        ids = self._ids(interaction)
+        ids, offsets, seq = self._batch(interaction, True)
         E, W = self._tables()
-        ops.fm_train_step(E, W, self._bias3, self._state, ids, self._offsets, interaction[self.LABEL].contiguous(),
-                          self._optim, self._loss_out, loss_accum, self._workspace(ids.shape[0]),
-                          floats=self._floats(interaction))
+        ops.fm_train_step(E, W, self._bias3, self._state, ids, offsets, interaction[self.LABEL].contiguous(),
+                          self._optim, self._loss_out, loss_accum, self._workspace(ids.shape[0], ids.shape[1]),
+                          floats=self._floats(interaction), seq=seq)
         self.first_order_linear.bias.data.copy_(self._bias3[0:1])
         return self._loss_out
 
     def _loss_value(self, interaction):
         self.flush()
-        self._ensure_device_state()
-        ids = self._ids(interaction)
+        ids, offsets, seq = self._batch(interaction, False)
         E, W = self._tables()
         out = torch.empty(1, dtype=torch.float32, device=E.device)
-        ops.fm_loss(E, W, self._bias3, ids, self._offsets, interaction[self.LABEL].contiguous(), out,
-                    self._workspace(ids.shape[0]), floats=self._floats(interaction))
+        ops.fm_loss(E, W, self._bias3, ids, offsets, interaction[self.LABEL].contiguous(), out,
+                    self._workspace(ids.shape[0], ids.shape[1]), floats=self._floats(interaction), seq=seq)
         return out[0]
 
     # ---- the reference's plugin API ---------------------------------------------------------------------
     def predict(self, interaction):  # fm.py:58-59
         self.flush()
-        self._ensure_device_state()
-        ids = self._ids(interaction)
+        ids, offsets, seq = self._batch(interaction, False)
         E, W = self._tables()
-        return ops.fm_predict(E, W, self._bias3, ids, self._offsets, self._workspace(ids.shape[0]),
-                              floats=self._floats(interaction))
+        return ops.fm_predict(E, W, self._bias3, ids, offsets, self._workspace(ids.shape[0], ids.shape[1]),
+                              floats=self._floats(interaction), seq=seq)
 
 
 class FusedMFSimple(_PointwiseMixin, nn.Module):

@@ -328,7 +328,23 @@ def _fm_float(fl, state=None):
     return ctypes.byref(c)
 
 
-def fm_train_step(E, W, bias3, state, ids, offsets, label, optim, loss_out, loss_accum, ws, floats=None):
+FM_MAX_SEQ = 16   # RB2_FM_MAX_SEQ
+
+
+def _fm_seq(seq):
+    """seq = dict(n_token_cols, seq_start int32[n_seq+1], col_seq int32[n_cols], seq_row_base, pooled, coef) or None."""
+    if seq is None:
+        return None
+    c = _lib.RB2FmSeq()
+    c.n_seq, c.n_token_cols = int(seq["seq_start"].numel()) - 1, int(seq["n_token_cols"])
+    c.seq_start, c.col_seq = _ptr(seq["seq_start"], torch.int32).value, _ptr(seq["col_seq"], torch.int32).value
+    c.seq_row_base = int(seq["seq_row_base"])
+    if seq.get("pooled") is not None:
+        c.pooled, c.coef = _ptr(seq["pooled"], torch.float32).value, _ptr(seq["coef"], torch.float32).value
+    return ctypes.byref(c)
+
+
+def fm_train_step(E, W, bias3, state, ids, offsets, label, optim, loss_out, loss_accum, ws, floats=None, seq=None):
     """One fused FM step (rb2_fm_train_step).  state: mE, vE, mW, vW for Adam (+ mEf, vEf, mWf, vWf with float fields:
     floats = (values [B, Ff], Ef [Ff, d], Wf [Ff]))."""
     optim.step += 1
@@ -340,7 +356,7 @@ def fm_train_step(E, W, bias3, state, ids, offsets, label, optim, loss_out, loss
                                 _ptr(ids, torch.int64),
                                 _ptr(offsets, torch.int64), ids.shape[1], _ptr(label, f32), ids.shape[0],
                                 ctypes.byref(o), _ptr(loss_out, f32), _ptr(loss_accum, torch.float64, True), ws.ptr(),
-                                ws.nbytes, _stream(), _fm_float(floats, state)))
+                                ws.nbytes, _stream(), _fm_float(floats, state), _fm_seq(seq)))
 
 
 def fm_lazy_flush(E, W, state, optim):
@@ -381,7 +397,7 @@ def scalar_step(p3, grad, optim, step=None):
     check(lib.rb2_scalar_step(_ptr(p3, torch.float32), _ptr(grad, torch.float32), ctypes.byref(o), _stream()))
 
 
-def fm_predict(E, W, bias3, ids, offsets, ws=None, floats=None):
+def fm_predict(E, W, bias3, ids, offsets, ws=None, floats=None, seq=None):
     B, F = ids.shape
     if ws is None:
         ws = fm_workspace(B, F, E.shape[1], E.device)
@@ -389,16 +405,16 @@ def fm_predict(E, W, bias3, ids, offsets, ws=None, floats=None):
     f32 = torch.float32
     check(lib.rb2_fm_predict(_ptr(E, f32), _ptr(W, f32), _ptr(bias3, f32), E.shape[0], E.shape[1],
                              _ptr(ids, torch.int64), _ptr(offsets, torch.int64), F, B, _ptr(y), ws.ptr(), ws.nbytes,
-                             _stream(), _fm_float(floats)))
+                             _stream(), _fm_float(floats), _fm_seq(seq)))
     return y
 
 
-def fm_loss(E, W, bias3, ids, offsets, label, loss_out, ws, floats=None):
+def fm_loss(E, W, bias3, ids, offsets, label, loss_out, ws, floats=None, seq=None):
     """Forward + mean BCE only (rb2_fm_loss); loss_out[0] = the batch's loss."""
     f32 = torch.float32
     check(lib.rb2_fm_loss(_ptr(E, f32), _ptr(W, f32), _ptr(bias3, f32), E.shape[0], E.shape[1], _ptr(ids, torch.int64),
                           _ptr(offsets, torch.int64), ids.shape[1], _ptr(label, f32), ids.shape[0], _ptr(loss_out, f32),
-                          ws.ptr(), ws.nbytes, _stream(), _fm_float(floats)))
+                          ws.ptr(), ws.nbytes, _stream(), _fm_float(floats), _fm_seq(seq)))
 
 
 def gather_dot(U, V, user, item):

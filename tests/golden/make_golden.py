@@ -20,6 +20,8 @@ modified or copied.  Every array saved here is an INPUT or an OUTPUT of referenc
   dense_adam_pointwise.npz  FM (wd 0 / 1e-3) and MFSimple (its yaml: wd 1e-8, lr 2e-3) under dense torch.optim.Adam for
                  4-5 steps on batches that leave most rows untouched (pins the fused 'adam_lazy' kind)
   fm_float.npz   recbole FM with TOKEN + FLOAT fields, embedding_size 10 (FM.yaml), dense Adam, 4 steps
+  fm_seq.npz     recbole FM with TOKEN + FLOAT + two TOKEN_SEQ fields (mean pooling over the non-zero ids, some samples
+                 with an empty sequence), embedding_size 10, dense Adam, 4 steps
   ce_backward.npz  torch autograd of that head w.r.t. seq_output and the item table + one dense Adam step
   ce_head.npz    the SASRec head expressions of sasrec.py:137-141,152-158
   cfg1_train.npz BASELINE config 1: the reference pipeline on ml-100k, 2 epochs of Trainer._train_epoch
@@ -514,6 +516,65 @@ def g_fm_float(out):
     np.savez_compressed(out, **d)
 
 
+def g_fm_seq(out):
+    """recbole FM with TOKEN, FLOAT and TOKEN_SEQ fields (abstract_recommender.py:277-314 masked mean pooling; first order
+    = masked sum, layers.py:989-1019) at embedding_size 10, dense torch.optim.Adam, 4 steps."""
+    from recbole.model.context_aware_recommender.fm import FM
+    from recbole.utils import FeatureType
+    torch.manual_seed(37)
+    token_dims = {"t0": 30, "t1": 200}
+    float_names = ["x0"]
+    seq_dims = {"q0": 25, "q1": 7}
+    seq_lens = {"q0": 6, "q1": 3}
+    dim, B, steps = 10, 64, 4
+    f2t = {k: FeatureType.TOKEN for k in token_dims}
+    f2t.update({k: FeatureType.FLOAT for k in float_names})
+    f2t.update({k: FeatureType.TOKEN_SEQ for k in seq_dims})
+    f2t["label"] = FeatureType.FLOAT
+    nums = dict(token_dims)
+    nums.update({k: 1 for k in float_names})
+    nums.update(seq_dims)
+    nums["label"] = 1
+    model = FM(StubConfig(LABEL_FIELD="label", embedding_size=dim, device="cpu", double_tower=None),
+               StubDataset(nums, f2t))
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(2.0)
+    rng = np.random.default_rng(43)
+    d = dict(token_dims=np.array(list(token_dims.values())), n_float=np.int64(len(float_names)),
+             seq_dims=np.array(list(seq_dims.values())), seq_lens=np.array(list(seq_lens.values())))
+    d["param_order"] = np.array([n for n, _ in model.named_parameters()])
+    for n, p in model.named_parameters():
+        d["p0_" + n] = p.detach().numpy().copy()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    for s in range(steps):
+        inter = {k: torch.from_numpy(rng.integers(0, v, B)) for k, v in token_dims.items()}
+        for k in float_names:
+            inter[k] = torch.from_numpy(rng.random(B).astype(np.float32))
+        for k, v in seq_dims.items():
+            # padded sequences: a random number (0 .. L) of non-zero ids first, zeros behind (dataset.py's padding)
+            L = seq_lens[k]
+            q = rng.integers(1, v, (B, L))
+            n = rng.integers(0, L + 1, B)
+            q[np.arange(L)[None, :] >= n[:, None]] = 0
+            inter[k] = torch.from_numpy(q)
+            d["%s_%d" % (k, s)] = q
+        inter["label"] = torch.from_numpy((rng.random(B) < 0.3).astype(np.float32))
+        d["ids%d" % s] = np.stack([inter[k].numpy() for k in token_dims], axis=1)
+        d["fx%d" % s] = np.stack([inter[k].numpy() for k in float_names], axis=1)
+        d["label%d" % s] = inter["label"].numpy()
+        opt.zero_grad()
+        loss = model.calculate_loss(inter)
+        loss.backward()
+        opt.step()
+        d["loss%d" % s] = np.float32(loss.item())
+    for n, p in model.named_parameters():
+        d["pN_" + n] = p.detach().numpy().copy()
+    with torch.no_grad():
+        d["predN"] = model.predict(inter).numpy().copy()
+    np.savez_compressed(out, **d)
+
+
 def g_ce(out):
     torch.manual_seed(9)
     B, N, H, K = 48, 700, 64, 10
@@ -561,6 +622,7 @@ if __name__ == "__main__":
     g_fm(o("fm_steps.npz"))
     g_dense_adam_pointwise(o("dense_adam_pointwise.npz"))
     g_fm_float(o("fm_float.npz"))
+    g_fm_seq(o("fm_seq.npz"))
     g_ce(o("ce_head.npz"))
     g_ce_backward(o("ce_backward.npz"))
     g_fullsort_small(o("fullsort_small.npz"))

@@ -308,3 +308,71 @@ def test_fm_float_fields_default_embedding_size_vs_reference_golden(golden):
     assert float(m._pads["E"][:, 10:].abs().max()) == 0.0 and float(m._pads["Ef"][:, 10:].abs().max()) == 0.0
     osd = opt.state_dict()
     assert sorted(osd["state"]) == [0, 1, 2, 3, 4] and tuple(osd["state"][1]["exp_avg"].shape) == (2, 10)
+
+
+def test_fm_token_seq_fields_vs_reference_golden(golden):
+    """The reference's FM with TOKEN + FLOAT + two TOKEN_SEQ fields (masked mean pooling, abstract_recommender.py:277-314;
+    first order = masked sum, layers.py:989-1019; samples with empty sequences) at embedding_size 10 under dense
+    torch.optim.Adam for 4 steps: losses, every parameter tensor in the reference's order, predictions."""
+    from recbole_b200 import FusedFM, Interaction
+    from gpu_util import rel_err
+    g = golden("fm_seq.npz")
+    tdims, sdims = g["token_dims"], g["seq_dims"]
+    tnames = ["t%d" % i for i in range(len(tdims))]
+    fnames = ["x%d" % i for i in range(int(g["n_float"]))]
+    snames = ["q%d" % i for i in range(len(sdims))]
+
+    class Cfg(dict):
+        def __getitem__(self, k):
+            return self.get(k)
+
+    class DS:
+        field2type = dict({n: "token" for n in tnames}, **{n: "float" for n in fnames},
+                          **{n: "token_seq" for n in snames}, label="float")
+
+        def fields(self):
+            return tnames + fnames + snames + ["label"]
+
+        def num(self, f):
+            if f in tnames:
+                return int(tdims[tnames.index(f)])
+            return int(sdims[snames.index(f)]) if f in snames else 1
+
+    m = FusedFM(Cfg(LABEL_FIELD="label", embedding_size=10, device="cuda", learner="adam", learning_rate=1e-2), DS())
+    assert [n for n, _ in m.named_parameters()] == [str(x) for x in g["param_order"]]
+    m = m.to("cuda")
+    m.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("p0_")})
+    opt = m.build_optimizer("adam_lazy", 1e-2)
+    for s in range(4):
+        cols = {n: torch.from_numpy(g["ids%d" % s][:, i].astype(np.int64)) for i, n in enumerate(tnames)}
+        cols.update({n: torch.from_numpy(g["fx%d" % s][:, i]) for i, n in enumerate(fnames)})
+        cols.update({n: torch.from_numpy(g["%s_%d" % (n, s)].astype(np.int64)) for n in snames})
+        inter = Interaction(dict(cols, label=torch.from_numpy(g["label%d" % s]))).to("cuda")
+        if s % 2 == 0:
+            loss = m.train_step(inter).item()
+        else:
+            opt.zero_grad()
+            lt = m.calculate_loss(inter)
+            loss = lt.item()
+            lt.backward()
+            opt.step()
+        ref = float(g["loss%d" % s])
+        assert abs(loss - ref) <= TOL * abs(ref), (s, loss, ref)
+    assert rel_err(m.predict(inter).cpu().numpy(), g["predN"]) < 10 * TOL
+    sd = m.state_dict()
+    assert sorted(sd) == sorted(str(x) for x in g["param_order"])
+    for n in sd:
+        a, b = sd[n].cpu().numpy().astype(np.float64), g["pN_" + n].astype(np.float64)
+        assert a.shape == b.shape, (n, a.shape, b.shape)
+        d = np.abs(a - b)
+        bad = d > TOL * np.abs(b).max()
+        assert bad.sum() <= 2 and d.max() <= 2e-4, (n, int(bad.sum()), float(d.max()))     # eps-conditioned elements
+    # row 0 of a sequence table (the padding id) never received a gradient; the optimizer state has the reference's layout
+    assert np.array_equal(sd["token_seq_embedding_table.0.weight"][0].cpu().numpy(),
+                          g["p0_token_seq_embedding_table.0.weight"][0])
+    osd = opt.state_dict()
+    assert sorted(osd["state"]) == list(range(9)) and tuple(osd["state"][3]["exp_avg"].shape) == (int(sdims[1]), 10)
+    # sequences of another padded length go through the same kernels (the column layout is per batch)
+    cols["q0"] = torch.cat([cols["q0"], torch.zeros((cols["q0"].shape[0], 2), dtype=torch.int64)], dim=1)
+    inter2 = Interaction(dict(cols, label=torch.from_numpy(g["label3"]))).to("cuda")
+    assert rel_err(m.predict(inter2).cpu().numpy(), g["predN"]) < 10 * TOL
