@@ -73,7 +73,12 @@ enum {
   RB2_OPT_SGD = 0,        /* p -= lr * (g + wd*p)                  (torch.optim.SGD, momentum 0)     */
   RB2_OPT_ADAM = 1,       /* row-sparse Adam: the dense formula on the rows touched by the batch    */
   RB2_OPT_ADAM_LAZY = 2   /* row-sparse Adam that replays the zero-gradient steps a row missed, so
-                             the trajectory equals the reference's dense Adam (needs *_last arrays) */
+                             the trajectory equals the reference's dense Adam (needs *_last arrays).
+                             A batch's rows are caught up ONCE per distinct row before the step reads them;
+                             the sharded entry points catch up the (local) user rows and let every owner
+                             take the zero-gradient step of the untouched rows of its item shard
+                             (rb2_dense_rows_update, rb2_bpr_train_step_p2p); refused with an item plan
+                             (sparse all-to-all exchange) */
 };
 
 typedef struct rb2_optim {
@@ -155,7 +160,9 @@ int rb2_item_plan(const int64_t *pos, const int64_t *neg, int64_t batch, int64_t
                   int64_t *cuts, void *plan_workspace, size_t plan_workspace_bytes, void *stream);
 
 /* Owner side of the replicated-small-table exchange (all-gather rows, reduce-scatter gradients):
- * rows with touched[row] > 0 take one optimizer step with grads[row, :]. */
+ * rows with touched[row] > 0 take one optimizer step with grads[row, :].  RB2_OPT_ADAM_LAZY: the other rows
+ * take the zero-gradient step of the reference's dense Adam (rows with zero moments and no weight decay do
+ * not move and are not written), so the shard is always current and needs no `last` array. */
 int rb2_dense_rows_update(float *p, float *m, float *v, int64_t n_rows, int32_t dim, const float *grads,
                           const int32_t *touched, const rb2_optim *h_opt, void *stream);
 
@@ -205,6 +212,10 @@ int rb2_bpr_loss(const float *user_p, const float *item_p, int64_t n_users, int6
  * the next call then passes prepared = 1 (same workspace, same ids) and skips that work.
  * item_cache: fp32 [world * item_block, dim] scratch.  A barrier that waits longer than 30 s gives up
  * and sets the workspace's peer_timeout flag (second int32 of the workspace) instead of hanging.
+ * RB2_OPT_ADAM_LAZY (the trajectory of the reference's DENSE torch.optim.Adam, trainer.py:116,173): user_last =
+ * int32 [n_users_local], zero-initialised (NULL for the other kinds) -- the batch's user rows replay the zero-gradient
+ * steps they missed once per row before the step; every owner additionally takes the zero-gradient step of the rows
+ * of its item shard that nobody touched (n_items / world rows: cheap), so item rows are always current.
  * ---------------------------------------------------------------------------------------- */
 #define RB2_MAX_PEERS 8
 typedef struct rb2_peers {
@@ -227,7 +238,7 @@ int rb2_bpr_train_step_p2p(float *user_p, float *user_m, float *user_v, float *i
                            const rb2_optim *h_opt, const rb2_peers *h_peers, float *item_cache,
                            float *loss_out, double *loss_accum, void *workspace, size_t workspace_bytes,
                            void *stream, int32_t prepared, const int64_t *next_user, const int64_t *next_pos,
-                           const int64_t *next_neg);
+                           const int64_t *next_neg, int32_t *user_last);
 
 /* Peer mapping helpers (cudaIpc*; legacy IPC handles work between processes on one GPU and across
  * NVLink peers).  rb2_ipc_export: 64-byte handle of the allocation that contains dev_ptr + the offset

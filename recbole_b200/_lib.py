@@ -83,7 +83,7 @@ SIGNATURES = {
     "rb2_bpr_p2p_workspace_bytes": (_sz, [_i64, _i32]),
     "rb2_bpr_train_step_p2p": (ctypes.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _i64, _p, _p, _i64, _i64,
                                               ctypes.POINTER(RB2Optim), ctypes.POINTER(RB2Peers), _p, _p, _p, _p, _sz,
-                                              _p, _i32, _p, _p, _p]),
+                                              _p, _i32, _p, _p, _p, _p]),
     "rb2_ipc_export": (ctypes.c_int, [_p, _p, ctypes.POINTER(_i64)]),
     "rb2_ipc_open": (ctypes.c_int, [_p, _i64, ctypes.POINTER(_p)]),
     "rb2_ipc_close_all": (ctypes.c_int, []),

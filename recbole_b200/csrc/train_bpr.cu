@@ -156,13 +156,19 @@ struct Tables {
 };
 
 __device__ __forceinline__ void bpr_sample(float x, float inv_b, float &loss_term, float &g) {
-  // loss.py:48   -log(gamma + sigmoid(x)) ;  d/dx = -sig*(1-sig)/(gamma+sig), times 1/B for the mean
-  // MUFU-based exp / log / reciprocal: ~1e-7 relative, two orders inside the 1e-5 parity tolerance; the
-  // optimizer arithmetic (common.cuh) keeps IEEE sqrt and division.
-  float e = __expf(-x);
-  float sig = __fdividef(1.f, 1.f + e);
-  float den = kGamma + sig;
-  loss_term = -__logf(den);
+  // loss.py:48   -log(gamma + sigmoid(x)) ;  d/dx = -sig*(1-sig)/(gamma+sig), times 1/B for the mean.
+  // For a trained model (x >> 0) the loss term log(den) ~ -(1 - den) and the factor (1 - sig) inherit the ABSOLUTE
+  // rounding of sig, in the reference too; what must not be added on top is an absolute error in the logarithm (the
+  // MUFU log2 has 2^-22: 1e-4 of the loss of a converged model) or a biased reciprocal.  So: correctly rounded
+  // reciprocal for sig, and near 1 the logarithm as 2 atanh((den - 1) / (den + 1)) -- den - 1 is exact, the series
+  // is RELATIVELY accurate (t^8 / 9 < 1e-7 for den in [0.75, 1.34]); __expf / __fdividef only where their error is
+  // relative to the quantity itself.
+  const float e = __expf(-x);
+  const float sig = __frcp_rn(1.f + e);
+  const float den = kGamma + sig;
+  const float t = __fdividef(den - 1.f, den + 1.f), t2 = t * t;
+  const float near1 = 2.f * t * fmaf(t2, fmaf(t2, fmaf(t2, 1.f / 7.f, 0.2f), 1.f / 3.f), 1.f);
+  loss_term = -((den > 0.75f) ? near1 : __logf(den));
   g = -inv_b * __fdividef(sig * (1.f - sig), den);
 }
 
@@ -580,7 +586,8 @@ int launch_step(Tables t, BprWs w, int64_t B, int64_t n_users, int64_t n_items, 
     ProfScope prof(RB2_ST_PLAN, st, 2);
     const float sb2 = sqrtf(o.beta2);
     k_lazy_catchup<D><<<blocks(B), kThreads, 0, st>>>(t.up, t.um, t.uv, t.ul, w.ukey_s, B, n_users, o, sb2);
-    k_lazy_catchup<D><<<blocks(2 * B), kThreads, 0, st>>>(t.ip, t.im, t.iv, t.il, w.ikey_s, 2 * B, n_items, o, sb2);
+    if (!t.ig)
+      k_lazy_catchup<D><<<blocks(2 * B), kThreads, 0, st>>>(t.ip, t.im, t.iv, t.il, w.ikey_s, 2 * B, n_items, o, sb2);
   }
   {
     ProfScope prof(RB2_ST_USER_SIDE, st);
@@ -784,11 +791,14 @@ static int bpr_step_impl(float *user_p, float *user_m, float *user_v, int32_t *u
     ProfScope prof(RB2_ST_KEYS, st);
     k_make_keys<<<(unsigned)((batch + 255) / 256), 256, 0, st>>>(user, pos, neg, batch, n_users, n_items, w);
   }
-  // with item_grad_out the item rows are read as they are (a compact table fetched from their owners,
-  // already brought up to date there), so the lazy catch-up only concerns the user side
-  const bool lazy = o.kind == RB2_OPT_ADAM_LAZY && !item_grad_out;
-  RB2_REQUIRE(!(o.kind == RB2_OPT_ADAM_LAZY && item_grad_out), RB2_EINVAL,
-              "rb2_bpr_train_step_sharded: adam_lazy is not available on the sharded path");
+  // with item_grad_out the item rows are read as they are (the all-gathered table).  RB2_OPT_ADAM_LAZY there: the user
+  // rows are caught up here; the owners keep their item shards current with the dense zero-gradient step of
+  // rb2_dense_rows_update, so the gathered rows already are what dense Adam holds.  The planned (sparse, all-to-all)
+  // exchange fetches rows nobody caught up: refused.
+  const bool lazy = o.kind == RB2_OPT_ADAM_LAZY;
+  RB2_REQUIRE(!(lazy && pre_ikey_s), RB2_EINVAL,
+              "rb2_bpr_train_step_sharded: adam_lazy is not available with an item plan (sparse exchange); use the "
+              "dense or the peer-memory exchange");
   RB2_DISPATCH_DIM(dim, {
     int rc = lazy ? launch_step<D_, true>(t, w, batch, n_users, n_items, o, loss_out, loss_accum, st, global_batch,
                                           pre_ikey_s, pre_ival_s, rows_ready)
@@ -886,14 +896,19 @@ __global__ void k_rows_keys(const int64_t *__restrict__ ids, int64_t M, int64_t 
 }  // namespace
 
 namespace {
-template <int D>
+template <int D, bool DENSE>
 __global__ void __launch_bounds__(kThreads) k_dense_rows_update(float *P, float *M, float *V, int64_t rows,
                                                                  const float *__restrict__ grads,
                                                                  const int32_t *__restrict__ touched, OptScalars o) {
   constexpr int LANES = RowCfg<D>::LANES;
   const int lane = threadIdx.x % LANES;
+  const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x % 32) / LANES * LANES));
   int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
-  if (row >= rows || touched[row] <= 0) return;
+  if (row >= rows) return;
+  if (touched[row] <= 0) {
+    if (DENSE) row_zero_grad_step<D>(P, M, V, row, lane, gmask, o);     // RB2_OPT_ADAM_LAZY: dense Adam moves it too
+    return;
+  }
   Row<D> p = row_ld<D>(P, row, lane);
   Row<D> g = row_ldg<D>(grads, row, lane);
   row_update<D>(P, M, V, row, lane, p, g, o);
@@ -907,7 +922,7 @@ extern "C" int rb2_dense_rows_update(float *p, float *m, float *v, int64_t n_row
                                      const int32_t *touched, const rb2_optim *h_opt, void *stream) {
   RB2_REQUIRE(p && grads && touched && h_opt, RB2_EINVAL, "rb2_dense_rows_update: null argument");
   OptScalars o = rb2_opt_scalars(h_opt);
-  RB2_REQUIRE(o.kind == RB2_OPT_SGD || o.kind == RB2_OPT_ADAM, RB2_EINVAL,
+  RB2_REQUIRE(o.kind == RB2_OPT_SGD || o.kind == RB2_OPT_ADAM || o.kind == RB2_OPT_ADAM_LAZY, RB2_EINVAL,
               "rb2_dense_rows_update: optimizer kind %d not supported here", o.kind);
   if (o.kind != RB2_OPT_SGD) RB2_REQUIRE(m && v, RB2_EINVAL, "rb2_dense_rows_update: Adam needs m and v");
   if (n_rows <= 0) return 0;
@@ -916,7 +931,8 @@ extern "C" int rb2_dense_rows_update(float *p, float *m, float *v, int64_t n_row
   RB2_DISPATCH_DIM(dim, {
     constexpr int LANES = RowCfg<D_>::LANES;
     unsigned blocks = (unsigned)((n_rows * LANES + kThreads - 1) / kThreads);
-    k_dense_rows_update<D_><<<blocks, kThreads, 0, st>>>(p, m, v, n_rows, grads, touched, o);
+    if (o.kind == RB2_OPT_ADAM_LAZY) k_dense_rows_update<D_, true><<<blocks, kThreads, 0, st>>>(p, m, v, n_rows, grads, touched, o);
+    else k_dense_rows_update<D_, false><<<blocks, kThreads, 0, st>>>(p, m, v, n_rows, grads, touched, o);
   });
   RB2_CUDA(cudaGetLastError());
   return 0;
@@ -1035,7 +1051,7 @@ extern "C" int rb2_bpr_train_step_p2p(float *user_p, float *user_m, float *user_
                                       const rb2_optim *h_opt, const rb2_peers *h_peers, float *item_cache,
                                       float *loss_out, double *loss_accum, void *workspace, size_t workspace_bytes,
                                       void *stream, int32_t prepared, const int64_t *next_user,
-                                      const int64_t *next_pos, const int64_t *next_neg) {
+                                      const int64_t *next_pos, const int64_t *next_neg, int32_t *user_last) {
   RB2_REQUIRE(user_p && user && pos && neg && h_opt && h_peers && item_cache && loss_out && workspace, RB2_EINVAL,
               "rb2_bpr_train_step_p2p: null argument");
   RB2_REQUIRE((next_user != nullptr) == (next_pos != nullptr) && (next_user != nullptr) == (next_neg != nullptr),
@@ -1050,8 +1066,15 @@ extern "C" int rb2_bpr_train_step_p2p(float *user_p, float *user_m, float *user_
   RB2_REQUIRE(n_users_local > 0 && n_items > 0 && n_users_local < ((int64_t)1 << 32) - 1 && n_items < ((int64_t)1 << 31),
               RB2_EINVAL, "rb2_bpr_train_step_p2p: table sizes must fit 32 / 31 bits");
   OptScalars o = rb2_opt_scalars(h_opt);
-  RB2_REQUIRE(o.kind == RB2_OPT_SGD || o.kind == RB2_OPT_ADAM, RB2_EINVAL,
-              "rb2_bpr_train_step_p2p: optimizer kind %d not supported (sgd, adam)", o.kind);
+  RB2_REQUIRE(o.kind == RB2_OPT_SGD || o.kind == RB2_OPT_ADAM || o.kind == RB2_OPT_ADAM_LAZY, RB2_EINVAL,
+              "rb2_bpr_train_step_p2p: optimizer kind %d not supported (sgd, adam, adam_lazy)", o.kind);
+  // RB2_OPT_ADAM_LAZY = the trajectory of the reference's dense Adam: the (local) user rows of the batch are caught
+  // up once per row before the step (k_lazy_catchup, user_last), the owner takes the zero-gradient step of every
+  // untouched row of its item shard (k_owner_update<DENSE>)
+  const bool lazy = o.kind == RB2_OPT_ADAM_LAZY;
+  if (lazy)
+    RB2_REQUIRE(user_last && o.lazy_step_size && o.lazy_bc2_sqrt, RB2_EINVAL,
+                "rb2_bpr_train_step_p2p: RB2_OPT_ADAM_LAZY needs user_last and the lazy tables");
   if (o.kind != RB2_OPT_SGD)
     RB2_REQUIRE(user_m && user_v && item_m && item_v, RB2_EINVAL, "rb2_bpr_train_step_p2p: Adam needs m and v");
   RB2_REQUIRE(hp.seq >= 1 && hp.seq < ((int64_t)1 << 31), RB2_EINVAL,
@@ -1131,8 +1154,11 @@ extern "C" int rb2_bpr_train_step_p2p(float *user_p, float *user_m, float *user_
     const int64_t ntu = (B + Tu - 1) / Tu, nti = (2 * B + Ti - 1) / Ti;
     auto blocks = [](int64_t groups) { return (unsigned)((groups * LANES + kThreads - 1) / kThreads); };
     {
-      ProfScope prof(RB2_ST_PLAN, st, 1);
+      ProfScope prof(RB2_ST_PLAN, st, lazy ? 2 : 1);
       k_plan_p2p<D_><<<(unsigned)((2 * B + 255) / 256), 256, 0, st>>>(w, pt, 2 * B);
+      if (lazy)
+        k_lazy_catchup<D_><<<blocks(B), kThreads, 0, st>>>(user_p, user_m, user_v, user_last, w.ukey_s, B,
+                                                           n_users_local, o, sqrtf(o.beta2));
     }
     {
       ProfScope prof(RB2_ST_FETCH, st, 1);
@@ -1189,8 +1215,10 @@ extern "C" int rb2_bpr_train_step_p2p(float *user_p, float *user_m, float *user_
     }
     {
       ProfScope prof(RB2_ST_OWNER, st, 2);
-      if (n_local > 0)
-        k_owner_update<D_><<<blocks(n_local), kThreads, 0, st>>>(item_local, item_m, item_v, pt, n_local, o);
+      if (n_local > 0) {
+        if (lazy) k_owner_update<D_, true><<<blocks(n_local), kThreads, 0, st>>>(item_local, item_m, item_v, pt, n_local, o);
+        else k_owner_update<D_, false><<<blocks(n_local), kThreads, 0, st>>>(item_local, item_m, item_v, pt, n_local, o);
+      }
       // signal half of the NEXT step's barrier A: my rows are up to date, peers may read them and reuse my slots
       k_peer_barrier<<<1, 32, 0, st>>>(ps, seq + 1u, 0, kBarSignal, nullptr, 0.0, nullptr, nullptr, w.hdr,
                                        timeout_ns);

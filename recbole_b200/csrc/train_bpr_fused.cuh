@@ -617,12 +617,34 @@ __global__ void k_loss_sum(const double *__restrict__ part, int64_t n, double *o
   if (threadIdx.x == 0) out[0] = sm[0];
 }
 
-// owner side: a local row takes one step with the sum (fixed sender order) of the slots stamped with this step
+// owner side: a local row takes one step with the sum (fixed sender order) of the slots stamped with this step.
+// DENSE (RB2_OPT_ADAM_LAZY on the sharded paths): the reference's dense Adam also moves the rows nobody touched (their
+// exp_avg keeps decaying into the parameter); an owner's shard is small enough (n_items / world rows) to simply take
+// that zero-gradient step for every row with non-zero moments, so item rows are always current and need no `last`.
 template <int D>
+__device__ __forceinline__ void row_zero_grad_step(float *P, float *M, float *V, int64_t row, int lane, unsigned gmask,
+                                                   const OptScalars &o) {
+  Row<D> m = row_ld<D>(M, row, lane), v = row_ld<D>(V, row, lane);
+  bool nz = o.wd != 0.f;
+#pragma unroll
+  for (int i = 0; i < RowCfg<D>::VPL; ++i)
+    nz |= (m.v[i].x != 0.f) | (m.v[i].y != 0.f) | (m.v[i].z != 0.f) | (m.v[i].w != 0.f) | (v.v[i].x != 0.f) |
+          (v.v[i].y != 0.f) | (v.v[i].z != 0.f) | (v.v[i].w != 0.f);
+  if (!(__ballot_sync(gmask, nz) & gmask)) return;       // never stepped: zero moments, the row does not move
+  Row<D> p = row_ld<D>(P, row, lane);
+  const Row<D> g = row_zero<D>();
+  row_step_regs<D>(p, m, v, g, o);
+  row_st<D>(P, row, lane, p);
+  row_st<D>(M, row, lane, m);
+  row_st<D>(V, row, lane, v);
+}
+
+template <int D, bool DENSE>
 __global__ void __launch_bounds__(kThreads) k_owner_update(float *P, float *M, float *V, PeerTable pt, int64_t n_local,
                                                             OptScalars o) {
   constexpr int LANES = RowCfg<D>::LANES;
   const int lane = threadIdx.x % LANES;
+  const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x % 32) / LANES * LANES));
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
   if (row >= n_local) return;
   const int32_t *__restrict__ stp = pt.stamp[pt.me];
@@ -635,7 +657,10 @@ __global__ void __launch_bounds__(kThreads) k_owner_update(float *P, float *M, f
     on[s] = s < pt.world && stp[(int64_t)s * pt.i_block + row] == pt.step;
     any |= on[s];
   }
-  if (!any) return;
+  if (!any) {
+    if (DENSE) row_zero_grad_step<D>(P, M, V, row, lane, gmask, o);
+    return;
+  }
 #pragma unroll
   for (int s = 0; s < RB2_MAX_PEERS; ++s)
     if (on[s]) part[s] = row_ld<D>(G, (int64_t)s * pt.i_block + row, lane);

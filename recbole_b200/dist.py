@@ -243,17 +243,39 @@ class ShardedBPR:
             ws.check_flags()
 
     def build_optimizer(self, kind="adam", lr=1e-3, weight_decay=0.0):
-        if kind not in ("adam", "sgd"):
-            raise ValueError("the sharded path implements learner in {adam, sgd}")
+        """'adam' (row-sparse), 'sgd', or 'adam_lazy' = the trajectory of the reference's DENSE torch.optim.Adam
+        (trainer.py:116,173) on the peer-memory and the dense exchange: the batch's (local) user rows replay the steps
+        they missed, every owner takes the zero-gradient step of the untouched rows of its item shard."""
+        if kind not in ("adam", "sgd", "adam_lazy"):
+            raise ValueError("the sharded path implements learner in {adam, adam_lazy, sgd}")
+        if kind == "adam_lazy" and self.comm.world > 1 and self.exchange == "sparse":
+            raise ValueError("adam_lazy is not available on the sparse (all-to-all) exchange: rows are fetched before "
+                             "their owner could bring them up to date; use exchange='p2p' or 'dense'")
         self.optim = self.ops.Optim(kind, lr, weight_decay)
         if kind != "sgd":
             z = torch.zeros_like
             self.state = dict(mU=z(self.U), vU=z(self.U), mV=z(self.V), vV=z(self.V))
+        if kind == "adam_lazy":
+            self.state["lastU"] = torch.zeros(self.U.shape[0], dtype=torch.int32, device=self.device)
+            if self.comm.world == 1 and self.exchange != "p2p":      # the single-GPU step keeps `last` for items too
+                self.state["lastV"] = torch.zeros(self.V.shape[0], dtype=torch.int32, device=self.device)
+
+    def flush(self):
+        """adam_lazy: bring every local row to the current step (before the tables are read: evaluation, checkpoints).
+        Item shards are always current on the sharded exchanges (the owner steps every row)."""
+        o = self.optim
+        if o is None or o.kind_name != "adam_lazy" or o.step == 0:
+            return
+        st = self.state
+        self.ops.adam_lazy_flush(self.U, st["mU"], st["vU"], st["lastU"], o)
+        if "lastV" in st:
+            self.ops.adam_lazy_flush(self.V, st["mV"], st["vV"], st["lastV"], o)
 
     # ---- checkpoint interop (trainer.py:191-232; SURVEY 8f-4) ------------------------------------------
     def state_dict(self):
         """The reference's parameter names with the FULL tables (every rank gets the same dict; the user table is
         all-gathered: 5 GB at cfg3 -- save from one rank)."""
+        self.flush()
         U = self.comm.all_gather_equal(self.U)
         V = self.comm.all_gather_equal(self.V)
         # blocks are padded to equal size: rank r's rows sit at [r * block, r * block + its count)
@@ -275,6 +297,7 @@ class ShardedBPR:
         (what `Trainer._save_checkpoint` stores, trainer.py:198-206)."""
         o = self.optim
         state = {}
+        self.flush()
         if o.kind_name != "sgd":
             step = torch.tensor(float(o.step))
             g = lambda t, b, blk: self._unpad(self.comm.all_gather_equal(t), b, blk)   # noqa: E731
@@ -295,6 +318,9 @@ class ShardedBPR:
                                         ("mV", 1, "exp_avg", self.i_lo, self.i_hi), ("vV", 1, "exp_avg_sq", self.i_lo, self.i_hi)):
                 self.state[k].zero_()
                 self.state[k][: hi - lo] = sd["state"][idx][key][lo:hi].to(self.device)
+            for k in ("lastU", "lastV"):          # a loaded state is current at its step
+                if k in self.state:
+                    self.state[k].fill_(o.step)
 
     @staticmethod
     def _unpad(full, bounds, block):
@@ -482,6 +508,7 @@ class ShardedBPR:
 
     # ---- evaluation ------------------------------------------------------------------------------------
     def gather_user_table(self):
+        self.flush()
         return self.comm.all_gather_equal(self.U)
 
     @torch.no_grad()
@@ -498,6 +525,7 @@ class ShardedBPR:
         """
         ops, comm = self.ops, self.comm
         K = evaluator.max_k
+        self.flush()
         if layout == "auto":
             layout = "replicate" if self.n_items * self.dim * 4 <= (8 << 30) else "sharded"
         if layout == "replicate":

@@ -240,7 +240,8 @@ def bpr_train_step_p2p(U, state, arena, user, user_base, pos, neg, n_items, glob
         _ptr(state.get("mV"), f32, True), _ptr(state.get("vV"), f32, True), U.shape[0], int(n_items), U.shape[1],
         _ptr(user, i64), int(user_base), _ptr(pos, i64), _ptr(neg, i64), user.numel(), int(global_batch),
         ctypes.byref(o), ctypes.byref(arena.peers), _ptr(arena.cache, f32), _ptr(loss_out, f32),
-        _ptr(loss_accum, torch.float64, True), ws.ptr(), ws.nbytes, _stream(), prepared, *nxt))
+        _ptr(loss_accum, torch.float64, True), ws.ptr(), ws.nbytes, _stream(), prepared, *nxt,
+        _ptr(state.get("lastU"), torch.int32, True)))
     arena.prepared_for = key_next
 
 

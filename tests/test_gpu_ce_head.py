@@ -75,6 +75,17 @@ def test_ce_head_tensor_core_vs_fp32_kernel_at_cfg4_size(scale):
     rel = ((a["lse"] - b["lse"]).abs() / b["lse"].abs()).max().item()
     assert rel < 1e-5, rel
     assert abs(a["loss"].item() - b["loss"].item()) <= 1e-5 * abs(b["loss"].item())
+    # a random subset of the rows against the ORACLE at full item count: top-k bit-exact, logsumexp within 1e-5
+    rows = np.sort(np.random.default_rng(7).choice(nq, 32, replace=False))
+    Xc, Ec, tc_ = X.cpu().numpy()[rows], E.cpu().numpy(), tgt.cpu().numpy()[rows]
+    o_ids, o_sc = oce.full_sort_topk(Xc, Ec, 10)
+    np.testing.assert_array_equal(a["ids"].cpu().numpy()[rows], o_ids)
+    np.testing.assert_array_equal(a["scores"].cpu().numpy()[rows], o_sc)
+    L = Xc.astype(np.float64) @ Ec.astype(np.float64).T
+    mx = L.max(axis=1)
+    lse64 = mx + np.log(np.exp(L - mx[:, None]).sum(axis=1))
+    got = a["lse"].cpu().numpy()[rows].astype(np.float64)
+    assert np.abs(got - lse64).max() <= 1e-5 * np.abs(lse64).max() and (np.abs(got - lse64) <= 1e-5 * np.abs(lse64) + 1e-6).all()
     ops.ce_head(X[:8], E[:100], tgt[:8] % 100, 10, scorer="auto")   # leaves the knob at its default
 
 

@@ -22,13 +22,19 @@ def _case(seed=0, n_users=400, n_items=301, d=64, B=3000, steps=2):
     return U0, V0, batches, pairs
 
 
+def _case_for(kind):
+    # adam_lazy (dense-Adam trajectory): small batches over several steps, so that most rows are NOT touched in a step
+    # and keep moving on their momentum
+    return _case(B=150, steps=5) if kind == "adam_lazy" else _case()
+
+
 def _rank_fn(rank, world, kind, mode, exchange):
     from oracle import fullsort as ofs
     from recbole_b200.dist import Comm, ShardedBPR, ShardedEvalIndex
     from recbole_b200.evaluator import FusedTopKEvaluator
     torch.cuda.set_device(0)
     dev = torch.device("cuda:0")
-    U0, V0, batches, pairs = _case()
+    U0, V0, batches, pairs = _case_for(kind)
     n_users, n_items, d = U0.shape[0], V0.shape[0], U0.shape[1]
     comm = Comm(staged=True)
     m = ShardedBPR(n_users, n_items, d, comm, dev, U_full=U0, V_full=V0, exchange=exchange)
@@ -40,6 +46,7 @@ def _rank_fn(rank, world, kind, mode, exchange):
         lo = m.train_step(t(u), t(p), t(n), global_batch=len(u))
         losses.append(float(lo.item()))
     m.check_flags()
+    m.flush()
     if exchange == "p2p":
         comm.barrier()          # peers may still be reading this rank's shard through their mappings
 
@@ -60,22 +67,33 @@ def _rank_fn(rank, world, kind, mode, exchange):
 
 @pytest.mark.parametrize("kind,mode,exchange", [("adam", "tc", "sparse"), ("sgd", "fp32", "sparse"),
                                                 ("adam", "fp32", "dense"), ("sgd", "tc", "dense"),
-                                                ("adam", "fp32", "p2p"), ("sgd", "tc", "p2p")])
+                                                ("adam", "fp32", "p2p"), ("sgd", "tc", "p2p"),
+                                                ("adam_lazy", "fp32", "p2p"), ("adam_lazy", "tc", "dense")])
 def test_two_ranks_equal_single_device_oracle(kind, mode, exchange):
+    """(adam_lazy: the oracle runs DENSE Adam -- every row moves at every step -- on the union batch.)"""
     from oracle import bpr as obpr
     from oracle import fullsort as ofs
     out = run_ranks(_rank_fn, 2, kind, mode, exchange, timeout=300)
-    U0, V0, batches, pairs = _case()
+    U0, V0, batches, pairs = _case_for(kind)
     st = obpr.new_state(U0, V0)
     lr = 0.05 if kind == "sgd" else 2e-3
     for s, (u, p, n) in enumerate(batches):
-        lo = obpr.bpr_train_step(st, u, p, n, s + 1, optimizer=kind, lr=lr, dense=False)
+        lo = obpr.bpr_train_step(st, u, p, n, s + 1, optimizer="sgd" if kind == "sgd" else "adam", lr=lr,
+                                 dense=(kind == "adam_lazy"))
         for r in range(2):
             assert abs(out[r]["losses"][s] - lo) <= 1e-5 * abs(lo)
     U = np.concatenate([out[0]["U"], out[1]["U"]])
     V = np.concatenate([out[0]["V"], out[1]["V"]])
-    assert np.abs(U - st["U"]).max() <= 1e-5 * np.abs(st["U"]).max()
-    assert np.abs(V - st["V"]).max() <= 1e-5 * np.abs(st["V"]).max()
+    for got_t, want_t in ((U, st["U"]), (V, st["V"])):
+        diff = np.abs(got_t - want_t)
+        bad = diff > 1e-5 * np.abs(want_t).max()
+        if kind == "adam_lazy":
+            # eps-conditioned elements: a gradient element of ~1e-8 (|g| ~ eps) is known to ~1e-3 relative only (fp32
+            # summation order), and Adam's normalised step lr * g / (|g| + eps) turns that into ~1e-3 of a full step,
+            # again at every zero-gradient step that follows; a handful of the 45 000 elements, bounded by 2e-4
+            assert bad.sum() <= 3 and diff.max() <= 2e-4, (int(bad.sum()), float(diff.max()))
+        else:
+            assert not bad.any(), float(diff.max())
     # evaluation on the tables the ranks actually hold (so that ids can be compared bit for bit)
     uid, hist, pos = ofs.eval_index(U0.shape[0], pairs, 2)
     o_ids, _ = ofs.full_sort_topk(U, V, uid, hist[0], hist[1], 10)

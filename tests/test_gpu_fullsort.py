@@ -340,6 +340,37 @@ def test_fullsort_tc_variants_agree_with_fp32_kernel_at_size(tc_variant, variant
     assert lib.rb2_fullsort_tc_last_fallback_rows() == 0
     ids_f, sc_f = ops.fullsort_topk(Q, None, V, 10, hp, hi, mode="fp32")
     assert torch.equal(ids_t, ids_f) and torch.equal(sc_t, sc_f)
+    # ... and a random subset of the rows against the ORACLE (all 300k items, the rows' own history lists)
+    rows = np.sort(np.random.default_rng(variant).choice(nq, 48, replace=False))
+    hi_c = hi.cpu().numpy().reshape(nq, h)[rows]
+    o_ids, o_sc = ofs.full_sort_topk(Q.cpu().numpy()[rows], V.cpu().numpy(), np.arange(len(rows)),
+                                     np.arange(0, h * len(rows) + 1, h, dtype=np.int64), hi_c.reshape(-1), 10)
+    np.testing.assert_array_equal(ids_t.cpu().numpy()[rows], o_ids)
+    np.testing.assert_array_equal(sc_t.cpu().numpy()[rows], o_sc)
+
+
+def test_fullsort_tc_vs_oracle_on_row_subset_at_cfg3_item_count():
+    """BASELINE config 3's item side (2,000,001 x 128) against 16 384 query rows with 40 history items each: the
+    tensor-core scorer's ids and canonical scores for 32 random rows equal the oracle's bit for bit (the oracle scores
+    those rows against all 2 M items on the CPU)."""
+    from recbole_b200 import ops
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(11)
+    nq, N, d, h = 16384, 2_000_001, 128, 40
+    Q = torch.randn(nq, d, device=dev, generator=gen) * 0.1
+    V = torch.randn(N, d, device=dev, generator=gen) * 0.1
+    hp = torch.arange(0, h * nq + 1, h, device=dev, dtype=torch.int64)
+    hi = torch.sort(torch.randint(1, N, (nq, h), device=dev, generator=gen), dim=1).values.reshape(-1).contiguous()
+    st = ops.ScorerState()
+    ids_t, sc_t = ops.fullsort_topk(Q, None, V, 10, hp, hi, mode="tc", state=st)
+    assert st.last_fallback_rows == 0
+    rows = np.sort(np.random.default_rng(3).choice(nq, 32, replace=False))
+    hi_c = hi.cpu().numpy().reshape(nq, h)[rows]
+    o_ids, o_sc = ofs.full_sort_topk(Q.cpu().numpy()[rows], V.cpu().numpy(), np.arange(len(rows)),
+                                     np.arange(0, h * len(rows) + 1, h, dtype=np.int64), hi_c.reshape(-1), 10)
+    np.testing.assert_array_equal(ids_t.cpu().numpy()[rows], o_ids)
+    np.testing.assert_array_equal(sc_t.cpu().numpy()[rows], o_sc)
 
 
 def test_fullsort_tc_cascade_and_adaptive_first_pass(tc_variant):

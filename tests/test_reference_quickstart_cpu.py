@@ -115,6 +115,25 @@ assert sorted(model.state_dict()) == ["first_order_linear.bias", "first_order_li
 batch = next(iter(train_data))
 ids = model._ids(batch)
 assert ids.shape == (len(batch), model.num_feature_field) and batch[model.LABEL].dtype == torch.float32
+# TOKEN_SEQ fields: the reference's own loader of token_seq columns fails under this image's pandas (a length check
+# in dataset.py's _remap), so the field set is described by a stub dataset; the reference's FM is built on the same stub
+from recbole.model.context_aware_recommender.fm import FM
+from recbole.utils import FeatureType
+class _DS:
+    field2type = {{"user_id": FeatureType.TOKEN, "item_id": FeatureType.TOKEN, "age": FeatureType.FLOAT,
+                  "class": FeatureType.TOKEN_SEQ, "tags": FeatureType.TOKEN_SEQ, "label": FeatureType.FLOAT}}
+    _num = {{"user_id": 944, "item_id": 1683, "age": 1, "class": 20, "tags": 300, "label": 1}}
+    def fields(self): return list(self._num)
+    def num(self, f): return self._num[f]
+class _Cfg(dict):
+    def __getitem__(self, k): return self.get(k)
+cfg3 = _Cfg(LABEL_FIELD="label", embedding_size=10, device="cpu")
+model3, ref3 = FusedFM(cfg3, _DS()), FM(cfg3, _DS())
+assert model3.token_seq_field_names == ["class", "tags"] and model3.n_seq == 2
+assert [(n, tuple(p.shape)) for n, p in ref3.named_parameters()] == [(n, tuple(p.shape)) for n, p in model3.named_parameters()]
+b3 = {{"user_id": torch.zeros(4, dtype=torch.int64), "item_id": torch.zeros(4, dtype=torch.int64),
+      "class": torch.zeros((4, 6), dtype=torch.int64), "tags": torch.zeros((4, 9), dtype=torch.int64)}}
+assert model3._ids(b3).shape == (4, 2 + 6 + 9)
 config2 = Config(model=FusedMFSimple, dataset="ml-100k",
                  config_dict={{"data_path": os.path.join(REF, "dataset"), "use_gpu": False,
                               "load_col": {{"inter": ["user_id", "item_id"]}}}})
