@@ -150,6 +150,20 @@ __device__ __forceinline__ void row_st(float *__restrict__ base, int64_t row, in
   for (int i = 0; i < RowCfg<D>::VPL; ++i) p[i * RowCfg<D>::LANES + lane] = r.v[i];
 }
 
+// acc += s * (a - b).  The user-row gradient g*vi - g*vj is formed this way: when vi == vj (pos == neg, or equal
+// elements) the reference's two products cancel EXACTLY, and so does this; two chained fmas would leave the rounding
+// error of g*vi behind (~1e-11), which Adam's normalised step lr * g / (|g| + eps) turns into ~1e-5 of a parameter.
+template <int D>
+__device__ __forceinline__ void row_fma_diff(Row<D> &acc, float s, const Row<D> &a, const Row<D> &b) {
+#pragma unroll
+  for (int i = 0; i < RowCfg<D>::VPL; ++i) {
+    acc.v[i].x = fmaf(s, a.v[i].x - b.v[i].x, acc.v[i].x);
+    acc.v[i].y = fmaf(s, a.v[i].y - b.v[i].y, acc.v[i].y);
+    acc.v[i].z = fmaf(s, a.v[i].z - b.v[i].z, acc.v[i].z);
+    acc.v[i].w = fmaf(s, a.v[i].w - b.v[i].w, acc.v[i].w);
+  }
+}
+
 // acc += s * a   (fused multiply-add per element)
 template <int D>
 __device__ __forceinline__ void row_fma(Row<D> &acc, float s, const Row<D> &a) {

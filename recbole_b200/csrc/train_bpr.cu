@@ -248,8 +248,7 @@ __global__ void __launch_bounds__(kThreads, LAZY ? 1 : (D <= 64 ? 3 : (D == 128 
       float lt, g;
       bpr_sample(x, inv_b, lt, g);
       loss_local += lt;
-      row_fma<D>(acc, g, a[j]);    // du += g*vi - g*vj
-      row_fma<D>(acc, -g, b[j]);
+      row_fma_diff<D>(acc, g, a[j], b[j]);    // du += g*(vi - vj)
       row_st<D>(w.gu, s[j], lane, row_scale<D>(g, u));  // dvi = g*u ; dvj = -g*u
     }
   }

@@ -263,8 +263,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_user_fused(Tables t, BprWs w, i
     float lt, g;
     bpr_sample(x, inv_b, lt, g);
     loss_local += lt;
-    row_fma<D>(acc, g, a);      // du += g*vi - g*vj
-    row_fma<D>(acc, -g, b);
+    row_fma_diff<D>(acc, g, a, b);      // du += g*(vi - vj)
     const Row<D> gu = row_scale<D>(g, u);          // dvi = g*u ; dvj = -g*u
     if (P2P) {
       const unsigned long long da = ptrs[i].z, db = ptrs[i].w;

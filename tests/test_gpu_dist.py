@@ -90,8 +90,9 @@ def test_two_ranks_equal_single_device_oracle(kind, mode, exchange):
         if kind == "adam_lazy":
             # eps-conditioned elements: a gradient element of ~1e-8 (|g| ~ eps) is known to ~1e-3 relative only (fp32
             # summation order), and Adam's normalised step lr * g / (|g| + eps) turns that into ~1e-3 of a full step,
-            # again at every zero-gradient step that follows; a handful of the 45 000 elements, bounded by 2e-4
-            assert bad.sum() <= 3 and diff.max() <= 2e-4, (int(bad.sum()), float(diff.max()))
+            # again at every zero-gradient step that follows.  (The samples with pos == neg in this random data have
+            # an EXACTLY zero user gradient in the reference; the kernels form g * (vi - vj) and keep it zero.)
+            assert bad.sum() <= 1 and diff.max() <= 2e-4, (int(bad.sum()), float(diff.max()))
         else:
             assert not bad.any(), float(diff.max())
     # evaluation on the tables the ranks actually hold (so that ids can be compared bit for bit)
