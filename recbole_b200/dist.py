@@ -311,7 +311,8 @@ class ShardedBPR:
     def load_optimizer_state_dict(self, sd):
         o = self.optim
         grp = sd["param_groups"][0]
-        o.lr, o.weight_decay = grp["lr"], grp["weight_decay"]
+        o.set_hyper(lr=grp["lr"], weight_decay=grp["weight_decay"], betas=tuple(grp.get("betas", o.betas)),
+                    eps=grp.get("eps", o.eps))          # (drops adam_lazy's bias-correction tables of the old lr)
         if sd["state"]:
             o.step = int(sd["state"][0]["step"])
             for k, idx, key, lo, hi in (("mU", 0, "exp_avg", self.u_lo, self.u_hi), ("vU", 0, "exp_avg_sq", self.u_lo, self.u_hi),
