@@ -321,3 +321,37 @@ def test_trained_tables_loss_and_step_vs_oracle(kind):
     for a, b in ((U, st_o["U"]), (V, st_o["V"])):
         assert rel_err(a.cpu().numpy(), b) < TOL
         assert elem_rel_err(a.cpu().numpy(), b) < 10 * TOL
+
+
+@pytest.mark.parametrize("dim", [64, 128])
+def test_adam_lazy_long_gaps_vs_dense_oracle(dim):
+    """30 steps of small batches: most rows are untouched for many steps in a row, so every catch-up path runs --
+    short gaps replayed in registers inside the fused user-side kernel (user rows, single items), long gaps and repeated
+    items in the separate catch-up pass, the final flush -- against the oracle's DENSE Adam (every row at every step)."""
+    from recbole_b200 import ops
+    from gpu_util import adam_state, t
+    rng = np.random.default_rng(dim)
+    n_users, n_items, B, steps = 900, 700, 96, 30
+    U0 = (rng.standard_normal((n_users, dim)) * 0.3).astype(np.float32)
+    V0 = (rng.standard_normal((n_items, dim)) * 0.3).astype(np.float32)
+    st_o = obpr.new_state(U0, V0)
+    U, V = t(U0), t(V0)
+    st = adam_state(U, V, lazy=True)
+    opt = ops.Optim("adam_lazy", lr=2e-3)
+    loss = torch.zeros(1, device=U.device)
+    ws = ops.bpr_workspace(B, dim, U.device)
+    for s in range(steps):
+        u, p = rng.integers(1, n_users, B), rng.integers(1, n_items, B)
+        n = (p + rng.integers(1, n_items - 1, B) - 1) % (n_items - 1) + 1          # never equal to p
+        p[: B // 4] = p[0]                                                          # a repeated item in every batch
+        n = np.where(n == p, n % (n_items - 1) + 1, n)
+        ops.bpr_train_step(U, V, st, t(u), t(p), t(n), opt, loss, None, ws)
+        lo = obpr.bpr_train_step(st_o, u, p, n, s + 1, optimizer="adam", lr=2e-3, dense=True)
+        assert abs(float(loss.item()) - lo) <= TOL * abs(lo), (s, float(loss.item()), lo)
+    ops.adam_lazy_flush(U, st["mU"], st["vU"], st["lastU"], opt)
+    ops.adam_lazy_flush(V, st["mV"], st["vV"], st["lastV"], opt)
+    ws.check_flags()
+    for got, want in ((U, st_o["U"]), (V, st_o["V"]), (st["mU"], st_o["mU"]), (st["vV"], st_o["vV"])):
+        d = np.abs(got.cpu().numpy() - want)
+        bad = d > TOL * np.abs(want).max()
+        assert bad.sum() <= 2 and d.max() <= 20 * TOL * np.abs(want).max(), (int(bad.sum()), float(d.max()))
