@@ -209,7 +209,10 @@ int rb2_bpr_loss(const float *user_p, const float *item_p, int64_t n_users, int6
  * [user_base, user_base + n_users_local) of the user table; pos / neg are global item ids.  item_m / item_v: Adam moments of the local shard.
  * next_user / next_pos / next_neg (all NULL, or the ids of the batch the NEXT call will train on, same batch size): their
  * keys and sorts are computed into the workspace's other batch slot while this call waits for its peers in barrier B;
- * the next call then passes prepared = 1 (same workspace, same ids) and skips that work.
+ * the next call then passes prepared = 1 (same workspace, same ids) and skips that work.  That work is issued on a
+ * side stream owned by the library (one per device and caller stream) right after this rank's barrier-B signal, so it
+ * also overlaps the owner update and barrier A; the next call on the same caller stream waits for it.  Keep the
+ * workspace and the next_* id arrays alive (and unchanged) until that next call, or synchronise the device first.
  * item_cache: fp32 [world * item_block, dim] scratch.  A barrier that waits longer than 30 s gives up
  * and sets the workspace's peer_timeout flag (second int32 of the workspace) instead of hanging.
  * RB2_OPT_ADAM_LAZY (the trajectory of the reference's DENSE torch.optim.Adam, trainer.py:116,173): user_last =

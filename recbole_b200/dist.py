@@ -239,8 +239,19 @@ class ShardedBPR:
 
     def check_flags(self):
         """Raise for sticky device-side errors (id out of range, peer barrier timeout); synchronises."""
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)      # (also drains the library's side stream of the peer-memory step)
         for ws in list(self._ws.values()) + ([self._p2p_ws[1]] if self._p2p_ws else []):
             ws.check_flags()
+
+    def __del__(self):
+        # the peer-memory step may have left the next batch's sorts running on the library's side stream: they write
+        # into this model's workspace, which must not go back to the allocator before they are done
+        try:
+            if getattr(self, "_p2p_ws", None) is not None and self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
+        except Exception:
+            pass
 
     def build_optimizer(self, kind="adam", lr=1e-3, weight_decay=0.0):
         """'adam' (row-sparse), 'sgd', or 'adam_lazy' = the trajectory of the reference's DENSE torch.optim.Adam
@@ -394,6 +405,9 @@ class ShardedBPR:
         if self.exchange == "p2p":
             self.last_exchange = "p2p"
             if self._p2p_ws is None or self._p2p_ws[0] < B:
+                if self._p2p_ws is not None:
+                    # the library's side stream may still be sorting the next batch's keys into the old workspace
+                    torch.cuda.synchronize(self.device)
                 self._p2p_ws = (B, ops.bpr_p2p_workspace(B, self.dim, self.device))
             # next_batch: its keys and sorts are computed inside this call, while it waits for the slower peers;
             # only sound when those id tensors are complete already (resident batches: ids_ready)
