@@ -128,3 +128,31 @@ def test_sharded_checkpoint_interop_world2():
 
 def test_sharded_checkpoint_interop_world3():
     assert run_ranks(_ckpt_rank, 3) == [True, True, True]
+
+
+def _lazy_rank(rank, world):
+    """adam_lazy on the sharded model: the exchanges that can keep item rows current accept it (and get a `last` array
+    for the local user rows only), the sparse all-to-all exchange refuses it; an optimizer state loaded from a
+    checkpoint counts as current at its step."""
+    import pytest
+    from recbole_b200.dist import Comm, ShardedBPR
+    comm = Comm()
+    dev = torch.device("cpu")
+    m = ShardedBPR(90, 70, 16, comm, dev, exchange="dense")
+    m.build_optimizer("adam_lazy", lr=1e-3)
+    assert m.state["lastU"].shape == (m.U.shape[0],) and m.state["lastU"].dtype == torch.int32 and "lastV" not in m.state
+    sd = m.optimizer_state_dict()             # nothing stepped yet: flush() is a no-op, the gathers run over gloo
+    assert sd["fused_kind"] == "adam_lazy" and tuple(sd["state"][1]["exp_avg"].shape) == (70, 16)
+    sd["state"][0]["step"] = torch.tensor(7.0)
+    sd["param_groups"][0]["lr"] = 5e-4
+    m.load_optimizer_state_dict(sd)
+    assert m.optim.step == 7 and m.optim.lr == 5e-4 and int(m.state["lastU"].min()) == 7
+    s = ShardedBPR(90, 70, 16, comm, dev, exchange="sparse")
+    with pytest.raises(ValueError, match="sparse"):
+        s.build_optimizer("adam_lazy")
+    s.build_optimizer("adam")
+    return True
+
+
+def test_sharded_adam_lazy_host_logic_world2():
+    assert run_ranks(_lazy_rank, 2) == [True, True]
