@@ -140,3 +140,64 @@ def test_bench_reference_arm_cfg4_prints_one_json_line():
               "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+
+
+def test_fused_fm_token_seq_host_layout_cpu():
+    """FusedFM with TOKEN + FLOAT + TOKEN_SEQ fields, host side only (no kernel runs on the CPU): the token table and the
+    sequence tables are views of ONE zero-padded row range, the state dict is compact and carries the reference's names,
+    and the per-batch column layout (offsets, column -> sequence field, column ranges) follows the padded lengths."""
+    import numpy as np
+    import torch
+    from recbole_b200 import FusedFM
+
+    class Cfg(dict):
+        def __getitem__(self, k):
+            return self.get(k)
+
+    class DS:
+        field2type = {"t0": "token", "t1": "token", "x0": "float", "q0": "token_seq", "q1": "token_seq", "label": "float"}
+        _num = {"t0": 30, "t1": 200, "x0": 1, "q0": 25, "q1": 7, "label": 1}
+
+        def fields(self):
+            return list(self._num)
+
+        def num(self, f):
+            return self._num[f]
+
+    m = FusedFM(Cfg(LABEL_FIELD="label", embedding_size=10, device="cpu"), DS())
+    assert (m.n_seq, m.n_float, m._dpad, m._tok_rows, m._seq_bases, m._all_rows) == (2, 1, 16, 230, [230, 255], 262)
+    w0 = m.token_seq_embedding_table[1].weight.detach().clone()
+    E, W = m._tables()
+    assert tuple(E.shape) == (262, 16) and tuple(W.shape) == (262,)
+    assert float(E[:, 10:].abs().max()) == 0.0                                   # the padding columns
+    assert torch.equal(E[255:262, :10], w0)                                      # values carried over ...
+    for p, base in ((m.token_embedding_table.embedding.weight, 0), (m.token_seq_embedding_table[0].weight, 230),
+                    (m.token_seq_embedding_table[1].weight, 255)):
+        assert p.data.data_ptr() == E.data_ptr() + 4 * 16 * base and p.data.stride(0) == 16      # ... and views now
+    E2, _ = m._tables()
+    assert E2.data_ptr() == E.data_ptr()                                          # stable: not rebuilt per call
+    sd = m.state_dict()
+    assert tuple(sd["token_seq_embedding_table.0.weight"].shape) == (25, 10)
+    assert sd["token_seq_embedding_table.0.weight"].is_contiguous()
+    assert tuple(sd["first_order_linear.token_seq_embedding_table.1.weight"].shape) == (7, 1)
+    B = 5
+    inter = {"t0": torch.zeros(B, dtype=torch.int64), "t1": torch.ones(B, dtype=torch.int64),
+             "x0": torch.rand(B), "q0": torch.zeros((B, 6), dtype=torch.int64),
+             "q1": torch.zeros((B, 3), dtype=torch.int64), "label": torch.zeros(B)}
+    ids, offsets, seq = m._batch(inter, train=True)
+    assert tuple(ids.shape) == (B, 2 + 6 + 3)
+    assert offsets.tolist() == [0, 30] + [230] * 6 + [255] * 3
+    assert seq["col_seq"].tolist() == [-1, -1] + [0] * 6 + [1] * 3 and seq["seq_start"].tolist() == [2, 8, 11]
+    assert seq["n_token_cols"] == 2 and seq["seq_row_base"] == 230
+    assert tuple(seq["pooled"].shape) == (B, 2, 16) and tuple(seq["coef"].shape) == (B, 2)
+    inter["q0"] = torch.zeros((B, 9), dtype=torch.int64)                          # another padded length: its own layout
+    ids2, offsets2, seq2 = m._batch(inter, train=False)
+    assert tuple(ids2.shape) == (B, 2 + 9 + 3) and seq2["seq_start"].tolist() == [2, 11, 14] and "pooled" not in seq2
+    # the optimizer-state entries follow the reference's parameter order (9 tensors)
+    m._state = dict(mE=torch.zeros_like(E), vE=torch.zeros_like(E), mW=torch.zeros_like(W), vW=torch.zeros_like(W),
+                    mEf=torch.zeros(1, 16), vEf=torch.zeros(1, 16), mWf=torch.zeros(1), vWf=torch.zeros(1))
+    m._bias3 = torch.zeros(3)
+    shapes = [tuple(a.shape) for a, _ in m._opt_entries()]
+    assert shapes == [(230, 10), (1, 10), (25, 10), (7, 10), (1,), (230,), (1,), (25,), (7,)]
+    assert [tuple(p.shape) for _, p in m.named_parameters()] == [(230, 10), (1, 10), (25, 10), (7, 10), (1,), (230, 1),
+                                                                  (1, 1), (25, 1), (7, 1)]
