@@ -81,15 +81,18 @@ static inline int rb2_bits_for(int64_t n) {
   return b;
 }
 
+// SM count of the CURRENT device (cached per device: a process may drive several)
 static inline int rb2_num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  constexpr int kMaxDev = 64;
+  static int cache[kMaxDev] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return 148;
+  if (!cache[dev]) {
+    int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    cache[dev] = n > 0 ? n : 148;
   }
-  return n;
+  return cache[dev];
 }
 
 static inline int rb2_pick_tile(int64_t n_occ, int lanes) {

@@ -142,6 +142,28 @@ def test_bench_reference_arm_cfg4_prints_one_json_line():
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
 
 
+def test_bench_reference_arm_default_workload_prints_one_json_line():
+    """The DEFAULT workload's reference arm (cfg3 shape, shrunk by --scale so that the CPU finishes in seconds): same
+    metric / unit / config keys as the GPU arm's line, full batches, e2e block with zero transfer bytes."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1", "--scale", "0.002", "--batch", "65536"], capture_output=True, text=True,
+                         timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "bpr_train_samples_per_s" and d["unit"] == "samples/s"
+    assert d["config"]["workload"] == "cfg3" and d["config"]["dim"] == 128 and d["higher_is_better"] is True
+    assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    assert d["eval"]["metric"] == "fullsort_eval_users_per_s" and d["eval"]["value"] > 0
+
+
 def test_fused_fm_token_seq_host_layout_cpu():
     """FusedFM with TOKEN + FLOAT + TOKEN_SEQ fields, host side only (no kernel runs on the CPU): the token table and the
     sequence tables are views of ONE zero-padded row range, the state dict is compact and carries the reference's names,
