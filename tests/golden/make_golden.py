@@ -11,6 +11,8 @@ modified or copied.  Every array saved here is an INPUT or an OUTPUT of referenc
   metrics.npz    recbole.evaluator.metrics.* on the known-answer case of
                  tests/metrics/test_topk_metrics.py:15-79 and on a random case
   bpr_steps.npz  recbole BPR + BPRLoss + torch.optim.Adam / SGD, 3 steps, duplicate ids in batch
+  bpr_gaps.npz   recbole BPR under dense Adam (with and without weight decay), 16 steps of small batches: most rows are
+                 untouched in most steps
   dot_steps.npz  the fork's MFSimple forward / BCELoss gradients (mfsimple.py:39-57)
   fullsort_small.npz / fullsort_ml100k.npz
                  Config -> create_dataset -> data_preparation -> GeneralFullDataLoader ->
@@ -133,6 +135,45 @@ def g_bpr(out):
         for s, inter in enumerate(ids):
             for k, v in inter.items():
                 d["d%d_%s%d" % (dim, k, s)] = v.numpy()
+    np.savez_compressed(out, **d)
+
+
+def g_bpr_gaps(out):
+    """The reference's BPR under dense torch.optim.Adam for 16 steps of SMALL batches: most rows are untouched in most
+    steps and keep moving on their momentum (and, with weight decay, on wd * p) -- the trajectory the fused 'adam_lazy'
+    kind replays (pins oracle.bpr's dense mode over long gaps)."""
+    from recbole.model.general_recommender.bpr import BPR
+    d = {}
+    n_users, n_items, B, dim, steps = 300, 200, 24, 64, 16
+    cfg = StubConfig(USER_ID_FIELD="user_id", ITEM_ID_FIELD="item_id", NEG_PREFIX="neg_", device="cpu", embedding_size=dim)
+    ds = StubDataset({"user_id": n_users, "item_id": n_items})
+    rng = np.random.default_rng(99)
+    ids = [dict(user_id=torch.from_numpy(rng.integers(1, n_users, B)), item_id=torch.from_numpy(rng.integers(1, n_items, B)),
+                neg_item_id=torch.from_numpy(rng.integers(1, n_items, B))) for _ in range(steps)]
+    for s, inter in enumerate(ids):
+        for k, v in inter.items():
+            d["%s%d" % (k, s)] = v.numpy()
+    for tag, wd in (("wd0", 0.0), ("wd", 1e-4)):
+        torch.manual_seed(77)
+        model = BPR(cfg, ds)
+        with torch.no_grad():
+            model.user_embedding.weight.mul_(4.0)
+            model.item_embedding.weight.mul_(4.0)
+        d[tag + "_U0"] = model.user_embedding.weight.detach().numpy().copy()
+        d[tag + "_V0"] = model.item_embedding.weight.detach().numpy().copy()
+        opt = torch.optim.Adam(model.parameters(), lr=5e-3, weight_decay=wd)      # trainer.py:115-116
+        for s, inter in enumerate(ids):
+            opt.zero_grad()
+            loss = model.calculate_loss(inter)
+            loss.backward()
+            opt.step()
+            d[tag + "_loss%d" % s] = np.float32(loss.item())
+        d[tag + "_UN"] = model.user_embedding.weight.detach().numpy().copy()
+        d[tag + "_VN"] = model.item_embedding.weight.detach().numpy().copy()
+        for nm, prm in (("U", model.user_embedding.weight), ("V", model.item_embedding.weight)):
+            d[tag + "_m" + nm] = opt.state[prm]["exp_avg"].numpy().copy()
+            d[tag + "_v" + nm] = opt.state[prm]["exp_avg_sq"].numpy().copy()
+    d["steps"] = np.int64(steps)
     np.savez_compressed(out, **d)
 
 
@@ -618,6 +659,7 @@ if __name__ == "__main__":
     o = lambda n: os.path.join(HERE, n)  # noqa: E731
     g_metrics(o("metrics.npz"))
     g_bpr(o("bpr_steps.npz"))
+    g_bpr_gaps(o("bpr_gaps.npz"))
     g_dot(o("dot_steps.npz"))
     g_fm(o("fm_steps.npz"))
     g_dense_adam_pointwise(o("dense_adam_pointwise.npz"))
